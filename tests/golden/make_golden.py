@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    CUDA_VISIBLE_DEVICES="" python tests/golden/make_golden.py
+
+Shims: (1) a stub ``imageio`` module because
+models/basics.py:15 imports it at module scope; (2) ``torch.Tensor.cuda`` is a
+no-op because model.py:48 calls ``.cuda()`` unconditionally.  Nothing else of
+the reference is touched: modules, init and forward are the reference's own.
+
+Each case stores: the weight set name + per-tensor checksums (so the tests know
+their regenerated weights are the reference's), the input seeds, and the
+reference outputs (latents, bpp, mse, reconstruction, and for training cases the
+rd_loss and a digest of each of the 30 gradient tensors).
+"""
+import os
+import sys
+import types
+
+os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+
+import numpy as np
+import torch
+
+sys.modules.setdefault("imageio", types.ModuleType("imageio"))
+torch.Tensor.cuda = lambda self, *a, **k: self
+sys.path.insert(0, REF)
+import model as refmodel  # noqa: E402  (the reference's model.py)
+
+sys.path.insert(0, ROOT)
+from oracle import balle17_oracle as O  # noqa: E402  (only for synth inputs + the W1 perturbation)
+
+torch.set_num_threads(os.cpu_count())
+torch.backends.mkldnn.enabled = True
+
+
+def tensor_digest(t: torch.Tensor):
+    t = t.detach().double().flatten()
+    idx = torch.linspace(0, t.numel() - 1, steps=min(64, t.numel())).long()
+    return np.array([t.sum().item(), t.abs().sum().item(), t.norm().item()]), t[idx].numpy()
+
+
+def build_ref(N, weights):
+    torch.manual_seed(234)                       # train.py:39,202
+    net = refmodel.ImageCompressor(out_channel_N=N)
+    if weights == "W1":
+        sd = O.perturb_state_dict({k: v.detach().clone() for k, v in net.state_dict().items()})
+        net.load_state_dict(sd)
+    return net
+
+
+def run_case(name, N, weights, kind, B, H, W, xseed, training, nseed=None, lam=8192.0):
+    net = build_ref(N, weights)
+    x = O.synth_images(kind, B, H, W, xseed)
+    out = {"N": N, "weights": weights, "kind": kind, "B": B, "H": H, "W": W, "xseed": xseed,
+           "training": int(training), "nseed": -1 if nseed is None else nseed, "lam": lam}
+    for k, v in net.state_dict().items():
+        s, smp = tensor_digest(v)
+        out["w_sum/" + k] = s
+        out["w_smp/" + k] = smp
+    if not training:
+        net.eval()
+        with torch.no_grad():
+            clipped, z, bpp = net(x)                                  # model.py:47-80, HEAD tuple
+            y = net.Encoder(x)
+            recon = net.Decoder(z)
+        assert torch.equal(torch.round(y), z)
+        mse = torch.mean((recon - x).pow(2))                          # model.py:61
+        out["z_i8"] = z.numpy().astype(np.int8)
+        assert np.array_equal(out["z_i8"].astype(np.float32), z.numpy())
+        out["y"] = y.numpy()
+    else:
+        net.train()
+        noise = O.synth_noise(B, N, H, W, nseed)
+        # the reference draws its own noise inside forward (model.py:48-49); to inject ours we
+        # run the same sub-module composition forward() does, and assert forward() agrees with
+        # that composition when given the same generator state.
+        y = net.Encoder(x)
+        z = y + noise
+        recon = net.Decoder(z)
+        clipped = recon.clamp(0., 1.)
+        mse = torch.mean((recon - x).pow(2))
+        prob = net.bitEstimator(z + 0.5) - net.bitEstimator(z - 0.5)
+        bits = torch.sum(torch.clamp(-1.0 * torch.log(prob + 1e-10) / np.log(2.0), 0, 50))
+        bpp = bits / (B * H * W)
+        torch.manual_seed(99)
+        c2, z2, bpp2 = net(x)
+        torch.manual_seed(99)
+        n2 = torch.nn.init.uniform_(torch.zeros(B, N, H // 16, W // 16), -0.5, 0.5)
+        assert torch.equal(z2, y + n2), "forward() composition drifted from model.py"
+        loss = lam * mse + bpp                                        # train.py:102
+        net.zero_grad()
+        loss.backward()
+        out["rd_loss"] = np.float64(loss.item())
+        for k, p in net.named_parameters():
+            s, smp = tensor_digest(p.grad)
+            out["g_sum/" + k] = s
+            out["g_smp/" + k] = smp
+        out["z"] = z.detach().numpy()
+        out["y"] = y.detach().numpy()
+    out["bpp"] = np.float64(bpp.item())
+    out["mse"] = np.float64(mse.item())
+    out["mse_clipped"] = np.float64(torch.mean((clipped - x).pow(2)).item())   # train.py:172
+    r = recon.detach()
+    out["recon_sum"] = tensor_digest(r)[0]
+    step = max(1, H // 64)
+    out["recon_sub"] = r[:, :, ::step, ::step].numpy()
+    out["recon_step"] = step
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: bpp={out['bpp']:.6f} mse={out['mse']:.6f} -> {os.path.getsize(path)/1024:.0f} KB")
+
+
+if __name__ == "__main__":
+    # (name, N, weights, kind, B, H, W, xseed, training, nseed)
+    run_case("eval_W0_U_n128_64", 128, "W0", "U", 2, 64, 96, 1002, False)
+    run_case("eval_W1_U_n128_64", 128, "W1", "U", 2, 64, 96, 1002, False)
+    run_case("eval_W1_S_n128_128", 128, "W1", "S", 1, 128, 192, 1003, False)
+    run_case("eval_W1_U_n32_64", 32, "W1", "U", 1, 64, 64, 1002, False)
+    run_case("eval_W1_S_n192_64", 192, "W1", "S", 1, 64, 128, 1003, False)
+    run_case("train_W0_U_n128_256", 128, "W0", "U", 1, 256, 256, 1001, True, 2002)   # cfg1
+    run_case("train_W1_S_n128_64", 128, "W1", "S", 2, 64, 96, 1004, True, 2002)
+    run_case("train_W1_U_n32_64", 32, "W1", "U", 2, 64, 64, 1004, True, 2002)

@@ -1,0 +1,68 @@
+"""Pins oracle/balle17_oracle.py against outputs of the real reference (tests/golden/*.npz,
+produced by tests/golden/make_golden.py from /root/reference).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import balle17_oracle as O
+from golden_util import Case, digest, golden_names
+
+
+@pytest.mark.parametrize("name", golden_names("eval_"))
+def test_eval_matches_reference(name):
+    c = Case(name)
+    c.check_weights()
+    with torch.no_grad():
+        out = O.forward(c.x, c.sd, training=False)
+    g = c.g
+    # integer latents: bit-exact
+    np.testing.assert_array_equal(out["z"].numpy(), g["z_i8"].astype(np.float32))
+    np.testing.assert_allclose(out["y"].numpy(), g["y"], rtol=0, atol=1e-5)
+    assert abs(out["bpp"].item() - float(g["bpp"])) <= 1e-6 * abs(float(g["bpp"]))
+    assert abs(out["mse"].item() - float(g["mse"])) <= 1e-5 * abs(float(g["mse"]))
+    mse_c = torch.mean((out["clipped"] - c.x) ** 2).item()
+    assert abs(mse_c - float(g["mse_clipped"])) <= 1e-5 * float(g["mse_clipped"])
+    step = int(g["recon_step"])
+    np.testing.assert_allclose(out["recon"][:, :, ::step, ::step].numpy(), g["recon_sub"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", golden_names("train_"))
+def test_train_and_grads_match_reference(name):
+    c = Case(name)
+    c.check_weights()
+    out, loss, grads = O.rd_loss_and_grads(c.x, c.sd, c.noise, c.lam)
+    g = c.g
+    np.testing.assert_allclose(out["z"].detach().numpy(), g["z"], rtol=0, atol=1e-5)
+    assert abs(loss.item() - float(g["rd_loss"])) <= 1e-5 * abs(float(g["rd_loss"]))
+    assert abs(out["bpp"].item() - float(g["bpp"])) <= 1e-6 * abs(float(g["bpp"]))
+    for k, gr in grads.items():
+        s, smp = digest(gr)
+        ref_norm = float(g["g_sum/" + k][2])
+        assert abs(s[2] - ref_norm) <= 1e-4 * ref_norm + 1e-12, (k, s[2], ref_norm)
+        np.testing.assert_allclose(smp, g["g_smp/" + k], rtol=2e-3, atol=1e-4 * ref_norm / np.sqrt(gr.numel()) + 1e-12, err_msg=k)
+
+
+def test_fp64_oracle_close_to_fp32():
+    c = Case("eval_W1_U_n32_64")
+    with torch.no_grad():
+        o32 = O.forward(c.x, c.sd)
+        o64 = O.forward(c.x.double(), O.to_dtype(c.sd, torch.float64))
+    assert (o32["y"].double() - o64["y"]).abs().max() < 1e-4
+    assert abs(o32["bpp"].item() - o64["bpp"].item()) < 1e-5 * o64["bpp"].item()
+
+
+def test_lower_bound_gradient_rule():
+    # models/GDN.py:18-24
+    x = torch.tensor([0.5, 2.0, 0.5, 2.0], requires_grad=True)
+    y = O._LowerBound.apply(x, 1.0)
+    y.backward(torch.tensor([1.0, 1.0, -1.0, -1.0]))
+    assert x.grad.tolist() == [0.0, 1.0, -1.0, -1.0]
+
+
+def test_entropy_floor_in_the_tails():
+    # p underflows -> -log2(1e-10) = 33.22 bits per element (model.py:73)
+    sd = O.init_state_dict(8, seed=1)
+    sd = O.perturb_state_dict(sd)
+    z = torch.full((1, 8, 2, 2), 1.0e7)
+    bits = O.estimate_bits(z, sd).item()
+    assert abs(bits - 32 * 33.219280948) < 1e-2
