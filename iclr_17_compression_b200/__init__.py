@@ -1,0 +1,9 @@
+"""iclr_17_compression_b200: the Balle-2017 learned-codec hot path of Yuval-H/iclr_17_compression
+(ImageCompressor: analysis transform, quantizer, factorized entropy model, synthesis transform) on
+hand-written sm_100a CUDA kernels behind a C ABI (include/b2c.h, libb2c.so)."""
+from . import _lib  # noqa: F401
+from .model import ImageCompressor, load_model, save_model  # noqa: F401
+from .models import GDN, Analysis_net_17, BitEstimator, Bitparm, Synthesis_net_17  # noqa: F401
+
+__all__ = ["ImageCompressor", "load_model", "save_model", "GDN", "Analysis_net_17", "Synthesis_net_17",
+           "BitEstimator", "Bitparm"]

@@ -1,0 +1,88 @@
+"""ctypes binding of libb2c.so (include/b2c.h).  There is no fallback: if the library has not been
+built, or the device is not sm_100, every entry point raises."""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb2c.so")
+
+_c_f = ctypes.c_void_p      # device pointers travel as void*
+_c_i = ctypes.c_int
+_c_sz = ctypes.c_size_t
+_PP = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol include/b2c.h declares
+SIGNATURES = {
+    "b2c_version": (_c_i, []),
+    "b2c_last_error": (ctypes.c_char_p, []),
+    "b2c_check_device": (_c_i, []),
+    "b2c_launch_count": (ctypes.c_uint64, []),
+    "b2c_conv2d_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
+    "b2c_conv_transpose2d_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f] + [_c_i] * 9 + [_c_f]),
+    "b2c_conv_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 10 + [_c_f]),
+    "b2c_channel_sum": (_c_i, [_c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_gdn_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_gdn_bwd_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
+    "b2c_gdn_bwd": (_c_i, [_c_f] * 7 + [_c_i] * 4 + [_c_f, _c_sz, _c_f]),
+    "b2c_quant_entropy_fwd": (_c_i, [_c_f, _c_f, _PP, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_entropy_bwd": (_c_i, [_c_f, _PP, _c_f, _c_f, _PP, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_clamp_sse_workspace_bytes": (_c_sz, [_c_i, _c_i]),
+    "b2c_clamp_sse_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_f, _c_sz, _c_f]),
+    "b2c_clamp_sse_bwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_f, _c_sz, _c_f]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class B2CError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libb2c.so and declare all prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise B2CError(
+                    f"{LIB_PATH} not found: build it with `python -m iclr_17_compression_b200.build` "
+                    "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = load().b2c_last_error().decode(errors="replace")
+        raise B2CError(f"libb2c {what} failed ({code}): {msg}")
+
+
+_device_ok = set()
+
+
+def require_device(dev_index):
+    """libb2c kernels exist for sm_100a only."""
+    if dev_index in _device_ok:
+        return
+    check(load().b2c_check_device(), "device check")
+    _device_ok.add(dev_index)
+
+
+def launch_count():
+    return int(load().b2c_launch_count())
+
+
+def ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return ctypes.cast(arr, _PP), arr     # keep `arr` alive during the call

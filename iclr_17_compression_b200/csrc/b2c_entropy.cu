@@ -1,0 +1,310 @@
+// Quantizer + factorized entropy model + distortion (all fp32, one pass each).
+//   quantizer   model.py:53-56        z = y + u (training) | rint(y) half-to-even (eval)
+//   Bitparm     bitEstimator.py:20-25 t = v*softplus(h)+b ; v' = t + tanh(t)*tanh(a) ; last: sigmoid(t)
+//   bits        model.py:71-73        p = CDF(z+.5) - CDF(z-.5) ; bits = sum clamp(-log(p+1e-10)/ln2, 0, 50)
+//   distortion  model.py:59,61        clipped = clamp(recon,0,1) ; mse on the UNclamped recon
+// The reference's formula is reproduced as written (difference of two fp32 sigmoids, +1e-10 floor),
+// not a numerically nicer one.  One CTA per (image, channel) plane so the per-channel constants
+// softplus(h_k), tanh(a_k), b_k are computed once per CTA; sums are fixed-order (deterministic).
+#include "b2c_common.cuh"
+
+namespace b2c {
+
+struct BitPtrs {
+  const float* p[B2C_NUM_BITPARAMS];
+};
+struct BitGradPtrs {
+  float* p[B2C_NUM_BITPARAMS];
+};
+
+struct ChanConst {
+  float sp[4];  // softplus(h_k)
+  float b[4];
+  float ta[3];  // tanh(a_k)
+};
+
+__device__ __forceinline__ float softplus_t(float h) {  // torch F.softplus, beta=1, threshold=20
+  return h > 20.f ? h : log1pf(expf(h));
+}
+__device__ __forceinline__ float sigmoid_t(float t) { return 1.f / (1.f + expf(-t)); }
+
+__device__ __forceinline__ ChanConst load_chan(const BitPtrs& bp, int c) {
+  ChanConst k;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    k.sp[i] = softplus_t(__ldg(bp.p[3 * i] + c));
+    k.b[i] = __ldg(bp.p[3 * i + 1] + c);
+    k.ta[i] = tanhf(__ldg(bp.p[3 * i + 2] + c));
+  }
+  k.sp[3] = softplus_t(__ldg(bp.p[9] + c));
+  k.b[3] = __ldg(bp.p[10] + c);
+  return k;
+}
+
+__device__ __forceinline__ float cdf(const ChanConst& k, float v) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float t = fmaf(v, k.sp[i], k.b[i]);
+    v = fmaf(tanhf(t), k.ta[i], t);
+  }
+  return sigmoid_t(fmaf(v, k.sp[3], k.b[3]));
+}
+
+__device__ __forceinline__ float elem_bits(const ChanConst& k, float z) {
+  const float p = cdf(k, z + 0.5f) - cdf(k, z - 0.5f);
+  const float bits = -logf(p + 1e-10f) / 0.6931471805599453f;
+  return fminf(fmaxf(bits, 0.f), 50.f);
+}
+
+__global__ void __launch_bounds__(256) quant_entropy_fwd_kernel(const float* __restrict__ y,
+                                                                const float* __restrict__ noise,
+                                                                BitPtrs bp, float* __restrict__ z,
+                                                                float* __restrict__ plane_bits, int C, int HW) {
+  __shared__ float red[32];
+  const int plane = blockIdx.x;  // n*C + c
+  const int c = plane % C;
+  const ChanConst k = load_chan(bp, c);
+  const size_t base = (size_t)plane * HW;
+  float sum = 0.f;
+  if ((HW & 3) == 0) {
+    const float4* y4 = reinterpret_cast<const float4*>(y + base);
+    const float4* n4 = noise ? reinterpret_cast<const float4*>(noise + base) : nullptr;
+    float4* z4 = reinterpret_cast<float4*>(z + base);
+    for (int i = threadIdx.x; i < (HW >> 2); i += blockDim.x) {
+      float4 v = __ldg(y4 + i);
+      if (n4) {
+        const float4 u = __ldg(n4 + i);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      } else {
+        v.x = rintf(v.x); v.y = rintf(v.y); v.z = rintf(v.z); v.w = rintf(v.w);
+      }
+      z4[i] = v;
+      sum += elem_bits(k, v.x);
+      sum += elem_bits(k, v.y);
+      sum += elem_bits(k, v.z);
+      sum += elem_bits(k, v.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float v = __ldg(y + base + i);
+      v = noise ? v + __ldg(noise + base + i) : rintf(v);
+      z[base + i] = v;
+      sum += elem_bits(k, v);
+    }
+  }
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) plane_bits[plane] = sum;
+}
+
+// image_bits[n] = sum_c plane_bits[n*C + c], fixed order
+__global__ void __launch_bounds__(256) plane_reduce_kernel(const float* __restrict__ plane_vals,
+                                                           float* __restrict__ out, int per_image) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < per_image; i += blockDim.x) s += plane_vals[(size_t)n * per_image + i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[n] = s;
+}
+
+// ---------------------------------------------------------------------------- backward
+// For each branch u = z +- 1/2:  lambda_4 = sgn * dL/dp * F(1-F) ... chain back through the 3 layers.
+struct Grad11 {
+  float g[B2C_NUM_BITPARAMS];
+};
+
+__device__ __forceinline__ float branch_bwd(const ChanConst& k, const float sig_h[4], float u, float dLdF, Grad11& acc) {
+  float v[4], t[4], th[3];
+  v[0] = u;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    t[i] = fmaf(v[i], k.sp[i], k.b[i]);
+    th[i] = tanhf(t[i]);
+    v[i + 1] = fmaf(th[i], k.ta[i], t[i]);
+  }
+  t[3] = fmaf(v[3], k.sp[3], k.b[3]);
+  const float F = sigmoid_t(t[3]);
+  float dt = dLdF * F * (1.f - F);
+  acc.g[9] += dt * v[3] * sig_h[3];  // dh4
+  acc.g[10] += dt;                   // db4
+  float dv = dt * k.sp[3];
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {
+    acc.g[3 * i + 2] += dv * th[i] * (1.f - k.ta[i] * k.ta[i]);  // da_k
+    dt = dv * (1.f + (1.f - th[i] * th[i]) * k.ta[i]);
+    acc.g[3 * i] += dt * v[i] * sig_h[i];  // dh_k
+    acc.g[3 * i + 1] += dt;                // db_k
+    dv = dt * k.sp[i];
+  }
+  return dv;  // dL/du
+}
+
+__global__ void __launch_bounds__(256) entropy_bwd_kernel(const float* __restrict__ z, BitPtrs bp,
+                                                          const float* __restrict__ g_bits, float* __restrict__ dz,
+                                                          BitGradPtrs gp, int C, int HW) {
+  __shared__ float red[32];
+  const int plane = blockIdx.x;
+  const int c = plane % C;
+  const ChanConst k = load_chan(bp, c);
+  float sig_h[4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sig_h[i] = sigmoid_t(__ldg(bp.p[3 * i] + c));
+  sig_h[3] = sigmoid_t(__ldg(bp.p[9] + c));
+  // torch softplus backward passes the gradient unchanged above the threshold
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (__ldg(bp.p[3 * i] + c) > 20.f) sig_h[i] = 1.f;
+  if (__ldg(bp.p[9] + c) > 20.f) sig_h[3] = 1.f;
+  const float gb = __ldg(g_bits);
+  const size_t base = (size_t)plane * HW;
+  Grad11 acc;
+#pragma unroll
+  for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) acc.g[i] = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float zv = __ldg(z + base + i);
+    const float p = cdf(k, zv + 0.5f) - cdf(k, zv - 0.5f);
+    const float q = p + 1e-10f;
+    const float bits = -logf(q) / 0.6931471805599453f;
+    // clamp(.,0,50) passes the gradient on the closed interval
+    const float dLdp = (bits >= 0.f && bits <= 50.f) ? -gb / (q * 0.6931471805599453f) : 0.f;
+    float d = 0.f;
+    d += branch_bwd(k, sig_h, zv + 0.5f, dLdp, acc);
+    d += branch_bwd(k, sig_h, zv - 0.5f, -dLdp, acc);
+    dz[base + i] = d;
+  }
+#pragma unroll
+  for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) {
+    const float s = block_sum(acc.g[i], red);
+    if (threadIdx.x == 0) atomicAdd(gp.p[i] + c, s);
+  }
+}
+
+// --------------------------------------------------------------------------- distortion
+__global__ void __launch_bounds__(256) clamp_sse_fwd_kernel(const float* __restrict__ recon,
+                                                            const float* __restrict__ x, float* __restrict__ clipped,
+                                                            float* __restrict__ partial, int CHW, int blocks_per_image) {
+  __shared__ float red[32];
+  const int n = blockIdx.x / blocks_per_image, b = blockIdx.x - n * blocks_per_image;
+  const size_t base = (size_t)n * CHW;
+  float s0 = 0.f, s1 = 0.f;
+  for (int i = b * blockDim.x + threadIdx.x; i < CHW; i += blocks_per_image * blockDim.x) {
+    const float r = __ldg(recon + base + i), xv = __ldg(x + base + i);
+    const float c = fminf(fmaxf(r, 0.f), 1.f);
+    clipped[base + i] = c;
+    const float d0 = r - xv, d1 = c - xv;
+    s0 = fmaf(d0, d0, s0);
+    s1 = fmaf(d1, d1, s1);
+  }
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  if (threadIdx.x == 0) {
+    partial[(size_t)blockIdx.x * 2 + 0] = s0;
+    partial[(size_t)blockIdx.x * 2 + 1] = s1;
+  }
+}
+
+__global__ void __launch_bounds__(256) sse_reduce_kernel(const float* __restrict__ partial, float* __restrict__ sse,
+                                                         int blocks_per_image) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  for (int i = threadIdx.x; i < blocks_per_image; i += blockDim.x) {
+    s0 += partial[((size_t)n * blocks_per_image + i) * 2 + 0];
+    s1 += partial[((size_t)n * blocks_per_image + i) * 2 + 1];
+  }
+  s0 = block_sum(s0, red);
+  s1 = block_sum(s1, red);
+  if (threadIdx.x == 0) {
+    sse[2 * n + 0] = s0;
+    sse[2 * n + 1] = s1;
+  }
+}
+
+__global__ void __launch_bounds__(256) clamp_sse_bwd_kernel(const float* __restrict__ recon,
+                                                            const float* __restrict__ x,
+                                                            const float* __restrict__ g_clipped,
+                                                            const float* __restrict__ g_sse, float* __restrict__ g_recon,
+                                                            size_t n) {
+  const float gs = 2.f * __ldg(g_sse);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float r = __ldg(recon + i);
+    float g = gs * (r - __ldg(x + i));
+    if (g_clipped && r >= 0.f && r <= 1.f) g += __ldg(g_clipped + i);
+    g_recon[i] = g;
+  }
+}
+
+static int clamp_blocks_per_image(int B, int CHW) {
+  int bpi = (CHW + 256 * 8 - 1) / (256 * 8);
+  const int cap = (148 * 8 + B - 1) / B;
+  if (bpi > cap) bpi = cap;
+  if (bpi < 1) bpi = 1;
+  return bpi;
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" {
+
+int b2c_quant_entropy_fwd(const float* y, const float* noise, const float* const* host_params, float* z,
+                          float* plane_bits, float* image_bits, int B, int C, int HW, void* stream) {
+  B2C_REQUIRE(y && host_params && z && plane_bits && image_bits && B > 0 && C > 0 && HW > 0,
+              "quant_entropy_fwd: bad arguments");
+  BitPtrs bp;
+  for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) {
+    B2C_REQUIRE(host_params[i], "quant_entropy_fwd: null parameter pointer %d", i);
+    bp.p[i] = host_params[i];
+  }
+  quant_entropy_fwd_kernel<<<B * C, 256, 0, (cudaStream_t)stream>>>(y, noise, bp, z, plane_bits, C, HW);
+  plane_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(plane_bits, image_bits, C);
+  count_launch(2);
+  return check_launch("quant_entropy_fwd");
+}
+
+int b2c_entropy_bwd(const float* z, const float* const* host_params, const float* g_bits, float* dz,
+                    float* const* host_dparams, int B, int C, int HW, void* stream) {
+  B2C_REQUIRE(z && host_params && g_bits && dz && host_dparams && B > 0 && C > 0 && HW > 0,
+              "entropy_bwd: bad arguments");
+  BitPtrs bp;
+  BitGradPtrs gp;
+  for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) {
+    B2C_REQUIRE(host_params[i] && host_dparams[i], "entropy_bwd: null parameter pointer %d", i);
+    bp.p[i] = host_params[i];
+    gp.p[i] = host_dparams[i];
+  }
+  entropy_bwd_kernel<<<B * C, 256, 0, (cudaStream_t)stream>>>(z, bp, g_bits, dz, gp, C, HW);
+  count_launch();
+  return check_launch("entropy_bwd");
+}
+
+size_t b2c_clamp_sse_workspace_bytes(int B, int CHW) {
+  return (size_t)B * clamp_blocks_per_image(B, CHW) * 2 * sizeof(float);
+}
+
+int b2c_clamp_sse_fwd(const float* recon, const float* x, float* clipped, float* sse, int B, int CHW,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  B2C_REQUIRE(recon && x && clipped && sse && workspace && B > 0 && CHW > 0, "clamp_sse_fwd: bad arguments");
+  if (workspace_bytes < b2c_clamp_sse_workspace_bytes(B, CHW)) {
+    set_error("clamp_sse_fwd: workspace too small");
+    return B2C_EWORKSPACE;
+  }
+  const int bpi = clamp_blocks_per_image(B, CHW);
+  clamp_sse_fwd_kernel<<<B * bpi, 256, 0, (cudaStream_t)stream>>>(recon, x, clipped, (float*)workspace, CHW, bpi);
+  sse_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, sse, bpi);
+  count_launch(2);
+  return check_launch("clamp_sse_fwd");
+}
+
+int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped, const float* g_sse,
+                      float* g_recon, size_t n, void* stream) {
+  B2C_REQUIRE(recon && x && g_sse && g_recon && n > 0, "clamp_sse_bwd: bad arguments");
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  clamp_sse_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(recon, x, g_clipped, g_sse, g_recon, n);
+  count_launch();
+  return check_launch("clamp_sse_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""autograd Functions over the libb2c C ABI (include/b2c.h): the exact-fp32 operator set of the
+Balle-2017 hot path.  Tensors are fp32 NCHW CUDA tensors, as in the reference.  PyTorch is used
+only for memory, streams and autograd bookkeeping; all arithmetic happens in libb2c kernels."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+
+def _p(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _prep(t, name):
+    if not t.is_cuda:
+        raise _lib.B2CError(f"{name} must be a CUDA tensor (this package has no CPU path)")
+    if t.dtype != torch.float32:
+        raise _lib.B2CError(f"{name} must be float32, got {t.dtype}")
+    _lib.require_device(t.device.index)
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------ raw calls
+def _conv2d_raw(x, w, b, stride, pad):
+    B, Cin, H, W = x.shape
+    Cout, Cin2, k, k2 = w.shape
+    if Cin2 != Cin or k != k2:
+        raise _lib.B2CError(f"conv2d: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2c_conv2d_fwd(_p(x), _p(w), _p(b), _p(y), B, Cin, H, W, Cout, k, stride, pad,
+                                              _stream()), "conv2d_fwd")
+    return y
+
+
+def _convT_raw(x, w, b, stride, pad, out_pad):
+    B, Cin, H, W = x.shape
+    Cin2, Cout, k, k2 = w.shape
+    if Cin2 != Cin or k != k2:
+        raise _lib.B2CError(f"conv_transpose2d: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
+    Ho, Wo = (H - 1) * stride - 2 * pad + k + out_pad, (W - 1) * stride - 2 * pad + k + out_pad
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2c_conv_transpose2d_fwd(_p(x), _p(w), _p(b), _p(y), B, Cin, H, W, Cout, k, stride,
+                                                        pad, out_pad, _stream()), "conv_transpose2d_fwd")
+    return y
+
+
+def _wgrad_raw(small, big, k, stride, pad):
+    B, Cs, hs, ws = small.shape
+    _, Cb, hb, wb = big.shape
+    dW = torch.zeros((Cs, Cb, k, k), device=small.device, dtype=torch.float32)
+    with torch.cuda.device(small.device):
+        _lib.check(_lib.load().b2c_conv_wgrad(_p(small), _p(big), _p(dW), B, Cs, hs, ws, Cb, hb, wb, k, stride, pad,
+                                              _stream()), "conv_wgrad")
+    return dW
+
+
+def _channel_sum_raw(t):
+    B, C = t.shape[0], t.shape[1]
+    out = torch.empty((C,), device=t.device, dtype=torch.float32)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().b2c_channel_sum(_p(t), _p(out), B, C, t[0, 0].numel(), _stream()), "channel_sum")
+    return out
+
+
+# ------------------------------------------------------------------------------ autograd
+class _Conv2d(torch.autograd.Function):
+    """nn.Conv2d (models/analysis_17.py:14,18,22)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad):
+        x, w = _prep(x, "input"), _prep(w, "weight")
+        b = _prep(b, "bias") if b is not None else None
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad, b is not None)
+        return _conv2d_raw(x, w, b, stride, pad)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        stride, pad, has_b = ctx.cfg
+        g = g.contiguous()
+        k = w.shape[2]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # dgrad(conv) = conv_transpose with the same weight memory (OIHW == IOHW of the transpose)
+            out_pad = x.shape[2] - ((g.shape[2] - 1) * stride - 2 * pad + k)
+            gx = _convT_raw(g, w, None, stride, pad, out_pad)
+        if ctx.needs_input_grad[1]:
+            gw = _wgrad_raw(g, x, k, stride, pad)
+        if has_b and ctx.needs_input_grad[2]:
+            gb = _channel_sum_raw(g)
+        return gx, gw, gb, None, None
+
+
+class _ConvTranspose2d(torch.autograd.Function):
+    """nn.ConvTranspose2d (models/synthesis_17.py:15,19,23)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, out_pad):
+        x, w = _prep(x, "input"), _prep(w, "weight")
+        b = _prep(b, "bias") if b is not None else None
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad, b is not None)
+        return _convT_raw(x, w, b, stride, pad, out_pad)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        stride, pad, has_b = ctx.cfg
+        g = g.contiguous()
+        k = w.shape[2]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _conv2d_raw(g, w, None, stride, pad)     # dgrad(convT) = conv with the same weight memory
+        if ctx.needs_input_grad[1]:
+            gw = _wgrad_raw(x, g, k, stride, pad)
+        if has_b and ctx.needs_input_grad[2]:
+            gb = _channel_sum_raw(g)
+        return gx, gw, gb, None, None, None
+
+
+class _GDN(torch.autograd.Function):
+    """models/GDN.py:64-94 incl. the LowerBound reparametrisation (GDN.py:10-24,73-79)."""
+
+    @staticmethod
+    def forward(ctx, x, beta, gamma, inverse):
+        x, beta, gamma = _prep(x, "input"), _prep(beta, "beta"), _prep(gamma, "gamma")
+        B, C = x.shape[0], x.shape[1]
+        if beta.numel() != C or gamma.numel() != C * C:
+            raise _lib.B2CError(f"GDN: beta/gamma do not match {C} channels")
+        HW = x[0, 0].numel()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b2c_gdn_fwd(_p(x), _p(beta), _p(gamma), _p(y), B, C, HW, int(inverse), _stream()),
+                       "gdn_fwd")
+        ctx.save_for_backward(x, beta, gamma)
+        ctx.inverse = bool(inverse)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, beta, gamma = ctx.saved_tensors
+        g = g.contiguous()
+        B, C = x.shape[0], x.shape[1]
+        HW = x[0, 0].numel()
+        lib = _lib.load()
+        gx = torch.empty_like(x)
+        dbeta = torch.empty_like(beta)
+        dgamma = torch.empty_like(gamma)
+        nbytes = lib.b2c_gdn_bwd_workspace_bytes(B, C, HW)
+        ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.b2c_gdn_bwd(_p(x), _p(beta), _p(gamma), _p(g), _p(gx), _p(dbeta), _p(dgamma), B, C, HW,
+                                       int(ctx.inverse), _p(ws), nbytes, _stream()), "gdn_bwd")
+        return gx, dbeta, dgamma, None
+
+
+class _QuantEntropy(torch.autograd.Function):
+    """model.py:53-56 (quantizer) + model.py:71-73 (bits) + models/bitEstimator.py:20-42."""
+
+    @staticmethod
+    def forward(ctx, y, noise, *params):
+        y = _prep(y, "latent")
+        params = [_prep(p, "bit-estimator parameter") for p in params]
+        assert len(params) == 11
+        B, C = y.shape[0], y.shape[1]
+        HW = y[0, 0].numel()
+        for p in params:
+            if p.numel() != C:
+                raise _lib.B2CError("bit-estimator parameter does not match the latent's channel count")
+        if noise is not None:
+            noise = _prep(noise, "noise")
+            if noise.shape != y.shape:
+                raise _lib.B2CError(f"quantization noise {tuple(noise.shape)} does not match latent {tuple(y.shape)}")
+        z = torch.empty_like(y)
+        plane_bits = torch.empty((B, C), device=y.device, dtype=torch.float32)
+        image_bits = torch.empty((B,), device=y.device, dtype=torch.float32)
+        pp, keep = _lib.ptr_array(params)
+        with torch.cuda.device(y.device):
+            _lib.check(_lib.load().b2c_quant_entropy_fwd(_p(y), _p(noise), pp, _p(z), _p(plane_bits), _p(image_bits),
+                                                         B, C, HW, _stream()), "quant_entropy_fwd")
+        total_bits = image_bits.sum()              # model.py:73 sums over the whole batch
+        ctx.save_for_backward(z, *params)
+        ctx.training = noise is not None
+        ctx.mark_non_differentiable(image_bits, plane_bits)
+        return z, total_bits, image_bits, plane_bits
+
+    @staticmethod
+    def backward(ctx, gz, g_total, _g_image, _g_plane):
+        z, *params = ctx.saved_tensors
+        B, C = z.shape[0], z.shape[1]
+        HW = z[0, 0].numel()
+        dparams = [torch.zeros_like(p) for p in params]
+        dz = None
+        if g_total is not None:
+            g_bits = g_total.reshape(1).contiguous().float()
+            dz = torch.empty_like(z)
+            pp, k1 = _lib.ptr_array(params)
+            dp, k2 = _lib.ptr_array(dparams)
+            with torch.cuda.device(z.device):
+                _lib.check(_lib.load().b2c_entropy_bwd(_p(z), pp, _p(g_bits), _p(dz), dp, B, C, HW, _stream()),
+                           "entropy_bwd")
+        gy = None
+        if ctx.needs_input_grad[0]:
+            if ctx.training:                       # z = y + u  ->  dz/dy = 1
+                gy = dz if gz is None else (gz if dz is None else gz + dz)
+            else:                                  # z = round(y) -> zero gradient (torch.round)
+                gy = torch.zeros_like(z)
+        return (gy, None, *dparams)
+
+
+class _Distortion(torch.autograd.Function):
+    """model.py:59 (clamp) + model.py:61 (squared error on the unclamped reconstruction)."""
+
+    @staticmethod
+    def forward(ctx, recon, x):
+        recon, x = _prep(recon, "reconstruction"), _prep(x, "input image")
+        if recon.shape != x.shape:
+            raise _lib.B2CError(f"reconstruction {tuple(recon.shape)} does not match input {tuple(x.shape)}")
+        B = x.shape[0]
+        CHW = x[0].numel()
+        lib = _lib.load()
+        clipped = torch.empty_like(recon)
+        sse = torch.empty((B, 2), device=x.device, dtype=torch.float32)
+        nbytes = lib.b2c_clamp_sse_workspace_bytes(B, CHW)
+        ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, CHW, _p(ws), nbytes,
+                                             _stream()), "clamp_sse_fwd")
+        sse_total = sse[:, 0].sum()                # model.py:61 averages over the whole batch
+        ctx.save_for_backward(recon, x)
+        ctx.mark_non_differentiable(sse)
+        return clipped, sse_total, sse
+
+    @staticmethod
+    def backward(ctx, g_clipped, g_total, _g_sse):
+        recon, x = ctx.saved_tensors
+        if g_total is None:
+            g_s = torch.zeros((1,), device=x.device, dtype=torch.float32)
+        else:
+            g_s = g_total.reshape(1).contiguous().float()
+        gc = g_clipped.contiguous() if g_clipped is not None else None
+        g_recon = torch.empty_like(recon)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b2c_clamp_sse_bwd(_p(recon), _p(x), _p(gc), _p(g_s), _p(g_recon), recon.numel(),
+                                                     _stream()), "clamp_sse_bwd")
+        return g_recon, None
+
+
+# ------------------------------------------------------------------------------ public ops
+def conv2d(x, weight, bias, stride, padding):
+    return _Conv2d.apply(x, weight, bias, stride, padding)
+
+
+def conv_transpose2d(x, weight, bias, stride, padding, output_padding):
+    return _ConvTranspose2d.apply(x, weight, bias, stride, padding, output_padding)
+
+
+def gdn(x, beta, gamma, inverse=False):
+    return _GDN.apply(x, beta, gamma, inverse)
+
+
+def quant_entropy(y, noise, params):
+    """returns (z, total_bits, image_bits[B], plane_bits[B,C]); noise=None selects the eval (round)
+    quantizer.  Only z and total_bits are differentiable."""
+    return _QuantEntropy.apply(y, noise, *params)
+
+
+def distortion(recon, x):
+    """returns (clipped, sse_total, sse[B,2]); sse[:,0] is the UNclamped and sse[:,1] the clamped squared
+    error per image, sse_total = sum(sse[:,0]).  Only clipped and sse_total are differentiable."""
+    return _Distortion.apply(recon, x)

@@ -1,0 +1,127 @@
+/* b2c.h - C ABI of libb2c.so: the B200 (sm_100a) kernels underneath the reference's
+ * ImageCompressor Python API (Balle-2017 codec hot path).
+ *
+ * The reference (Yuval-H/iclr_17_compression) is pure Python over PyTorch eager and has
+ * NO native interface of its own; each entry point below therefore cites the reference
+ * Python call site (file:line, relative to the reference root) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is DEVICE memory owned by the caller unless the name says host;
+ *     tensors are dense fp32 NCHW exactly as the reference holds them.
+ *   - the library never allocates or frees caller-visible memory and never synchronises
+ *     the device; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - returns 0 on success, a negative B2C_E* code otherwise; b2c_last_error() returns a
+ *     thread-local message.  No C++ exception crosses the boundary.
+ *   - re-entrant: no global mutable state apart from lazily created, mutex-guarded,
+ *     per-device caches (function attributes, tensor maps).
+ *   - there is no CPU fallback: a non-sm_100 device is an error (B2C_EARCH).
+ */
+#ifndef B2C_H_
+#define B2C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_OK 0
+#define B2C_EINVAL (-1)  /* bad shape / null pointer / unsupported geometry */
+#define B2C_EARCH (-2)   /* device is not sm_100 */
+#define B2C_ECUDA (-3)   /* CUDA runtime / launch failure */
+#define B2C_EWORKSPACE (-4) /* workspace too small */
+
+/* number of per-channel parameter vectors of the factorized entropy model:
+ * f1.{h,b,a}, f2.{h,b,a}, f3.{h,b,a}, f4.{h,b}  (models/bitEstimator.py:13-18,33-36) */
+#define B2C_NUM_BITPARAMS 11
+
+int b2c_version(void);
+const char* b2c_last_error(void);
+/* 0 if the CURRENT device is compute capability 10.x, B2C_EARCH otherwise. */
+int b2c_check_device(void);
+/* counts kernels launched by this library in this process (bench.py's gpu_launches). */
+uint64_t b2c_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * Convolutions (exact-fp32 path).
+ * --------------------------------------------------------------------------------- */
+/* nn.Conv2d forward: models/analysis_17.py:14,18,22 + :33-35.
+ * x[B,Cin,H,W], w[Cout,Cin,k,k] (OIHW), bias[Cout] or NULL -> y[B,Cout,Ho,Wo],
+ * Ho = (H+2p-k)/s+1.  Also serves as dgrad of conv_transpose2d (same weight memory). */
+int b2c_conv2d_fwd(const float* x, const float* w, const float* bias, float* y,
+                   int B, int Cin, int H, int W, int Cout, int k, int stride, int pad,
+                   void* stream);
+
+/* nn.ConvTranspose2d forward: models/synthesis_17.py:15,19,23 + :28-30.
+ * x[B,Cin,H,W], w[Cin,Cout,k,k] (IOHW), bias[Cout] or NULL -> y[B,Cout,Ho,Wo],
+ * Ho = (H-1)s-2p+k+out_pad.  Computed in s*s sub-pixel phases (no zero insertion).
+ * Also serves as dgrad of conv2d (same weight memory, Cin:=conv Cout). */
+int b2c_conv_transpose2d_fwd(const float* x, const float* w, const float* bias, float* y,
+                             int B, int Cin, int H, int W, int Cout, int k, int stride,
+                             int pad, int out_pad, void* stream);
+
+/* weight gradient shared by both layer types (autograd of the above; train.py:105).
+ *   dW[Cs][Cb][k][k] (+)= sum_{n,ys,xs} small[n,Cs,ys,xs] * big[n,Cb,s*ys-p+ky,s*xs-p+kx]
+ * conv2d:            small = grad_out [B,Cout,Ho,Wo], big = x  [B,Cin,H,W]  -> dW is OIHW
+ * conv_transpose2d:  small = x [B,Cin,H,W],          big = grad_out [B,Cout,Ho,Wo] -> IOHW
+ * dW must be zero-filled by the caller (split-K partial sums are added atomically). */
+int b2c_conv_wgrad(const float* small_t, const float* big_t, float* dW,
+                   int B, int Cs, int hs, int ws, int Cb, int hb, int wb,
+                   int k, int stride, int pad, void* stream);
+
+/* out[c] = sum_{n,pix} t[n,c,pix]  (bias gradients). */
+int b2c_channel_sum(const float* t, float* out, int B, int C, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * GDN / IGDN: models/GDN.py:64-94 (forward), :10-24 (LowerBound), autograd for bwd.
+ * beta_p[C], gamma_p[C,C] are the raw (reparametrised) parameters as in state_dict.
+ * --------------------------------------------------------------------------------- */
+int b2c_gdn_fwd(const float* x, const float* beta_p, const float* gamma_p, float* y,
+                int B, int C, int HW, int inverse, void* stream);
+/* gx[B,C,HW]; dbeta_p[C], dgamma_p[C,C] must be zero-filled by the caller;
+ * workspace: B*C*HW floats (dL/dnorm) + C + C*C floats. */
+size_t b2c_gdn_bwd_workspace_bytes(int B, int C, int HW);
+int b2c_gdn_bwd(const float* x, const float* beta_p, const float* gamma_p, const float* gy,
+                float* gx, float* dbeta_p, float* dgamma_p,
+                int B, int C, int HW, int inverse, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Quantizer + factorized entropy model: model.py:53-56 (quantizer), model.py:71-78 +
+ * models/bitEstimator.py:20-25,38-42 (bits).
+ * y[B,C,HW]; noise[B,C,HW] (training: z = y + noise) or NULL (eval: z = rint(y), half to
+ * even).  host_params: HOST array of B2C_NUM_BITPARAMS device pointers, each [C], order
+ * f1.h f1.b f1.a f2.h f2.b f2.a f3.h f3.b f3.a f4.h f4.b.
+ * z[B,C,HW] out; plane_bits[B*C] out (bits of each (image, channel) plane);
+ * image_bits[B] out (deterministic fixed-order sum over channels).
+ * --------------------------------------------------------------------------------- */
+int b2c_quant_entropy_fwd(const float* y, const float* noise, const float* const* host_params,
+                          float* z, float* plane_bits, float* image_bits,
+                          int B, int C, int HW, void* stream);
+/* backward of total_bits = sum(image_bits): g_bits is a DEVICE scalar (dL/dtotal_bits).
+ * dz[B,C,HW] out (assigned); host_dparams: HOST array of 11 device pointers [C], must be
+ * zero-filled by the caller (atomically accumulated). */
+int b2c_entropy_bwd(const float* z, const float* const* host_params, const float* g_bits,
+                    float* dz, float* const* host_dparams, int B, int C, int HW, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Distortion: model.py:59 (clamp) and :61 (mse on the UNclamped reconstruction),
+ * train.py:172 (mse on the clamped one).
+ * sse[2*B]: per image {sum (recon-x)^2, sum (clamp(recon)-x)^2}; deterministic.
+ * --------------------------------------------------------------------------------- */
+int b2c_clamp_sse_fwd(const float* recon, const float* x, float* clipped, float* sse,
+                      int B, int CHW, void* workspace, size_t workspace_bytes, void* stream);
+size_t b2c_clamp_sse_workspace_bytes(int B, int CHW);
+/* grad_recon = g_clipped * 1[0<=recon<=1] + g_sse[0] * 2 (recon - x);
+ * g_clipped may be NULL; g_sse is a DEVICE scalar (dL/d total unclamped SSE). */
+int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped,
+                      const float* g_sse, float* g_recon, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2C_H_ */
