@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the Balle-2017 codec hot path (BASELINE.json metric: Mpix/s encode+decode at 768x512).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one ImageCompressor eval forward (encode -> round -> bits -> decode -> clamp/SSE) over a batch
+of 24 synthetic Kodak-shape images (BASELINE.json configs[1]) per GPU.  Multi-GPU inference shards per
+image with no collective (weak scaling: 24 images per rank).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+IMAGES, H, W, N_CH = 24, 512, 768, 128
+MPIX_PER_IMAGE = H * W / 1e6
+FLOP_PER_PIXEL = 45015.0          # convs 39776 + GDN matmuls 5120 + pointwise 119
+METRIC = "Mpix/s encode+decode (768x512) per B200"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_throughput(budget_s, images_per_step, steps=None, warmup=1):
+    """Times the reference algorithm's CPU path (the oracle port: plain torch CPU ops, all host threads) on a
+    bounded sample of the same workload.  Returns (Mpix/s, cores, sample description, ms per step)."""
+    from oracle import balle17_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.init_state_dict(N_CH, seed=234)
+    x = O.synth_images("U", images_per_step, H, W, 1002)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.forward(x[:1], sd)
+        t0 = time.perf_counter()
+        done = 0
+        nsteps = 0
+        while True:
+            for i in range(images_per_step):          # batch 1 per call, as the reference's testKodak does (train.py:162)
+                O.forward(x[i:i + 1], sd)
+                done += 1
+            nsteps += 1
+            el = time.perf_counter() - t0
+            if (steps is not None and nsteps >= steps) or (steps is None and el >= budget_s):
+                break
+    return done * MPIX_PER_IMAGE / el, cores, f"{done} of the {IMAGES} 3x{H}x{W} images, batch 1, eval forward", el / nsteps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 2
+    val, cores, sample, ms = cpu_reference_throughput(None, per_step, steps=args.steps, warmup=max(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"kodak-shape inference, {IMAGES}x3x{H}x{W}, N={N_CH}, eval (configs[1])",
+                       "step": f"bounded sample: {per_step} images per step, batch 1"},
+            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-train", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import iclr_17_compression_b200 as P
+    from iclr_17_compression_b200 import _lib, functional as B2F
+    from oracle import balle17_oracle as O      # synthetic inputs + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(234)
+    model = P.ImageCompressor(N_CH).to(dev).eval()
+    x_host = O.synth_images("U", IMAGES, H, W, 1002 + rank).pin_memory()
+    x = x_host.to(dev)
+    lat_host = torch.empty((IMAGES, N_CH, H // 16, W // 16), dtype=torch.float32).pin_memory()
+    stat_host = torch.empty((IMAGES, 3), dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        with torch.no_grad():
+            return model(inp)
+
+    for _ in range(args.warmup):
+        step(x)
+    barrier()
+
+    # ---- timed region: K steps, device time, inputs resident in HBM
+    sampler = ClockSampler(local)
+    sampler.start()
+    timer = B2F.start_timing()
+    n0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(x)
+    ev1.record()
+    barrier()
+    B2F.stop_timing()
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = IMAGES * world * MPIX_PER_IMAGE / (ms / 1e3)
+
+    # ---- end to end: pinned host input -> H2D -> forward -> D2H of latents + per-image (bits, sse, sse_clipped)
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            clipped, z, bpp = model(xd)
+        lat_host.copy_(z, non_blocking=True)
+        stats = torch.cat([model.last["image_bits"][:, None], model.last["sse"]], dim=1)
+        stat_host.copy_(stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()
+    e2e_val = IMAGES * world * MPIX_PER_IMAGE / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (largest share of the step), from the in-region event pairs
+    pk, pk_kind = peaks()
+    ops = timer.summary()
+    total_ms = sum(d["ms_total"] for d in ops.values())
+    top_name, top = max(ops.items(), key=lambda kv: kv[1]["ms_total"])
+    tensor_bound = top_name.startswith("conv")
+    if tensor_bound:
+        achieved = top["flops"] / (top["ms_avg"] * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak}
+    else:
+        achieved = top["bytes"] / (top["ms_avg"] * 1e-3) / 1e9
+        peak = pk["hbm_gbs"]
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
+    roof.update({"traffic": None, "kernel": top_name, "kernel_ms": top["ms_avg"],
+                 "share_of_step": top["ms_total"] / total_ms, "peak_source": pk_kind,
+                 "pipeline_frac_of_tensor_roofline": (FLOP_PER_PIXEL * IMAGES * H * W / (ms * 1e-3) / 1e12)
+                 / pk["bf16_tflops_sustained"]})
+
+    line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"kodak-shape inference, {IMAGES}x3x{H}x{W} per GPU, N={N_CH}, eval, one batch "
+                                   f"of {IMAGES} (configs[1])",
+                       "weights": "seed-234 random init", "parallelism": f"per-image sharding x{world}, no collective",
+                       "l2": "per-step working set (226 MB in/out + >600 MB intermediates) exceeds the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(x_host.numel() * 4),
+                    "d2h_bytes_per_step": int(lat_host.numel() * 4 + stat_host.numel() * 4)},
+            "roofline": roof,
+            "ops": {k: {"ms_avg": round(v["ms_avg"], 4), "calls": v["calls"]} for k, v in ops.items()}}
+
+    # ---- training step (cfg3): batch 8 of 3x256x256, noise quantizer, fwd+bwd of 8192*mse + bpp
+    if not args.no_train:
+        try:
+            line["train"] = train_bench(model, dev, world, rank, barrier)
+        except Exception as e:   # the inference line must still print
+            line["train"] = {"error": repr(e)}
+
+    if rank == 0 and world == 1:
+        val, cores, sample, _ = cpu_reference_throughput(args.cpu_budget, 4)
+        line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
+    import torch.distributed as dist
+    from oracle import balle17_oracle as O
+    model.train()
+    model.return_mode = "mse"
+    sync = None
+    if world > 1:
+        from iclr_17_compression_b200.ddp import GradSync
+        sync = GradSync(model)
+    xb = O.synth_images("U", 8, 256, 256, 1004 + rank).to(dev)
+
+    def tstep():
+        for p in model.parameters():
+            p.grad = None
+        _, mse, bpp = model(xb)
+        (8192.0 * mse + bpp).backward()
+        if sync is not None:
+            sync.finish()
+
+    for _ in range(warmup):
+        tstep()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tstep()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    model.eval()
+    model.return_mode = "latent"
+    return {"metric": "train img/s (batch 8 of 3x256x256 per GPU, fwd+bwd, noise quantizer, lambda=8192)",
+            "value": 8 * world / (ms / 1e3), "unit": "img/s", "ms_per_step": ms,
+            "allreduce": "nccl bucketed, overlapped with backward" if world > 1 else "none (1 GPU)",
+            "flop_per_step": 68.7e9, "frac_of_tensor_roofline": 68.7e9 / (ms * 1e-3) / 1e12 / peaks()[0]["bf16_tflops_sustained"]}
+
+
+if __name__ == "__main__":
+    main()

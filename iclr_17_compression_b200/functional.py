@@ -1,6 +1,7 @@
 """autograd Functions over the libb2c C ABI (include/b2c.h): the exact-fp32 operator set of the
 Balle-2017 hot path.  Tensors are fp32 NCHW CUDA tensors, as in the reference.  PyTorch is used
 only for memory, streams and autograd bookkeeping; all arithmetic happens in libb2c kernels."""
+import contextlib
 import ctypes
 
 import torch
@@ -8,6 +9,53 @@ import torch
 from . import _lib
 
 _vp = ctypes.c_void_p
+
+# ------------------------------------------------------------------------------ op timing (bench.py)
+_timer = None
+
+
+class OpTimer:
+    """CUDA-event pairs around every libb2c call on the launching stream (torch's current stream is
+    the stream handed to the library), with the call's algorithmic FLOPs / bytes."""
+
+    def __init__(self):
+        self.records = []          # (name, flops, bytes, start_event, end_event)
+
+    def summary(self):
+        """name -> dict(calls, ms_total, ms_avg, flops, bytes); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, fl, by, s, e in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms_total": 0.0, "flops": fl, "bytes": by})
+            d["calls"] += 1
+            d["ms_total"] += s.elapsed_time(e)
+        for d in out.values():
+            d["ms_avg"] = d["ms_total"] / d["calls"]
+        return out
+
+
+def start_timing():
+    global _timer
+    _timer = OpTimer()
+    return _timer
+
+
+def stop_timing():
+    global _timer
+    t, _timer = _timer, None
+    return t
+
+
+@contextlib.contextmanager
+def _timed(name, flops=0, nbytes=0):
+    if _timer is None:
+        yield
+        return
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    yield
+    e.record()
+    _timer.records.append((name, flops, nbytes, s, e))
 
 
 def _p(t):
@@ -35,7 +83,9 @@ def _conv2d_raw(x, w, b, stride, pad):
         raise _lib.B2CError(f"conv2d: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    name = f"conv2d_fwd[{B}x{Cin}x{H}x{W}->{Cout},k{k}s{stride}]"
+    with torch.cuda.device(x.device), _timed(name, 2 * B * Ho * Wo * Cin * k * k * Cout,
+                                             4 * (x.numel() + w.numel() + y.numel())):
         _lib.check(_lib.load().b2c_conv2d_fwd(_p(x), _p(w), _p(b), _p(y), B, Cin, H, W, Cout, k, stride, pad,
                                               _stream()), "conv2d_fwd")
     return y
@@ -48,7 +98,9 @@ def _convT_raw(x, w, b, stride, pad, out_pad):
         raise _lib.B2CError(f"conv_transpose2d: weight {tuple(w.shape)} does not match input {tuple(x.shape)}")
     Ho, Wo = (H - 1) * stride - 2 * pad + k + out_pad, (W - 1) * stride - 2 * pad + k + out_pad
     y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device):
+    name = f"conv_transpose2d_fwd[{B}x{Cin}x{H}x{W}->{Cout},k{k}s{stride}]"
+    with torch.cuda.device(x.device), _timed(name, 2 * B * H * W * Cin * k * k * Cout,
+                                             4 * (x.numel() + w.numel() + y.numel())):
         _lib.check(_lib.load().b2c_conv_transpose2d_fwd(_p(x), _p(w), _p(b), _p(y), B, Cin, H, W, Cout, k, stride,
                                                         pad, out_pad, _stream()), "conv_transpose2d_fwd")
     return y
@@ -58,7 +110,9 @@ def _wgrad_raw(small, big, k, stride, pad):
     B, Cs, hs, ws = small.shape
     _, Cb, hb, wb = big.shape
     dW = torch.zeros((Cs, Cb, k, k), device=small.device, dtype=torch.float32)
-    with torch.cuda.device(small.device):
+    name = f"conv_wgrad[{B}x{Cs}x{hs}x{ws}*{Cb}x{hb}x{wb},k{k}s{stride}]"
+    with torch.cuda.device(small.device), _timed(name, 2 * B * hs * ws * Cs * Cb * k * k,
+                                                 4 * (small.numel() + big.numel() + dW.numel())):
         _lib.check(_lib.load().b2c_conv_wgrad(_p(small), _p(big), _p(dW), B, Cs, hs, ws, Cb, hb, wb, k, stride, pad,
                                               _stream()), "conv_wgrad")
     return dW
@@ -140,7 +194,8 @@ class _GDN(torch.autograd.Function):
             raise _lib.B2CError(f"GDN: beta/gamma do not match {C} channels")
         HW = x[0, 0].numel()
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed(f"gdn_fwd[{B}x{C}x{HW}]", B * HW * C * (2 * C + 4),
+                                                 8 * x.numel()):
             _lib.check(_lib.load().b2c_gdn_fwd(_p(x), _p(beta), _p(gamma), _p(y), B, C, HW, int(inverse), _stream()),
                        "gdn_fwd")
         ctx.save_for_backward(x, beta, gamma)
@@ -159,7 +214,8 @@ class _GDN(torch.autograd.Function):
         dgamma = torch.empty_like(gamma)
         nbytes = lib.b2c_gdn_bwd_workspace_bytes(B, C, HW)
         ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed(f"gdn_bwd[{B}x{C}x{HW}]", 3 * B * HW * C * (2 * C + 4),
+                                                 16 * x.numel()):
             _lib.check(lib.b2c_gdn_bwd(_p(x), _p(beta), _p(gamma), _p(g), _p(gx), _p(dbeta), _p(dgamma), B, C, HW,
                                        int(ctx.inverse), _p(ws), nbytes, _stream()), "gdn_bwd")
         return gx, dbeta, dgamma, None
@@ -186,7 +242,8 @@ class _QuantEntropy(torch.autograd.Function):
         plane_bits = torch.empty((B, C), device=y.device, dtype=torch.float32)
         image_bits = torch.empty((B,), device=y.device, dtype=torch.float32)
         pp, keep = _lib.ptr_array(params)
-        with torch.cuda.device(y.device):
+        nb = (12 if noise is not None else 8) * y.numel()
+        with torch.cuda.device(y.device), _timed(f"quant_entropy_fwd[{B}x{C}x{HW}]", 60 * y.numel(), nb):
             _lib.check(_lib.load().b2c_quant_entropy_fwd(_p(y), _p(noise), pp, _p(z), _p(plane_bits), _p(image_bits),
                                                          B, C, HW, _stream()), "quant_entropy_fwd")
         total_bits = image_bits.sum()              # model.py:73 sums over the whole batch
@@ -207,7 +264,7 @@ class _QuantEntropy(torch.autograd.Function):
             dz = torch.empty_like(z)
             pp, k1 = _lib.ptr_array(params)
             dp, k2 = _lib.ptr_array(dparams)
-            with torch.cuda.device(z.device):
+            with torch.cuda.device(z.device), _timed(f"entropy_bwd[{B}x{C}x{HW}]", 150 * z.numel(), 8 * z.numel()):
                 _lib.check(_lib.load().b2c_entropy_bwd(_p(z), pp, _p(g_bits), _p(dz), dp, B, C, HW, _stream()),
                            "entropy_bwd")
         gy = None
@@ -234,7 +291,7 @@ class _Distortion(torch.autograd.Function):
         sse = torch.empty((B, 2), device=x.device, dtype=torch.float32)
         nbytes = lib.b2c_clamp_sse_workspace_bytes(B, CHW)
         ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed(f"clamp_sse_fwd[{B}x{CHW}]", 8 * x.numel(), 12 * x.numel()):
             _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, CHW, _p(ws), nbytes,
                                              _stream()), "clamp_sse_fwd")
         sse_total = sse[:, 0].sum()                # model.py:61 averages over the whole batch
@@ -251,7 +308,7 @@ class _Distortion(torch.autograd.Function):
             g_s = g_total.reshape(1).contiguous().float()
         gc = g_clipped.contiguous() if g_clipped is not None else None
         g_recon = torch.empty_like(recon)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed("clamp_sse_bwd", 4 * x.numel(), 16 * x.numel()):
             _lib.check(_lib.load().b2c_clamp_sse_bwd(_p(recon), _p(x), _p(gc), _p(g_s), _p(g_recon), recon.numel(),
                                                      _stream()), "clamp_sse_bwd")
         return g_recon, None
