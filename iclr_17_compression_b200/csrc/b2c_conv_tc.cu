@@ -1,0 +1,689 @@
+// tcgen05 implicit-GEMM convolution family for the inference path (out_channel_N = 128).
+//
+//   CONV1      9x9 s4  3->128   A tile built in shared memory from the fp32 NCHW image (K 243 -> 256)
+//   CONV5S2    5x5 s2 128->128  A tiles = TMA boxes of the NHWC bf16 input with traversal stride 2
+//   DECONV5S2  5x5 s2 transposed, 4 sub-pixel phases, each a stride-1 tap subset (no zero insertion)
+//   DECONV3    9x9 s4 transposed 128->3, as a 3x3 stride-1 conv to 48 = 16 phases x 3 channels
+//
+// One CTA = one 8x16-pixel output tile (M = 128 rows = TMEM lanes) x all output channels.
+//   warp 0    TMA producer  (A boxes + tap-major weight panels, SWIZZLE_128B, mbarrier ring)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulators in TMEM)
+//   warps 2-5 row workers: software A tiles (CONV1, x^2 for GDN) and the epilogue (tcgen05.ld)
+// GDN / IGDN is a second MMA in the same CTA: the workers square the biased accumulator, write it
+// as a K-major swizzled bf16 tile, the MMA warp multiplies it by gamma (TMA) into a second TMEM
+// accumulator, and the workers finish y = x / sqrt(beta + norm)  (or x * sqrt).
+// SPLIT3: every operand is a (hi, lo) bf16 pair and each product is hi*hi + hi*lo + lo*hi
+// (fp32 accumulate) - the error-compensated mode the analysis transform needs for round().
+#include <mutex>
+
+#include "b2c_common.cuh"
+#include "b2c_tc.cuh"
+
+namespace b2c {
+namespace tc {
+
+constexpr int TH = 8, TW = 16;            // output tile (pixels)
+constexpr int TILE_M = TH * TW;           // 128
+constexpr int KBLK = 64;                  // bf16 per k-block row (128 B)
+constexpr int SLOT_BYTES = TILE_M * KBLK * 2;  // 16 KB operand slot
+constexpr int NTHREADS = 192;
+constexpr int C128 = 128;
+
+enum { OUT_BF16 = 0, OUT_F32_NCHW = 1, OUT_F32_NCHW_PS4 = 2 };
+
+struct TcParams {
+  int B, Hin, Win;      // input grid
+  int Hg, Wg;           // tile grid (pixels): conv -> output dims; deconv -> input dims
+  int tiles_x;          // tiles per row
+  int Hfull, Wfull;     // full output dims
+  int ps;               // output lattice stride (1 conv, 2 deconv5s2, 4 deconv3)
+  const float* img;     // CONV1: fp32 NCHW image
+  const float* bias;
+  const float* beta_eff;
+  void* out_hi;
+  void* out_lo;
+};
+
+// (c, ky, kx) of flattened K index for CONV1, K = c*81 + ky*9 + kx
+__constant__ uint16_t c_conv1_ktab[256];
+
+template <bool SPLIT3>
+__device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_lo, int r, int cidx,
+                                                const float (&v)[8]) {
+  // K-major SWIZZLE_128B: row r at r*128, 16-byte chunk index XORed with (r & 7)
+  const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cidx ^ (r & 7)) << 4);
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (SPLIT3) {
+      split_bf16(v[i], h[i], l[i]);
+    } else {
+      h[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+  uint4 qh = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
+                        pack_bf16x2(h[6], h[7]));
+  *reinterpret_cast<uint4*>(slot_hi + off) = qh;
+  if (SPLIT3) {
+    uint4 ql = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]),
+                          pack_bf16x2(l[6], l[7]));
+    *reinterpret_cast<uint4*>(slot_lo + off) = ql;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ int num_steps(int phase) {
+  if (KIND == B2C_TC_CONV1) return 4;
+  if (KIND == B2C_TC_CONV5S2) return 50;
+  if (KIND == B2C_TC_DECONV3) return 18;
+  const int ry = phase >> 1, rx = phase & 1;  // DECONV5S2: (3-ry) x (3-rx) taps x 2 channel blocks
+  return (3 - ry) * (3 - rx) * 2;
+}
+
+// step -> A box offset (dy, dx in input pixels), channel block, weight-panel group
+template <int KIND>
+__device__ __forceinline__ void decode_step(int s, int phase, int& dy, int& dx, int& cb, int& group) {
+  if (KIND == B2C_TC_CONV1) {
+    dy = dx = 0; cb = 0; group = s;
+  } else if (KIND == B2C_TC_CONV5S2) {
+    cb = s & 1;
+    const int t = s >> 1, ky = t / 5, kx = t - ky * 5;
+    dy = ky - 2; dx = kx - 2; group = t;                 // iy = 2*oy - 2 + ky
+  } else if (KIND == B2C_TC_DECONV3) {
+    cb = s & 1;
+    const int t = s >> 1, sy = t / 3, sx = t - sy * 3;
+    dy = sy - 1; dx = sx - 1; group = t;                 // iy = my + dy
+  } else {                                               // DECONV5S2: ky = ry + 2 - 2*dy, dy = 1 - jy
+    const int ry = phase >> 1, rx = phase & 1;
+    cb = s & 1;
+    const int t = s >> 1, ntx = 3 - rx, jy = t / ntx, jx = t - jy * ntx;
+    dy = 1 - jy; dx = 1 - jx;
+    group = (ry + 2 * jy) * 5 + (rx + 2 * jx);
+  }
+}
+
+template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
+__global__ void __launch_bounds__(NTHREADS, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo,
+                const TcParams p) {
+  constexpr int NOPS = SPLIT3 ? 4 : 2;                 // operand slots per stage
+  constexpr int STAGE_BYTES = NOPS * SLOT_BYTES;
+  constexpr int STAGES = SPLIT3 ? 3 : 6;
+  constexpr int IN_STRIDE = (KIND == B2C_TC_CONV5S2) ? 2 : 1;
+  constexpr bool SOFT_A = (KIND == B2C_TC_CONV1);
+  constexpr uint32_t TMEM_COLS = GDN ? 256 : (N_TILE > 64 ? 128 : 64);
+  constexpr uint32_t B_BYTES = N_TILE * KBLK * 2;
+  static_assert(GDN == 0 || N_TILE == 128, "fused GDN needs all 128 channels in the tile");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                    // [STAGES] TMA bytes landed
+  uint64_t* empty = bars + STAGES;          // [STAGES] MMAs that read the stage completed
+  uint64_t* afull = bars + 2 * STAGES;      // [STAGES] software-written A tile ready (128 arrivals)
+  uint64_t* accum_full = bars + 3 * STAGES;
+  uint64_t* norm_full = bars + 3 * STAGES + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int phase = blockIdx.y;
+  const int n_img = blockIdx.z;
+  const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
+  const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+  const int nsteps = num_steps<KIND>(phase);
+  const int total_steps = nsteps + (GDN ? 2 : 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&afull[i], 128);
+    }
+    mbar_init(accum_full, 1);
+    mbar_init(norm_full, 1);
+    fence_barrier_init();
+    if (!SOFT_A) { tma_prefetch_desc(&tmA_hi); if (SPLIT3) tma_prefetch_desc(&tmA_lo); }
+    tma_prefetch_desc(&tmB_hi);
+    if (SPLIT3) tma_prefetch_desc(&tmB_lo);
+    if (GDN) { tma_prefetch_desc(&tmG_hi); if (SPLIT3) tma_prefetch_desc(&tmG_lo); }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      for (int s = 0; s < total_steps; ++s) {
+        const int stage = s % STAGES, it = s / STAGES;
+        mbar_wait(&empty[stage], (it & 1) ^ 1);
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        uint8_t* a_hi = st;
+        uint8_t* a_lo = st + SLOT_BYTES;
+        uint8_t* b_hi = st + (SPLIT3 ? 2 : 1) * SLOT_BYTES;
+        uint8_t* b_lo = b_hi + SLOT_BYTES;
+        if (s < nsteps) {
+          int dy, dx, cb, group;
+          decode_step<KIND>(s, phase, dy, dx, cb, group);
+          const uint32_t a_bytes = SOFT_A ? 0u : (uint32_t)SLOT_BYTES;
+          mbar_arrive_expect_tx(&full[stage], (a_bytes + B_BYTES) * (SPLIT3 ? 2u : 1u));
+          if (!SOFT_A) {
+            const int cx = ox0 * IN_STRIDE + dx, cy = oy0 * IN_STRIDE + dy;
+            tma_load_4d(a_hi, &tmA_hi, &full[stage], cb * KBLK, cx, cy, n_img);
+            if (SPLIT3) tma_load_4d(a_lo, &tmA_lo, &full[stage], cb * KBLK, cx, cy, n_img);
+          }
+          tma_load_2d(b_hi, &tmB_hi, &full[stage], cb * KBLK, group * N_TILE);
+          if (SPLIT3) tma_load_2d(b_lo, &tmB_lo, &full[stage], cb * KBLK, group * N_TILE);
+        } else {
+          const int g = s - nsteps;  // GDN k-block: gamma[:, g*64 .. g*64+63]
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(C128 * KBLK * 2) * (SPLIT3 ? 2u : 1u));
+          tma_load_2d(b_hi, &tmG_hi, &full[stage], g * KBLK, 0);
+          if (SPLIT3) tma_load_2d(b_lo, &tmG_lo, &full[stage], g * KBLK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_main = umma_idesc_bf16(N_TILE);
+      constexpr uint32_t idesc_gdn = umma_idesc_bf16(C128);
+      for (int s = 0; s < total_steps; ++s) {
+        const int stage = s % STAGES, it = s / STAGES;
+        const bool is_gdn = s >= nsteps;
+        mbar_wait(&full[stage], it & 1);
+        if (SOFT_A) mbar_wait(&afull[stage], it & 1);
+        else if (is_gdn) mbar_wait(&afull[stage], 0);
+        tcgen05_fence_after();
+        const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + SLOT_BYTES;
+        const uint32_t b_hi = st + (SPLIT3 ? 2 : 1) * SLOT_BYTES, b_lo = b_hi + SLOT_BYTES;
+        const uint32_t d = tmem_base + (is_gdn ? (uint32_t)C128 : 0u);
+        const uint32_t idesc = is_gdn ? idesc_gdn : idesc_main;
+        const int first = is_gdn ? nsteps : 0;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {  // 4 x (K = 16) per 64-wide k-block: +32 B inside the swizzle atom
+          const uint64_t da_hi = umma_desc_sw128(a_hi + k4 * 32), db_hi = umma_desc_sw128(b_hi + k4 * 32);
+          umma_bf16(d, da_hi, db_hi, idesc, (s > first || k4 > 0) ? 1u : 0u);
+          if (SPLIT3) {
+            const uint64_t da_lo = umma_desc_sw128(a_lo + k4 * 32), db_lo = umma_desc_sw128(b_lo + k4 * 32);
+            umma_bf16(d, da_hi, db_lo, idesc, 1u);
+            umma_bf16(d, da_lo, db_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (s == nsteps - 1) umma_commit(accum_full);
+        if (GDN && s == total_steps - 1) umma_commit(norm_full);
+      }
+    }
+  } else {
+    // ================================================================ row workers (128 threads)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;            // tile row = pixel
+    const int ty = r / TW, tx = r - ty * TW;
+    const int oy = oy0 + ty, ox = ox0 + tx;
+    const bool valid = oy < p.Hg && ox < p.Wg;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    if (SOFT_A) {
+      // CONV1: im2col row of this pixel straight from the fp32 NCHW image, 64 K-values per step
+      const size_t plane = (size_t)p.Hin * p.Win;
+      const float* img = p.img + (size_t)n_img * 3 * plane;
+      const int iy0 = oy * 4 - 4, ix0 = ox * 4 - 4;
+      for (int s = 0; s < nsteps; ++s) {
+        const int stage = s % STAGES, it = s / STAGES;
+        mbar_wait(&empty[stage], (it & 1) ^ 1);
+        uint8_t* st = smem + stage * STAGE_BYTES;
+#pragma unroll 1
+        for (int cidx = 0; cidx < 8; ++cidx) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t e = c_conv1_ktab[s * 64 + cidx * 8 + j];
+            const int c = e >> 8, ky = (e >> 4) & 15, kx = e & 15;
+            const int iy = iy0 + ky, ix = ix0 + kx;
+            const bool ok = valid && c < 3 && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+            v[j] = ok ? __ldg(img + c * plane + (size_t)iy * p.Win + ix) : 0.f;
+          }
+          store_row_chunk<SPLIT3>(st, st + SLOT_BYTES, r, cidx, v);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&afull[stage]);
+      }
+    }
+
+    mbar_wait(accum_full, 0);
+    tcgen05_fence_after();
+
+    if (GDN) {
+      // ---- pass 1: (acc + bias)^2 -> K-major swizzled bf16 A tile for the gamma product
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const int stage = (nsteps + g) % STAGES;
+        uint8_t* st = smem + stage * STAGE_BYTES;
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {          // 16 channels per TMEM load
+          uint32_t raw[16];
+          tmem_ld16(t_row + (uint32_t)(g * 64 + h * 16), raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = g * 64 + h * 16 + half * 8 + j;
+              const float xv = __uint_as_float(raw[half * 8 + j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+              v[j] = xv * xv;
+            }
+            store_row_chunk<SPLIT3>(st, st + SLOT_BYTES, r, h * 2 + half, v);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&afull[stage]);
+      }
+      mbar_wait(norm_full, 0);
+      tcgen05_fence_after();
+    }
+
+    // ---- final pass: TMEM -> registers -> global
+    const int oyf = oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0);
+    const int oxf = ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0);
+    if (OUT_MODE == OUT_F32_NCHW_PS4) {
+      // DECONV3: column = (ry*4+rx)*3 + o  ->  out[n, o, 4*oy+ry, 4*ox+rx]
+      float acc[48];
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        uint32_t raw[16];
+        tmem_ld16(t_row + (uint32_t)(h * 16), raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[h * 16 + j] = __uint_as_float(raw[j]);
+      }
+      if (valid) {
+        float* out = reinterpret_cast<float*>(p.out_hi);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const float bv = p.bias ? __ldg(p.bias + o) : 0.f;
+#pragma unroll
+          for (int ry = 0; ry < 4; ++ry) {
+            float4 v4 = make_float4(acc[(ry * 4 + 0) * 3 + o] + bv, acc[(ry * 4 + 1) * 3 + o] + bv,
+                                    acc[(ry * 4 + 2) * 3 + o] + bv, acc[(ry * 4 + 3) * 3 + o] + bv);
+            float* dst = out + (((size_t)n_img * 3 + o) * p.Hfull + (oy * 4 + ry)) * p.Wfull + ox * 4;
+            *reinterpret_cast<float4*>(dst) = v4;
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int h = 0; h < N_TILE / 16; ++h) {
+        uint32_t raw[16], rawn[16];
+        tmem_ld16(t_row + (uint32_t)(h * 16), raw);
+        if (GDN) tmem_ld16(t_row + (uint32_t)(C128 + h * 16), rawn);
+        tmem_ld_wait();
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = h * 16 + j;
+          float xv = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+          if (GDN) {
+            const float nrm = sqrtf(__uint_as_float(rawn[j]) + __ldg(p.beta_eff + c));
+            xv = (GDN == 2) ? xv * nrm : xv / nrm;
+          }
+          y[j] = xv;
+        }
+        if (!valid) {
+          // masked row: nothing to store (no `continue`: the next tcgen05.ld must be warp-convergent)
+        } else if (OUT_MODE == OUT_F32_NCHW) {
+          float* out = reinterpret_cast<float*>(p.out_hi);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            out[(((size_t)n_img * N_TILE + h * 16 + j) * p.Hfull + oyf) * p.Wfull + oxf] = y[j];
+        } else {
+          const size_t pix = ((size_t)n_img * p.Hfull + oyf) * p.Wfull + oxf;
+          __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (SPLIT3) split_bf16(y[j], hi[j], lo[j]);
+            else hi[j] = __float2bfloat16_rn(y[j]);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + pix * C128 + h * 16);
+          dh[0] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
+                             pack_bf16x2(hi[6], hi[7]));
+          dh[1] = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]),
+                             pack_bf16x2(hi[14], hi[15]));
+          if (SPLIT3) {
+            uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * C128 + h * 16);
+            dl[0] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
+                               pack_bf16x2(lo[6], lo[7]));
+            dl[1] = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]),
+                               pack_bf16x2(lo[14], lo[15]));
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ packing kernels
+// weights -> bf16 (hi, lo) panels, row = (group, out channel), 128-byte K-major rows
+__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float v = 0.f;
+  if (kind == B2C_TC_CONV1) {            // [kb 4][o 128][j 64], k = kb*64 + j, w OIHW [128][3][9][9]
+    const int j = idx & 63, o = (idx >> 6) & 127, kb = idx >> 13;
+    const int k = kb * 64 + j;
+    if (k < 243) v = w[o * 243 + k];
+  } else if (kind == B2C_TC_CONV5S2) {   // [tap 25][o 128][c 128], w OIHW [128][128][5][5]
+    const int c = idx & 127, o = (idx >> 7) & 127, t = idx >> 14;
+    v = w[(o * 128 + c) * 25 + t];
+  } else if (kind == B2C_TC_DECONV5S2) { // [tap 25][o 128][c 128], w IOHW [128 c][128 o][5][5]
+    const int c = idx & 127, o = (idx >> 7) & 127, t = idx >> 14;
+    v = w[(c * 128 + o) * 25 + t];
+  } else {                               // DECONV3: [shift 9][n 48][c 128], n = (ry*4+rx)*3+o, w IOHW [128][3][9][9]
+    const int c = idx & 127, n = (idx >> 7) % 48, sh = idx / (128 * 48);
+    const int o = n % 3, ph = n / 3, ry = ph >> 2, rx = ph & 3;
+    const int dy = sh / 3 - 1, dx = sh % 3 - 1;
+    const int ky = ry + 4 - 4 * dy, kx = rx + 4 - 4 * dx;
+    if (ky >= 0 && ky < 9 && kx >= 0 && kx < 9) v = w[((c * 3 + o) * 9 + ky) * 9 + kx];
+  }
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  hi[idx] = h;
+  if (lo) lo[idx] = l;
+}
+
+__global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
+                                __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
+                                float* __restrict__ beta_eff) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < C128 * C128) {
+    const float b = fmaxf(gamma_p[idx], 3.814697265625e-06f);
+    const float g = b * b - 1.4551915228366852e-11f;
+    __nv_bfloat16 h, l;
+    split_bf16(g, h, l);
+    ghi[idx] = h;
+    if (glo) glo[idx] = l;
+  }
+  if (idx < C128) {
+    const float b = fmaxf(beta_p[idx], (float)0.0010000072759311445);
+    beta_eff[idx] = b * b - 1.4551915228366852e-11f;
+  }
+}
+
+// fp32 NCHW -> NHWC bf16 (hi[,lo]) through a 32x32 shared-memory transpose
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int C, int HW) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pix = p0 + threadIdx.x;
+    t[i][threadIdx.x] = (c < C && pix < HW) ? in[((size_t)n * C + c) * HW + pix] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pix = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && pix < HW) {
+      __nv_bfloat16 h, l;
+      split_bf16(t[threadIdx.x][i], h, l);
+      hi[((size_t)n * HW + pix) * C + c] = h;
+      if (lo) lo[((size_t)n * HW + pix) * C + c] = l;
+    }
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                    float* __restrict__ out, int C, int HW) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pix = p0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && pix < HW) {
+      const size_t a = ((size_t)n * HW + pix) * C + c;
+      v = __bfloat162float(hi[a]) + (lo ? __bfloat162float(lo[a]) : 0.f);
+    }
+    t[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pix = p0 + threadIdx.x;
+    if (c < C && pix < HW) out[((size_t)n * C + c) * HW + pix] = t[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  });
+  return fn;
+}
+
+// NHWC bf16 activation [B][H][W][128]: box = 64 channels x TW x TH pixels with traversal stride S
+static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int S) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C128, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C128 * 2, (cuuint64_t)W * C128 * 2, (cuuint64_t)H * W * C128 * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)(TW * S), (cuuint32_t)(TH * S), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)S, (cuuint32_t)S, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: %d", (int)r); return B2C_ECUDA; }
+  return B2C_OK;
+}
+
+// bf16 matrix [rows][cols] (cols contiguous): box = 64 cols x box_rows
+static int make_mat_map(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(matrix) failed: %d", (int)r); return B2C_ECUDA; }
+  return B2C_OK;
+}
+
+static int upload_conv1_table() {
+  // constant memory is per device: upload once on every device that runs CONV1
+  static bool done[64] = {false};
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 64 && done[dev]) return B2C_OK;
+  uint16_t tab[256];
+  for (int k = 0; k < 256; ++k) {
+    if (k < 243) {
+      const int c = k / 81, r = k % 81, ky = r / 9, kx = r % 9;
+      tab[k] = (uint16_t)((c << 8) | (ky << 4) | kx);
+    } else {
+      tab[k] = (uint16_t)(3 << 8);  // c = 3 -> masked
+    }
+  }
+  cudaError_t err = cudaMemcpyToSymbol(c_conv1_ktab, tab, sizeof(tab));
+  if (err != cudaSuccess) { set_error("conv1 table upload: %s", cudaGetErrorString(err)); return B2C_ECUDA; }
+  if (dev < 64) done[dev] = true;
+  return B2C_OK;
+}
+
+template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
+static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int STAGES = SPLIT3 ? 3 : 6;
+  constexpr int STAGE_BYTES = (SPLIT3 ? 4 : 2) * SLOT_BYTES;
+  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  auto kern = igemm_tc_kernel<N_TILE, SPLIT3, KIND, GDN, OUT_MODE>;
+  static std::once_flag once;   // one per instantiation
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  });
+  // function attributes are per device; re-apply cheaply (idempotent) when several devices are in use
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return B2C_ECUDA; }
+
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo;
+  memset(&mA_hi, 0, sizeof(mA_hi)); memset(&mA_lo, 0, sizeof(mA_lo));
+  memset(&mG_hi, 0, sizeof(mG_hi)); memset(&mG_lo, 0, sizeof(mG_lo));
+  memset(&mB_lo, 0, sizeof(mB_lo));
+  int rc;
+  constexpr int S = (KIND == B2C_TC_CONV5S2) ? 2 : 1;
+  if (KIND != B2C_TC_CONV1) {
+    if ((rc = make_act_map(&mA_hi, L->in_hi, L->B, L->Hin, L->Win, S))) return rc;
+    if (SPLIT3 && (rc = make_act_map(&mA_lo, L->in_lo, L->B, L->Hin, L->Win, S))) return rc;
+  }
+  const int groups = KIND == B2C_TC_CONV1 ? 4 : (KIND == B2C_TC_DECONV3 ? 9 : 25);
+  const int wcols = KIND == B2C_TC_CONV1 ? 64 : 128;
+  if ((rc = make_mat_map(&mB_hi, L->w_hi, groups * N_TILE, wcols, N_TILE))) return rc;
+  if (SPLIT3 && (rc = make_mat_map(&mB_lo, L->w_lo, groups * N_TILE, wcols, N_TILE))) return rc;
+  if (GDN) {
+    if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C128, C128, C128))) return rc;
+    if (SPLIT3 && (rc = make_mat_map(&mG_lo, L->gamma_lo, C128, C128, C128))) return rc;
+  }
+  kern<<<grid, NTHREADS, SMEM, stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, p);
+  count_launch();
+  return check_launch("tc_layer_run");
+}
+
+}  // namespace tc
+}  // namespace b2c
+
+using namespace b2c;
+using namespace b2c::tc;
+
+extern "C" {
+
+size_t b2c_tc_packed_weight_elems(int kind) {
+  switch (kind) {
+    case B2C_TC_CONV1: return 4 * 128 * 64;
+    case B2C_TC_CONV5S2:
+    case B2C_TC_DECONV5S2: return 25 * 128 * 128;
+    case B2C_TC_DECONV3: return 9 * 48 * 128;
+    default: return 0;
+  }
+}
+
+int b2c_tc_pack_weights(int kind, const float* w, void* w_hi, void* w_lo, void* stream) {
+  const size_t n = b2c_tc_packed_weight_elems(kind);
+  B2C_REQUIRE(n > 0 && w && w_hi, "tc_pack_weights: bad arguments");
+  pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      kind, w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, (int)n);
+  count_launch();
+  return check_launch("tc_pack_weights");
+}
+
+int b2c_tc_pack_gdn(const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo, float* beta_eff,
+                    void* stream) {
+  B2C_REQUIRE(beta_p && gamma_p && gamma_hi && beta_eff, "tc_pack_gdn: bad arguments");
+  pack_gdn_kernel<<<(C128 * C128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      beta_p, gamma_p, (__nv_bfloat16*)gamma_hi, (__nv_bfloat16*)gamma_lo, beta_eff);
+  count_launch();
+  return check_launch("tc_pack_gdn");
+}
+
+int b2c_tc_nchw_to_nhwc(const float* in, void* out_hi, void* out_lo, int B, int C, int HW, void* stream) {
+  B2C_REQUIRE(in && out_hi && B > 0 && C > 0 && HW > 0, "tc_nchw_to_nhwc: bad arguments");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, C,
+                                                                HW);
+  count_launch();
+  return check_launch("tc_nchw_to_nhwc");
+}
+
+int b2c_tc_nhwc_to_nchw(const void* in_hi, const void* in_lo, float* out, int B, int C, int HW, void* stream) {
+  B2C_REQUIRE(in_hi && out && B > 0 && C > 0 && HW > 0, "tc_nhwc_to_nchw: bad arguments");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in_hi,
+                                                                (const __nv_bfloat16*)in_lo, out, C, HW);
+  count_launch();
+  return check_launch("tc_nhwc_to_nchw");
+}
+
+int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
+  B2C_REQUIRE(L, "tc_layer_run: null layer");
+  B2C_REQUIRE(L->in_hi && L->w_hi && L->out_hi, "tc_layer_run: null tensor pointer");
+  B2C_REQUIRE(L->B > 0 && L->B <= 65535 && L->Hin > 0 && L->Win > 0, "tc_layer_run: bad geometry");
+  B2C_REQUIRE(!L->split3 || (L->w_lo && (L->kind == B2C_TC_CONV1 || L->in_lo)), "tc_layer_run: split3 needs lo planes");
+  B2C_REQUIRE(!L->gdn || (L->gamma_hi && L->beta_eff && (!L->split3 || L->gamma_lo)), "tc_layer_run: gdn needs gamma/beta");
+  B2C_REQUIRE(L->out_f32_nchw || !L->split3 || L->out_lo, "tc_layer_run: split3 bf16 output needs out_lo");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = L->B; p.Hin = L->Hin; p.Win = L->Win;
+  p.bias = L->bias; p.beta_eff = L->beta_eff; p.out_hi = L->out_hi; p.out_lo = L->out_lo;
+  int phases = 1;
+  switch (L->kind) {
+    case B2C_TC_CONV1:
+      B2C_REQUIRE(L->Hin % 4 == 0 && L->Win % 4 == 0, "tc conv1: H, W must be multiples of 4");
+      p.Hg = L->Hin / 4; p.Wg = L->Win / 4; p.ps = 1; p.img = (const float*)L->in_hi;
+      break;
+    case B2C_TC_CONV5S2:
+      p.Hg = (L->Hin - 1) / 2 + 1; p.Wg = (L->Win - 1) / 2 + 1; p.ps = 1;
+      break;
+    case B2C_TC_DECONV5S2:
+      p.Hg = L->Hin; p.Wg = L->Win; p.ps = 2; phases = 4;
+      break;
+    case B2C_TC_DECONV3:
+      p.Hg = L->Hin; p.Wg = L->Win; p.ps = 4;
+      break;
+    default:
+      set_error("tc_layer_run: unknown kind %d", L->kind);
+      return B2C_EINVAL;
+  }
+  p.Hfull = p.Hg * p.ps; p.Wfull = p.Wg * p.ps;
+  p.tiles_x = (p.Wg + TW - 1) / TW;
+  const int tiles_y = (p.Hg + TH - 1) / TH;
+  dim3 grid(p.tiles_x * tiles_y, phases, L->B);
+  if (L->kind == B2C_TC_CONV1) {
+    int rc = upload_conv1_table();
+    if (rc) return rc;
+  }
+
+  const int key = L->kind * 1000 + (L->split3 ? 100 : 0) + L->gdn * 10 + (L->out_f32_nchw ? 1 : 0);
+  switch (key) {
+    // analysis transform (error-compensated)
+    case B2C_TC_CONV1 * 1000 + 100 + 10 + 0: return launch<128, true, B2C_TC_CONV1, 1, OUT_BF16>(L, p, grid, stream);
+    case B2C_TC_CONV1 * 1000 + 100 + 0 + 1: return launch<128, true, B2C_TC_CONV1, 0, OUT_F32_NCHW>(L, p, grid, stream);
+    case B2C_TC_CONV5S2 * 1000 + 100 + 10 + 0: return launch<128, true, B2C_TC_CONV5S2, 1, OUT_BF16>(L, p, grid, stream);
+    case B2C_TC_CONV5S2 * 1000 + 100 + 0 + 1: return launch<128, true, B2C_TC_CONV5S2, 0, OUT_F32_NCHW>(L, p, grid, stream);
+    case B2C_TC_CONV5S2 * 1000 + 100 + 10 + 1: return launch<128, true, B2C_TC_CONV5S2, 1, OUT_F32_NCHW>(L, p, grid, stream);
+    // synthesis transform (plain bf16)
+    case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 0: return launch<128, false, B2C_TC_DECONV5S2, 2, OUT_BF16>(L, p, grid, stream);
+    case B2C_TC_DECONV5S2 * 1000 + 0 + 0 + 1: return launch<128, false, B2C_TC_DECONV5S2, 0, OUT_F32_NCHW>(L, p, grid, stream);
+    case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 1: return launch<128, false, B2C_TC_DECONV5S2, 2, OUT_F32_NCHW>(L, p, grid, stream);
+    case B2C_TC_DECONV3 * 1000 + 0 + 0 + 1: return launch<48, false, B2C_TC_DECONV3, 0, OUT_F32_NCHW_PS4>(L, p, grid, stream);
+    default:
+      set_error("tc_layer_run: unsupported combination kind=%d split3=%d gdn=%d out_f32_nchw=%d", L->kind, L->split3,
+                L->gdn, L->out_f32_nchw);
+      return B2C_EINVAL;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+"""Host side of the tensor-core (tcgen05) inference path: packed weights, NHWC bf16 (hi, lo)
+activations and fused layer launches through libb2c's C ABI (include/b2c.h, b2c_tc_*).
+Inference only (no autograd); out_channel_N must be 128."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import TC_CONV1, TC_CONV5S2, TC_DECONV3, TC_DECONV5S2, TcLayer  # noqa: F401
+from .functional import _timed
+
+_vp = ctypes.c_void_p
+
+
+def _p(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def pack_weights(kind, w, need_lo):
+    """state_dict weight (fp32 OIHW / IOHW) -> (hi, lo) bf16 tap-major panels."""
+    lib = _lib.load()
+    n = lib.b2c_tc_packed_weight_elems(kind)
+    w = w.detach().contiguous().float()
+    hi = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
+    lo = torch.empty((n,), device=w.device, dtype=torch.bfloat16) if need_lo else None
+    with torch.cuda.device(w.device):
+        _lib.check(lib.b2c_tc_pack_weights(kind, _p(w), _p(hi), _p(lo), _stream()), "tc_pack_weights")
+    return hi, lo
+
+
+def pack_gdn(beta, gamma, need_lo):
+    lib = _lib.load()
+    beta, gamma = beta.detach().contiguous().float(), gamma.detach().contiguous().float()
+    if beta.numel() != 128 or gamma.numel() != 128 * 128:
+        raise _lib.B2CError("tensor-core GDN needs 128 channels")
+    ghi = torch.empty((128, 128), device=beta.device, dtype=torch.bfloat16)
+    glo = torch.empty((128, 128), device=beta.device, dtype=torch.bfloat16) if need_lo else None
+    be = torch.empty((128,), device=beta.device, dtype=torch.float32)
+    with torch.cuda.device(beta.device):
+        _lib.check(lib.b2c_tc_pack_gdn(_p(beta), _p(gamma), _p(ghi), _p(glo), _p(be), _stream()), "tc_pack_gdn")
+    return ghi, glo, be
+
+
+def nchw_to_nhwc(x, need_lo):
+    """fp32 NCHW -> NHWC bf16 hi[,lo]"""
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    hi = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if need_lo else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().b2c_tc_nchw_to_nhwc(_p(x), _p(hi), _p(lo), B, C, H * W, _stream()), "tc_nchw_to_nhwc")
+    return hi, lo
+
+
+def nhwc_to_nchw(hi, lo=None):
+    B, H, W, C = hi.shape
+    out = torch.empty((B, C, H, W), device=hi.device, dtype=torch.float32)
+    with torch.cuda.device(hi.device):
+        _lib.check(_lib.load().b2c_tc_nhwc_to_nchw(_p(hi), _p(lo), _p(out), B, C, H * W, _stream()), "tc_nhwc_to_nchw")
+    return out
+
+
+_FLOPS_PER_OUT_PIXEL = {TC_CONV1: 2 * 243 * 128, TC_CONV5S2: 2 * 3200 * 128, TC_DECONV5S2: 2 * 3200 * 128 / 4,
+                        TC_DECONV3: 2 * 128 * 243 / 16}
+
+
+def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False):
+    """One fused layer.  x_hi/x_lo: NHWC bf16 (CONV1: x_hi = fp32 NCHW image).  w = (w_hi, w_lo);
+    gdn = (gamma_hi, gamma_lo, beta_eff) with gdn_mode 1 (GDN) / 2 (IGDN).
+    Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
+    if kind == TC_CONV1:
+        B, _, Hin, Win = x_hi.shape
+        Ho, Wo, Cout = Hin // 4, Win // 4, 128
+    else:
+        B, Hin, Win, _ = x_hi.shape
+        if kind == TC_CONV5S2:
+            Ho, Wo, Cout = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1, 128
+        elif kind == TC_DECONV5S2:
+            Ho, Wo, Cout = Hin * 2, Win * 2, 128
+        else:
+            Ho, Wo, Cout = Hin * 4, Win * 4, 3
+    dev = x_hi.device
+    if out_f32_nchw:
+        out_hi = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
+        out_lo = None
+    else:
+        out_hi = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.bfloat16)
+        out_lo = torch.empty_like(out_hi) if split3 else None
+    L = TcLayer()
+    L.kind, L.split3, L.gdn, L.out_f32_nchw = kind, int(split3), int(gdn_mode), int(out_f32_nchw)
+    L.B, L.Hin, L.Win = B, Hin, Win
+    L.in_hi, L.in_lo = x_hi.data_ptr(), (x_lo.data_ptr() if x_lo is not None else 0)
+    L.w_hi, L.w_lo = w[0].data_ptr(), (w[1].data_ptr() if w[1] is not None else 0)
+    L.bias = bias.data_ptr() if bias is not None else 0
+    if gdn_mode:
+        L.gamma_hi, L.gamma_lo, L.beta_eff = gdn[0].data_ptr(), (gdn[1].data_ptr() if gdn[1] is not None else 0), \
+            gdn[2].data_ptr()
+    L.out_hi, L.out_lo = out_hi.data_ptr(), (out_lo.data_ptr() if out_lo is not None else 0)
+    flops = int(_FLOPS_PER_OUT_PIXEL[kind] * B * Ho * Wo) + (2 * 128 * 128 * B * Ho * Wo if gdn_mode else 0)
+    name = f"tc_layer[kind{kind},{B}x{Hin}x{Win},split{int(split3)},gdn{gdn_mode}]"
+    with torch.cuda.device(dev), _timed(name, flops, 0):
+        _lib.check(_lib.load().b2c_tc_layer_run(ctypes.byref(L), _stream()), "tc_layer_run")
+    return out_hi if out_f32_nchw else (out_hi, out_lo)

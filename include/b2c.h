@@ -82,7 +82,7 @@ int b2c_channel_sum(const float* t, float* out, int B, int C, int HW, void* stre
  * --------------------------------------------------------------------------------- */
 int b2c_gdn_fwd(const float* x, const float* beta_p, const float* gamma_p, float* y,
                 int B, int C, int HW, int inverse, void* stream);
-/* gx[B,C,HW]; dbeta_p[C], dgamma_p[C,C] must be zero-filled by the caller;
+/* gx[B,C,HW], dbeta_p[C], dgamma_p[C,C] are assigned;
  * workspace: B*C*HW floats (dL/dnorm) + C + C*C floats. */
 size_t b2c_gdn_bwd_workspace_bytes(int B, int C, int HW);
 int b2c_gdn_bwd(const float* x, const float* beta_p, const float* gamma_p, const float* gy,
@@ -120,6 +120,52 @@ size_t b2c_clamp_sse_workspace_bytes(int B, int CHW);
  * g_clipped may be NULL; g_sse is a DEVICE scalar (dL/d total unclamped SSE). */
 int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped,
                       const float* g_sse, float* g_recon, size_t n, void* stream);
+
+/* =================================================================================
+ * Tensor-core inference path (tcgen05 implicit GEMM, TMA-staged NHWC bf16 tiles, TMEM
+ * accumulators) for out_channel_N = 128.  Activations between layers are NHWC bf16; the
+ * analysis transform carries every tensor as a (hi, lo) bf16 pair and issues three MMAs
+ * per product (hi*hi + hi*lo + lo*hi) so that rounded latents match the fp32 reference;
+ * the synthesis transform runs in plain bf16 (split3 = 0).  GDN / IGDN (models/GDN.py:64-94)
+ * is fused into the producing convolution's epilogue as a second tcgen05 MMA.
+ * ================================================================================= */
+#define B2C_TC_CONV1 0     /* 9x9 s4 p4, 3->128, input = fp32 NCHW image   (models/analysis_17.py:14,33)  */
+#define B2C_TC_CONV5S2 1   /* 5x5 s2 p2, 128->128                          (models/analysis_17.py:18,22)  */
+#define B2C_TC_DECONV5S2 2 /* 5x5 s2 p2 op1 transposed, 128->128, 4 phases (models/synthesis_17.py:15,19) */
+#define B2C_TC_DECONV3 3   /* 9x9 s4 p4 op3 transposed, 128->3, as a 3x3 conv to 16 phases x 3 channels
+                              (models/synthesis_17.py:23) */
+
+/* bf16 elements in ONE packed weight plane (hi or lo) of a layer kind. */
+size_t b2c_tc_packed_weight_elems(int kind);
+/* fp32 OIHW (conv) / IOHW (deconv) weights as in state_dict -> tap-major bf16 panels; w_lo may be NULL. */
+int b2c_tc_pack_weights(int kind, const float* w, void* w_hi, void* w_lo, void* stream);
+/* GDN parameters (raw, reparametrised) -> gamma_eff as bf16 hi/lo [128][128] and beta_eff fp32 [128]. */
+int b2c_tc_pack_gdn(const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo, float* beta_eff,
+                    void* stream);
+
+typedef struct b2c_tc_layer {
+  int kind;         /* B2C_TC_*                                                                   */
+  int split3;       /* 1: (hi,lo) operands, 3 MMAs per product; 0: plain bf16                      */
+  int gdn;          /* 0: none, 1: GDN, 2: IGDN fused after bias                                   */
+  int out_f32_nchw; /* 1: fp32 NCHW output in out_hi (required for DECONV3), 0: NHWC bf16 hi[/lo]  */
+  int B, Hin, Win;  /* input grid                                                                  */
+  const void* in_hi; /* NHWC bf16 [B,Hin,Win,128]  (CONV1: fp32 NCHW image [B,3,Hin,Win])          */
+  const void* in_lo; /* NHWC bf16 low part when split3 (unused for CONV1)                          */
+  const void* w_hi;  /* packed weights (b2c_tc_pack_weights)                                       */
+  const void* w_lo;
+  const float* bias; /* [Cout] or NULL                                                             */
+  const void* gamma_hi; /* b2c_tc_pack_gdn outputs, when gdn != 0                                  */
+  const void* gamma_lo;
+  const float* beta_eff;
+  void* out_hi;
+  void* out_lo;
+} b2c_tc_layer;
+
+int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
+
+/* layout / precision converters between the reference's fp32 NCHW and the NHWC bf16 (hi[,lo]) tiles */
+int b2c_tc_nchw_to_nhwc(const float* in, void* out_hi, void* out_lo, int B, int C, int HW, void* stream);
+int b2c_tc_nhwc_to_nchw(const void* in_hi, const void* in_lo, float* out, int B, int C, int HW, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,132 @@
+"""Tensor-core (tcgen05) layers vs the exact fp32 operators of the same library and torch, op by op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _maxabs(a, b):
+    return (a.double().cpu() - b.double().cpu()).abs().max().item()
+
+
+@pytest.fixture(scope="module")
+def tc():
+    import iclr_17_compression_b200.tc as t
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return t
+
+
+def _gdn_params(g):
+    from oracle import balle17_oracle as O
+    beta = torch.sqrt(0.5 + torch.rand(128, generator=g))
+    gamma = torch.sqrt(0.1 * torch.eye(128) + 0.02 * torch.rand(128, 128, generator=g) + O.PEDESTAL)
+    beta[:3] = O.BETA_BOUND * 0.5
+    gamma.view(-1)[5:40:7] = O.GAMMA_BOUND * 0.25
+    return beta, gamma
+
+
+def test_layout_roundtrip(tc):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 128, 9, 13, generator=g).cuda()
+    hi, lo = tc.nchw_to_nhwc(x, True)
+    assert _maxabs(tc.nhwc_to_nchw(hi, lo), x) < 2e-5
+    assert torch.equal(hi, x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 32), (2, 32, 48), (1, 24, 40), (1, 128, 192)])
+def test_conv5s2_split3_matches_fp32(tc, shape):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 128, H, W, generator=g).cuda()
+    w = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+    ref = F.conv2d(x.double(), w.double(), None, stride=2, padding=2)
+    xh, xl = tc.nchw_to_nhwc(x, True)
+    wp = tc.pack_weights(tc.TC_CONV5S2, w, True)
+    y = tc.layer_run(tc.TC_CONV5S2, xh, xl, wp, None, split3=True, out_f32_nchw=True)
+    assert y.shape == ref.shape
+    assert _rel(y, ref) < 3e-5, _rel(y, ref)
+    assert _maxabs(y, ref) < 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("inverse", [False])
+def test_conv5s2_fused_gdn(tc, inverse):
+    from oracle import balle17_oracle as O
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 128, 32, 48, generator=g).cuda()
+    w = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    beta, gamma = _gdn_params(g)
+    ref = O.gdn(F.conv2d(x.double().cpu(), w.double().cpu(), b.double().cpu(), stride=2, padding=2),
+                beta.double(), gamma.double(), inverse)
+    xh, xl = tc.nchw_to_nhwc(x, True)
+    wp = tc.pack_weights(tc.TC_CONV5S2, w, True)
+    gp = tc.pack_gdn(beta.cuda(), gamma.cuda(), True)
+    yh, yl = tc.layer_run(tc.TC_CONV5S2, xh, xl, wp, b, gdn=gp, gdn_mode=1, split3=True)
+    y = tc.nhwc_to_nchw(yh, yl)
+    assert _rel(y, ref) < 5e-5, _rel(y, ref)
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 96), (2, 128, 64), (1, 48, 80)])
+def test_conv1_split3_fused_gdn(tc, shape):
+    from oracle import balle17_oracle as O
+    B, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(B, 3, H, W, generator=g).cuda()
+    w = (torch.randn(128, 3, 9, 9, generator=g) * 0.2).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    beta, gamma = _gdn_params(g)
+    conv = F.conv2d(x.double().cpu(), w.double().cpu(), b.double().cpu(), stride=4, padding=4)
+    wp = tc.pack_weights(tc.TC_CONV1, w, True)
+    y0 = tc.layer_run(tc.TC_CONV1, x, None, wp, b, split3=True, out_f32_nchw=True)
+    assert _rel(y0, conv) < 3e-5, _rel(y0, conv)
+    gp = tc.pack_gdn(beta.cuda(), gamma.cuda(), True)
+    yh, yl = tc.layer_run(tc.TC_CONV1, x, None, wp, b, gdn=gp, gdn_mode=1, split3=True)
+    ref = O.gdn(conv, beta.double(), gamma.double(), False)
+    assert _rel(tc.nhwc_to_nchw(yh, yl), ref) < 5e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 16), (2, 32, 48), (1, 12, 20)])
+def test_deconv5s2_bf16_fused_igdn(tc, shape):
+    from oracle import balle17_oracle as O
+    B, H, W = shape
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 128, H, W, generator=g).cuda()
+    w = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    beta, gamma = _gdn_params(g)
+    xh, _ = tc.nchw_to_nhwc(x, False)
+    xq = xh.float().permute(0, 3, 1, 2).double().cpu()              # the bf16-rounded input the kernel sees
+    wq = w.to(torch.bfloat16).double().cpu()
+    dec = F.conv_transpose2d(xq, wq, b.double().cpu(), stride=2, padding=2, output_padding=1)
+    wp = tc.pack_weights(tc.TC_DECONV5S2, w, False)
+    y0 = tc.layer_run(tc.TC_DECONV5S2, xh, None, wp, b, split3=False, out_f32_nchw=True)
+    assert y0.shape == dec.shape
+    assert _rel(y0, dec) < 2e-5, _rel(y0, dec)                       # fp32 accumulation of exact bf16 products
+    gp = tc.pack_gdn(beta.cuda(), gamma.cuda(), False)
+    yh, _ = tc.layer_run(tc.TC_DECONV5S2, xh, None, wp, b, gdn=gp, gdn_mode=2, split3=False)
+    ref = O.gdn(dec, beta.double(), gamma.double(), True)
+    assert _rel(tc.nhwc_to_nchw(yh), ref) < 6e-3                     # plain-bf16 GDN operands + bf16 output
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 32), (2, 32, 48), (1, 20, 24)])
+def test_deconv3_bf16(tc, shape):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 128, H, W, generator=g).cuda()
+    w = (torch.randn(128, 3, 9, 9, generator=g) * 0.05).cuda()
+    b = torch.randn(3, generator=g).cuda()
+    xh, _ = tc.nchw_to_nhwc(x, False)
+    xq = xh.float().permute(0, 3, 1, 2).double().cpu()
+    wq = w.to(torch.bfloat16).double().cpu()
+    ref = F.conv_transpose2d(xq, wq, b.double().cpu(), stride=4, padding=4, output_padding=3)
+    wp = tc.pack_weights(tc.TC_DECONV3, w, False)
+    y = tc.layer_run(tc.TC_DECONV3, xh, None, wp, b, split3=False, out_f32_nchw=True)
+    assert y.shape == ref.shape
+    assert _rel(y, ref) < 2e-5, _rel(y, ref)
