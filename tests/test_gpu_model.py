@@ -145,3 +145,73 @@ def test_full_kodak_size_vs_oracle_on_gpu(kind):
     assert torch.equal(c1, clipped[1:2])
     per_image_bpp = m.last["image_bits"][0].item() / (512 * 768)
     assert per_image_bpp > 0
+
+
+# ------------------------------------------------------------------------------ tensor-core pipeline
+@pytest.mark.parametrize("name", [n for n in golden_names("eval_") if "_n128_" in n])
+def test_tc_eval_matches_reference_golden(name):
+    """eval + no_grad + N=128 runs the tcgen05 pipeline: latents bit-exact away from rounding boundaries
+    (bf16x3 analysis), bpp / MSE within 1e-3 relative (bf16 synthesis)."""
+    from oracle import balle17_oracle as O
+    c = Case(name)
+    m = _model(c).eval()
+    with torch.no_grad():
+        clipped, z, bpp = m(c.x.cuda())
+        assert m.last_path == "tcgen05"
+        o64 = O.forward(c.x.double(), O.to_dtype(c.sd, torch.float64))
+    g = c.g
+    check_latents(z, torch.from_numpy(g["z_i8"].astype(np.float32)), o64["y"])
+    assert abs(bpp.item() - float(g["bpp"])) <= REL_BPP_MSE * float(g["bpp"])
+    mse = (m.last["sse"][:, 0].sum() / c.x.numel()).item()
+    assert abs(mse - float(g["mse"])) <= REL_BPP_MSE * float(g["mse"]), (mse, float(g["mse"]))
+    mse_c = torch.mean((clipped.cpu() - c.x) ** 2).item()
+    assert abs(mse_c - float(g["mse_clipped"])) <= REL_BPP_MSE * float(g["mse_clipped"])
+
+
+@pytest.mark.parametrize("kind,weights", [("U", "W1"), ("S", "W1"), ("S", "W0")])
+def test_tc_full_kodak_size_vs_fp64_oracle(kind, weights):
+    """cfg2 size, 3 images: tcgen05 pipeline vs the fp64 oracle on the same device."""
+    from oracle import balle17_oracle as O
+    from golden_util import weights as W
+    import iclr_17_compression_b200 as P
+    sd = W(128, weights)
+    m = P.ImageCompressor(128)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = O.synth_images(kind, 3, 512, 768, 1002 if kind == "U" else 1003).cuda()
+    sd64 = {k: v.cuda().double() for k, v in sd.items()}
+    with torch.no_grad():
+        clipped, z, bpp = m(x)
+        assert m.last_path == "tcgen05"
+        ref = O.forward(x.double(), sd64)
+    ndiff = check_latents(z, ref["z"].float(), ref["y"])
+    assert ndiff <= 2e-3 * z.numel()
+    assert abs(bpp.item() - ref["bpp"].item()) <= REL_BPP_MSE * ref["bpp"].item()
+    mse = (m.last["sse"][:, 0].sum() / x.numel()).item()
+    assert abs(mse - ref["mse"].item()) <= REL_BPP_MSE * ref["mse"].item(), (mse, ref["mse"].item())
+    # fp32 path on the same input agrees too (path switch is transparent)
+    m.fast_inference = False
+    with torch.no_grad():
+        c2, z2, bpp2 = m(x)
+    assert m.last_path == "fp32"
+    check_latents(z, z2, ref["y"])
+    assert abs(bpp.item() - bpp2.item()) <= REL_BPP_MSE * bpp2.item()
+    # batch independence on the tensor-core path
+    m.fast_inference = True
+    with torch.no_grad():
+        c1, z1, _ = m(x[2:3])
+    assert torch.equal(z1, z[2:3]) and torch.equal(c1, clipped[2:3])
+
+
+def test_tc_repacks_after_weight_update():
+    c = Case("eval_W1_U_n128_64")
+    m = _model(c).eval()
+    x = c.x.cuda()
+    with torch.no_grad():
+        _, z0, bpp0 = m(x)
+        m.Encoder.conv3.weight.mul_(1.5)             # in-place update bumps _version -> panels re-packed
+        _, z1, bpp1 = m(x)
+        m.fast_inference = False
+        _, z2, bpp2 = m(x)
+    assert not torch.equal(z0, z1)
+    assert (z1 != z2).float().mean().item() < 1e-3
