@@ -221,7 +221,7 @@ def main():
     ops = timer.summary()
     total_ms = sum(d["ms_total"] for d in ops.values())
     top_name, top = max(ops.items(), key=lambda kv: kv[1]["ms_total"])
-    tensor_bound = top_name.startswith("conv")
+    tensor_bound = top_name.startswith("conv") or top_name.startswith("tc_layer")
     if tensor_bound:
         achieved = top["flops"] / (top["ms_avg"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]

@@ -26,7 +26,8 @@ constexpr int TH = 8, TW = 16;            // output tile (pixels)
 constexpr int TILE_M = TH * TW;           // 128
 constexpr int KBLK = 64;                  // bf16 per k-block row (128 B)
 constexpr int SLOT_BYTES = TILE_M * KBLK * 2;  // 16 KB operand slot
-constexpr int NTHREADS = 192;
+constexpr int NWORKERS = 256;             // 8 row-worker warps
+constexpr int NTHREADS = 64 + NWORKERS;   // + TMA producer warp + MMA warp
 constexpr int C128 = 128;
 
 enum { OUT_BF16 = 0, OUT_F32_NCHW = 1, OUT_F32_NCHW_PS4 = 2 };
@@ -37,15 +38,17 @@ struct TcParams {
   int tiles_x;          // tiles per row
   int Hfull, Wfull;     // full output dims
   int ps;               // output lattice stride (1 conv, 2 deconv5s2, 4 deconv3)
-  const float* img;     // CONV1: fp32 NCHW image
   const float* bias;
   const float* beta_eff;
   void* out_hi;
   void* out_lo;
 };
 
-// (c, ky, kx) of flattened K index for CONV1, K = c*81 + ky*9 + kx
-__constant__ uint16_t c_conv1_ktab[256];
+// CONV1 input patch of one 8x16 output tile: 3 channels x 37 rows x 69 (->72) columns of fp32
+constexpr int P1_W = 72, P1_H = 37;
+constexpr int P1_PLANE = P1_W * P1_H;
+constexpr int P1_BYTES = 3 * P1_PLANE * 4;          // 31968
+constexpr int P1_SLOT = 32768;
 
 template <bool SPLIT3>
 __device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_lo, int r, int cidx,
@@ -68,6 +71,25 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_
     uint4 ql = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]),
                           pack_bf16x2(l[6], l[7]));
     *reinterpret_cast<uint4*>(slot_lo + off) = ql;
+  }
+}
+
+// CONV1: the 64 im2col values k = KB*64 .. KB*64+63 (k = c*81 + ky*9 + kx, zero for k >= 243) of the
+// pixel whose patch origin is `pp`, written as one swizzled 128-byte K-major row (hi, lo).
+// All patch offsets are compile-time constants -> LDS with immediate offsets.
+template <int KB, int HALF>
+__device__ __forceinline__ void conv1_build_row(const float* __restrict__ pp, uint8_t* slot_hi, uint8_t* slot_lo,
+                                                int r) {
+#pragma unroll
+  for (int cidx = HALF * 4; cidx < HALF * 4 + 4; ++cidx) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = KB * 64 + cidx * 8 + j;
+      const int c = k / 81, ky = (k % 81) / 9, kx = k % 9;
+      v[j] = (k < 243) ? pp[c * P1_PLANE + ky * P1_W + kx] : 0.f;
+    }
+    store_row_chunk<true>(slot_hi, slot_lo, r, cidx, v);
   }
 }
 
@@ -102,15 +124,26 @@ __device__ __forceinline__ void decode_step(int s, int phase, int& dy, int& dx, 
   }
 }
 
+// pipeline depth / CTAs per SM: plain bf16 and CONV1 keep <= 113 KB of shared memory so two CTAs share an
+// SM and one CTA's epilogue overlaps the other's MMA main loop.
+template <bool SPLIT3, int KIND>
+struct TcCfg {
+  static constexpr int STAGES = (KIND == B2C_TC_CONV1) ? 1 : 3;
+  static constexpr int STAGE_BYTES = (SPLIT3 ? 4 : 2) * SLOT_BYTES;
+  static constexpr int PATCH = (KIND == B2C_TC_CONV1) ? P1_SLOT : 0;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + PATCH + 1024 /*align*/ + 1024 /*bias, beta*/ + 256 /*barriers*/;
+  static constexpr int MIN_CTAS = (SMEM <= 113 * 1024) ? 2 : 1;
+};
+
 template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, TcCfg<SPLIT3, KIND>::MIN_CTAS)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo,
                 const TcParams p) {
-  constexpr int NOPS = SPLIT3 ? 4 : 2;                 // operand slots per stage
-  constexpr int STAGE_BYTES = NOPS * SLOT_BYTES;
-  constexpr int STAGES = SPLIT3 ? 3 : 6;
+  using Cfg = TcCfg<SPLIT3, KIND>;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int STAGES = Cfg::STAGES;
   constexpr int IN_STRIDE = (KIND == B2C_TC_CONV5S2) ? 2 : 1;
   constexpr bool SOFT_A = (KIND == B2C_TC_CONV1);
   constexpr uint32_t TMEM_COLS = GDN ? 256 : (N_TILE > 64 ? 128 : 64);
@@ -119,13 +152,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* patch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);   // CONV1 only
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + Cfg::PATCH);
+  float* s_beta = s_bias + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint64_t* full = bars;                    // [STAGES] TMA bytes landed
   uint64_t* empty = bars + STAGES;          // [STAGES] MMAs that read the stage completed
-  uint64_t* afull = bars + 2 * STAGES;      // [STAGES] software-written A tile ready (128 arrivals)
+  uint64_t* afull = bars + 2 * STAGES;      // [STAGES] software-written A tile ready (NWORKERS arrivals)
   uint64_t* accum_full = bars + 3 * STAGES;
   uint64_t* norm_full = bars + 3 * STAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+  uint64_t* patch_full = bars + 3 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int phase = blockIdx.y;
@@ -139,17 +176,24 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
-      mbar_init(&afull[i], 128);
+      mbar_init(&afull[i], NWORKERS);
     }
     mbar_init(accum_full, 1);
     mbar_init(norm_full, 1);
+    mbar_init(patch_full, 1);
     fence_barrier_init();
-    if (!SOFT_A) { tma_prefetch_desc(&tmA_hi); if (SPLIT3) tma_prefetch_desc(&tmA_lo); }
+    tma_prefetch_desc(&tmA_hi);
+    if (!SOFT_A && SPLIT3) tma_prefetch_desc(&tmA_lo);
     tma_prefetch_desc(&tmB_hi);
     if (SPLIT3) tma_prefetch_desc(&tmB_lo);
     if (GDN) { tma_prefetch_desc(&tmG_hi); if (SPLIT3) tma_prefetch_desc(&tmG_lo); }
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {   // per-channel epilogue constants
+    const int c = threadIdx.x - 64;
+    s_bias[c] = (p.bias && c < (KIND == B2C_TC_DECONV3 ? 3 : 128)) ? __ldg(p.bias + c) : 0.f;
+    s_beta[c] = (GDN && p.beta_eff) ? __ldg(p.beta_eff + c) : 1.f;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -158,6 +202,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
+      if (SOFT_A) {  // fp32 image patch (tmA_hi is the [B][3][H][W] fp32 map); OOB rows / columns are zero-filled
+        mbar_arrive_expect_tx(patch_full, (uint32_t)P1_BYTES);
+        tma_load_4d(patch, &tmA_hi, patch_full, ox0 * 4 - 4, oy0 * 4 - 4, 0, n_img);
+      }
       for (int s = 0; s < total_steps; ++s) {
         const int stage = s % STAGES, it = s / STAGES;
         mbar_wait(&empty[stage], (it & 1) ^ 1);
@@ -191,12 +239,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc_main = umma_idesc_bf16(N_TILE);
       constexpr uint32_t idesc_gdn = umma_idesc_bf16(C128);
+      int soft_uses[STAGES];     // completed software-A fills per stage -> afull parity
+#pragma unroll
+      for (int i = 0; i < STAGES; ++i) soft_uses[i] = 0;
       for (int s = 0; s < total_steps; ++s) {
         const int stage = s % STAGES, it = s / STAGES;
         const bool is_gdn = s >= nsteps;
         mbar_wait(&full[stage], it & 1);
-        if (SOFT_A) mbar_wait(&afull[stage], it & 1);
-        else if (is_gdn) mbar_wait(&afull[stage], 0);
+        if (SOFT_A || is_gdn) {
+          mbar_wait(&afull[stage], soft_uses[stage] & 1);
+          ++soft_uses[stage];
+        }
         tcgen05_fence_after();
         const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t a_hi = st, a_lo = st + SLOT_BYTES;
@@ -220,8 +273,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
     }
   } else {
-    // ================================================================ row workers (128 threads)
+    // ================================================================ row workers (8 warps, 256 threads)
+    // two threads per tile row: `half` selects which 64 of the 128 channels (or which k-chunks) it owns
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;            // tile row = pixel
     const int ty = r / TW, tx = r - ty * TW;
     const int oy = oy0 + ty, ox = ox0 + tx;
@@ -229,26 +284,24 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
 
     if (SOFT_A) {
-      // CONV1: im2col row of this pixel straight from the fp32 NCHW image, 64 K-values per step
-      const size_t plane = (size_t)p.Hin * p.Win;
-      const float* img = p.img + (size_t)n_img * 3 * plane;
-      const int iy0 = oy * 4 - 4, ix0 = ox * 4 - 4;
-      for (int s = 0; s < nsteps; ++s) {
+      // CONV1: im2col rows from the TMA-staged fp32 patch; pixel (ty,tx) starts at patch[4*ty][4*tx]
+      const float* pp = patch + (4 * ty) * P1_W + 4 * tx;
+      mbar_wait(patch_full, 0);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
         const int stage = s % STAGES, it = s / STAGES;
         mbar_wait(&empty[stage], (it & 1) ^ 1);
         uint8_t* st = smem + stage * STAGE_BYTES;
-#pragma unroll 1
-        for (int cidx = 0; cidx < 8; ++cidx) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t e = c_conv1_ktab[s * 64 + cidx * 8 + j];
-            const int c = e >> 8, ky = (e >> 4) & 15, kx = e & 15;
-            const int iy = iy0 + ky, ix = ix0 + kx;
-            const bool ok = valid && c < 3 && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-            v[j] = ok ? __ldg(img + c * plane + (size_t)iy * p.Win + ix) : 0.f;
-          }
-          store_row_chunk<SPLIT3>(st, st + SLOT_BYTES, r, cidx, v);
+        if (half == 0) {
+          if (s == 0) conv1_build_row<0, 0>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 1) conv1_build_row<1, 0>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 2) conv1_build_row<2, 0>(pp, st, st + SLOT_BYTES, r);
+          else conv1_build_row<3, 0>(pp, st, st + SLOT_BYTES, r);
+        } else {
+          if (s == 0) conv1_build_row<0, 1>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 1) conv1_build_row<1, 1>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 2) conv1_build_row<2, 1>(pp, st, st + SLOT_BYTES, r);
+          else conv1_build_row<3, 1>(pp, st, st + SLOT_BYTES, r);
         }
         fence_proxy_async_smem();
         mbar_arrive(&afull[stage]);
@@ -259,29 +312,33 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tcgen05_fence_after();
 
     if (GDN) {
-      // ---- pass 1: (acc + bias)^2 -> K-major swizzled bf16 A tile for the gamma product
+      // ---- pass 1: (acc + bias)^2 -> K-major swizzled bf16 A tile for the gamma product.
+      // thread (r, half) writes k-block g = half (its 64 channels) and only arrives on the other one.
 #pragma unroll 1
       for (int g = 0; g < 2; ++g) {
-        const int stage = (nsteps + g) % STAGES;
-        uint8_t* st = smem + stage * STAGE_BYTES;
-#pragma unroll 1
-        for (int h = 0; h < 4; ++h) {          // 16 channels per TMEM load
-          uint32_t raw[16];
-          tmem_ld16(t_row + (uint32_t)(g * 64 + h * 16), raw);
+        const int s = nsteps + g;
+        const int stage = s % STAGES, it = s / STAGES;
+        // every worker waits for the slot (with one stage, k-block 1 reuses k-block 0's slot and barrier:
+        // arriving early would be counted in the previous phase)
+        mbar_wait(&empty[stage], (it & 1) ^ 1);
+        if (g == half) {
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          uint32_t raw[64];
+          tmem_ld32(t_row + (uint32_t)(g * 64), *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+          tmem_ld32(t_row + (uint32_t)(g * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
           tmem_ld_wait();
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int cidx = 0; cidx < 8; ++cidx) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int c = g * 64 + h * 16 + half * 8 + j;
-              const float xv = __uint_as_float(raw[half * 8 + j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+              const float xv = __uint_as_float(raw[cidx * 8 + j]) + s_bias[g * 64 + cidx * 8 + j];
               v[j] = xv * xv;
             }
-            store_row_chunk<SPLIT3>(st, st + SLOT_BYTES, r, h * 2 + half, v);
+            store_row_chunk<SPLIT3>(st, st + SLOT_BYTES, r, cidx, v);
           }
+          fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
         mbar_arrive(&afull[stage]);
       }
       mbar_wait(norm_full, 0);
@@ -292,25 +349,24 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int oyf = oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0);
     const int oxf = ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0);
     if (OUT_MODE == OUT_F32_NCHW_PS4) {
-      // DECONV3: column = (ry*4+rx)*3 + o  ->  out[n, o, 4*oy+ry, 4*ox+rx]
-      float acc[48];
-#pragma unroll
-      for (int h = 0; h < 3; ++h) {
-        uint32_t raw[16];
-        tmem_ld16(t_row + (uint32_t)(h * 16), raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[h * 16 + j] = __uint_as_float(raw[j]);
-      }
+      // DECONV3: column = (ry*4+rx)*3 + o  ->  out[n, o, 4*oy+ry, 4*ox+rx]; this thread owns ry = 2*half, 2*half+1
+      uint32_t raw[24];
+      tmem_ld8(t_row + (uint32_t)(half * 24), *reinterpret_cast<uint32_t(*)[8]>(&raw[0]));
+      tmem_ld8(t_row + (uint32_t)(half * 24 + 8), *reinterpret_cast<uint32_t(*)[8]>(&raw[8]));
+      tmem_ld8(t_row + (uint32_t)(half * 24 + 16), *reinterpret_cast<uint32_t(*)[8]>(&raw[16]));
+      tmem_ld_wait();
       if (valid) {
         float* out = reinterpret_cast<float*>(p.out_hi);
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
-          const float bv = p.bias ? __ldg(p.bias + o) : 0.f;
+          const float bv = s_bias[o];
 #pragma unroll
-          for (int ry = 0; ry < 4; ++ry) {
-            float4 v4 = make_float4(acc[(ry * 4 + 0) * 3 + o] + bv, acc[(ry * 4 + 1) * 3 + o] + bv,
-                                    acc[(ry * 4 + 2) * 3 + o] + bv, acc[(ry * 4 + 3) * 3 + o] + bv);
+          for (int ryl = 0; ryl < 2; ++ryl) {
+            const int ry = half * 2 + ryl;
+            float4 v4 = make_float4(__uint_as_float(raw[(ryl * 4 + 0) * 3 + o]) + bv,
+                                    __uint_as_float(raw[(ryl * 4 + 1) * 3 + o]) + bv,
+                                    __uint_as_float(raw[(ryl * 4 + 2) * 3 + o]) + bv,
+                                    __uint_as_float(raw[(ryl * 4 + 3) * 3 + o]) + bv);
             float* dst = out + (((size_t)n_img * 3 + o) * p.Hfull + (oy * 4 + ry)) * p.Wfull + ox * 4;
             *reinterpret_cast<float4*>(dst) = v4;
           }
@@ -318,19 +374,20 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
     } else {
 #pragma unroll 1
-      for (int h = 0; h < N_TILE / 16; ++h) {
-        uint32_t raw[16], rawn[16];
-        tmem_ld16(t_row + (uint32_t)(h * 16), raw);
-        if (GDN) tmem_ld16(t_row + (uint32_t)(C128 + h * 16), rawn);
+      for (int h = 0; h < 2; ++h) {            // 2 x 32 channels of this thread's 64
+        const int c0 = half * 64 + h * 32;
+        uint32_t raw[32], rawn[32];
+        tmem_ld32(t_row + (uint32_t)c0, raw);
+        if (GDN) tmem_ld32(t_row + (uint32_t)(C128 + c0), rawn);
         tmem_ld_wait();
-        float y[16];
+        float y[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = h * 16 + j;
-          float xv = __uint_as_float(raw[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+        for (int j = 0; j < 32; ++j) {
+          float xv = __uint_as_float(raw[j]) + s_bias[c0 + j];
           if (GDN) {
-            const float nrm = sqrtf(__uint_as_float(rawn[j]) + __ldg(p.beta_eff + c));
-            xv = (GDN == 2) ? xv * nrm : xv / nrm;
+            const float nb = __uint_as_float(rawn[j]) + s_beta[c0 + j];
+            const float rs = rsqrtf(nb);
+            xv = (GDN == 2) ? xv * (nb * rs) : xv * rs;
           }
           y[j] = xv;
         }
@@ -339,27 +396,25 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         } else if (OUT_MODE == OUT_F32_NCHW) {
           float* out = reinterpret_cast<float*>(p.out_hi);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            out[(((size_t)n_img * N_TILE + h * 16 + j) * p.Hfull + oyf) * p.Wfull + oxf] = y[j];
+          for (int j = 0; j < 32; ++j)
+            out[(((size_t)n_img * N_TILE + c0 + j) * p.Hfull + oyf) * p.Wfull + oxf] = y[j];
         } else {
           const size_t pix = ((size_t)n_img * p.Hfull + oyf) * p.Wfull + oxf;
-          __nv_bfloat16 hi[16], lo[16];
+          uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + pix * C128 + c0);
+          uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * C128 + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (SPLIT3) split_bf16(y[j], hi[j], lo[j]);
-            else hi[j] = __float2bfloat16_rn(y[j]);
-          }
-          uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + pix * C128 + h * 16);
-          dh[0] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
-                             pack_bf16x2(hi[6], hi[7]));
-          dh[1] = make_uint4(pack_bf16x2(hi[8], hi[9]), pack_bf16x2(hi[10], hi[11]), pack_bf16x2(hi[12], hi[13]),
-                             pack_bf16x2(hi[14], hi[15]));
-          if (SPLIT3) {
-            uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * C128 + h * 16);
-            dl[0] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
-                               pack_bf16x2(lo[6], lo[7]));
-            dl[1] = make_uint4(pack_bf16x2(lo[8], lo[9]), pack_bf16x2(lo[10], lo[11]), pack_bf16x2(lo[12], lo[13]),
-                               pack_bf16x2(lo[14], lo[15]));
+          for (int cidx = 0; cidx < 4; ++cidx) {
+            __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (SPLIT3) split_bf16(y[cidx * 8 + j], hi[j], lo[j]);
+              else hi[j] = __float2bfloat16_rn(y[cidx * 8 + j]);
+            }
+            dh[cidx] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
+                                  pack_bf16x2(hi[6], hi[7]));
+            if (SPLIT3)
+              dl[cidx] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
+                                    pack_bf16x2(lo[6], lo[7]));
           }
         }
       }
@@ -511,34 +566,24 @@ static int make_mat_map(CUtensorMap* m, const void* base, int rows, int cols, in
   return B2C_OK;
 }
 
-static int upload_conv1_table() {
-  // constant memory is per device: upload once on every device that runs CONV1
-  static bool done[64] = {false};
-  static std::mutex mu;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lk(mu);
-  if (dev < 64 && done[dev]) return B2C_OK;
-  uint16_t tab[256];
-  for (int k = 0; k < 256; ++k) {
-    if (k < 243) {
-      const int c = k / 81, r = k % 81, ky = r / 9, kx = r % 9;
-      tab[k] = (uint16_t)((c << 8) | (ky << 4) | kx);
-    } else {
-      tab[k] = (uint16_t)(3 << 8);  // c = 3 -> masked
-    }
-  }
-  cudaError_t err = cudaMemcpyToSymbol(c_conv1_ktab, tab, sizeof(tab));
-  if (err != cudaSuccess) { set_error("conv1 table upload: %s", cudaGetErrorString(err)); return B2C_ECUDA; }
-  if (dev < 64) done[dev] = true;
+// fp32 NCHW image [B][3][H][W]: box = 72 x 37 x 3 (the im2col support of one 8x16 CONV1 output tile)
+static int make_image_map(CUtensorMap* m, const void* base, int B, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+  cuuint32_t box[4] = {(cuuint32_t)P1_W, (cuuint32_t)P1_H, 3, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image) failed: %d", (int)r); return B2C_ECUDA; }
   return B2C_OK;
 }
 
 template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
 static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr int STAGES = SPLIT3 ? 3 : 6;
-  constexpr int STAGE_BYTES = (SPLIT3 ? 4 : 2) * SLOT_BYTES;
-  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr size_t SMEM = TcCfg<SPLIT3, KIND>::SMEM;
   auto kern = igemm_tc_kernel<N_TILE, SPLIT3, KIND, GDN, OUT_MODE>;
   static std::once_flag once;   // one per instantiation
   static cudaError_t attr_err = cudaSuccess;
@@ -555,7 +600,9 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
   memset(&mB_lo, 0, sizeof(mB_lo));
   int rc;
   constexpr int S = (KIND == B2C_TC_CONV5S2) ? 2 : 1;
-  if (KIND != B2C_TC_CONV1) {
+  if (KIND == B2C_TC_CONV1) {
+    if ((rc = make_image_map(&mA_hi, L->in_hi, L->B, L->Hin, L->Win))) return rc;
+  } else {
     if ((rc = make_act_map(&mA_hi, L->in_hi, L->B, L->Hin, L->Win, S))) return rc;
     if (SPLIT3 && (rc = make_act_map(&mA_lo, L->in_lo, L->B, L->Hin, L->Win, S))) return rc;
   }
@@ -642,7 +689,7 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   switch (L->kind) {
     case B2C_TC_CONV1:
       B2C_REQUIRE(L->Hin % 4 == 0 && L->Win % 4 == 0, "tc conv1: H, W must be multiples of 4");
-      p.Hg = L->Hin / 4; p.Wg = L->Win / 4; p.ps = 1; p.img = (const float*)L->in_hi;
+      p.Hg = L->Hin / 4; p.Wg = L->Win / 4; p.ps = 1;
       break;
     case B2C_TC_CONV5S2:
       p.Hg = (L->Hin - 1) / 2 + 1; p.Wg = (L->Win - 1) / 2 + 1; p.ps = 1;
@@ -661,10 +708,6 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   p.tiles_x = (p.Wg + TW - 1) / TW;
   const int tiles_y = (p.Hg + TH - 1) / TH;
   dim3 grid(p.tiles_x * tiles_y, phases, L->B);
-  if (L->kind == B2C_TC_CONV1) {
-    int rc = upload_conv1_table();
-    if (rc) return rc;
-  }
 
   const int key = L->kind * 1000 + (L->split3 ? 100 : 0) + L->gdn * 10 + (L->out_f32_nchw ? 1 : 0);
   switch (key) {
