@@ -42,6 +42,7 @@ struct TcParams {
   const float* beta_eff;
   void* out_hi;
   void* out_lo;
+  long long* trace;     // debug: clock64 timeline of CTA (0,0,0): [3 roles][64 marks]
 };
 
 // CONV1 input patch of one 8x16 output tile: 3 channels x 37 rows x 69 (->72) columns of fp32
@@ -124,8 +125,8 @@ __device__ __forceinline__ void decode_step(int s, int phase, int& dy, int& dx, 
   }
 }
 
-// pipeline depth / CTAs per SM: plain bf16 and CONV1 keep <= 113 KB of shared memory so two CTAs share an
-// SM and one CTA's epilogue overlaps the other's MMA main loop.
+// pipeline depth / CTAs per SM: the plain-bf16 kernels keep <= 113 KB of shared memory so two CTAs share an
+// SM and one CTA's epilogue overlaps the other's MMA main loop; the split (hi, lo) kernels use the whole SM.
 template <bool SPLIT3, int KIND>
 struct TcCfg {
   static constexpr int STAGES = (KIND == B2C_TC_CONV1) ? 1 : 3;
@@ -171,6 +172,12 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int oy0 = tile_y * TH, ox0 = tile_x * TW;
   const int nsteps = num_steps<KIND>(phase);
   const int total_steps = nsteps + (GDN ? 2 : 0);
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  int tmark = 0;
+#define TC_MARK(role)                                                       \
+  do {                                                                      \
+    if (tracing && tmark < 64) p.trace[(role) * 64 + tmark++] = clock64(); \
+  } while (0)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -206,9 +213,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_arrive_expect_tx(patch_full, (uint32_t)P1_BYTES);
         tma_load_4d(patch, &tmA_hi, patch_full, ox0 * 4 - 4, oy0 * 4 - 4, 0, n_img);
       }
+      TC_MARK(0);
       for (int s = 0; s < total_steps; ++s) {
         const int stage = s % STAGES, it = s / STAGES;
         mbar_wait(&empty[stage], (it & 1) ^ 1);
+        TC_MARK(0);
         uint8_t* st = smem + stage * STAGE_BYTES;
         uint8_t* a_hi = st;
         uint8_t* a_lo = st + SLOT_BYTES;
@@ -251,6 +260,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           ++soft_uses[stage];
         }
         tcgen05_fence_after();
+        TC_MARK(1);
         const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t a_hi = st, a_lo = st + SLOT_BYTES;
         const uint32_t b_hi = st + (SPLIT3 ? 2 : 1) * SLOT_BYTES, b_lo = b_hi + SLOT_BYTES;
@@ -282,11 +292,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int oy = oy0 + ty, ox = ox0 + tx;
     const bool valid = oy < p.Hg && ox < p.Wg;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool wtrace = tracing && r == 0 && half == 0;
+#define TC_WMARK()                                                     \
+  do {                                                                 \
+    if (wtrace && tmark < 64) p.trace[2 * 64 + tmark++] = clock64();   \
+  } while (0)
+    TC_WMARK();
 
     if (SOFT_A) {
       // CONV1: im2col rows from the TMA-staged fp32 patch; pixel (ty,tx) starts at patch[4*ty][4*tx]
       const float* pp = patch + (4 * ty) * P1_W + 4 * tx;
       mbar_wait(patch_full, 0);
+      TC_WMARK();
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int stage = s % STAGES, it = s / STAGES;
@@ -305,11 +322,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
         fence_proxy_async_smem();
         mbar_arrive(&afull[stage]);
+        TC_WMARK();
       }
     }
 
     mbar_wait(accum_full, 0);
     tcgen05_fence_after();
+    TC_WMARK();
 
     if (GDN) {
       // ---- pass 1: (acc + bias)^2 -> K-major swizzled bf16 A tile for the gamma product.
@@ -341,8 +360,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
         mbar_arrive(&afull[stage]);
       }
+      TC_WMARK();
       mbar_wait(norm_full, 0);
       tcgen05_fence_after();
+      TC_WMARK();
     }
 
     // ---- final pass: TMEM -> registers -> global
@@ -419,6 +440,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
       }
     }
+    TC_WMARK();
   }
 
   tcgen05_fence_before();
@@ -427,6 +449,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+#undef TC_MARK
+#undef TC_WMARK
 }
 
 // ------------------------------------------------------------------------------------ packing kernels
@@ -625,7 +649,12 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
 using namespace b2c;
 using namespace b2c::tc;
 
+static long long* g_tc_trace = nullptr;
+
 extern "C" {
+
+/* debug hook (not part of the stable ABI): device buffer of 3*64 int64 receiving a clock64 timeline */
+void b2c_tc_debug_set_trace(void* device_buffer) { g_tc_trace = (long long*)device_buffer; }
 
 size_t b2c_tc_packed_weight_elems(int kind) {
   switch (kind) {
@@ -685,6 +714,7 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   memset(&p, 0, sizeof(p));
   p.B = L->B; p.Hin = L->Hin; p.Win = L->Win;
   p.bias = L->bias; p.beta_eff = L->beta_eff; p.out_hi = L->out_hi; p.out_lo = L->out_lo;
+  p.trace = g_tc_trace;
   int phases = 1;
   switch (L->kind) {
     case B2C_TC_CONV1:
