@@ -1,0 +1,125 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed over NCCL/NVLink.
+
+Training: pure data parallel.  The reference wraps the model in single-process
+nn.DataParallel (train.py:228: broadcast parameters + reduce gradients to GPU 0 every step); here every
+rank keeps a replica and ``GradSync`` all-reduces the 7.07 MB of fp32 gradients in a few buckets in
+reverse layer order, each launched asynchronously from a post-accumulate-grad hook the moment its last
+gradient is produced, so the transfer overlaps the rest of backward.  ``finish()`` waits, averages and
+hands the gradients back before ``optimizer.step()``.
+
+Inference: images are independent -> ``shard_range`` splits them across ranks; there is no data-path
+collective, only a host-side gather of per-image statistics (``gather_stats``).
+
+Works with any backend (the CPU tests use gloo, world_size 2).
+"""
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """contiguous, balanced [start, stop) of this rank (first n_items % world ranks get one extra)."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_stats(local: torch.Tensor, group=None) -> torch.Tensor:
+    """host-side gather of per-image rows [n_local, k] from every rank -> [n_total, k] (all ranks)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local.detach().cpu()
+    objs: List[Optional[torch.Tensor]] = [None] * dist.get_world_size(group)
+    dist.all_gather_object(objs, local.detach().cpu(), group=group)
+    return torch.cat(objs, dim=0)
+
+
+# reverse layer order = order in which backward produces the gradients (decoder first)
+DEFAULT_BUCKETS: Sequence[Sequence[str]] = (
+    ("Decoder.",),
+    ("bitEstimator.", "Encoder.conv3", "Encoder.gdn2", "Encoder.conv2"),
+    ("Encoder.gdn1", "Encoder.conv1"),
+)
+
+
+class GradSync:
+    """Bucketed, overlapped gradient all-reduce (mean) for a replicated module."""
+
+    def __init__(self, module: torch.nn.Module, buckets: Optional[Sequence[Sequence[str]]] = None, group=None,
+                 broadcast_parameters: bool = True, auto_finish: bool = False):
+        if not dist.is_initialized():
+            raise RuntimeError("GradSync needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        # auto_finish: finish() runs inside the hook that launches the last bucket, so an unmodified training
+        # loop (train.py:105-112: backward(); clip; optimizer.step()) sees averaged gradients.
+        self.auto_finish = auto_finish
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        prefixes = buckets if buckets is not None else DEFAULT_BUCKETS
+        assigned = {}
+        self.buckets = []
+        for prefs in prefixes:
+            members = [(n, p) for n, p in named if n not in assigned and any(n.startswith(pf) for pf in prefs)]
+            if members:
+                self._add_bucket(members, assigned)
+        rest = [(n, p) for n, p in named if n not in assigned]
+        if rest:
+            self._add_bucket(rest, assigned)
+        if broadcast_parameters:                      # replicas start identical (rank 0's weights)
+            with torch.no_grad():
+                for _, p in module.named_parameters():
+                    dist.broadcast(p.data, src=0, group=group)
+                for _, b in module.named_buffers():
+                    dist.broadcast(b.data, src=0, group=group)
+        self._handles = []
+        for bi, b in enumerate(self.buckets):
+            for j, (n, p) in enumerate(b["members"]):
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi, j)))
+
+    def _add_bucket(self, members, assigned):
+        numel = sum(p.numel() for _, p in members)
+        p0 = members[0][1]
+        flat = torch.zeros(numel, dtype=p0.dtype, device=p0.device)
+        offs, o = [], 0
+        for n, p in members:
+            offs.append(o)
+            o += p.numel()
+            assigned[n] = len(self.buckets)
+        self.buckets.append({"members": members, "flat": flat, "offsets": offs, "ready": 0, "work": None})
+
+    def _make_hook(self, bi, j):
+        def hook(p):
+            b = self.buckets[bi]
+            o = b["offsets"][j]
+            b["flat"][o:o + p.numel()].copy_(p.grad.reshape(-1))
+            b["ready"] += 1
+            if b["ready"] == len(b["members"]):
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                if self.auto_finish and all(x["work"] is not None for x in self.buckets):
+                    self.finish()
+        return hook
+
+    def finish(self):
+        """wait for every bucket, average, write the reduced gradients back into .grad"""
+        for b in self.buckets:
+            if b["ready"] == 0:
+                continue
+            if b["ready"] != len(b["members"]):
+                # some parameter received no gradient this step: reduce what we have (zeros for the rest)
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            b["work"].wait()
+            b["flat"].div_(self.world)
+            for (n, p), o in zip(b["members"], b["offsets"]):
+                if p.grad is not None:
+                    p.grad.copy_(b["flat"][o:o + p.numel()].view_as(p))
+            b["ready"] = 0
+            b["work"] = None
+            b["flat"].zero_()
+
+    def bucket_bytes(self):
+        return [b["flat"].numel() * b["flat"].element_size() for b in self.buckets]
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

@@ -65,6 +65,21 @@ class ImageCompressor(nn.Module):
         self.last_path = None
         self._packed = None
         self._packed_key = None
+        self._grad_sync = None
+
+    def _maybe_join_process_group(self):
+        """multi-process data parallel without touching train.py: when the launcher
+        (run_reference_script.py) set B2C_DDP=1, join the NCCL group on the first training forward,
+        take rank 0's weights and all-reduce gradients from backward hooks."""
+        if self._grad_sync is not None or os.environ.get("B2C_DDP") != "1":
+            return
+        if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+            return
+        import torch.distributed as dist
+        from .ddp import GradSync
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if next(self.parameters()).is_cuda else "gloo")
+        self._grad_sync = GradSync(self, auto_finish=True)
 
     # ------------------------------------------------------------------ tensor-core inference path
     def _pack_key(self):
@@ -126,6 +141,8 @@ class ImageCompressor(nn.Module):
         if x.size(2) % 16 or x.size(3) % 16:
             # the reference fails here too (noise is H//16 but the convs give ceil(H/16), model.py:48,54)
             raise RuntimeError(f"H and W must be multiples of 16, got {x.size(2)}x{x.size(3)}")
+        if self.training:
+            self._maybe_join_process_group()
         tc_path = self._use_tc(x)
         self.last_path = "tcgen05" if tc_path else "fp32"
         if tc_path:
