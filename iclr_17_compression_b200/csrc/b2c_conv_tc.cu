@@ -42,6 +42,9 @@ struct TcParams {
   const float* beta_eff;
   void* out_hi;
   void* out_lo;
+  const float* ref_image;  // DECONV3 fused distortion: input image x (fp32 NCHW) or null
+  float* sse_partial;      // [B][tiles][2] per-CTA {sum (r-x)^2, sum (clamp(r)-x)^2}
+  int tiles_per_image;
   long long* trace;     // debug: clock64 timeline of CTA (0,0,0): [3 roles][64 marks]
 };
 
@@ -75,22 +78,41 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_
   }
 }
 
-// CONV1: the 64 im2col values k = KB*64 .. KB*64+63 (k = c*81 + ky*9 + kx, zero for k >= 243) of the
-// pixel whose patch origin is `pp`, written as one swizzled 128-byte K-major row (hi, lo).
-// All patch offsets are compile-time constants -> LDS with immediate offsets.
+// CONV1: the 32 im2col values k = KB*64 + HALF*32 .. +31 (k = c*81 + ky*9 + kx, zero for k >= 243) of the
+// pixel whose patch origin is `pp` (16-byte aligned), written as four swizzled 16-byte chunks (hi, lo) of the
+// pixel's 128-byte K-major row.  Each (c, ky) patch row is fetched with three conflict-free LDS.128
+// (12 floats, 9 used); every index below is a compile-time constant.
 template <int KB, int HALF>
 __device__ __forceinline__ void conv1_build_row(const float* __restrict__ pp, uint8_t* slot_hi, uint8_t* slot_lo,
                                                 int r) {
+  constexpr int K0 = KB * 64 + HALF * 32;
+  constexpr int G0 = K0 / 9;
+  constexpr int G1 = (K0 + 31) / 9;
+  constexpr int NG = G1 - G0 + 1;
+  float vals[NG * 12];
 #pragma unroll
-  for (int cidx = HALF * 4; cidx < HALF * 4 + 4; ++cidx) {
+  for (int gi = 0; gi < NG; ++gi) {
+    const int g = G0 + gi;
+    if (g < 27) {
+      const float4* row = reinterpret_cast<const float4*>(pp + (g / 9) * P1_PLANE + (g % 9) * P1_W);
+      const float4 a = row[0], b = row[1], c = row[2];
+      vals[gi * 12 + 0] = a.x; vals[gi * 12 + 1] = a.y; vals[gi * 12 + 2] = a.z; vals[gi * 12 + 3] = a.w;
+      vals[gi * 12 + 4] = b.x; vals[gi * 12 + 5] = b.y; vals[gi * 12 + 6] = b.z; vals[gi * 12 + 7] = b.w;
+      vals[gi * 12 + 8] = c.x; vals[gi * 12 + 9] = c.y; vals[gi * 12 + 10] = c.z; vals[gi * 12 + 11] = c.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) vals[gi * 12 + t] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = KB * 64 + cidx * 8 + j;
-      const int c = k / 81, ky = (k % 81) / 9, kx = k % 9;
-      v[j] = (k < 243) ? pp[c * P1_PLANE + ky * P1_W + kx] : 0.f;
+      const int k = K0 + ci * 8 + j;
+      v[j] = (k < 243) ? vals[(k / 9 - G0) * 12 + (k % 9)] : 0.f;
     }
-    store_row_chunk<true>(slot_hi, slot_lo, r, cidx, v);
+    store_row_chunk<true>(slot_hi, slot_lo, r, HALF * 4 + ci, v);
   }
 }
 
@@ -127,6 +149,12 @@ __device__ __forceinline__ void decode_step(int s, int phase, int& dy, int& dx, 
 
 // pipeline depth / CTAs per SM: the plain-bf16 kernels keep <= 113 KB of shared memory so two CTAs share an
 // SM and one CTA's epilogue overlaps the other's MMA main loop; the split (hi, lo) kernels use the whole SM.
+// NHWC bf16 output tiles leave through TMA stores: conv kinds use [0] = hi plane, [1] = lo plane; DECONV5S2
+// uses one strided map per sub-pixel phase (the phase's output lattice as a dense 4-D tensor).
+struct TcOutMaps {
+  CUtensorMap m[4];
+};
+
 template <bool SPLIT3, int KIND>
 struct TcCfg {
   static constexpr int STAGES = (KIND == B2C_TC_CONV1) ? 1 : 3;
@@ -141,7 +169,7 @@ __global__ void __launch_bounds__(NTHREADS, TcCfg<SPLIT3, KIND>::MIN_CTAS)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo,
-                const TcParams p) {
+                const __grid_constant__ TcOutMaps tmO, const TcParams p) {
   using Cfg = TcCfg<SPLIT3, KIND>;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int STAGES = Cfg::STAGES;
@@ -370,12 +398,15 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int oyf = oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0);
     const int oxf = ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0);
     if (OUT_MODE == OUT_F32_NCHW_PS4) {
-      // DECONV3: column = (ry*4+rx)*3 + o  ->  out[n, o, 4*oy+ry, 4*ox+rx]; this thread owns ry = 2*half, 2*half+1
+      // DECONV3: column = (ry*4+rx)*3 + o  ->  out[n, o, 4*oy+ry, 4*ox+rx]; this thread owns ry = 2*half, 2*half+1.
+      // With a reference image the distortion is fused: out = clamp(r, 0, 1) (model.py:59) and the CTA's
+      // partial sums of (r - x)^2 (model.py:61) and (clamp(r) - x)^2 (train.py:172) go to sse_partial.
       uint32_t raw[24];
       tmem_ld8(t_row + (uint32_t)(half * 24), *reinterpret_cast<uint32_t(*)[8]>(&raw[0]));
       tmem_ld8(t_row + (uint32_t)(half * 24 + 8), *reinterpret_cast<uint32_t(*)[8]>(&raw[8]));
       tmem_ld8(t_row + (uint32_t)(half * 24 + 16), *reinterpret_cast<uint32_t(*)[8]>(&raw[16]));
       tmem_ld_wait();
+      float s0 = 0.f, s1 = 0.f;
       if (valid) {
         float* out = reinterpret_cast<float*>(p.out_hi);
 #pragma unroll
@@ -388,12 +419,41 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                     __uint_as_float(raw[(ryl * 4 + 1) * 3 + o]) + bv,
                                     __uint_as_float(raw[(ryl * 4 + 2) * 3 + o]) + bv,
                                     __uint_as_float(raw[(ryl * 4 + 3) * 3 + o]) + bv);
-            float* dst = out + (((size_t)n_img * 3 + o) * p.Hfull + (oy * 4 + ry)) * p.Wfull + ox * 4;
-            *reinterpret_cast<float4*>(dst) = v4;
+            const size_t off = (((size_t)n_img * 3 + o) * p.Hfull + (oy * 4 + ry)) * p.Wfull + ox * 4;
+            if (p.ref_image) {
+              const float4 x4 = __ldg(reinterpret_cast<const float4*>(p.ref_image + off));
+              const float4 c4 = make_float4(fminf(fmaxf(v4.x, 0.f), 1.f), fminf(fmaxf(v4.y, 0.f), 1.f),
+                                            fminf(fmaxf(v4.z, 0.f), 1.f), fminf(fmaxf(v4.w, 0.f), 1.f));
+              float d;
+              d = v4.x - x4.x; s0 = fmaf(d, d, s0); d = v4.y - x4.y; s0 = fmaf(d, d, s0);
+              d = v4.z - x4.z; s0 = fmaf(d, d, s0); d = v4.w - x4.w; s0 = fmaf(d, d, s0);
+              d = c4.x - x4.x; s1 = fmaf(d, d, s1); d = c4.y - x4.y; s1 = fmaf(d, d, s1);
+              d = c4.z - x4.z; s1 = fmaf(d, d, s1); d = c4.w - x4.w; s1 = fmaf(d, d, s1);
+              v4 = c4;
+            }
+            *reinterpret_cast<float4*>(out + off) = v4;
           }
         }
       }
-    } else {
+      if (p.ref_image) {   // fixed-order CTA reduction: warp shuffle, then the 8 worker warps through smem
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        float* red = s_beta;   // unused by DECONV3 (no GDN)
+        if (lane == 0) { red[(warp - 2) * 2] = s0; red[(warp - 2) * 2 + 1] = s1; }
+        asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory");
+        if (warp == 2 && lane == 0) {
+          float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { t0 += red[w * 2]; t1 += red[w * 2 + 1]; }
+          float* dst = p.sse_partial + ((size_t)n_img * p.tiles_per_image + blockIdx.x) * 2;
+          dst[0] = t0;
+          dst[1] = t1;
+        }
+      }
+    } else if (OUT_MODE == OUT_F32_NCHW) {
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {            // 2 x 32 channels of this thread's 64
         const int c0 = half * 64 + h * 32;
@@ -401,43 +461,65 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tmem_ld32(t_row + (uint32_t)c0, raw);
         if (GDN) tmem_ld32(t_row + (uint32_t)(C128 + c0), rawn);
         tmem_ld_wait();
-        float y[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float xv = __uint_as_float(raw[j]) + s_bias[c0 + j];
-          if (GDN) {
-            const float nb = __uint_as_float(rawn[j]) + s_beta[c0 + j];
-            const float rs = rsqrtf(nb);
-            xv = (GDN == 2) ? xv * (nb * rs) : xv * rs;
-          }
-          y[j] = xv;
-        }
-        if (!valid) {
-          // masked row: nothing to store (no `continue`: the next tcgen05.ld must be warp-convergent)
-        } else if (OUT_MODE == OUT_F32_NCHW) {
+        if (valid) {
           float* out = reinterpret_cast<float*>(p.out_hi);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            out[(((size_t)n_img * N_TILE + c0 + j) * p.Hfull + oyf) * p.Wfull + oxf] = y[j];
-        } else {
-          const size_t pix = ((size_t)n_img * p.Hfull + oyf) * p.Wfull + oxf;
-          uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + pix * C128 + c0);
-          uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * C128 + c0);
-#pragma unroll
-          for (int cidx = 0; cidx < 4; ++cidx) {
-            __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (SPLIT3) split_bf16(y[cidx * 8 + j], hi[j], lo[j]);
-              else hi[j] = __float2bfloat16_rn(y[cidx * 8 + j]);
+          for (int j = 0; j < 32; ++j) {
+            float xv = __uint_as_float(raw[j]) + s_bias[c0 + j];
+            if (GDN) {
+              const float nb = __uint_as_float(rawn[j]) + s_beta[c0 + j];
+              const float rs = rsqrtf(nb);
+              xv = (GDN == 2) ? xv * (nb * rs) : xv * rs;
             }
-            dh[cidx] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
-                                  pack_bf16x2(hi[6], hi[7]));
-            if (SPLIT3)
-              dl[cidx] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]),
-                                    pack_bf16x2(lo[6], lo[7]));
+            out[(((size_t)n_img * N_TILE + c0 + j) * p.Hfull + oyf) * p.Wfull + oxf] = xv;
           }
         }
+      }
+    } else {
+      // NHWC bf16 (hi[, lo]): stage the 128 x 64-channel half tiles in the (now idle) ring slots in the same
+      // swizzled K-major layout the loads use, then one elected thread issues TMA stores (coalesced 128-byte
+      // rows, image-border clipping done by the TMA unit).
+      uint8_t* stg_hi = smem + half * SLOT_BYTES;                       // slots 0,1: hi k-blocks 0,1
+      uint8_t* stg_lo = smem + (2 + half) * SLOT_BYTES;                 // slots 2,3: lo k-blocks 0,1 (SPLIT3)
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {            // 2 x 32 channels of this thread's 64
+        const int c0 = half * 64 + h * 32;
+        uint32_t raw[32], rawn[32];
+        tmem_ld32(t_row + (uint32_t)c0, raw);
+        if (GDN) tmem_ld32(t_row + (uint32_t)(C128 + c0), rawn);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float xv = __uint_as_float(raw[ci * 8 + j]) + s_bias[c0 + ci * 8 + j];
+            if (GDN) {
+              const float nb = __uint_as_float(rawn[ci * 8 + j]) + s_beta[c0 + ci * 8 + j];
+              const float rs = rsqrtf(nb);
+              xv = (GDN == 2) ? xv * (nb * rs) : xv * rs;
+            }
+            v[j] = xv;
+          }
+          store_row_chunk<SPLIT3>(stg_hi, stg_lo, r, h * 4 + ci, v);
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory");
+      if (warp == 2 && lane == 0) {
+        const int oxs = ox0, oys = oy0;      // tile origin in the (phase) output lattice
+        if (KIND == B2C_TC_DECONV5S2) {
+          tma_store_4d(&tmO.m[phase], smem, 0, oxs, oys, n_img);
+          tma_store_4d(&tmO.m[phase], smem + SLOT_BYTES, KBLK, oxs, oys, n_img);
+        } else {
+          tma_store_4d(&tmO.m[0], smem, 0, oxs, oys, n_img);
+          tma_store_4d(&tmO.m[0], smem + SLOT_BYTES, KBLK, oxs, oys, n_img);
+          if (SPLIT3) {
+            tma_store_4d(&tmO.m[1], smem + 2 * SLOT_BYTES, 0, oxs, oys, n_img);
+            tma_store_4d(&tmO.m[1], smem + 3 * SLOT_BYTES, KBLK, oxs, oys, n_img);
+          }
+        }
+        tma_store_commit_and_wait();
       }
     }
     TC_WMARK();
@@ -575,6 +657,25 @@ static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, i
   return B2C_OK;
 }
 
+// NHWC bf16 output lattice: pixel (oy*ps + ry, ox*ps + rx) of [B][Hfull][Wfull][128] seen as a dense
+// [B][Hg][Wg][128] tensor with strides; box = 64 channels x TW x TH pixels (TMA clips at the image border)
+static int make_out_map(CUtensorMap* m, const void* base, int B, int Hg, int Wg, int Hfull, int Wfull, int ps, int ry,
+                        int rx) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
+  const char* origin = reinterpret_cast<const char*>(base) + ((size_t)ry * Wfull + rx) * C128 * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C128, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ps * C128 * 2, (cuuint64_t)ps * Wfull * C128 * 2,
+                           (cuuint64_t)Hfull * Wfull * C128 * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(origin), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output) failed: %d", (int)r); return B2C_ECUDA; }
+  return B2C_OK;
+}
+
 // bf16 matrix [rows][cols] (cols contiguous): box = 64 cols x box_rows
 static int make_mat_map(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
   EncodeTiledFn enc = get_encode();
@@ -638,7 +739,18 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
     if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C128, C128, C128))) return rc;
     if (SPLIT3 && (rc = make_mat_map(&mG_lo, L->gamma_lo, C128, C128, C128))) return rc;
   }
-  kern<<<grid, NTHREADS, SMEM, stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, p);
+  TcOutMaps mO;
+  memset(&mO, 0, sizeof(mO));
+  if (OUT_MODE == OUT_BF16) {
+    if (KIND == B2C_TC_DECONV5S2) {
+      for (int ph = 0; ph < 4; ++ph)
+        if ((rc = make_out_map(&mO.m[ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, 2, ph >> 1, ph & 1))) return rc;
+    } else {
+      if ((rc = make_out_map(&mO.m[0], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, 1, 0, 0))) return rc;
+      if (SPLIT3 && (rc = make_out_map(&mO.m[1], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, 1, 0, 0))) return rc;
+    }
+  }
+  kern<<<grid, NTHREADS, SMEM, stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
   count_launch();
   return check_launch("tc_layer_run");
 }
@@ -702,6 +814,18 @@ int b2c_tc_nhwc_to_nchw(const void* in_hi, const void* in_lo, float* out, int B,
   return check_launch("tc_nhwc_to_nchw");
 }
 
+int b2c_tc_tiles_per_image(int kind, int Hin, int Win) {
+  int Hg, Wg;
+  switch (kind) {
+    case B2C_TC_CONV1: Hg = Hin / 4; Wg = Win / 4; break;
+    case B2C_TC_CONV5S2: Hg = (Hin - 1) / 2 + 1; Wg = (Win - 1) / 2 + 1; break;
+    case B2C_TC_DECONV5S2:
+    case B2C_TC_DECONV3: Hg = Hin; Wg = Win; break;
+    default: return 0;
+  }
+  return ((Wg + TW - 1) / TW) * ((Hg + TH - 1) / TH);
+}
+
 int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   B2C_REQUIRE(L, "tc_layer_run: null layer");
   B2C_REQUIRE(L->in_hi && L->w_hi && L->out_hi, "tc_layer_run: null tensor pointer");
@@ -715,6 +839,9 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   p.B = L->B; p.Hin = L->Hin; p.Win = L->Win;
   p.bias = L->bias; p.beta_eff = L->beta_eff; p.out_hi = L->out_hi; p.out_lo = L->out_lo;
   p.trace = g_tc_trace;
+  p.ref_image = L->ref_image; p.sse_partial = L->sse_partial;
+  B2C_REQUIRE(!L->ref_image || (L->kind == B2C_TC_DECONV3 && L->sse_partial),
+              "tc_layer_run: ref_image/sse_partial are for DECONV3 only and go together");
   int phases = 1;
   switch (L->kind) {
     case B2C_TC_CONV1:
@@ -737,6 +864,7 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   p.Hfull = p.Hg * p.ps; p.Wfull = p.Wg * p.ps;
   p.tiles_x = (p.Wg + TW - 1) / TW;
   const int tiles_y = (p.Hg + TH - 1) / TH;
+  p.tiles_per_image = p.tiles_x * tiles_y;
   dim3 grid(p.tiles_x * tiles_y, phases, L->B);
 
   const int key = L->kind * 1000 + (L->split3 ? 100 : 0) + L->gdn * 10 + (L->out_f32_nchw ? 1 : 0);

@@ -234,6 +234,18 @@ __global__ void __launch_bounds__(256) clamp_sse_bwd_kernel(const float* __restr
   }
 }
 
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial,
+                                                             float* __restrict__ out, int per_image, int width) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  for (int j = 0; j < width; ++j) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < per_image; i += blockDim.x) s += partial[((size_t)n * per_image + i) * width + j];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[n * width + j] = s;
+  }
+}
+
 static int clamp_blocks_per_image(int B, int CHW) {
   int bpi = (CHW + 256 * 8 - 1) / (256 * 8);
   const int cap = (148 * 8 + B - 1) / B;
@@ -295,6 +307,13 @@ int b2c_clamp_sse_fwd(const float* recon, const float* x, float* clipped, float*
   sse_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, sse, bpi);
   count_launch(2);
   return check_launch("clamp_sse_fwd");
+}
+
+int b2c_partial_reduce(const float* partial, float* out, int B, int per_image, int width, void* stream) {
+  B2C_REQUIRE(partial && out && B > 0 && per_image > 0 && width > 0 && width <= 4, "partial_reduce: bad arguments");
+  partial_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(partial, out, per_image, width);
+  count_launch();
+  return check_launch("partial_reduce");
 }
 
 int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped, const float* g_sse,

@@ -115,13 +115,15 @@ class ImageCompressor(nn.Module):
                            split3=True)
         return B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv3"], None, split3=True, out_f32_nchw=True)
 
-    def decode_tc(self, z):
-        """synthesis transform on tensor cores (bf16) -> unclamped reconstruction, fp32 NCHW"""
+    def decode_tc(self, z, ref_image=None):
+        """synthesis transform on tensor cores (bf16) -> unclamped reconstruction, fp32 NCHW; with ref_image
+        the distortion is fused into the last layer: returns (clamped reconstruction, sse[B,2])"""
         P, D = self._packed_weights(), self.Decoder
         zh, _ = B2TC.nchw_to_nhwc(z, False)        # integer latents |z| <= 256 are exact in bf16
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, zh, None, P["deconv1"], D.deconv1.bias, gdn=P["igdn1"], gdn_mode=2)
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, h[0], None, P["deconv2"], D.deconv2.bias, gdn=P["igdn2"], gdn_mode=2)
-        return B2TC.layer_run(B2TC.TC_DECONV3, h[0], None, P["deconv3"], D.deconv3.bias, out_f32_nchw=True)
+        return B2TC.layer_run(B2TC.TC_DECONV3, h[0], None, P["deconv3"], D.deconv3.bias, out_f32_nchw=True,
+                              ref_image=ref_image)
 
     def _use_tc(self, x):
         return (self.fast_inference and not self.training and not torch.is_grad_enabled()
@@ -153,8 +155,12 @@ class ImageCompressor(nn.Module):
             feature = self.Encoder(x)
         noise = self._noise(x) if self.training else None
         z, total_bits, image_bits, plane_bits = self.bitEstimator.bits(feature, noise)
-        recon_image = self.decode_tc(z) if tc_path else self.Decoder(z)
-        clipped_recon_image, sse_total, sse = B2F.distortion(recon_image, x)
+        if tc_path:
+            clipped_recon_image, sse = self.decode_tc(z, ref_image=x)
+            sse_total = sse[:, 0].sum()
+        else:
+            recon_image = self.Decoder(z)
+            clipped_recon_image, sse_total, sse = B2F.distortion(recon_image, x)
         mse_loss = sse_total / x.numel()                                   # model.py:61
         bpp_feature = total_bits / (x.size(0) * x.size(2) * x.size(3))      # model.py:78
         self.last = {"image_bits": image_bits, "plane_bits": plane_bits, "sse": sse, "mse_loss": mse_loss}

@@ -68,7 +68,7 @@ _FLOPS_PER_OUT_PIXEL = {TC_CONV1: 2 * 243 * 128, TC_CONV5S2: 2 * 3200 * 128, TC_
                         TC_DECONV3: 2 * 128 * 243 / 16}
 
 
-def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False):
+def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False, ref_image=None):
     """One fused layer.  x_hi/x_lo: NHWC bf16 (CONV1: x_hi = fp32 NCHW image).  w = (w_hi, w_lo);
     gdn = (gamma_hi, gamma_lo, beta_eff) with gdn_mode 1 (GDN) / 2 (IGDN).
     Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
@@ -100,8 +100,19 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         L.gamma_hi, L.gamma_lo, L.beta_eff = gdn[0].data_ptr(), (gdn[1].data_ptr() if gdn[1] is not None else 0), \
             gdn[2].data_ptr()
     L.out_hi, L.out_lo = out_hi.data_ptr(), (out_lo.data_ptr() if out_lo is not None else 0)
+    sse = None
+    if ref_image is not None:                      # DECONV3: fused clamp + squared errors
+        lib = _lib.load()
+        tiles = lib.b2c_tc_tiles_per_image(kind, Hin, Win)
+        partial = torch.empty((B, tiles, 2), device=dev, dtype=torch.float32)
+        sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
+        L.ref_image, L.sse_partial = ref_image.data_ptr(), partial.data_ptr()
     flops = int(_FLOPS_PER_OUT_PIXEL[kind] * B * Ho * Wo) + (2 * 128 * 128 * B * Ho * Wo if gdn_mode else 0)
     name = f"tc_layer[kind{kind},{B}x{Hin}x{Win},split{int(split3)},gdn{gdn_mode}]"
     with torch.cuda.device(dev), _timed(name, flops, 0):
         _lib.check(_lib.load().b2c_tc_layer_run(ctypes.byref(L), _stream()), "tc_layer_run")
+        if sse is not None:
+            _lib.check(_lib.load().b2c_partial_reduce(_p(partial), _p(sse), B, tiles, 2, _stream()), "partial_reduce")
+    if sse is not None:
+        return out_hi, sse
     return out_hi if out_f32_nchw else (out_hi, out_lo)

@@ -116,6 +116,8 @@ int b2c_entropy_bwd(const float* z, const float* const* host_params, const float
 int b2c_clamp_sse_fwd(const float* recon, const float* x, float* clipped, float* sse,
                       int B, int CHW, void* workspace, size_t workspace_bytes, void* stream);
 size_t b2c_clamp_sse_workspace_bytes(int B, int CHW);
+/* out[n*width + j] = sum_i partial[(n*per_image + i)*width + j], fixed order (deterministic); width <= 4. */
+int b2c_partial_reduce(const float* partial, float* out, int B, int per_image, int width, void* stream);
 /* grad_recon = g_clipped * 1[0<=recon<=1] + g_sse[0] * 2 (recon - x);
  * g_clipped may be NULL; g_sse is a DEVICE scalar (dL/d total unclamped SSE). */
 int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped,
@@ -159,7 +161,15 @@ typedef struct b2c_tc_layer {
   const float* beta_eff;
   void* out_hi;
   void* out_lo;
+  /* DECONV3 only, optional fused distortion (model.py:59,61; train.py:172): with ref_image = x (fp32 NCHW)
+   * out_hi receives clamp(recon, 0, 1) and sse_partial[B][tiles][2] the per-tile sums of (recon - x)^2 and
+   * (clamp(recon) - x)^2; reduce them with b2c_partial_reduce(sse_partial, sse, B, tiles, 2). */
+  const float* ref_image;
+  float* sse_partial;
 } b2c_tc_layer;
+
+/* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid */
+int b2c_tc_tiles_per_image(int kind, int Hin, int Win);
 
 int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
 
