@@ -710,14 +710,18 @@ template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
 static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStream_t stream) {
   constexpr size_t SMEM = TcCfg<SPLIT3, KIND>::SMEM;
   auto kern = igemm_tc_kernel<N_TILE, SPLIT3, KIND, GDN, OUT_MODE>;
-  static std::once_flag once;   // one per instantiation
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-  });
-  // function attributes are per device; re-apply cheaply (idempotent) when several devices are in use
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err)); return B2C_ECUDA; }
+  {  // opt in to > 48 KB dynamic shared memory once per (instantiation, device); never during graph capture replays
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+  }
 
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo;
   memset(&mA_hi, 0, sizeof(mA_hi)); memset(&mA_lo, 0, sizeof(mA_lo));

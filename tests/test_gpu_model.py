@@ -215,3 +215,22 @@ def test_tc_repacks_after_weight_update():
         _, z2, bpp2 = m(x)
     assert not torch.equal(z0, z1)
     assert (z1 != z2).float().mean().item() < 1e-3
+
+
+def test_host_pipeline_matches_direct_forward():
+    """inference.HostPipeline (pinned host in/out, chunked, CUDA graphs) == model(x) on the same images."""
+    from iclr_17_compression_b200.inference import HostPipeline
+    from oracle import balle17_oracle as O
+    c = Case("eval_W1_U_n128_64")
+    m = _model(c).eval()
+    x = O.synth_images("S", 8, 128, 192, 77)
+    with torch.no_grad():
+        clipped, z, bpp = m(x.cuda())
+        bits = m.last["image_bits"].cpu()
+        sse = m.last["sse"].cpu()
+    for graphs in (True, False):
+        pipe = HostPipeline(m, 8, 128, 192, chunk=2, use_graphs=graphs)
+        for _ in range(2):                                   # second call reuses buffers / graphs
+            lat, stats = pipe.compress(x.pin_memory())
+        assert torch.equal(lat, z.cpu())
+        assert torch.allclose(stats[:, 0], bits, rtol=1e-6) and torch.allclose(stats[:, 1:], sse, rtol=1e-5)
