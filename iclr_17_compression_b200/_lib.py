@@ -51,6 +51,7 @@ SIGNATURES.update({
     "b2c_tc_pack_gdn": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_f, _c_f]),
     "b2c_tc_layer_run": (_c_i, [ctypes.POINTER(TcLayer), _c_f]),
     "b2c_tc_tiles_per_image": (_c_i, [_c_i, _c_i, _c_i]),
+    "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
     "b2c_partial_reduce": (_c_i, [_c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_tc_nchw_to_nhwc": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_tc_nhwc_to_nchw": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),

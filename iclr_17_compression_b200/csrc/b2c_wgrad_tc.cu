@@ -1,0 +1,241 @@
+// tcgen05 weight-gradient kernels for the bf16 training path (out_channel_N = 128).
+//
+//   dW[m][n][tap] += sum_{pixels} S[pix][m] * G[stride*pix - pad + tap][n]
+//
+// Both operands are NHWC bf16 activations, i.e. the reduction index (pixels) is the row index of
+// the TMA-staged tiles and the channel index is contiguous: the MMA operands are therefore
+// MN-major (UMMA a_major = b_major = 1) SWIZZLE_128B tiles, 16 pixels (K = 16) per instruction,
+// M = N = 128 channels = two 64-channel boxes 16 KB apart.  The tiles are the very TMA boxes the
+// forward convolution loads (traversal stride 2 for the stride-2 layers, OOB zero-fill = padding
+// and tile masking).  One CTA owns up to 4 taps (4 x 128 TMEM columns) and a strided share of the
+// pixel tiles; partial sums are added to the fp32 gradient with red.global.
+//
+// Covers conv2/conv3/deconv1/deconv2 weight gradients (25 taps, stride 2) and the GDN gamma
+// gradient d gamma[i][j] = sum_pix dn[pix][i] * x^2[pix][j] (1 tap, stride 1).
+#include <mutex>
+
+#include "b2c_common.cuh"
+#include "b2c_tc.cuh"
+
+namespace b2c {
+namespace tc {
+
+constexpr int W_TH = 8, W_TW = 16;
+constexpr int W_PAIR_BYTES = 2 * 128 * 64 * 2;  // two 64-channel boxes of 128 pixels: 32 KB
+constexpr int W_STAGES = 6;
+constexpr int W_TAPS = 4;                       // taps per CTA (4 x 128 fp32 columns = all of TMEM)
+constexpr int W_THREADS = 192;                  // producer warp, MMA warp, 4 epilogue warps
+
+struct WgParams {
+  int B, hs, ws;          // small (tile) grid
+  int tiles_x, tiles_per_image, total_tiles;
+  int ksz, stride, pad, ntaps;
+  float* dW;              // [128][128][ntaps]
+};
+
+// MN-major SWIZZLE_128B operand: 64 channels (128 B) x 8 pixels per swizzle atom; atoms along the channel
+// (M/N) direction are `lbo` bytes apart, atoms along the pixel (K) direction 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(W_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmG, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W_STAGES * W_PAIR_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + W_STAGES;
+  uint64_t* done = bars + 2 * W_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap0 = blockIdx.x * W_TAPS;
+  const int ntap = min(W_TAPS, p.ntaps - tap0);
+  const int split = blockIdx.y, nsplit = gridDim.y;
+  const int my_tiles = (p.total_tiles - split + nsplit - 1) / nsplit;   // tiles split, split+nsplit, ...
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int slot_ctr = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = split + t * nsplit;
+        const int n_img = tile / p.tiles_per_image, tt = tile - n_img * p.tiles_per_image;
+        const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+        const int y0 = ty * W_TH, x0 = tx * W_TW;
+        for (int j = -1; j < ntap; ++j, ++slot_ctr) {     // j = -1: the S tile, then one G tile per tap
+          const int slot = slot_ctr % W_STAGES, it = slot_ctr / W_STAGES;
+          mbar_wait(&empty[slot], (it & 1) ^ 1);
+          uint8_t* dst = smem + slot * W_PAIR_BYTES;
+          mbar_arrive_expect_tx(&full[slot], (uint32_t)W_PAIR_BYTES);
+          if (j < 0) {
+            tma_load_4d(dst, &tmS, &full[slot], 0, x0, y0, n_img);
+            tma_load_4d(dst + W_PAIR_BYTES / 2, &tmS, &full[slot], 64, x0, y0, n_img);
+          } else {
+            const int tap = tap0 + j, ky = tap / p.ksz, kx = tap - ky * p.ksz;
+            const int cx = x0 * p.stride - p.pad + kx, cy = y0 * p.stride - p.pad + ky;
+            tma_load_4d(dst, &tmG, &full[slot], 0, cx, cy, n_img);
+            tma_load_4d(dst + W_PAIR_BYTES / 2, &tmG, &full[slot], 64, cx, cy, n_img);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_mn(128);
+      int slot_ctr = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int s_slot = slot_ctr % W_STAGES, s_it = slot_ctr / W_STAGES;
+        ++slot_ctr;
+        mbar_wait(&full[s_slot], s_it & 1);
+        const uint32_t a_base = smem_u32(smem + s_slot * W_PAIR_BYTES);
+        for (int j = 0; j < ntap; ++j, ++slot_ctr) {
+          const int slot = slot_ctr % W_STAGES, it = slot_ctr / W_STAGES;
+          mbar_wait(&full[slot], it & 1);
+          tcgen05_fence_after();
+          const uint32_t b_base = smem_u32(smem + slot * W_PAIR_BYTES);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {                   // 8 x 16 pixels
+            const uint64_t da = umma_desc_mn_sw128(a_base + k * 2048, W_PAIR_BYTES / 2);
+            const uint64_t db = umma_desc_mn_sw128(b_base + k * 2048, W_PAIR_BYTES / 2);
+            umma_bf16(tmem_base + (uint32_t)(j * 128), da, db, idesc, (t > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[slot]);
+        }
+        umma_commit(&empty[s_slot]);                      // S tile is free once its last tap has been issued
+      }
+      umma_commit(done);
+    }
+  } else {
+    // epilogue: 4 warps, thread = output row m (TMEM lane), all 128 columns n of each tap
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    mbar_wait(done, 0);
+    tcgen05_fence_after();
+    if (my_tiles > 0) {
+      for (int j = 0; j < ntap; ++j) {
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + (uint32_t)(j * 128 + h * 32), raw);
+          tmem_ld_wait();
+          float* dst = p.dW + ((size_t)m * 128 + h * 32) * p.ntaps + tap0 + j;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) atomicAdd(dst + (size_t)c * p.ntaps, __uint_as_float(raw[c]));
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn2 get_encode2() {
+  static EncodeTiledFn2 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn2)ptr;
+  });
+  return fn;
+}
+
+static int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, int S) {
+  EncodeTiledFn2 enc = get_encode2();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
+  cuuint64_t dims[4] = {128, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {256, (cuuint64_t)W * 256, (cuuint64_t)H * W * 256};
+  cuuint32_t box[4] = {64, (cuuint32_t)(W_TW * S), (cuuint32_t)(W_TH * S), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)S, (cuuint32_t)S, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(wgrad) failed: %d", (int)r); return B2C_ECUDA; }
+  return B2C_OK;
+}
+
+}  // namespace tc
+}  // namespace b2c
+
+using namespace b2c;
+using namespace b2c::tc;
+
+extern "C" {
+
+int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
+                 int stride, int pad, void* stream) {
+  B2C_REQUIRE(small_t && big_t && dW, "tc_wgrad: null pointer");
+  B2C_REQUIRE(B > 0 && hs > 0 && ws > 0 && hb > 0 && wb > 0 && (k == 1 || k == 5) && (stride == 1 || stride == 2) &&
+                  pad >= 0,
+              "tc_wgrad: unsupported geometry (k in {1,5}, stride in {1,2})");
+  constexpr size_t SMEM = (size_t)W_STAGES * W_PAIR_BYTES + 1024 + 256;
+  {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+  }
+  WgParams p;
+  p.B = B; p.hs = hs; p.ws = ws;
+  p.tiles_x = (ws + W_TW - 1) / W_TW;
+  p.tiles_per_image = p.tiles_x * ((hs + W_TH - 1) / W_TH);
+  p.total_tiles = B * p.tiles_per_image;
+  p.ksz = k; p.stride = stride; p.pad = pad; p.ntaps = k * k;
+  p.dW = dW;
+  CUtensorMap mS, mG;
+  int rc;
+  if ((rc = make_nhwc_map(&mS, small_t, B, hs, ws, 1))) return rc;
+  if ((rc = make_nhwc_map(&mG, big_t, B, hb, wb, stride))) return rc;
+  const int groups = (p.ntaps + W_TAPS - 1) / W_TAPS;
+  int splits = 148 / groups;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  dim3 grid(groups, splits);
+  wgrad_tc_kernel<<<grid, W_THREADS, SMEM, (cudaStream_t)stream>>>(mS, mG, p);
+  count_launch();
+  return check_launch("tc_wgrad");
+}
+
+}  // extern "C"

@@ -116,3 +116,15 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
     if sse is not None:
         return out_hi, sse
     return out_hi if out_f32_nchw else (out_hi, out_lo)
+
+
+def wgrad(small, big, k, stride, pad):
+    """dW[m][n][ky][kx] = sum small[.,ys,xs,m] * big[., stride*ys-pad+ky, stride*xs-pad+kx, n]; NHWC bf16 in, fp32 out"""
+    B, hs, ws, _ = small.shape
+    _, hb, wb, _ = big.shape
+    dW = torch.zeros((128, 128, k, k), device=small.device, dtype=torch.float32)
+    flops = 2 * B * hs * ws * 128 * 128 * k * k
+    with torch.cuda.device(small.device), _timed(f"tc_wgrad[{B}x{hs}x{ws},k{k}s{stride}]", flops, 0):
+        _lib.check(_lib.load().b2c_tc_wgrad(_p(small), _p(big), _p(dW), B, hs, ws, hb, wb, k, stride, pad, _stream()),
+                   "tc_wgrad")
+    return dW

@@ -173,6 +173,15 @@ int b2c_tc_tiles_per_image(int kind, int Hin, int Win);
 
 int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
 
+/* Tensor-core weight gradient (bf16 training path):
+ *   dW[m][n][ky][kx] += sum_{img,ys,xs} small[img,ys,xs,m] * big[img, stride*ys - pad + ky, stride*xs - pad + kx, n]
+ * small [B,hs,ws,128], big [B,hb,wb,128]: NHWC bf16; dW fp32 [128][128][k][k], zero-filled by the caller
+ * (partial sums are added with red.global).  k in {1,5}, stride in {1,2}.
+ *   conv2d weight grad (OIHW): small = grad_out, big = input;  conv_transpose2d (IOHW): small = input, big = grad_out;
+ *   GDN gamma grad: k = 1, small = dL/dnorm, big = x^2.                               (autograd of train.py:105) */
+int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
+                 int stride, int pad, void* stream);
+
 /* layout / precision converters between the reference's fp32 NCHW and the NHWC bf16 (hi[,lo]) tiles */
 int b2c_tc_nchw_to_nhwc(const float* in, void* out_hi, void* out_lo, int B, int C, int HW, void* stream);
 int b2c_tc_nhwc_to_nchw(const void* in_hi, const void* in_lo, float* out, int B, int C, int HW, void* stream);

@@ -130,3 +130,35 @@ def test_deconv3_bf16(tc, shape):
     y = tc.layer_run(tc.TC_DECONV3, xh, None, wp, b, split3=False, out_f32_nchw=True)
     assert y.shape == ref.shape
     assert _rel(y, ref) < 2e-5, _rel(y, ref)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 32), (2, 32, 32), (3, 24, 40)])
+def test_wgrad_5x5s2(tc, shape):
+    """tensor-core weight gradient (MN-major MMAs) vs autograd, conv and transposed-conv forms."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, 128, H, W, generator=g).cuda()
+    go = torch.randn(B, 128, H // 2, W // 2, generator=g).cuda()
+    xh, _ = tc.nchw_to_nhwc(x, False)
+    gh, _ = tc.nchw_to_nhwc(go, False)
+    xq = xh.float().permute(0, 3, 1, 2).double().cpu()
+    gq = gh.float().permute(0, 3, 1, 2).double().cpu()
+    w = torch.zeros(128, 128, 5, 5, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(xq, w, None, stride=2, padding=2) * gq).sum().backward()
+    dW = tc.wgrad(gh, xh, 5, 2, 2)                      # conv: small = grad_out, big = input -> OIHW
+    assert _rel(dW, w.grad) < 1e-5, _rel(dW, w.grad)
+    wt = torch.zeros(128, 128, 5, 5, dtype=torch.float64, requires_grad=True)
+    (F.conv_transpose2d(gq, wt, None, stride=2, padding=2, output_padding=1) * xq).sum().backward()
+    dWt = tc.wgrad(gh, xh, 5, 2, 2)                     # convT with input gq, grad_out xq: small = input, big = grad_out
+    assert _rel(dWt, wt.grad) < 1e-5
+
+
+def test_wgrad_1x1_gamma_form(tc):
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(2, 128, 16, 24, generator=g).cuda()
+    b = torch.randn(2, 128, 16, 24, generator=g).cuda()
+    ah, _ = tc.nchw_to_nhwc(a, False)
+    bh, _ = tc.nchw_to_nhwc(b, False)
+    ref = torch.einsum("nihw,njhw->ij", ah.float().permute(0, 3, 1, 2).double(), bh.float().permute(0, 3, 1, 2).double())
+    d = tc.wgrad(ah, bh, 1, 1, 0).view(128, 128)
+    assert _rel(d, ref) < 1e-5
