@@ -42,6 +42,8 @@ struct TcParams {
   const float* beta_eff;
   void* out_hi;
   void* out_lo;
+  const __nv_bfloat16* saved_y;  // GDN backward epilogue: forward output y and norm n = beta + gamma x^2
+  const __nv_bfloat16* saved_n;  //   (NHWC bf16, indexed like the output of this launch)
   const float* ref_image;  // DECONV3 fused distortion: input image x (fp32 NCHW) or null
   float* sse_partial;      // [B][tiles][2] per-CTA {sum (r-x)^2, sum (clamp(r)-x)^2}
   int tiles_per_image;
@@ -82,7 +84,7 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_
 // pixel whose patch origin is `pp` (16-byte aligned), written as four swizzled 16-byte chunks (hi, lo) of the
 // pixel's 128-byte K-major row.  Each (c, ky) patch row is fetched with three conflict-free LDS.128
 // (12 floats, 9 used); every index below is a compile-time constant.
-template <int KB, int HALF>
+template <int KB, int HALF, bool SPLIT3>
 __device__ __forceinline__ void conv1_build_row(const float* __restrict__ pp, uint8_t* slot_hi, uint8_t* slot_lo,
                                                 int r) {
   constexpr int K0 = KB * 64 + HALF * 32;
@@ -112,7 +114,7 @@ __device__ __forceinline__ void conv1_build_row(const float* __restrict__ pp, ui
       const int k = K0 + ci * 8 + j;
       v[j] = (k < 243) ? vals[(k / 9 - G0) * 12 + (k % 9)] : 0.f;
     }
-    store_row_chunk<true>(slot_hi, slot_lo, r, HALF * 4 + ci, v);
+    store_row_chunk<SPLIT3>(slot_hi, slot_lo, r, HALF * 4 + ci, v);
   }
 }
 
@@ -152,12 +154,12 @@ __device__ __forceinline__ void decode_step(int s, int phase, int& dy, int& dx, 
 // NHWC bf16 output tiles leave through TMA stores: conv kinds use [0] = hi plane, [1] = lo plane; DECONV5S2
 // uses one strided map per sub-pixel phase (the phase's output lattice as a dense 4-D tensor).
 struct TcOutMaps {
-  CUtensorMap m[4];
+  CUtensorMap m[8];   // [0..3] primary plane (conv: [0]; deconv: per phase), [4..7] second plane (lo / norm / dnorm)
 };
 
 template <bool SPLIT3, int KIND>
 struct TcCfg {
-  static constexpr int STAGES = (KIND == B2C_TC_CONV1) ? 1 : 3;
+  static constexpr int STAGES = (KIND == B2C_TC_CONV1 && SPLIT3) ? 1 : 3;
   static constexpr int STAGE_BYTES = (SPLIT3 ? 4 : 2) * SLOT_BYTES;
   static constexpr int PATCH = (KIND == B2C_TC_CONV1) ? P1_SLOT : 0;
   static constexpr int SMEM = STAGES * STAGE_BYTES + PATCH + 1024 /*align*/ + 1024 /*bias, beta*/ + 256 /*barriers*/;
@@ -178,6 +180,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   constexpr uint32_t TMEM_COLS = GDN ? 256 : (N_TILE > 64 ? 128 : 64);
   constexpr uint32_t B_BYTES = N_TILE * KBLK * 2;
   static_assert(GDN == 0 || N_TILE == 128, "fused GDN needs all 128 channels in the tile");
+  // GDN: 0 none, 1 GDN forward, 2 IGDN forward, 3 GDN backward, 4 IGDN backward (epilogue of the dgrad conv)
+  constexpr bool GDN_BWD = (GDN == 3 || GDN == 4);
+  static_assert(!GDN_BWD || !SPLIT3, "the GDN backward epilogue is bf16 only");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -338,15 +343,15 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         mbar_wait(&empty[stage], (it & 1) ^ 1);
         uint8_t* st = smem + stage * STAGE_BYTES;
         if (half == 0) {
-          if (s == 0) conv1_build_row<0, 0>(pp, st, st + SLOT_BYTES, r);
-          else if (s == 1) conv1_build_row<1, 0>(pp, st, st + SLOT_BYTES, r);
-          else if (s == 2) conv1_build_row<2, 0>(pp, st, st + SLOT_BYTES, r);
-          else conv1_build_row<3, 0>(pp, st, st + SLOT_BYTES, r);
+          if (s == 0) conv1_build_row<0, 0, SPLIT3>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 1) conv1_build_row<1, 0, SPLIT3>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 2) conv1_build_row<2, 0, SPLIT3>(pp, st, st + SLOT_BYTES, r);
+          else conv1_build_row<3, 0, SPLIT3>(pp, st, st + SLOT_BYTES, r);
         } else {
-          if (s == 0) conv1_build_row<0, 1>(pp, st, st + SLOT_BYTES, r);
-          else if (s == 1) conv1_build_row<1, 1>(pp, st, st + SLOT_BYTES, r);
-          else if (s == 2) conv1_build_row<2, 1>(pp, st, st + SLOT_BYTES, r);
-          else conv1_build_row<3, 1>(pp, st, st + SLOT_BYTES, r);
+          if (s == 0) conv1_build_row<0, 1, SPLIT3>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 1) conv1_build_row<1, 1, SPLIT3>(pp, st, st + SLOT_BYTES, r);
+          else if (s == 2) conv1_build_row<2, 1, SPLIT3>(pp, st, st + SLOT_BYTES, r);
+          else conv1_build_row<3, 1, SPLIT3>(pp, st, st + SLOT_BYTES, r);
         }
         fence_proxy_async_smem();
         mbar_arrive(&afull[stage]);
@@ -374,15 +379,38 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tmem_ld32(t_row + (uint32_t)(g * 64), *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
           tmem_ld32(t_row + (uint32_t)(g * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
           tmem_ld_wait();
+          if (GDN_BWD) {
+            // acc = dL/dy.  dL/dnorm = -+ 1/2 * g * y / n  (GDN: y = x n^-1/2, IGDN: y = x n^1/2)
+            const size_t pixb = (((size_t)n_img * p.Hfull + (oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0))) *
+                                     p.Wfull + (ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0))) * C128 + g * 64;
+            const uint4* py = reinterpret_cast<const uint4*>(p.saved_y + pixb);
+            const uint4* pn = reinterpret_cast<const uint4*>(p.saved_n + pixb);
 #pragma unroll
-          for (int cidx = 0; cidx < 8; ++cidx) {
-            float v[8];
+            for (int cidx = 0; cidx < 8; ++cidx) {
+              uint4 qy = make_uint4(0, 0, 0, 0), qn = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+              if (valid) { qy = __ldg(py + cidx); qn = __ldg(pn + cidx); }
+              const uint32_t wy[4] = {qy.x, qy.y, qy.z, qy.w}, wn[4] = {qn.x, qn.y, qn.z, qn.w};
+              float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float xv = __uint_as_float(raw[cidx * 8 + j]) + s_bias[g * 64 + cidx * 8 + j];
-              v[j] = xv * xv;
+              for (int j = 0; j < 8; ++j) {
+                const float yv = __uint_as_float((j & 1) ? (wy[j >> 1] & 0xffff0000u) : (wy[j >> 1] << 16));
+                const float nv = __uint_as_float((j & 1) ? (wn[j >> 1] & 0xffff0000u) : (wn[j >> 1] << 16));
+                const float gv = __uint_as_float(raw[cidx * 8 + j]);
+                v[j] = (GDN == 3 ? -0.5f : 0.5f) * gv * yv / nv;
+              }
+              store_row_chunk<false>(st, st + SLOT_BYTES, r, cidx, v);
             }
-            store_row_chunk<SPLIT3>(st, st + SLOT_BYTES, r, cidx, v);
+          } else {
+#pragma unroll
+            for (int cidx = 0; cidx < 8; ++cidx) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float xv = __uint_as_float(raw[cidx * 8 + j]) + s_bias[g * 64 + cidx * 8 + j];
+                v[j] = xv * xv;
+              }
+              store_row_chunk<SPLIT3>(st, st + SLOT_BYTES, r, cidx, v);
+            }
           }
           fence_proxy_async_smem();
         }
@@ -476,11 +504,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         }
       }
     } else {
-      // NHWC bf16 (hi[, lo]): stage the 128 x 64-channel half tiles in the (now idle) ring slots in the same
-      // swizzled K-major layout the loads use, then one elected thread issues TMA stores (coalesced 128-byte
-      // rows, image-border clipping done by the TMA unit).
-      uint8_t* stg_hi = smem + half * SLOT_BYTES;                       // slots 0,1: hi k-blocks 0,1
-      uint8_t* stg_lo = smem + (2 + half) * SLOT_BYTES;                 // slots 2,3: lo k-blocks 0,1 (SPLIT3)
+      // NHWC bf16: stage the 128 x 64-channel half tiles in idle ring slots in the same swizzled K-major
+      // layout the loads use, then one elected thread issues TMA stores (coalesced 128-byte rows,
+      // image-border clipping done by the TMA unit).
+      //   SPLIT3: stage 0 = {hi k-blocks 0,1 ; lo k-blocks 0,1}.
+      //   bf16:   primary plane -> both slots of the stage the GDN steps did not touch; second plane (forward:
+      //           norm n, for training; backward: dL/dnorm, which already sits in the GDN steps' A slots).
+      const int st_c = SPLIT3 ? 0 : (nsteps + 2) % STAGES;
+      uint8_t* stg_hi = smem + st_c * STAGE_BYTES + half * SLOT_BYTES;
+      uint8_t* stg_lo = smem + (2 + half) * SLOT_BYTES;                                   // SPLIT3 only
+      const bool second_plane = !SPLIT3 && GDN != 0 && p.out_lo != nullptr;
+      uint8_t* stg_n = smem + ((nsteps + half) % STAGES) * STAGE_BYTES + SLOT_BYTES;     // forward norm: B slot
+      const size_t pixb = (((size_t)n_img * p.Hfull + oyf) * p.Wfull + oxf) * C128;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {            // 2 x 32 channels of this thread's 64
         const int c0 = half * 64 + h * 32;
@@ -490,34 +525,51 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tmem_ld_wait();
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-          float v[8];
+          float v[8], vn[8];
+          uint32_t wy[4] = {0, 0, 0, 0}, wn[4] = {0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
+          if (GDN_BWD && valid) {
+            const uint4 qy = __ldg(reinterpret_cast<const uint4*>(p.saved_y + pixb + c0) + ci);
+            const uint4 qn = __ldg(reinterpret_cast<const uint4*>(p.saved_n + pixb + c0) + ci);
+            wy[0] = qy.x; wy[1] = qy.y; wy[2] = qy.z; wy[3] = qy.w;
+            wn[0] = qn.x; wn[1] = qn.y; wn[2] = qn.z; wn[3] = qn.w;
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float xv = __uint_as_float(raw[ci * 8 + j]) + s_bias[c0 + ci * 8 + j];
-            if (GDN) {
+            if (GDN == 1 || GDN == 2) {
               const float nb = __uint_as_float(rawn[ci * 8 + j]) + s_beta[c0 + ci * 8 + j];
               const float rs = rsqrtf(nb);
               xv = (GDN == 2) ? xv * (nb * rs) : xv * rs;
+              vn[j] = nb;
+            } else if (GDN_BWD) {
+              // dL/dx = g * n^-+1/2 + 2 x * (gamma^T dn),  x = y n^+-1/2
+              const float yv = __uint_as_float((j & 1) ? (wy[j >> 1] & 0xffff0000u) : (wy[j >> 1] << 16));
+              const float nv = __uint_as_float((j & 1) ? (wn[j >> 1] & 0xffff0000u) : (wn[j >> 1] << 16));
+              const float rs = rsqrtf(nv), sq = nv * rs;
+              const float t = __uint_as_float(rawn[ci * 8 + j]);
+              xv = (GDN == 3) ? fmaf(2.f * yv * sq, t, xv * rs) : fmaf(2.f * yv * rs, t, xv * sq);
             }
             v[j] = xv;
           }
           store_row_chunk<SPLIT3>(stg_hi, stg_lo, r, h * 4 + ci, v);
+          if (second_plane && !GDN_BWD) store_row_chunk<false>(stg_n, stg_n, r, h * 4 + ci, vn);
         }
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory");
       if (warp == 2 && lane == 0) {
-        const int oxs = ox0, oys = oy0;      // tile origin in the (phase) output lattice
-        if (KIND == B2C_TC_DECONV5S2) {
-          tma_store_4d(&tmO.m[phase], smem, 0, oxs, oys, n_img);
-          tma_store_4d(&tmO.m[phase], smem + SLOT_BYTES, KBLK, oxs, oys, n_img);
-        } else {
-          tma_store_4d(&tmO.m[0], smem, 0, oxs, oys, n_img);
-          tma_store_4d(&tmO.m[0], smem + SLOT_BYTES, KBLK, oxs, oys, n_img);
-          if (SPLIT3) {
-            tma_store_4d(&tmO.m[1], smem + 2 * SLOT_BYTES, 0, oxs, oys, n_img);
-            tma_store_4d(&tmO.m[1], smem + 3 * SLOT_BYTES, KBLK, oxs, oys, n_img);
-          }
+        const int mi = (KIND == B2C_TC_DECONV5S2) ? phase : 0;
+        uint8_t* c_base = smem + st_c * STAGE_BYTES;
+        tma_store_4d(&tmO.m[mi], c_base, 0, ox0, oy0, n_img);
+        tma_store_4d(&tmO.m[mi], c_base + SLOT_BYTES, KBLK, ox0, oy0, n_img);
+        if (SPLIT3) {
+          tma_store_4d(&tmO.m[4 + mi], smem + 2 * SLOT_BYTES, 0, ox0, oy0, n_img);
+          tma_store_4d(&tmO.m[4 + mi], smem + 3 * SLOT_BYTES, KBLK, ox0, oy0, n_img);
+        } else if (second_plane) {
+          // forward: norm tiles in the B slots; backward: dnorm tiles still in the A slots of the GDN steps
+          const int off = GDN_BWD ? 0 : SLOT_BYTES;
+          tma_store_4d(&tmO.m[4 + mi], smem + ((nsteps + 0) % STAGES) * STAGE_BYTES + off, 0, ox0, oy0, n_img);
+          tma_store_4d(&tmO.m[4 + mi], smem + ((nsteps + 1) % STAGES) * STAGE_BYTES + off, KBLK, ox0, oy0, n_img);
         }
         tma_store_commit_and_wait();
       }
@@ -567,10 +619,11 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
 
 __global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
                                 __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
-                                float* __restrict__ beta_eff) {
+                                float* __restrict__ beta_eff, int transpose) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < C128 * C128) {
-    const float b = fmaxf(gamma_p[idx], 3.814697265625e-06f);
+    const int src = transpose ? ((idx & 127) * C128 + (idx >> 7)) : idx;
+    const float b = fmaxf(gamma_p[src], 3.814697265625e-06f);
     const float g = b * b - 1.4551915228366852e-11f;
     __nv_bfloat16 h, l;
     split_bf16(g, h, l);
@@ -746,12 +799,13 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
   TcOutMaps mO;
   memset(&mO, 0, sizeof(mO));
   if (OUT_MODE == OUT_BF16) {
-    if (KIND == B2C_TC_DECONV5S2) {
-      for (int ph = 0; ph < 4; ++ph)
-        if ((rc = make_out_map(&mO.m[ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, 2, ph >> 1, ph & 1))) return rc;
-    } else {
-      if ((rc = make_out_map(&mO.m[0], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, 1, 0, 0))) return rc;
-      if (SPLIT3 && (rc = make_out_map(&mO.m[1], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, 1, 0, 0))) return rc;
+    const int nph = (KIND == B2C_TC_DECONV5S2) ? 4 : 1;
+    const int ps = (KIND == B2C_TC_DECONV5S2) ? 2 : 1;
+    for (int ph = 0; ph < nph; ++ph) {
+      const int ry = nph == 4 ? (ph >> 1) : 0, rx = nph == 4 ? (ph & 1) : 0;
+      if ((rc = make_out_map(&mO.m[ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, ps, ry, rx))) return rc;
+      if (L->out_lo && (rc = make_out_map(&mO.m[4 + ph], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, ps, ry, rx)))
+        return rc;
     }
   }
   kern<<<grid, NTHREADS, SMEM, stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
@@ -795,9 +849,17 @@ int b2c_tc_pack_gdn(const float* beta_p, const float* gamma_p, void* gamma_hi, v
                     void* stream) {
   B2C_REQUIRE(beta_p && gamma_p && gamma_hi && beta_eff, "tc_pack_gdn: bad arguments");
   pack_gdn_kernel<<<(C128 * C128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      beta_p, gamma_p, (__nv_bfloat16*)gamma_hi, (__nv_bfloat16*)gamma_lo, beta_eff);
+      beta_p, gamma_p, (__nv_bfloat16*)gamma_hi, (__nv_bfloat16*)gamma_lo, beta_eff, 0);
   count_launch();
   return check_launch("tc_pack_gdn");
+}
+
+int b2c_tc_pack_gdn_t(const float* beta_p, const float* gamma_p, void* gamma_t, float* beta_eff, void* stream) {
+  B2C_REQUIRE(beta_p && gamma_p && gamma_t && beta_eff, "tc_pack_gdn_t: bad arguments");
+  pack_gdn_kernel<<<(C128 * C128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      beta_p, gamma_p, (__nv_bfloat16*)gamma_t, nullptr, beta_eff, 1);
+  count_launch();
+  return check_launch("tc_pack_gdn_t");
 }
 
 int b2c_tc_nchw_to_nhwc(const float* in, void* out_hi, void* out_lo, int B, int C, int HW, void* stream) {
@@ -844,6 +906,9 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   p.bias = L->bias; p.beta_eff = L->beta_eff; p.out_hi = L->out_hi; p.out_lo = L->out_lo;
   p.trace = g_tc_trace;
   p.ref_image = L->ref_image; p.sse_partial = L->sse_partial;
+  p.saved_y = (const __nv_bfloat16*)L->saved_y; p.saved_n = (const __nv_bfloat16*)L->saved_n;
+  B2C_REQUIRE(L->gdn < 3 || (L->saved_y && L->saved_n && !L->split3 && !L->out_f32_nchw),
+              "tc_layer_run: GDN backward epilogue needs saved_y/saved_n, bf16 operands and NHWC output");
   B2C_REQUIRE(!L->ref_image || (L->kind == B2C_TC_DECONV3 && L->sse_partial),
               "tc_layer_run: ref_image/sse_partial are for DECONV3 only and go together");
   int phases = 1;
@@ -879,6 +944,13 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
     case B2C_TC_CONV5S2 * 1000 + 100 + 10 + 0: return launch<128, true, B2C_TC_CONV5S2, 1, OUT_BF16>(L, p, grid, stream);
     case B2C_TC_CONV5S2 * 1000 + 100 + 0 + 1: return launch<128, true, B2C_TC_CONV5S2, 0, OUT_F32_NCHW>(L, p, grid, stream);
     case B2C_TC_CONV5S2 * 1000 + 100 + 10 + 1: return launch<128, true, B2C_TC_CONV5S2, 1, OUT_F32_NCHW>(L, p, grid, stream);
+    // bf16 training: forward (saves the norm plane when out_lo is given) and dgrad + GDN-backward epilogues
+    case B2C_TC_CONV1 * 1000 + 0 + 10 + 0: return launch<128, false, B2C_TC_CONV1, 1, OUT_BF16>(L, p, grid, stream);
+    case B2C_TC_CONV5S2 * 1000 + 0 + 10 + 0: return launch<128, false, B2C_TC_CONV5S2, 1, OUT_BF16>(L, p, grid, stream);
+    case B2C_TC_CONV5S2 * 1000 + 0 + 0 + 1: return launch<128, false, B2C_TC_CONV5S2, 0, OUT_F32_NCHW>(L, p, grid, stream);
+    case B2C_TC_CONV1 * 1000 + 0 + 40 + 0: return launch<128, false, B2C_TC_CONV1, 4, OUT_BF16>(L, p, grid, stream);
+    case B2C_TC_CONV5S2 * 1000 + 0 + 40 + 0: return launch<128, false, B2C_TC_CONV5S2, 4, OUT_BF16>(L, p, grid, stream);
+    case B2C_TC_DECONV5S2 * 1000 + 0 + 30 + 0: return launch<128, false, B2C_TC_DECONV5S2, 3, OUT_BF16>(L, p, grid, stream);
     // synthesis transform (plain bf16)
     case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 0: return launch<128, false, B2C_TC_DECONV5S2, 2, OUT_BF16>(L, p, grid, stream);
     case B2C_TC_DECONV5S2 * 1000 + 0 + 0 + 1: return launch<128, false, B2C_TC_DECONV5S2, 0, OUT_F32_NCHW>(L, p, grid, stream);

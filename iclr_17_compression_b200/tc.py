@@ -68,7 +68,19 @@ _FLOPS_PER_OUT_PIXEL = {TC_CONV1: 2 * 243 * 128, TC_CONV5S2: 2 * 3200 * 128, TC_
                         TC_DECONV3: 2 * 128 * 243 / 16}
 
 
-def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False, ref_image=None):
+def pack_gdn_t(beta, gamma):
+    """gamma_eff^T (bf16) and beta_eff, for the GDN backward epilogue"""
+    lib = _lib.load()
+    beta, gamma = beta.detach().contiguous().float(), gamma.detach().contiguous().float()
+    gt = torch.empty((128, 128), device=beta.device, dtype=torch.bfloat16)
+    be = torch.empty((128,), device=beta.device, dtype=torch.float32)
+    with torch.cuda.device(beta.device):
+        _lib.check(lib.b2c_tc_pack_gdn_t(_p(beta), _p(gamma), _p(gt), _p(be), _stream()), "tc_pack_gdn_t")
+    return gt, None, be
+
+
+def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False, ref_image=None,
+              second_plane=False, saved=None):
     """One fused layer.  x_hi/x_lo: NHWC bf16 (CONV1: x_hi = fp32 NCHW image).  w = (w_hi, w_lo);
     gdn = (gamma_hi, gamma_lo, beta_eff) with gdn_mode 1 (GDN) / 2 (IGDN).
     Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
@@ -89,7 +101,7 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         out_lo = None
     else:
         out_hi = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.bfloat16)
-        out_lo = torch.empty_like(out_hi) if split3 else None
+        out_lo = torch.empty_like(out_hi) if (split3 or second_plane) else None
     L = TcLayer()
     L.kind, L.split3, L.gdn, L.out_f32_nchw = kind, int(split3), int(gdn_mode), int(out_f32_nchw)
     L.B, L.Hin, L.Win = B, Hin, Win
@@ -100,6 +112,8 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         L.gamma_hi, L.gamma_lo, L.beta_eff = gdn[0].data_ptr(), (gdn[1].data_ptr() if gdn[1] is not None else 0), \
             gdn[2].data_ptr()
     L.out_hi, L.out_lo = out_hi.data_ptr(), (out_lo.data_ptr() if out_lo is not None else 0)
+    if saved is not None:
+        L.saved_y, L.saved_n = saved[0].data_ptr(), saved[1].data_ptr()
     sse = None
     if ref_image is not None:                      # DECONV3: fused clamp + squared errors
         lib = _lib.load()

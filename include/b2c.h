@@ -145,10 +145,15 @@ int b2c_tc_pack_weights(int kind, const float* w, void* w_hi, void* w_lo, void* 
 int b2c_tc_pack_gdn(const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo, float* beta_eff,
                     void* stream);
 
+/* gamma_eff transposed (bf16 [128][128]) for the GDN backward epilogue, and beta_eff */
+int b2c_tc_pack_gdn_t(const float* beta_p, const float* gamma_p, void* gamma_t, float* beta_eff, void* stream);
+
 typedef struct b2c_tc_layer {
   int kind;         /* B2C_TC_*                                                                   */
   int split3;       /* 1: (hi,lo) operands, 3 MMAs per product; 0: plain bf16                      */
-  int gdn;          /* 0: none, 1: GDN, 2: IGDN fused after bias                                   */
+  int gdn;          /* 0: none, 1: GDN, 2: IGDN fused after bias; 3 / 4: backward of GDN / IGDN applied to
+                       the result (the launch is then the dgrad conv of the layer that consumed the GDN
+                       output): out_hi = dL/dx (pre-GDN), out_lo = dL/dnorm, gamma_hi = gamma_eff^T        */
   int out_f32_nchw; /* 1: fp32 NCHW output in out_hi (required for DECONV3), 0: NHWC bf16 hi[/lo]  */
   int B, Hin, Win;  /* input grid                                                                  */
   const void* in_hi; /* NHWC bf16 [B,Hin,Win,128]  (CONV1: fp32 NCHW image [B,3,Hin,Win])          */
@@ -166,6 +171,10 @@ typedef struct b2c_tc_layer {
    * (clamp(recon) - x)^2; reduce them with b2c_partial_reduce(sse_partial, sse, B, tiles, 2). */
   const float* ref_image;
   float* sse_partial;
+  /* gdn 3 / 4: the forward GDN output y and norm n = beta + gamma x^2 saved by the forward launch
+   * (a bf16 forward launch with gdn 1 / 2 writes n to out_lo), NHWC bf16 shaped like this launch's output */
+  const void* saved_y;
+  const void* saved_n;
 } b2c_tc_layer;
 
 /* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid */

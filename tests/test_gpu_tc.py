@@ -162,3 +162,69 @@ def test_wgrad_1x1_gamma_form(tc):
     ref = torch.einsum("nihw,njhw->ij", ah.float().permute(0, 3, 1, 2).double(), bh.float().permute(0, 3, 1, 2).double())
     d = tc.wgrad(ah, bh, 1, 1, 0).view(128, 128)
     assert _rel(d, ref) < 1e-5
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).double()
+
+
+def test_train_forward_saves_norm_plane(tc):
+    """bf16 forward with fused GDN: out_lo receives n = beta + gamma x^2 (needed by the backward)."""
+    from oracle import balle17_oracle as O
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 128, 32, 48, generator=g).cuda()
+    w = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    beta, gamma = _gdn_params(g)
+    xh, _ = tc.nchw_to_nhwc(x, False)
+    conv = F.conv2d(_bf(x).cpu(), _bf(w).cpu(), b.double().cpu(), stride=2, padding=2)
+    be, ge = O.gdn_effective_params(beta.double(), gamma.double())
+    n_ref = F.conv2d(conv ** 2, ge.view(128, 128, 1, 1), be)
+    y_ref = conv / n_ref.sqrt()
+    wp = tc.pack_weights(tc.TC_CONV5S2, w, False)
+    gp = tc.pack_gdn(beta.cuda(), gamma.cuda(), False)
+    yh, nh = tc.layer_run(tc.TC_CONV5S2, xh, None, wp, b, gdn=gp, gdn_mode=1, split3=False, second_plane=True)
+    assert _rel(tc.nhwc_to_nchw(yh), y_ref) < 6e-3
+    assert _rel(tc.nhwc_to_nchw(nh), n_ref) < 6e-3
+
+
+@pytest.mark.parametrize("kind_name,inverse", [("deconv", False), ("conv", True), ("conv1", True)])
+def test_dgrad_with_gdn_backward_epilogue(tc, kind_name, inverse):
+    """dgrad conv + fused (I)GDN backward: out_hi = dL/dx (pre-GDN), out_lo = dL/dnorm."""
+    from oracle import balle17_oracle as O
+    g = torch.Generator().manual_seed(9)
+    beta, gamma = _gdn_params(g)
+    be, ge = O.gdn_effective_params(beta.double(), gamma.double())
+    if kind_name == "deconv":      # dgrad of a 5x5/2 conv: conv_transpose of g with the conv's OIHW weight
+        gin = torch.randn(2, 128, 16, 24, generator=g).cuda()
+        w = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+        gy = F.conv_transpose2d(_bf(gin).cpu(), _bf(w).cpu(), None, stride=2, padding=2, output_padding=1)
+        kind, xin = tc.TC_DECONV5S2, tc.nchw_to_nhwc(gin, False)[0]
+    elif kind_name == "conv":      # dgrad of a 5x5/2 transposed conv: conv of g with the IOHW weight
+        gin = torch.randn(2, 128, 32, 48, generator=g).cuda()
+        w = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+        gy = F.conv2d(_bf(gin).cpu(), _bf(w).cpu(), None, stride=2, padding=2)
+        kind, xin = tc.TC_CONV5S2, tc.nchw_to_nhwc(gin, False)[0]
+    else:                          # dgrad of deconv3 (9x9/4 transposed, 128->3): conv 9x9/4 of the fp32 image grad
+        gin = torch.randn(2, 3, 64, 96, generator=g).cuda()
+        w = (torch.randn(128, 3, 9, 9, generator=g) * 0.1).cuda()
+        gy = F.conv2d(_bf(gin).cpu(), _bf(w).cpu(), None, stride=4, padding=4)
+        kind, xin = tc.TC_CONV1, gin
+    # a consistent forward state (x -> n, y), stored as bf16 like the training forward does
+    x = torch.randn(gy.shape, generator=g, dtype=torch.float64)
+    n = F.conv2d(x ** 2, ge.view(128, 128, 1, 1), be)
+    y = x * n.sqrt() if inverse else x / n.sqrt()
+    yq, nq = _bf(y), _bf(n)
+    yh, nh = tc.nchw_to_nhwc(yq.float().cuda(), False)[0], tc.nchw_to_nhwc(nq.float().cuda(), False)[0]
+    # reference backward from the stored (y, n)
+    s = nq.sqrt()
+    xq = yq / s if inverse else yq * s
+    dn = (0.5 if inverse else -0.5) * gy * yq / nq
+    t = F.conv2d(dn, ge.t().contiguous().view(128, 128, 1, 1))
+    dx = (gy * s if inverse else gy / s) + 2 * xq * t
+    wp = tc.pack_weights(kind, w, False)
+    gp = tc.pack_gdn_t(beta.cuda(), gamma.cuda())
+    dxh, dnh = tc.layer_run(kind, xin, None, wp, None, gdn=gp, gdn_mode=4 if inverse else 3, split3=False,
+                            second_plane=True, saved=(yh, nh))
+    assert _rel(tc.nhwc_to_nchw(dnh), dn) < 8e-3, _rel(tc.nhwc_to_nchw(dnh), dn)
+    assert _rel(tc.nhwc_to_nchw(dxh), dx) < 8e-3, _rel(tc.nhwc_to_nchw(dxh), dx)
