@@ -241,6 +241,15 @@ int b2c_gdn_fwd(const float* x, const float* beta_p, const float* gamma_p, float
   return check_launch("gdn_fwd");
 }
 
+int b2c_gdn_reparam_bwd(const float* beta_p, const float* gamma_p, const float* dbeta_eff, const float* dgamma_eff,
+                        float* dbeta_p, float* dgamma_p, int C, void* stream) {
+  B2C_REQUIRE(beta_p && gamma_p && dbeta_eff && dgamma_eff && dbeta_p && dgamma_p && C > 0, "gdn_reparam_bwd: bad arguments");
+  gdn_reparam_bwd_kernel<<<(C * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(beta_p, gamma_p, dbeta_eff, dgamma_eff,
+                                                                                 dbeta_p, dgamma_p, C);
+  count_launch();
+  return check_launch("gdn_reparam_bwd");
+}
+
 size_t b2c_gdn_bwd_workspace_bytes(int B, int C, int HW) {
   return ((size_t)B * C * HW + (size_t)C * C + (size_t)C) * sizeof(float);
 }

@@ -190,6 +190,39 @@ static int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, 
   return B2C_OK;
 }
 
+// x^2 of the GDN input from the saved (y, n): GDN x^2 = y^2 n, IGDN x^2 = y^2 / n   (bf16, 8 per thread)
+__global__ void __launch_bounds__(256) xsq_kernel(const uint4* __restrict__ y, const uint4* __restrict__ n,
+                                                  uint4* __restrict__ out, size_t nvec, int inverse) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 qy = __ldg(y + i), qn = __ldg(n + i);
+    const uint32_t wy[4] = {qy.x, qy.y, qy.z, qy.w}, wn[4] = {qn.x, qn.y, qn.z, qn.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float y0 = __uint_as_float(wy[k] << 16), y1 = __uint_as_float(wy[k] & 0xffff0000u);
+      const float n0 = __uint_as_float(wn[k] << 16), n1 = __uint_as_float(wn[k] & 0xffff0000u);
+      const float r0 = inverse ? y0 * y0 / n0 : y0 * y0 * n0;
+      const float r1 = inverse ? y1 * y1 / n1 : y1 * y1 * n1;
+      o[k] = pack_bf16x2(__float2bfloat16_rn(r0), __float2bfloat16_rn(r1));
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// out[c] += sum over pixel rows of a bf16 [P][128] tensor (bias / beta gradients); out zero-filled by the caller
+__global__ void __launch_bounds__(256) nhwc_colsum_kernel(const __nv_bfloat16* __restrict__ t, float* __restrict__ out,
+                                                          size_t P, int rows_per_block) {
+  __shared__ float red[2][128];
+  const int c = threadIdx.x & 127, hf = threadIdx.x >> 7;
+  const size_t r0 = (size_t)blockIdx.x * rows_per_block;
+  const size_t r1 = min(P, r0 + (size_t)rows_per_block);
+  float s = 0.f;
+  for (size_t r = r0 + hf; r < r1; r += 2) s += __bfloat162float(t[r * 128 + c]);
+  red[hf][c] = s;
+  __syncthreads();
+  if (hf == 0) atomicAdd(out + c, red[0][c] + red[1][c]);
+}
+
 }  // namespace tc
 }  // namespace b2c
 
@@ -197,6 +230,27 @@ using namespace b2c;
 using namespace b2c::tc;
 
 extern "C" {
+
+int b2c_tc_xsq(const void* y, const void* n, void* out, size_t count, int inverse, void* stream) {
+  B2C_REQUIRE(y && n && out && count > 0 && count % 8 == 0, "tc_xsq: bad arguments");
+  const size_t nvec = count / 8;
+  size_t blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  xsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y, (const uint4*)n, (uint4*)out, nvec,
+                                                                 inverse);
+  count_launch();
+  return check_launch("tc_xsq");
+}
+
+int b2c_tc_nhwc_colsum(const void* t, float* out, size_t P, void* stream) {
+  B2C_REQUIRE(t && out && P > 0, "tc_nhwc_colsum: bad arguments");
+  const int rows_per_block = 256;
+  const size_t blocks = (P + rows_per_block - 1) / rows_per_block;
+  nhwc_colsum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)t, out, P,
+                                                                        rows_per_block);
+  count_launch();
+  return check_launch("tc_nhwc_colsum");
+}
 
 int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
                  int stride, int pad, void* stream) {

@@ -1,0 +1,204 @@
+"""bf16 tensor-core training step for ImageCompressor(out_channel_N=128): one autograd Function whose
+forward runs the fused tcgen05 layers (conv + bias + GDN, saving the GDN norm plane) and whose backward
+runs dgrad convs with the fused (I)GDN backward epilogue, tcgen05 weight gradients (MN-major MMAs), and
+the fp32 entropy / distortion backward kernels - all through libb2c's C ABI.
+
+Mirrors autograd of model.py:47-80 as driven by train.py:97-105: quantizer = additive uniform noise,
+loss terms = sum of squared error on the UNclamped reconstruction and total bits.  Activations between
+layers are NHWC bf16; parameters and their gradients are fp32 in the reference's layouts.
+Tolerance target (north star): every gradient tensor within 1e-2 relative L2 of the fp32 reference.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import tc as T
+from .functional import _p, _stream, _timed
+
+_vp = ctypes.c_void_p
+
+PARAM_ORDER = [
+    "Encoder.conv1.weight", "Encoder.conv1.bias", "Encoder.gdn1.beta", "Encoder.gdn1.gamma",
+    "Encoder.conv2.weight", "Encoder.conv2.bias", "Encoder.gdn2.beta", "Encoder.gdn2.gamma",
+    "Encoder.conv3.weight",
+    "Decoder.deconv1.weight", "Decoder.deconv1.bias", "Decoder.igdn1.beta", "Decoder.igdn1.gamma",
+    "Decoder.deconv2.weight", "Decoder.deconv2.bias", "Decoder.igdn2.beta", "Decoder.igdn2.gamma",
+    "Decoder.deconv3.weight", "Decoder.deconv3.bias",
+    "bitEstimator.f1.h", "bitEstimator.f1.b", "bitEstimator.f1.a",
+    "bitEstimator.f2.h", "bitEstimator.f2.b", "bitEstimator.f2.a",
+    "bitEstimator.f3.h", "bitEstimator.f3.b", "bitEstimator.f3.a",
+    "bitEstimator.f4.h", "bitEstimator.f4.b",
+]
+
+
+def _xsq(y, n, inverse):
+    out = torch.empty_like(y)
+    with torch.cuda.device(y.device), _timed("tc_xsq", 0, 6 * y.numel()):
+        _lib.check(_lib.load().b2c_tc_xsq(_p(y), _p(n), _p(out), y.numel(), int(inverse), _stream()), "tc_xsq")
+    return out
+
+
+def _colsum(t):
+    out = torch.zeros((128,), device=t.device, dtype=torch.float32)
+    with torch.cuda.device(t.device), _timed("tc_nhwc_colsum", 0, 2 * t.numel()):
+        _lib.check(_lib.load().b2c_tc_nhwc_colsum(_p(t), _p(out), t.numel() // 128, _stream()), "tc_nhwc_colsum")
+    return out
+
+
+def _gdn_param_grads(beta_p, gamma_p, y, n, dn, inverse):
+    """d beta_p, d gamma_p from dL/dnorm: d gamma_eff = sum_pix dn_i x_j^2 (tcgen05 wgrad, 1 tap), d beta_eff = sum dn,
+    then the LowerBound / square reparametrisation (models/GDN.py:18-24,73-79)."""
+    xsq = _xsq(y, n, inverse)
+    dgamma_eff = T.wgrad(dn, xsq, 1, 1, 0).view(128, 128)
+    dbeta_eff = _colsum(dn)
+    dbeta_p, dgamma_p = torch.empty_like(beta_p), torch.empty_like(gamma_p)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.load().b2c_gdn_reparam_bwd(_p(beta_p), _p(gamma_p), _p(dbeta_eff), _p(dgamma_eff), _p(dbeta_p),
+                                                   _p(dgamma_p), 128, _stream()), "gdn_reparam_bwd")
+    return dbeta_p, dgamma_p
+
+
+def _wgrad_simt(small, big, k, stride, pad):
+    from .functional import _wgrad_raw
+    return _wgrad_raw(small, big, k, stride, pad)
+
+
+class TrainStepTC(torch.autograd.Function):
+    """(x, noise, *30 params in PARAM_ORDER) -> (clipped, sse_total, total_bits, z)"""
+
+    @staticmethod
+    def forward(ctx, x, noise, *params):
+        lib = _lib.load()
+        prm = dict(zip(PARAM_ORDER, [p.detach().contiguous().float() for p in params]))
+        x = x.detach().contiguous().float()
+        noise = noise.detach().contiguous().float()
+        B, _, H, W = x.shape
+        dev = x.device
+        W1, W2, W3 = prm["Encoder.conv1.weight"], prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
+        D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
+        gp1 = T.pack_gdn(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], False)
+        gp2 = T.pack_gdn(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], False)
+        gi1 = T.pack_gdn(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], False)
+        gi2 = T.pack_gdn(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], False)
+        # ---- analysis transform
+        h1, n1 = T.layer_run(T.TC_CONV1, x, None, T.pack_weights(T.TC_CONV1, W1, False), prm["Encoder.conv1.bias"],
+                             gdn=gp1, gdn_mode=1, second_plane=True)
+        h2, n2 = T.layer_run(T.TC_CONV5S2, h1, None, T.pack_weights(T.TC_CONV5S2, W2, False),
+                             prm["Encoder.conv2.bias"], gdn=gp2, gdn_mode=1, second_plane=True)
+        y = T.layer_run(T.TC_CONV5S2, h2, None, T.pack_weights(T.TC_CONV5S2, W3, False), None, out_f32_nchw=True)
+        # ---- quantizer (noise) + bits
+        bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
+        C, HW = 128, y.shape[2] * y.shape[3]
+        z = torch.empty_like(y)
+        plane_bits = torch.empty((B, C), device=dev, dtype=torch.float32)
+        image_bits = torch.empty((B,), device=dev, dtype=torch.float32)
+        pp, keep = _lib.ptr_array(bitp)
+        with torch.cuda.device(dev), _timed("quant_entropy_fwd[train]", 60 * y.numel(), 12 * y.numel()):
+            _lib.check(lib.b2c_quant_entropy_fwd(_p(y), _p(noise), pp, _p(z), _p(plane_bits), _p(image_bits), B, C, HW,
+                                                 _stream()), "quant_entropy_fwd")
+        total_bits = image_bits.sum()
+        # ---- synthesis transform
+        zh, _ = T.nchw_to_nhwc(z, False)
+        i1, m1 = T.layer_run(T.TC_DECONV5S2, zh, None, T.pack_weights(T.TC_DECONV5S2, D1, False),
+                             prm["Decoder.deconv1.bias"], gdn=gi1, gdn_mode=2, second_plane=True)
+        i2, m2 = T.layer_run(T.TC_DECONV5S2, i1, None, T.pack_weights(T.TC_DECONV5S2, D2, False),
+                             prm["Decoder.deconv2.bias"], gdn=gi2, gdn_mode=2, second_plane=True)
+        recon = T.layer_run(T.TC_DECONV3, i2, None, T.pack_weights(T.TC_DECONV3, D3, False), prm["Decoder.deconv3.bias"],
+                            out_f32_nchw=True)
+        # ---- distortion
+        clipped = torch.empty_like(recon)
+        sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
+        nbytes = lib.b2c_clamp_sse_workspace_bytes(B, x[0].numel())
+        ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev), _timed("clamp_sse_fwd[train]", 8 * x.numel(), 12 * x.numel()):
+            _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, x[0].numel(), _p(ws), nbytes,
+                                             _stream()), "clamp_sse_fwd")
+        sse_total = sse[:, 0].sum()
+        ctx.prm = prm
+        ctx.saved = (x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon)
+        ctx.stats = (image_bits, plane_bits, sse)
+        ctx.mark_non_differentiable(clipped, z)
+        return clipped, sse_total, total_bits, z
+
+    @staticmethod
+    def backward(ctx, _g_clipped, g_sse, g_bits, _g_z):
+        lib = _lib.load()
+        prm = ctx.prm
+        x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon = ctx.saved
+        dev = x.device
+        B = x.shape[0]
+        grads = {}
+        zero = torch.zeros((1,), device=dev, dtype=torch.float32)
+        g_sse = g_sse.reshape(1).float().contiguous() if g_sse is not None else zero
+        g_bits = g_bits.reshape(1).float().contiguous() if g_bits is not None else zero
+        # ---- distortion
+        g_recon = torch.empty_like(recon)
+        with torch.cuda.device(dev):
+            _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _vp(0), _p(g_sse), _p(g_recon), recon.numel(), _stream()),
+                       "clamp_sse_bwd")
+        # ---- deconv3 (9x9/4, 128 -> 3): weight grad on the fp32 kernel, dgrad (= conv 9x9/4) + IGDN2 backward fused
+        D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
+        grads["Decoder.deconv3.weight"] = _wgrad_simt(T.nhwc_to_nchw(i2), g_recon, 9, 4, 4)
+        from .functional import _channel_sum_raw
+        grads["Decoder.deconv3.bias"] = _channel_sum_raw(g_recon)
+        gt = T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"])
+        gp_d2, dn = T.layer_run(T.TC_CONV1, g_recon, None, T.pack_weights(T.TC_CONV1, D3, False), None, gdn=gt,
+                                gdn_mode=4, second_plane=True, saved=(i2, m2))
+        grads["Decoder.igdn2.beta"], grads["Decoder.igdn2.gamma"] = _gdn_param_grads(
+            prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn, True)
+        # ---- deconv2
+        grads["Decoder.deconv2.weight"] = T.wgrad(i1, gp_d2, 5, 2, 2)
+        grads["Decoder.deconv2.bias"] = _colsum(gp_d2)
+        gt = T.pack_gdn_t(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"])
+        gp_d1, dn = T.layer_run(T.TC_CONV5S2, gp_d2, None, T.pack_weights(T.TC_CONV5S2, D2, False), None, gdn=gt,
+                                gdn_mode=4, second_plane=True, saved=(i1, m1))
+        grads["Decoder.igdn1.beta"], grads["Decoder.igdn1.gamma"] = _gdn_param_grads(
+            prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn, True)
+        # ---- deconv1
+        grads["Decoder.deconv1.weight"] = T.wgrad(zh, gp_d1, 5, 2, 2)
+        grads["Decoder.deconv1.bias"] = _colsum(gp_d1)
+        g_z = T.layer_run(T.TC_CONV5S2, gp_d1, None, T.pack_weights(T.TC_CONV5S2, D1, False), None, out_f32_nchw=True)
+        # ---- entropy model: d bits / dz and the 11 parameter vectors
+        bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
+        dbit = [torch.zeros_like(p) for p in bitp]
+        dz = torch.empty_like(z)
+        pp, k1 = _lib.ptr_array(bitp)
+        dp, k2 = _lib.ptr_array(dbit)
+        C, HW = 128, z.shape[2] * z.shape[3]
+        with torch.cuda.device(dev):
+            _lib.check(lib.b2c_entropy_bwd(_p(z), pp, _p(g_bits), _p(dz), dp, B, C, HW, _stream()), "entropy_bwd")
+        for k, g in zip(PARAM_ORDER[19:], dbit):
+            grads[k] = g.view(1, -1, 1, 1)
+        g_y = g_z + dz                                     # z = y + noise -> dz/dy = 1
+        gyh, _ = T.nchw_to_nhwc(g_y, False)
+        # ---- conv3 (no bias): wgrad, dgrad (= transposed conv) + GDN2 backward fused
+        W1, W2, W3 = prm["Encoder.conv1.weight"], prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
+        grads["Encoder.conv3.weight"] = T.wgrad(gyh, h2, 5, 2, 2)
+        gt = T.pack_gdn_t(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"])
+        gp_c2, dn = T.layer_run(T.TC_DECONV5S2, gyh, None, T.pack_weights(T.TC_DECONV5S2, W3, False), None, gdn=gt,
+                                gdn_mode=3, second_plane=True, saved=(h2, n2))
+        grads["Encoder.gdn2.beta"], grads["Encoder.gdn2.gamma"] = _gdn_param_grads(
+            prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dn, False)
+        # ---- conv2
+        grads["Encoder.conv2.weight"] = T.wgrad(gp_c2, h1, 5, 2, 2)
+        grads["Encoder.conv2.bias"] = _colsum(gp_c2)
+        gt = T.pack_gdn_t(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"])
+        gp_c1, dn = T.layer_run(T.TC_DECONV5S2, gp_c2, None, T.pack_weights(T.TC_DECONV5S2, W2, False), None, gdn=gt,
+                                gdn_mode=3, second_plane=True, saved=(h1, n1))
+        grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = _gdn_param_grads(
+            prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dn, False)
+        # ---- conv1 (9x9/4, 3 -> 128): weight grad on the fp32 kernel; the image needs no gradient
+        grads["Encoder.conv1.weight"] = _wgrad_simt(T.nhwc_to_nchw(gp_c1), x, 9, 4, 4)
+        grads["Encoder.conv1.bias"] = _colsum(gp_c1)
+        ctx.saved = None
+        return (None, None) + tuple(grads[k].reshape(prm[k].shape) for k in PARAM_ORDER)
+
+
+def train_forward(model, x, noise):
+    """ImageCompressor training forward on tensor cores: returns (clipped, mse_loss, bpp, z) and fills model.last"""
+    params = dict(model.named_parameters())
+    clipped, sse_total, total_bits, z = TrainStepTC.apply(x, noise, *[params[k] for k in PARAM_ORDER])
+    mse = sse_total / x.numel()
+    bpp = total_bits / (x.size(0) * x.size(2) * x.size(3))
+    return clipped, mse, bpp, z

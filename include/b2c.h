@@ -90,6 +90,11 @@ int b2c_gdn_bwd(const float* x, const float* beta_p, const float* gamma_p, const
                 int B, int C, int HW, int inverse, void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* chain rule through eff = max(p, bound)^2 - pedestal with LowerBound's gradient rule (models/GDN.py:18-24,73-79):
+ * (dL/dbeta_eff, dL/dgamma_eff) -> (dL/dbeta_p, dL/dgamma_p); all fp32, gamma [C][C]. */
+int b2c_gdn_reparam_bwd(const float* beta_p, const float* gamma_p, const float* dbeta_eff, const float* dgamma_eff,
+                        float* dbeta_p, float* dgamma_p, int C, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Quantizer + factorized entropy model: model.py:53-56 (quantizer), model.py:71-78 +
  * models/bitEstimator.py:20-25,38-42 (bits).
@@ -190,6 +195,11 @@ int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
  *   GDN gamma grad: k = 1, small = dL/dnorm, big = x^2.                               (autograd of train.py:105) */
 int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
                  int stride, int pad, void* stream);
+
+/* helpers of the bf16 training path: x^2 of a GDN input from the saved output and norm (GDN: y^2 n, IGDN: y^2/n;
+ * count bf16 elements, multiple of 8), and out[c] += sum_rows t[row][c] for a bf16 [P][128] tensor (out zero-filled). */
+int b2c_tc_xsq(const void* y, const void* n, void* out, size_t count, int inverse, void* stream);
+int b2c_tc_nhwc_colsum(const void* t, float* out, size_t P, void* stream);
 
 /* layout / precision converters between the reference's fp32 NCHW and the NHWC bf16 (hi[,lo]) tiles */
 int b2c_tc_nchw_to_nhwc(const float* in, void* out_hi, void* out_lo, int B, int C, int HW, void* stream);

@@ -65,6 +65,7 @@ def test_train_step_matches_reference_golden(name):
     from oracle import balle17_oracle as O
     c = Case(name)
     m = _model(c, return_mode="mse").train()
+    m.fast_training = False                                      # the exact-fp32 kernels
     m.noise_override = c.noise.cuda()
     clipped, mse, bpp = m(c.x.cuda())
     loss = c.lam * mse + bpp                                     # train.py:102
@@ -234,3 +235,35 @@ def test_host_pipeline_matches_direct_forward():
             lat, stats = pipe.compress(x.pin_memory())
         assert torch.equal(lat, z.cpu())
         assert torch.allclose(stats[:, 0], bits, rtol=1e-6) and torch.allclose(stats[:, 1:], sse, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------ bf16 tensor-core training step
+@pytest.mark.parametrize("name", [n for n in golden_names("train_") if "_n128_" in n])
+def test_tc_train_step_gradients(name):
+    """training forward/backward on tensor cores (bf16): loss within 1e-3, every gradient within 1e-2 rel-L2 of
+    the oracle (north-star bar), and of the real reference's recorded gradient norms."""
+    from oracle import balle17_oracle as O
+    c = Case(name)
+    m = _model(c, return_mode="mse").train()
+    m.fast_training = True
+    m.noise_override = c.noise.cuda()
+    clipped, mse, bpp = m(c.x.cuda())
+    assert m.last_path == "tcgen05-bf16-train"
+    loss = c.lam * mse + bpp
+    loss.backward()
+    g = c.g
+    assert abs(loss.item() - float(g["rd_loss"])) <= 2e-3 * float(g["rd_loss"]), (loss.item(), float(g["rd_loss"]))
+    assert abs(bpp.item() - float(g["bpp"])) <= REL_BPP_MSE * float(g["bpp"])
+    _, _, grads = O.rd_loss_and_grads(c.x, c.sd, c.noise, c.lam)
+    worst = {}
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        worst[k] = _rel(p.grad, grads[k])
+    bad = {k: v for k, v in worst.items() if v > REL_GRAD}
+    assert not bad, bad
+    # exact path on the same inputs still available
+    m.fast_training = False
+    m.zero_grad()
+    _, mse2, bpp2 = m(c.x.cuda())
+    assert m.last_path == "fp32"
+    assert abs(mse2.item() - mse.item()) <= 2e-3 * mse2.item()
