@@ -30,7 +30,7 @@ struct WgParams {
   int B, hs, ws;          // small (tile) grid
   int tiles_x, tiles_per_image, total_tiles;
   int ksz, stride, pad, ntaps;
-  float* dW;              // [128][128][ntaps]
+  float* dW;              // [ntaps][128][128] (tap-major)
 };
 
 // MN-major SWIZZLE_128B operand: 64 channels (128 B) x 8 pixels per swizzle atom; atoms along the channel
@@ -143,9 +143,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
           uint32_t raw[32];
           tmem_ld32(t_row + (uint32_t)(j * 128 + h * 32), raw);
           tmem_ld_wait();
-          float* dst = p.dW + ((size_t)m * 128 + h * 32) * p.ntaps + tap0 + j;
+          // tap-major partial layout dW[tap][m][n]: each thread adds 32 contiguous floats with 16-byte reductions
+          float* dst = p.dW + ((size_t)(tap0 + j) * 128 + m) * 128 + h * 32;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) atomicAdd(dst + (size_t)c * p.ntaps, __uint_as_float(raw[c]));
+          for (int c = 0; c < 32; c += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(__uint_as_float(raw[c])),
+                         "f"(__uint_as_float(raw[c + 1])), "f"(__uint_as_float(raw[c + 2])),
+                         "f"(__uint_as_float(raw[c + 3]))
+                         : "memory");
         }
       }
     }
@@ -284,7 +289,7 @@ int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int h
   if ((rc = make_nhwc_map(&mG, big_t, B, hb, wb, stride))) return rc;
   const int groups = (p.ntaps + W_TAPS - 1) / W_TAPS;
   int splits = 148 / groups;
-  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits > (p.total_tiles + 3) / 4) splits = (p.total_tiles + 3) / 4;   // >= 4 pixel tiles per CTA: fewer reductions
   if (splits < 1) splits = 1;
   dim3 grid(groups, splits);
   wgrad_tc_kernel<<<grid, W_THREADS, SMEM, (cudaStream_t)stream>>>(mS, mG, p);

@@ -116,6 +116,17 @@ class GradSync:
             b["work"] = None
             b["flat"].zero_()
 
+    def reduce_now(self):
+        """no-hook variant (e.g. after a CUDA-graph replay of forward+backward): pack, all-reduce and average
+        every bucket from the current .grad tensors"""
+        for b in self.buckets:
+            for (n, p), o in zip(b["members"], b["offsets"]):
+                if p.grad is not None:
+                    b["flat"][o:o + p.numel()].copy_(p.grad.reshape(-1))
+            b["ready"] = len(b["members"])
+            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.finish()
+
     def bucket_bytes(self):
         return [b["flat"].numel() * b["flat"].element_size() for b in self.buckets]
 

@@ -136,9 +136,9 @@ def wgrad(small, big, k, stride, pad):
     """dW[m][n][ky][kx] = sum small[.,ys,xs,m] * big[., stride*ys-pad+ky, stride*xs-pad+kx, n]; NHWC bf16 in, fp32 out"""
     B, hs, ws, _ = small.shape
     _, hb, wb, _ = big.shape
-    dW = torch.zeros((128, 128, k, k), device=small.device, dtype=torch.float32)
+    dW = torch.zeros((k, k, 128, 128), device=small.device, dtype=torch.float32)       # tap-major partial layout
     flops = 2 * B * hs * ws * 128 * 128 * k * k
     with torch.cuda.device(small.device), _timed(f"tc_wgrad[{B}x{hs}x{ws},k{k}s{stride}]", flops, 0):
         _lib.check(_lib.load().b2c_tc_wgrad(_p(small), _p(big), _p(dW), B, hs, ws, hb, wb, k, stride, pad, _stream()),
                    "tc_wgrad")
-    return dW
+    return dW.permute(2, 3, 0, 1).contiguous() if k > 1 else dW.view(128, 128, 1, 1)

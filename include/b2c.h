@@ -188,8 +188,9 @@ int b2c_tc_tiles_per_image(int kind, int Hin, int Win);
 int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
 
 /* Tensor-core weight gradient (bf16 training path):
- *   dW[m][n][ky][kx] += sum_{img,ys,xs} small[img,ys,xs,m] * big[img, stride*ys - pad + ky, stride*xs - pad + kx, n]
- * small [B,hs,ws,128], big [B,hb,wb,128]: NHWC bf16; dW fp32 [128][128][k][k], zero-filled by the caller
+ *   dW[ky][kx][m][n] += sum_{img,ys,xs} small[img,ys,xs,m] * big[img, stride*ys - pad + ky, stride*xs - pad + kx, n]
+ * small [B,hs,ws,128], big [B,hb,wb,128]: NHWC bf16; dW fp32 TAP-MAJOR [k][k][128][128] (permute to
+ * [m][n][ky][kx] for the state_dict layout), zero-filled by the caller
  * (partial sums are added with red.global).  k in {1,5}, stride in {1,2}.
  *   conv2d weight grad (OIHW): small = grad_out, big = input;  conv_transpose2d (IOHW): small = input, big = grad_out;
  *   GDN gamma grad: k = 1, small = dL/dnorm, big = x^2.                               (autograd of train.py:105) */
