@@ -53,6 +53,7 @@ SIGNATURES.update({
     "b2c_tc_pack_gdn_t": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_f]),
     "b2c_tc_tiles_per_image": (_c_i, [_c_i, _c_i, _c_i]),
     "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
+    "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_tc_xsq": (_c_i, [_c_f, _c_f, _c_f, _c_sz, _c_i, _c_f]),
     "b2c_tc_nhwc_colsum": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),
     "b2c_gdn_reparam_bwd": (_c_i, [_c_f] * 6 + [_c_i, _c_f]),

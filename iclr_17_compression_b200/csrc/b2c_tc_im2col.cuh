@@ -1,0 +1,81 @@
+// Shared-memory operand builders used by the tensor-core kernels: swizzled K-major row chunks and the
+// 9x9 / stride-4 im2col rows (CONV1 forward, deconv3 dgrad, and the 9x9 weight gradients).
+#pragma once
+#include "b2c_tc.cuh"
+
+namespace b2c {
+namespace tc {
+
+constexpr int IM_SLOT_BYTES = 128 * 64 * 2;  // one 128-row x 64-element bf16 tile
+
+// CONV1 input patch of one 8x16 output tile: 3 channels x 37 rows x 69 (->72) columns of fp32
+constexpr int P1_W = 72, P1_H = 37;
+constexpr int P1_PLANE = P1_W * P1_H;
+constexpr int P1_BYTES = 3 * P1_PLANE * 4;          // 31968
+constexpr int P1_SLOT = 32768;
+
+template <bool SPLIT3>
+__device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_lo, int r, int cidx,
+                                                const float (&v)[8]) {
+  // K-major SWIZZLE_128B: row r at r*128, 16-byte chunk index XORed with (r & 7)
+  const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cidx ^ (r & 7)) << 4);
+  __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (SPLIT3) {
+      split_bf16(v[i], h[i], l[i]);
+    } else {
+      h[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+  uint4 qh = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
+                        pack_bf16x2(h[6], h[7]));
+  *reinterpret_cast<uint4*>(slot_hi + off) = qh;
+  if (SPLIT3) {
+    uint4 ql = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]),
+                          pack_bf16x2(l[6], l[7]));
+    *reinterpret_cast<uint4*>(slot_lo + off) = ql;
+  }
+}
+
+// CONV1: the 32 im2col values k = KB*64 + HALF*32 .. +31 (k = c*81 + ky*9 + kx, zero for k >= 243) of the
+// pixel whose patch origin is `pp` (16-byte aligned), written as four swizzled 16-byte chunks (hi, lo) of the
+// pixel's 128-byte K-major row.  Each (c, ky) patch row is fetched with three conflict-free LDS.128
+// (12 floats, 9 used); every index below is a compile-time constant.
+template <int KB, int HALF, bool SPLIT3>
+__device__ __forceinline__ void conv1_build_row(const float* __restrict__ pp, uint8_t* slot_hi, uint8_t* slot_lo,
+                                                int r) {
+  constexpr int K0 = KB * 64 + HALF * 32;
+  constexpr int G0 = K0 / 9;
+  constexpr int G1 = (K0 + 31) / 9;
+  constexpr int NG = G1 - G0 + 1;
+  float vals[NG * 12];
+#pragma unroll
+  for (int gi = 0; gi < NG; ++gi) {
+    const int g = G0 + gi;
+    if (g < 27) {
+      const float4* row = reinterpret_cast<const float4*>(pp + (g / 9) * P1_PLANE + (g % 9) * P1_W);
+      const float4 a = row[0], b = row[1], c = row[2];
+      vals[gi * 12 + 0] = a.x; vals[gi * 12 + 1] = a.y; vals[gi * 12 + 2] = a.z; vals[gi * 12 + 3] = a.w;
+      vals[gi * 12 + 4] = b.x; vals[gi * 12 + 5] = b.y; vals[gi * 12 + 6] = b.z; vals[gi * 12 + 7] = b.w;
+      vals[gi * 12 + 8] = c.x; vals[gi * 12 + 9] = c.y; vals[gi * 12 + 10] = c.z; vals[gi * 12 + 11] = c.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) vals[gi * 12 + t] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = K0 + ci * 8 + j;
+      v[j] = (k < 243) ? vals[(k / 9 - G0) * 12 + (k % 9)] : 0.f;
+    }
+    store_row_chunk<SPLIT3>(slot_hi, slot_lo, r, HALF * 4 + ci, v);
+  }
+}
+
+
+}  // namespace tc
+}  // namespace b2c

@@ -16,6 +16,7 @@
 
 #include "b2c_common.cuh"
 #include "b2c_tc.cuh"
+#include "b2c_tc_im2col.cuh"
 
 namespace b2c {
 namespace tc {
@@ -195,6 +196,159 @@ static int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, 
   return B2C_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// 9x9 / stride-4 weight gradients (conv1: OIHW [128][3][9][9]; deconv3: IOHW [128][3][9][9]):
+//   dW[m][k] += sum_pix S[pix][m] * im2col(image)[pix][k],  k = c*81 + ky*9 + kx  (243 -> 256)
+// S: NHWC bf16 [B][h][w][128] (TMA, MN-major A operand); image: fp32 NCHW [B][3][4h][4w]; its im2col rows are
+// built in shared memory from a TMA-staged patch exactly as the CONV1 forward does, and used as an MN-major B
+// operand with N = 256 (four 64-wide k-block tiles).  Persistent CTAs, double-buffered S / patch.
+constexpr int W9_THREADS = 64 + 256;
+constexpr int W9_S_BYTES = 2 * IM_SLOT_BYTES;   // 32 KB
+constexpr int W9_B_BYTES = 4 * IM_SLOT_BYTES;   // 64 KB
+
+struct Wg9Params {
+  int tiles_x, tiles_per_image, total_tiles;
+  float* dW;   // [128][243]
+};
+
+__global__ void __launch_bounds__(W9_THREADS, 1)
+wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmI, const Wg9Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_buf = smem;                                  // [2][32 KB]
+  uint8_t* p_buf = smem + 2 * W9_S_BYTES;                 // [2][32 KB] fp32 patches
+  uint8_t* b_buf = smem + 2 * W9_S_BYTES + 2 * P1_SLOT;   // 64 KB im2col tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + W9_B_BYTES);
+  uint64_t* s_full = bars;          // [2]
+  uint64_t* p_full = bars + 2;      // [2]
+  uint64_t* s_empty = bars + 4;     // [2] MMA done with S[b]
+  uint64_t* p_empty = bars + 6;     // [2] builders done with patch[b]
+  uint64_t* b_full = bars + 8;      // builders -> MMA
+  uint64_t* b_empty = bars + 9;     // MMA -> builders
+  uint64_t* done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 1); mbar_init(&s_empty[i], 1); mbar_init(&p_empty[i], 256);
+    }
+    mbar_init(b_full, 256); mbar_init(b_empty, 1); mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmI);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = blockIdx.x + t * gridDim.x;
+        const int n_img = tile / p.tiles_per_image, tt = tile - n_img * p.tiles_per_image;
+        const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+        const int y0 = ty * W_TH, x0 = tx * W_TW;
+        const int b = t & 1, it = t >> 1;
+        mbar_wait(&s_empty[b], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&s_full[b], (uint32_t)W9_S_BYTES);
+        tma_load_4d(s_buf + b * W9_S_BYTES, &tmS, &s_full[b], 0, x0, y0, n_img);
+        tma_load_4d(s_buf + b * W9_S_BYTES + IM_SLOT_BYTES, &tmS, &s_full[b], 64, x0, y0, n_img);
+        mbar_wait(&p_empty[b], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&p_full[b], (uint32_t)P1_BYTES);
+        tma_load_4d(p_buf + b * P1_SLOT, &tmI, &p_full[b], x0 * 4 - 4, y0 * 4 - 4, 0, n_img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_mn(256);
+      for (int t = 0; t < my_tiles; ++t) {
+        const int b = t & 1, it = t >> 1;
+        mbar_wait(&s_full[b], it & 1);
+        mbar_wait(b_full, t & 1);
+        tcgen05_fence_after();
+        const uint32_t a_base = smem_u32(s_buf + b * W9_S_BYTES), b_base = smem_u32(b_buf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = umma_desc_mn_sw128(a_base + k * 2048, IM_SLOT_BYTES);
+          const uint64_t db = umma_desc_mn_sw128(b_base + k * 2048, IM_SLOT_BYTES);
+          umma_bf16(tmem_base, da, db, idesc, (t > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&s_empty[b]);
+        umma_commit(b_empty);
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int ty = r / W_TW, tx = r - ty * W_TW;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int b = t & 1, it = t >> 1;
+      const float* pp = reinterpret_cast<const float*>(p_buf + b * P1_SLOT) + (4 * ty) * P1_W + 4 * tx;
+      mbar_wait(&p_full[b], it & 1);
+      mbar_wait(b_empty, (t & 1) ^ 1);
+      if (half == 0) {
+        conv1_build_row<0, 0, false>(pp, b_buf + 0 * IM_SLOT_BYTES, b_buf, r);
+        conv1_build_row<1, 0, false>(pp, b_buf + 1 * IM_SLOT_BYTES, b_buf, r);
+        conv1_build_row<2, 0, false>(pp, b_buf + 2 * IM_SLOT_BYTES, b_buf, r);
+        conv1_build_row<3, 0, false>(pp, b_buf + 3 * IM_SLOT_BYTES, b_buf, r);
+      } else {
+        conv1_build_row<0, 1, false>(pp, b_buf + 0 * IM_SLOT_BYTES, b_buf, r);
+        conv1_build_row<1, 1, false>(pp, b_buf + 1 * IM_SLOT_BYTES, b_buf, r);
+        conv1_build_row<2, 1, false>(pp, b_buf + 2 * IM_SLOT_BYTES, b_buf, r);
+        conv1_build_row<3, 1, false>(pp, b_buf + 3 * IM_SLOT_BYTES, b_buf, r);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(b_full);
+      mbar_arrive(&p_empty[b]);
+    }
+    mbar_wait(done, 0);
+    tcgen05_fence_after();
+    if (my_tiles > 0) {
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int m = r;
+#pragma unroll 1
+      for (int h = 0; h < 4; ++h) {
+        uint32_t raw[32];
+        const int k0 = half * 128 + h * 32;
+        tmem_ld32(t_row + (uint32_t)k0, raw);
+        tmem_ld_wait();
+        float* dst = p.dW + (size_t)m * 243 + k0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (k0 + c < 243) atomicAdd(dst + c, __uint_as_float(raw[c]));
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int make_image_map9(CUtensorMap* m, const void* base, int B, int H, int W) {
+  EncodeTiledFn2 enc = get_encode2();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+  cuuint32_t box[4] = {(cuuint32_t)P1_W, (cuuint32_t)P1_H, 3, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image) failed: %d", (int)r); return B2C_ECUDA; }
+  return B2C_OK;
+}
+
 // x^2 of the GDN input from the saved (y, n): GDN x^2 = y^2 n, IGDN x^2 = y^2 / n   (bf16, 8 per thread)
 __global__ void __launch_bounds__(256) xsq_kernel(const uint4* __restrict__ y, const uint4* __restrict__ n,
                                                   uint4* __restrict__ out, size_t nvec, int inverse) {
@@ -235,6 +389,38 @@ using namespace b2c;
 using namespace b2c::tc;
 
 extern "C" {
+
+int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int h, int w, void* stream) {
+  B2C_REQUIRE(small_t && image && dW && B > 0 && h > 0 && w > 0, "tc_wgrad9: bad arguments");
+  constexpr size_t SMEM = 2 * W9_S_BYTES + 2 * P1_SLOT + W9_B_BYTES + 1024 + 256;
+  {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad9_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+  }
+  Wg9Params p;
+  p.tiles_x = (w + W_TW - 1) / W_TW;
+  p.tiles_per_image = p.tiles_x * ((h + W_TH - 1) / W_TH);
+  p.total_tiles = B * p.tiles_per_image;
+  p.dW = dW;
+  CUtensorMap mS, mI;
+  int rc;
+  if ((rc = make_nhwc_map(&mS, small_t, B, h, w, 1))) return rc;
+  if ((rc = make_image_map9(&mI, image, B, 4 * h, 4 * w))) return rc;
+  int ctas = (p.total_tiles + 3) / 4;
+  if (ctas > 148) ctas = 148;
+  if (ctas < 1) ctas = 1;
+  wgrad9_tc_kernel<<<ctas, W9_THREADS, SMEM, (cudaStream_t)stream>>>(mS, mI, p);
+  count_launch();
+  return check_launch("tc_wgrad9");
+}
 
 int b2c_tc_xsq(const void* y, const void* n, void* out, size_t count, int inverse, void* stream) {
   B2C_REQUIRE(y && n && out && count > 0 && count % 8 == 0, "tc_xsq: bad arguments");

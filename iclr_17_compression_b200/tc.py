@@ -142,3 +142,12 @@ def wgrad(small, big, k, stride, pad):
         _lib.check(_lib.load().b2c_tc_wgrad(_p(small), _p(big), _p(dW), B, hs, ws, hb, wb, k, stride, pad, _stream()),
                    "tc_wgrad")
     return dW.permute(2, 3, 0, 1).contiguous() if k > 1 else dW.view(128, 128, 1, 1)
+
+
+def wgrad9(small, image):
+    """9x9/4 weight gradient: small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w] -> fp32 [128,3,9,9]"""
+    B, h, w, _ = small.shape
+    dW = torch.zeros((128, 3, 9, 9), device=small.device, dtype=torch.float32)
+    with torch.cuda.device(small.device), _timed(f"tc_wgrad9[{B}x{h}x{w}]", 2 * B * h * w * 128 * 243, 0):
+        _lib.check(_lib.load().b2c_tc_wgrad9(_p(small), _p(image), _p(dW), B, h, w, _stream()), "tc_wgrad9")
+    return dW

@@ -137,9 +137,9 @@ class TrainStepTC(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _vp(0), _p(g_sse), _p(g_recon), recon.numel(), _stream()),
                        "clamp_sse_bwd")
-        # ---- deconv3 (9x9/4, 128 -> 3): weight grad on the fp32 kernel, dgrad (= conv 9x9/4) + IGDN2 backward fused
+        # ---- deconv3 (9x9/4, 128 -> 3): weight grad (im2col MN-major tcgen05), dgrad (= conv 9x9/4) + IGDN2 backward fused
         D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
-        grads["Decoder.deconv3.weight"] = _wgrad_simt(T.nhwc_to_nchw(i2), g_recon, 9, 4, 4)
+        grads["Decoder.deconv3.weight"] = T.wgrad9(i2, g_recon)
         from .functional import _channel_sum_raw
         grads["Decoder.deconv3.bias"] = _channel_sum_raw(g_recon)
         gt = T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"])
@@ -188,8 +188,8 @@ class TrainStepTC(torch.autograd.Function):
                                 gdn_mode=3, second_plane=True, saved=(h1, n1))
         grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = _gdn_param_grads(
             prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dn, False)
-        # ---- conv1 (9x9/4, 3 -> 128): weight grad on the fp32 kernel; the image needs no gradient
-        grads["Encoder.conv1.weight"] = _wgrad_simt(T.nhwc_to_nchw(gp_c1), x, 9, 4, 4)
+        # ---- conv1 (9x9/4, 3 -> 128): weight grad (im2col MN-major tcgen05); the image needs no gradient
+        grads["Encoder.conv1.weight"] = T.wgrad9(gp_c1, x)
         grads["Encoder.conv1.bias"] = _colsum(gp_c1)
         ctx.saved = None
         return (None, None) + tuple(grads[k].reshape(prm[k].shape) for k in PARAM_ORDER)

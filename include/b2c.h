@@ -197,6 +197,11 @@ int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
 int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
                  int stride, int pad, void* stream);
 
+/* 9x9 / stride-4 / pad-4 weight gradient on tensor cores: dW[m][c][ky][kx] += sum small[img,ys,xs,m] *
+ * image[img,c,4ys-4+ky,4xs-4+kx]; small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w], dW fp32 [128][3][9][9]
+ * zero-filled by the caller.  conv1 (OIHW): small = grad_out, image = x; deconv3 (IOHW): small = input, image = grad_out. */
+int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int h, int w, void* stream);
+
 /* helpers of the bf16 training path: x^2 of a GDN input from the saved output and norm (GDN: y^2 n, IGDN: y^2/n;
  * count bf16 elements, multiple of 8), and out[c] += sum_rows t[row][c] for a bf16 [P][128] tensor (out zero-filled). */
 int b2c_tc_xsq(const void* y, const void* n, void* out, size_t count, int inverse, void* stream);

@@ -228,3 +228,16 @@ def test_dgrad_with_gdn_backward_epilogue(tc, kind_name, inverse):
                             second_plane=True, saved=(yh, nh))
     assert _rel(tc.nhwc_to_nchw(dnh), dn) < 8e-3, _rel(tc.nhwc_to_nchw(dnh), dn)
     assert _rel(tc.nhwc_to_nchw(dxh), dx) < 8e-3, _rel(tc.nhwc_to_nchw(dxh), dx)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 32), (2, 64, 64), (1, 24, 40)])
+def test_wgrad9_im2col(tc, shape):
+    B, h, w = shape
+    g = torch.Generator().manual_seed(10)
+    s = torch.randn(B, 128, h, w, generator=g).cuda()
+    img = torch.randn(B, 3, 4 * h, 4 * w, generator=g).cuda()
+    sh, _ = tc.nchw_to_nhwc(s, False)
+    wt = torch.zeros(128, 3, 9, 9, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(_bf(img).cpu(), wt, None, stride=4, padding=4) * _bf(s).cpu()).sum().backward()
+    d = tc.wgrad9(sh, img)
+    assert _rel(d, wt.grad) < 1e-5, _rel(d, wt.grad)
