@@ -59,6 +59,43 @@ def _gdn_param_grads(beta_p, gamma_p, y, n, dn, inverse):
     return dbeta_p, dgamma_p
 
 
+class _Fork:
+    """Runs parameter-gradient kernels (weight / bias / GDN gradients, entropy backward) on side streams while the
+    dgrad chain continues on the main stream; at batch 8 of 256x256 no single kernel fills 148 SMs, so the
+    independent branches are overlapped (also inside a captured CUDA graph, where they become parallel branches)."""
+    _streams = {}
+
+    def __init__(self, dev, n=3):
+        self.main = torch.cuda.current_stream(dev)
+        key = (dev.index, n)
+        if key not in _Fork._streams:
+            _Fork._streams[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        self.sides = _Fork._streams[key]
+        self.i = 0
+        self.used = []
+        self.outs = []
+
+    def run(self, fn, *inputs):
+        s = self.sides[self.i % len(self.sides)]
+        self.i += 1
+        s.wait_stream(self.main)                  # inputs were produced on the main stream
+        for t in inputs:
+            t.record_stream(s)
+        with torch.cuda.stream(s):
+            out = fn()
+        if s not in self.used:
+            self.used.append(s)
+        for o in (out if isinstance(out, (tuple, list)) else (out,)):
+            self.outs.append(o)
+        return out
+
+    def join(self):
+        for s in self.used:
+            self.main.wait_stream(s)
+        for o in self.outs:
+            o.record_stream(self.main)
+
+
 def _wgrad_simt(small, big, k, stride, pad):
     from .functional import _wgrad_raw
     return _wgrad_raw(small, big, k, stride, pad)
@@ -132,6 +169,24 @@ class TrainStepTC(torch.autograd.Function):
         zero = torch.zeros((1,), device=dev, dtype=torch.float32)
         g_sse = g_sse.reshape(1).float().contiguous() if g_sse is not None else zero
         g_bits = g_bits.reshape(1).float().contiguous() if g_bits is not None else zero
+        fork = _Fork(dev)
+        from .functional import _channel_sum_raw
+        # ---- entropy model: d bits / dz and the 11 parameter vectors (independent of the synthesis chain)
+        bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
+        C, HW = 128, z.shape[2] * z.shape[3]
+
+        def entropy_bwd():
+            dbit = [torch.zeros_like(p) for p in bitp]
+            dz_ = torch.empty_like(z)
+            pp, k1 = _lib.ptr_array(bitp)
+            dp, k2 = _lib.ptr_array(dbit)
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2c_entropy_bwd(_p(z), pp, _p(g_bits), _p(dz_), dp, B, C, HW, _stream()), "entropy_bwd")
+            return [dz_] + dbit
+        ent = fork.run(entropy_bwd, g_bits)
+        dz, dbit = ent[0], ent[1:]
+        for k, g in zip(PARAM_ORDER[19:], dbit):
+            grads[k] = g.view(1, -1, 1, 1)
         # ---- distortion
         g_recon = torch.empty_like(recon)
         with torch.cuda.device(dev):
@@ -139,58 +194,48 @@ class TrainStepTC(torch.autograd.Function):
                        "clamp_sse_bwd")
         # ---- deconv3 (9x9/4, 128 -> 3): weight grad (im2col MN-major tcgen05), dgrad (= conv 9x9/4) + IGDN2 backward fused
         D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
-        grads["Decoder.deconv3.weight"] = T.wgrad9(i2, g_recon)
-        from .functional import _channel_sum_raw
-        grads["Decoder.deconv3.bias"] = _channel_sum_raw(g_recon)
+        grads["Decoder.deconv3.weight"] = fork.run(lambda: T.wgrad9(i2, g_recon), g_recon)
+        grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon), g_recon)
         gt = T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"])
-        gp_d2, dn = T.layer_run(T.TC_CONV1, g_recon, None, T.pack_weights(T.TC_CONV1, D3, False), None, gdn=gt,
-                                gdn_mode=4, second_plane=True, saved=(i2, m2))
-        grads["Decoder.igdn2.beta"], grads["Decoder.igdn2.gamma"] = _gdn_param_grads(
-            prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn, True)
+        gp_d2, dn2 = T.layer_run(T.TC_CONV1, g_recon, None, T.pack_weights(T.TC_CONV1, D3, False), None, gdn=gt,
+                                 gdn_mode=4, second_plane=True, saved=(i2, m2))
+        grads["Decoder.igdn2.beta"], grads["Decoder.igdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
+            prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn2, True), dn2)
         # ---- deconv2
-        grads["Decoder.deconv2.weight"] = T.wgrad(i1, gp_d2, 5, 2, 2)
-        grads["Decoder.deconv2.bias"] = _colsum(gp_d2)
+        grads["Decoder.deconv2.weight"] = fork.run(lambda: T.wgrad(i1, gp_d2, 5, 2, 2), gp_d2)
+        grads["Decoder.deconv2.bias"] = fork.run(lambda: _colsum(gp_d2), gp_d2)
         gt = T.pack_gdn_t(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"])
-        gp_d1, dn = T.layer_run(T.TC_CONV5S2, gp_d2, None, T.pack_weights(T.TC_CONV5S2, D2, False), None, gdn=gt,
-                                gdn_mode=4, second_plane=True, saved=(i1, m1))
-        grads["Decoder.igdn1.beta"], grads["Decoder.igdn1.gamma"] = _gdn_param_grads(
-            prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn, True)
+        gp_d1, dn1 = T.layer_run(T.TC_CONV5S2, gp_d2, None, T.pack_weights(T.TC_CONV5S2, D2, False), None, gdn=gt,
+                                 gdn_mode=4, second_plane=True, saved=(i1, m1))
+        grads["Decoder.igdn1.beta"], grads["Decoder.igdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
+            prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn1, True), dn1)
         # ---- deconv1
-        grads["Decoder.deconv1.weight"] = T.wgrad(zh, gp_d1, 5, 2, 2)
-        grads["Decoder.deconv1.bias"] = _colsum(gp_d1)
+        grads["Decoder.deconv1.weight"] = fork.run(lambda: T.wgrad(zh, gp_d1, 5, 2, 2), gp_d1)
+        grads["Decoder.deconv1.bias"] = fork.run(lambda: _colsum(gp_d1), gp_d1)
         g_z = T.layer_run(T.TC_CONV5S2, gp_d1, None, T.pack_weights(T.TC_CONV5S2, D1, False), None, out_f32_nchw=True)
-        # ---- entropy model: d bits / dz and the 11 parameter vectors
-        bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
-        dbit = [torch.zeros_like(p) for p in bitp]
-        dz = torch.empty_like(z)
-        pp, k1 = _lib.ptr_array(bitp)
-        dp, k2 = _lib.ptr_array(dbit)
-        C, HW = 128, z.shape[2] * z.shape[3]
-        with torch.cuda.device(dev):
-            _lib.check(lib.b2c_entropy_bwd(_p(z), pp, _p(g_bits), _p(dz), dp, B, C, HW, _stream()), "entropy_bwd")
-        for k, g in zip(PARAM_ORDER[19:], dbit):
-            grads[k] = g.view(1, -1, 1, 1)
+        fork.main.wait_stream(fork.sides[0])               # dz comes from the entropy backward (first forked task)
         g_y = g_z + dz                                     # z = y + noise -> dz/dy = 1
         gyh, _ = T.nchw_to_nhwc(g_y, False)
         # ---- conv3 (no bias): wgrad, dgrad (= transposed conv) + GDN2 backward fused
         W1, W2, W3 = prm["Encoder.conv1.weight"], prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
-        grads["Encoder.conv3.weight"] = T.wgrad(gyh, h2, 5, 2, 2)
+        grads["Encoder.conv3.weight"] = fork.run(lambda: T.wgrad(gyh, h2, 5, 2, 2), gyh)
         gt = T.pack_gdn_t(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"])
-        gp_c2, dn = T.layer_run(T.TC_DECONV5S2, gyh, None, T.pack_weights(T.TC_DECONV5S2, W3, False), None, gdn=gt,
-                                gdn_mode=3, second_plane=True, saved=(h2, n2))
-        grads["Encoder.gdn2.beta"], grads["Encoder.gdn2.gamma"] = _gdn_param_grads(
-            prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dn, False)
+        gp_c2, dng2 = T.layer_run(T.TC_DECONV5S2, gyh, None, T.pack_weights(T.TC_DECONV5S2, W3, False), None, gdn=gt,
+                                  gdn_mode=3, second_plane=True, saved=(h2, n2))
+        grads["Encoder.gdn2.beta"], grads["Encoder.gdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
+            prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dng2, False), dng2)
         # ---- conv2
-        grads["Encoder.conv2.weight"] = T.wgrad(gp_c2, h1, 5, 2, 2)
-        grads["Encoder.conv2.bias"] = _colsum(gp_c2)
+        grads["Encoder.conv2.weight"] = fork.run(lambda: T.wgrad(gp_c2, h1, 5, 2, 2), gp_c2)
+        grads["Encoder.conv2.bias"] = fork.run(lambda: _colsum(gp_c2), gp_c2)
         gt = T.pack_gdn_t(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"])
-        gp_c1, dn = T.layer_run(T.TC_DECONV5S2, gp_c2, None, T.pack_weights(T.TC_DECONV5S2, W2, False), None, gdn=gt,
-                                gdn_mode=3, second_plane=True, saved=(h1, n1))
-        grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = _gdn_param_grads(
-            prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dn, False)
+        gp_c1, dng1 = T.layer_run(T.TC_DECONV5S2, gp_c2, None, T.pack_weights(T.TC_DECONV5S2, W2, False), None, gdn=gt,
+                                  gdn_mode=3, second_plane=True, saved=(h1, n1))
+        grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
+            prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dng1, False), dng1)
         # ---- conv1 (9x9/4, 3 -> 128): weight grad (im2col MN-major tcgen05); the image needs no gradient
-        grads["Encoder.conv1.weight"] = T.wgrad9(gp_c1, x)
-        grads["Encoder.conv1.bias"] = _colsum(gp_c1)
+        grads["Encoder.conv1.weight"] = fork.run(lambda: T.wgrad9(gp_c1, x), gp_c1)
+        grads["Encoder.conv1.bias"] = fork.run(lambda: _colsum(gp_c1), gp_c1)
+        fork.join()
         ctx.saved = None
         return (None, None) + tuple(grads[k].reshape(prm[k].shape) for k in PARAM_ORDER)
 
