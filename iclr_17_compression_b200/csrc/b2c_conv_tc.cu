@@ -93,10 +93,11 @@ struct TcOutMaps {
 template <bool SPLIT3, int KIND>
 struct TcCfg {
   static constexpr int STAGES = (KIND == B2C_TC_CONV1 && SPLIT3) ? 1 : 3;
-  static constexpr int STAGE_BYTES = (SPLIT3 ? 4 : 2) * SLOT_BYTES;
+  // DECONV3's weight tile is 48 rows (6 KB): 24 KB stages, three CTAs per SM keep 9 stages in flight
+  static constexpr int STAGE_BYTES = (KIND == B2C_TC_DECONV3) ? SLOT_BYTES + 8192 : (SPLIT3 ? 4 : 2) * SLOT_BYTES;
   static constexpr int PATCH = (KIND == B2C_TC_CONV1) ? P1_SLOT : 0;
   static constexpr int SMEM = STAGES * STAGE_BYTES + PATCH + 1024 /*align*/ + 1024 /*bias, beta*/ + 256 /*barriers*/;
-  static constexpr int MIN_CTAS = (SMEM <= 113 * 1024) ? 2 : 1;
+  static constexpr int MIN_CTAS = (SMEM <= 75 * 1024) ? 3 : (SMEM <= 113 * 1024) ? 2 : 1;
 };
 
 template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
@@ -265,6 +266,22 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } while (0)
     TC_WMARK();
 
+    // DECONV3 fused distortion: fetch this thread's 2 rows x 3 channels x 4 pixels of the reference image now, so
+    // the HBM latency hides behind the main loop instead of serialising the epilogue
+    float4 xref[6];
+    if (OUT_MODE == OUT_F32_NCHW_PS4) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) xref[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.ref_image && valid) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+#pragma unroll
+          for (int ryl = 0; ryl < 2; ++ryl)
+            xref[o * 2 + ryl] = __ldg(reinterpret_cast<const float4*>(
+                p.ref_image + (((size_t)n_img * 3 + o) * p.Hfull + (oy * 4 + half * 2 + ryl)) * p.Wfull + ox * 4));
+      }
+    }
+
     if (SOFT_A) {
       // CONV1: im2col rows from the TMA-staged fp32 patch; pixel (ty,tx) starts at patch[4*ty][4*tx]
       const float* pp = patch + (4 * ty) * P1_W + 4 * tx;
@@ -382,7 +399,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                                     __uint_as_float(raw[(ryl * 4 + 3) * 3 + o]) + bv);
             const size_t off = (((size_t)n_img * 3 + o) * p.Hfull + (oy * 4 + ry)) * p.Wfull + ox * 4;
             if (p.ref_image) {
-              const float4 x4 = __ldg(reinterpret_cast<const float4*>(p.ref_image + off));
+              const float4 x4 = xref[o * 2 + ryl];
               const float4 c4 = make_float4(fminf(fmaxf(v4.x, 0.f), 1.f), fminf(fmaxf(v4.y, 0.f), 1.f),
                                             fminf(fmaxf(v4.z, 0.f), 1.f), fminf(fmaxf(v4.w, 0.f), 1.f));
               float d;

@@ -39,3 +39,4 @@ with torch.no_grad():
     d1 = run("deconv1+igdn1", lambda: tc.layer_run(tc.TC_DECONV5S2, zh, None, Pk["deconv1"], D.deconv1.bias, gdn=Pk["igdn1"], gdn_mode=2))
     d2 = run("deconv2+igdn2", lambda: tc.layer_run(tc.TC_DECONV5S2, d1[0], None, Pk["deconv2"], D.deconv2.bias, gdn=Pk["igdn2"], gdn_mode=2))
     r = run("deconv3", lambda: tc.layer_run(tc.TC_DECONV3, d2[0], None, Pk["deconv3"], D.deconv3.bias, out_f32_nchw=True))
+    r = run("deconv3+clamp+sse", lambda: tc.layer_run(tc.TC_DECONV3, d2[0], None, Pk["deconv3"], D.deconv3.bias, out_f32_nchw=True, ref_image=x))
