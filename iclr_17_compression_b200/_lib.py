@@ -26,6 +26,8 @@ SIGNATURES = {
     "b2c_gdn_bwd_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
     "b2c_gdn_bwd": (_c_i, [_c_f] * 7 + [_c_i] * 4 + [_c_f, _c_sz, _c_f]),
     "b2c_quant_entropy_fwd": (_c_i, [_c_f, _c_f, _PP, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_quant_entropy_infer_workspace_bytes": (_c_sz, [_c_i, _c_i]),
+    "b2c_quant_entropy_infer": (_c_i, [_c_f, _PP, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_entropy_bwd": (_c_i, [_c_f, _PP, _c_f, _c_f, _PP, _c_i, _c_i, _c_i, _c_f]),
     "b2c_clamp_sse_workspace_bytes": (_c_sz, [_c_i, _c_i]),
     "b2c_clamp_sse_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_f, _c_sz, _c_f]),

@@ -6,6 +6,8 @@
 // The reference's formula is reproduced as written (difference of two fp32 sigmoids, +1e-10 floor),
 // not a numerically nicer one.  One CTA per (image, channel) plane so the per-channel constants
 // softplus(h_k), tanh(a_k), b_k are computed once per CTA; sums are fixed-order (deterministic).
+#include <cuda_bf16.h>
+
 #include "b2c_common.cuh"
 
 namespace b2c {
@@ -105,6 +107,76 @@ __global__ void __launch_bounds__(256) plane_reduce_kernel(const float* __restri
   for (int i = threadIdx.x; i < per_image; i += blockDim.x) s += plane_vals[(size_t)n * per_image + i];
   s = block_sum(s, red);
   if (threadIdx.x == 0) out[n] = s;
+}
+
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int per_image,
+                                      int width);
+
+// ---------------------------------------------------------------------------- inference variant
+// Same formula (model.py:53-56,71-73) with the hardware approximations tanh.approx / ex2.approx / lg2.approx for the
+// per-element chain (relative error ~2^-11 per tanh changes the total bit count by ~1e-6 relative, far inside the
+// 1e-3 bpp bar; the per-channel softplus / tanh constants stay exact).  One CTA = 32 pixels x all channels of one
+// image, so the rounded latent is also emitted as the NHWC bf16 tensor the tensor-core synthesis transform reads.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float cdf_fast(const float* k, float v) {   // k: sp1 b1 ta1 sp2 b2 ta2 sp3 b3 ta3 sp4 b4
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float t = fmaf(v, k[3 * i], k[3 * i + 1]);
+    v = fmaf(tanh_fast(t), k[3 * i + 2], t);
+  }
+  const float t4 = fmaf(v, k[9], k[10]);
+  return __fdividef(1.f, 1.f + __expf(-t4));
+}
+
+constexpr int QI_PIX = 32;
+
+__global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* __restrict__ y, BitPtrs bp,
+                                                                  float* __restrict__ z,
+                                                                  __nv_bfloat16* __restrict__ z_nhwc,
+                                                                  float* __restrict__ partial, int C, int HW,
+                                                                  int chunks) {
+  extern __shared__ float qi_smem[];
+  float* kc = qi_smem;                                   // [C][12]
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(qi_smem + (size_t)C * 12);   // [QI_PIX][C]
+  __shared__ float red[32];
+  const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+  const int pix0 = chunk * QI_PIX;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const ChanConst k = load_chan(bp, c);
+    float* d = kc + c * 12;
+    d[0] = k.sp[0]; d[1] = k.b[0]; d[2] = k.ta[0];
+    d[3] = k.sp[1]; d[4] = k.b[1]; d[5] = k.ta[1];
+    d[6] = k.sp[2]; d[7] = k.b[2]; d[8] = k.ta[2];
+    d[9] = k.sp[3]; d[10] = k.b[3]; d[11] = 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int pix = pix0 + lane;
+  float sum = 0.f;
+  for (int c = warp; c < C; c += nwarps) {
+    float zv = 0.f;
+    if (pix < HW) {
+      const size_t a = ((size_t)n * C + c) * HW + pix;
+      zv = rintf(__ldg(y + a));
+      z[a] = zv;
+      const float* k = kc + c * 12;
+      const float p = cdf_fast(k, zv + 0.5f) - cdf_fast(k, zv - 0.5f);
+      sum += fminf(fmaxf(-__log2f(p + 1e-10f), 0.f), 50.f);
+    }
+    tile[lane * C + c] = __float2bfloat16_rn(zv);
+  }
+  sum = block_sum(sum, red);                              // also a __syncthreads() for `tile`
+  if (threadIdx.x == 0) partial[blockIdx.x] = sum;
+  if (z_nhwc) {
+    const int npix = min(QI_PIX, HW - pix0);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(z_nhwc + ((size_t)n * HW + pix0) * C);
+    for (int i = threadIdx.x; i < npix * C / 2; i += blockDim.x) dst[i] = src[i];
+  }
 }
 
 // ---------------------------------------------------------------------------- backward
@@ -273,6 +345,34 @@ int b2c_quant_entropy_fwd(const float* y, const float* noise, const float* const
   plane_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(plane_bits, image_bits, C);
   count_launch(2);
   return check_launch("quant_entropy_fwd");
+}
+
+size_t b2c_quant_entropy_infer_workspace_bytes(int B, int HW) {
+  return (size_t)B * ((HW + QI_PIX - 1) / QI_PIX) * sizeof(float);
+}
+
+int b2c_quant_entropy_infer(const float* y, const float* const* host_params, float* z, void* z_nhwc_bf16,
+                            float* image_bits, int B, int C, int HW, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  B2C_REQUIRE(y && host_params && z && image_bits && workspace && B > 0 && C > 0 && C % 2 == 0 && HW > 0,
+              "quant_entropy_infer: bad arguments");
+  if (workspace_bytes < b2c_quant_entropy_infer_workspace_bytes(B, HW)) {
+    set_error("quant_entropy_infer: workspace too small");
+    return B2C_EWORKSPACE;
+  }
+  BitPtrs bp;
+  for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) {
+    B2C_REQUIRE(host_params[i], "quant_entropy_infer: null parameter pointer %d", i);
+    bp.p[i] = host_params[i];
+  }
+  const int chunks = (HW + QI_PIX - 1) / QI_PIX;
+  const size_t smem = (size_t)C * 12 * sizeof(float) + (size_t)QI_PIX * C * 2;
+  B2C_REQUIRE(smem <= 48 * 1024, "quant_entropy_infer: too many channels");
+  quant_entropy_infer_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(
+      y, bp, z, (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks);
+  partial_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, image_bits, chunks, 1);
+  count_launch(2);
+  return check_launch("quant_entropy_infer");
 }
 
 int b2c_entropy_bwd(const float* z, const float* const* host_params, const float* g_bits, float* dz,

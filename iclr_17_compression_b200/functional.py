@@ -314,6 +314,25 @@ class _Distortion(torch.autograd.Function):
         return g_recon, None
 
 
+def quant_entropy_infer(y, params):
+    """eval quantizer + bits for the tensor-core pipeline (no autograd): (z fp32 NCHW, z NHWC bf16, image_bits[B])"""
+    y = _prep(y, "latent")
+    params = [_prep(p, "bit-estimator parameter") for p in params]
+    B, C, H, W = y.shape
+    HW = H * W
+    lib = _lib.load()
+    z = torch.empty_like(y)
+    zh = torch.empty((B, H, W, C), device=y.device, dtype=torch.bfloat16)
+    image_bits = torch.empty((B,), device=y.device, dtype=torch.float32)
+    nbytes = lib.b2c_quant_entropy_infer_workspace_bytes(B, HW)
+    ws = torch.empty((nbytes,), device=y.device, dtype=torch.uint8)
+    pp, keep = _lib.ptr_array(params)
+    with torch.cuda.device(y.device), _timed(f"quant_entropy_infer[{B}x{C}x{HW}]", 60 * y.numel(), 10 * y.numel()):
+        _lib.check(lib.b2c_quant_entropy_infer(_p(y), pp, _p(z), _p(zh), _p(image_bits), B, C, HW, _p(ws), nbytes,
+                                               _stream()), "quant_entropy_infer")
+    return z, zh, image_bits
+
+
 # ------------------------------------------------------------------------------ public ops
 def conv2d(x, weight, bias, stride, padding):
     return _Conv2d.apply(x, weight, bias, stride, padding)

@@ -118,11 +118,11 @@ class ImageCompressor(nn.Module):
                            split3=True)
         return B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv3"], None, split3=True, out_f32_nchw=True)
 
-    def decode_tc(self, z, ref_image=None):
+    def decode_tc(self, z, ref_image=None, z_nhwc=None):
         """synthesis transform on tensor cores (bf16) -> unclamped reconstruction, fp32 NCHW; with ref_image
         the distortion is fused into the last layer: returns (clamped reconstruction, sse[B,2])"""
         P, D = self._packed_weights(), self.Decoder
-        zh, _ = B2TC.nchw_to_nhwc(z, False)        # integer latents |z| <= 256 are exact in bf16
+        zh = z_nhwc if z_nhwc is not None else B2TC.nchw_to_nhwc(z, False)[0]   # integer |z| <= 256: exact in bf16
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, zh, None, P["deconv1"], D.deconv1.bias, gdn=P["igdn1"], gdn_mode=2)
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, h[0], None, P["deconv2"], D.deconv2.bias, gdn=P["igdn2"], gdn_mode=2)
         return B2TC.layer_run(B2TC.TC_DECONV3, h[0], None, P["deconv3"], D.deconv3.bias, out_f32_nchw=True,
@@ -161,17 +161,17 @@ class ImageCompressor(nn.Module):
         tc_path = self._use_tc(x)
         self.last_path = "tcgen05" if tc_path else "fp32"
         if tc_path:
-            x = x.contiguous().float()
-            _lib_check = B2F._prep(x, "input image")
-            feature = self.encode_tc(_lib_check)
-        else:
-            feature = self.Encoder(x)
-        noise = self._noise(x) if self.training else None
-        z, total_bits, image_bits, plane_bits = self.bitEstimator.bits(feature, noise)
-        if tc_path:
-            clipped_recon_image, sse = self.decode_tc(z, ref_image=x)
+            x = B2F._prep(x.float(), "input image")
+            feature = self.encode_tc(x)
+            z, zh, image_bits = B2F.quant_entropy_infer(feature, [p.detach().reshape(-1) for p in
+                                                                  self.bitEstimator.param_list()])
+            total_bits, plane_bits = image_bits.sum(), None      # per-plane bits only on the fp32 path
+            clipped_recon_image, sse = self.decode_tc(z, ref_image=x, z_nhwc=zh)
             sse_total = sse[:, 0].sum()
         else:
+            feature = self.Encoder(x)
+            noise = self._noise(x) if self.training else None
+            z, total_bits, image_bits, plane_bits = self.bitEstimator.bits(feature, noise)
             recon_image = self.Decoder(z)
             clipped_recon_image, sse_total, sse = B2F.distortion(recon_image, x)
         mse_loss = sse_total / x.numel()                                   # model.py:61

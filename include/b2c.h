@@ -107,6 +107,14 @@ int b2c_gdn_reparam_bwd(const float* beta_p, const float* gamma_p, const float* 
 int b2c_quant_entropy_fwd(const float* y, const float* noise, const float* const* host_params,
                           float* z, float* plane_bits, float* image_bits,
                           int B, int C, int HW, void* stream);
+/* Inference form of the same pass (eval quantizer only): hardware tanh / exp2 / log2 approximations in the
+ * per-element chain (bits change by ~1e-6 relative), per-image bits only, and the rounded latent is also written
+ * as NHWC bf16 (z_nhwc_bf16, may be NULL) for the tensor-core synthesis transform.  workspace: one float per
+ * (image, 32-pixel chunk). */
+size_t b2c_quant_entropy_infer_workspace_bytes(int B, int HW);
+int b2c_quant_entropy_infer(const float* y, const float* const* host_params, float* z, void* z_nhwc_bf16,
+                            float* image_bits, int B, int C, int HW, void* workspace, size_t workspace_bytes,
+                            void* stream);
 /* backward of total_bits = sum(image_bits): g_bits is a DEVICE scalar (dL/dtotal_bits).
  * dz[B,C,HW] out (assigned); host_dparams: HOST array of 11 device pointers [C], must be
  * zero-filled by the caller (atomically accumulated). */
