@@ -23,6 +23,9 @@
 namespace b2c {
 namespace tc {
 
+#ifndef B2C_CONV1_STAGES
+#define B2C_CONV1_STAGES 1
+#endif
 constexpr int TH = 8, TW = 16;            // output tile (pixels)
 constexpr int TILE_M = TH * TW;           // 128
 constexpr int KBLK = 64;                  // bf16 per k-block row (128 B)
@@ -92,7 +95,7 @@ struct TcOutMaps {
 
 template <bool SPLIT3, int KIND>
 struct TcCfg {
-  static constexpr int STAGES = (KIND == B2C_TC_CONV1 && SPLIT3) ? 1 : 3;
+  static constexpr int STAGES = (KIND == B2C_TC_CONV1 && SPLIT3) ? B2C_CONV1_STAGES : 3;
   // DECONV3's weight tile is 48 rows (6 KB): 24 KB stages, three CTAs per SM keep 9 stages in flight
   static constexpr int STAGE_BYTES = (KIND == B2C_TC_DECONV3) ? SLOT_BYTES + 8192 : (SPLIT3 ? 4 : 2) * SLOT_BYTES;
   static constexpr int PATCH = (KIND == B2C_TC_CONV1) ? P1_SLOT : 0;

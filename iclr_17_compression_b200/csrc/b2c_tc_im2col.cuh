@@ -14,28 +14,30 @@ constexpr int P1_PLANE = P1_W * P1_H;
 constexpr int P1_BYTES = 3 * P1_PLANE * 4;          // 31968
 constexpr int P1_SLOT = 32768;
 
+// fp32 pair -> packed bf16x2 (one F2FP instruction; the scalar F2F conversions run at quarter rate and were
+// the bottleneck of every operand builder / epilogue), low half = a
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 template <bool SPLIT3>
 __device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_lo, int r, int cidx,
                                                 const float (&v)[8]) {
   // K-major SWIZZLE_128B: row r at r*128, 16-byte chunk index XORed with (r & 7)
   const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cidx ^ (r & 7)) << 4);
-  __nv_bfloat16 h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (SPLIT3) {
-      split_bf16(v[i], h[i], l[i]);
-    } else {
-      h[i] = __float2bfloat16_rn(v[i]);
+  for (int i = 0; i < 4; ++i) {
+    h[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
+    if (SPLIT3) {   // lo = bf16(x - float(hi)): the residual is exact in fp32
+      const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+      const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+      l[i] = cvt_bf16x2(r0, r1);
     }
   }
-  uint4 qh = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]),
-                        pack_bf16x2(h[6], h[7]));
-  *reinterpret_cast<uint4*>(slot_hi + off) = qh;
-  if (SPLIT3) {
-    uint4 ql = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]),
-                          pack_bf16x2(l[6], l[7]));
-    *reinterpret_cast<uint4*>(slot_lo + off) = ql;
-  }
+  *reinterpret_cast<uint4*>(slot_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (SPLIT3) *reinterpret_cast<uint4*>(slot_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // CONV1: the 32 im2col values k = KB*64 + HALF*32 .. +31 (k = c*81 + ky*9 + kx, zero for k >= 243) of the
