@@ -224,7 +224,17 @@ def main():
         achieved = top["bytes"] / (top["ms_avg"] * 1e-3) / 1e9
         peak = pk["hbm_gbs"]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
-    roof.update({"traffic": None, "kernel": top_name, "kernel_ms": top["ms_avg"],
+    traffic = None
+    try:   # DRAM bytes of this kernel from the committed ncu --set full capture (8 images), scaled to this batch
+        nt = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        for key, v in nt["kernels"].items():
+            if top_name.startswith(key):
+                traffic = v["dram_mbytes_per_launch_8_images"] * 1e6 * IMAGES / nt["images"]
+                roof["tensor_pipe_active_pct_ncu"] = v["tensor_pipe_active_pct"]
+    except Exception:
+        pass
+    roof.update({"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, scaled from 8 images)",
+                 "kernel": top_name, "kernel_ms": top["ms_avg"],
                  "share_of_step": top["ms_total"] / total_ms, "peak_source": pk_kind,
                  "pipeline_frac_of_tensor_roofline": (FLOP_PER_PIXEL * IMAGES * H * W / (ms * 1e-3) / 1e12)
                  / pk["bf16_tflops_sustained"]})
