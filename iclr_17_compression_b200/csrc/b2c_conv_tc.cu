@@ -23,6 +23,9 @@
 namespace b2c {
 namespace tc {
 
+#ifndef B2C_TC_PAIRS_DEFAULT
+#define B2C_TC_PAIRS_DEFAULT 1
+#endif
 #ifndef B2C_CONV1_STAGES
 #define B2C_CONV1_STAGES 1
 #endif
@@ -103,7 +106,7 @@ struct TcCfg {
   static constexpr int MIN_CTAS = (SMEM <= 75 * 1024) ? 3 : (SMEM <= 113 * 1024) ? 2 : 1;
 };
 
-template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
+template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, TcCfg<SPLIT3, KIND>::MIN_CTAS)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -115,7 +118,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   constexpr int IN_STRIDE = (KIND == B2C_TC_CONV5S2) ? 2 : 1;
   constexpr bool SOFT_A = (KIND == B2C_TC_CONV1);
   constexpr uint32_t TMEM_COLS = GDN ? 256 : (N_TILE > 64 ? 128 : 64);
-  constexpr uint32_t B_BYTES = N_TILE * KBLK * 2;
+  // PAIR: two CTAs (adjacent tiles) form a cta_group::2 pair: one M = 256 MMA per step issued by the leader,
+  // each CTA stages its own A tile and HALF of the weight tile, halving B fill and B operand reads per SM.
+  static_assert(!PAIR || (KIND != B2C_TC_CONV1 && N_TILE == 128), "CTA pairs: TMA-fed 128-channel kinds only");
+  constexpr uint32_t B_BYTES = N_TILE * KBLK * 2 / (PAIR ? 2 : 1);
   static_assert(GDN == 0 || N_TILE == 128, "fused GDN needs all 128 channels in the tile");
   // GDN: 0 none, 1 GDN forward, 2 IGDN forward, 3 GDN backward, 4 IGDN backward (epilogue of the dgrad conv)
   constexpr bool GDN_BWD = (GDN == 3 || GDN == 4);
@@ -142,6 +148,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int oy0 = tile_y * TH, ox0 = tile_x * TW;
   const int nsteps = num_steps<KIND>(phase);
   const int total_steps = nsteps + (GDN ? 2 : 0);
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   int tmark = 0;
 #define TC_MARK(role)                                                       \
@@ -153,7 +161,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
-      mbar_init(&afull[i], NWORKERS);
+      mbar_init(&afull[i], NWORKERS * (PAIR ? 2 : 1));
     }
     mbar_init(accum_full, 1);
     mbar_init(norm_full, 1);
@@ -165,7 +173,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (SPLIT3) tma_prefetch_desc(&tmB_lo);
     if (GDN) { tma_prefetch_desc(&tmG_hi); if (SPLIT3) tma_prefetch_desc(&tmG_lo); }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {   // per-channel epilogue constants
     const int c = threadIdx.x - 64;
     s_bias[c] = (p.bias && c < (KIND == B2C_TC_DECONV3 ? 3 : 128)) ? __ldg(p.bias + c) : 0.f;
@@ -173,6 +184,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / TMA signal
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -197,59 +209,97 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           int dy, dx, cb, group;
           decode_step<KIND>(s, phase, dy, dx, cb, group);
           const uint32_t a_bytes = SOFT_A ? 0u : (uint32_t)SLOT_BYTES;
-          mbar_arrive_expect_tx(&full[stage], (a_bytes + B_BYTES) * (SPLIT3 ? 2u : 1u));
-          if (!SOFT_A) {
+          if (PAIR) {
+            // bytes of BOTH CTAs are counted on the leader's barrier
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2u * (a_bytes + B_BYTES) * (SPLIT3 ? 2u : 1u));
             const int cx = ox0 * IN_STRIDE + dx, cy = oy0 * IN_STRIDE + dy;
-            tma_load_4d(a_hi, &tmA_hi, &full[stage], cb * KBLK, cx, cy, n_img);
-            if (SPLIT3) tma_load_4d(a_lo, &tmA_lo, &full[stage], cb * KBLK, cx, cy, n_img);
+            const int brow = group * N_TILE + (int)cta_rank * (N_TILE / 2);
+            tma_load_4d_pair(a_hi, &tmA_hi, &full[stage], cb * KBLK, cx, cy, n_img);
+            if (SPLIT3) tma_load_4d_pair(a_lo, &tmA_lo, &full[stage], cb * KBLK, cx, cy, n_img);
+            tma_load_2d_pair(b_hi, &tmB_hi, &full[stage], cb * KBLK, brow);
+            if (SPLIT3) tma_load_2d_pair(b_lo, &tmB_lo, &full[stage], cb * KBLK, brow);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], (a_bytes + B_BYTES) * (SPLIT3 ? 2u : 1u));
+            if (!SOFT_A) {
+              const int cx = ox0 * IN_STRIDE + dx, cy = oy0 * IN_STRIDE + dy;
+              tma_load_4d(a_hi, &tmA_hi, &full[stage], cb * KBLK, cx, cy, n_img);
+              if (SPLIT3) tma_load_4d(a_lo, &tmA_lo, &full[stage], cb * KBLK, cx, cy, n_img);
+            }
+            tma_load_2d(b_hi, &tmB_hi, &full[stage], cb * KBLK, group * N_TILE);
+            if (SPLIT3) tma_load_2d(b_lo, &tmB_lo, &full[stage], cb * KBLK, group * N_TILE);
           }
-          tma_load_2d(b_hi, &tmB_hi, &full[stage], cb * KBLK, group * N_TILE);
-          if (SPLIT3) tma_load_2d(b_lo, &tmB_lo, &full[stage], cb * KBLK, group * N_TILE);
         } else {
           const int g = s - nsteps;  // GDN k-block: gamma[:, g*64 .. g*64+63]
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)(C128 * KBLK * 2) * (SPLIT3 ? 2u : 1u));
-          tma_load_2d(b_hi, &tmG_hi, &full[stage], g * KBLK, 0);
-          if (SPLIT3) tma_load_2d(b_lo, &tmG_lo, &full[stage], g * KBLK, 0);
+          if (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&full[stage], (uint32_t)(C128 * KBLK * 2) * (SPLIT3 ? 2u : 1u));
+            tma_load_2d_pair(b_hi, &tmG_hi, &full[stage], g * KBLK, (int)cta_rank * (C128 / 2));
+            if (SPLIT3) tma_load_2d_pair(b_lo, &tmG_lo, &full[stage], g * KBLK, (int)cta_rank * (C128 / 2));
+          } else {
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)(C128 * KBLK * 2) * (SPLIT3 ? 2u : 1u));
+            tma_load_2d(b_hi, &tmG_hi, &full[stage], g * KBLK, 0);
+            if (SPLIT3) tma_load_2d(b_lo, &tmG_lo, &full[stage], g * KBLK, 0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_main = umma_idesc_bf16(N_TILE);
-      constexpr uint32_t idesc_gdn = umma_idesc_bf16(C128);
-      int soft_uses[STAGES];     // completed software-A fills per stage -> afull parity
-#pragma unroll
-      for (int i = 0; i < STAGES; ++i) soft_uses[i] = 0;
+    // The whole warp runs the (warp-uniform) loop and one elected lane issues: descriptors, TMEM addresses and
+    // loop state then live in uniform registers.  (A single-lane region forced a R2UR/ELECT round trip in front
+    // of every UTCHMMA and made the kernel MMA-issue bound at ~100 clk per instruction.)
+    if (leader) {
+      constexpr uint32_t idesc_main = PAIR ? umma_idesc_bf16_m256(N_TILE) : umma_idesc_bf16(N_TILE);
+      constexpr uint32_t idesc_gdn = PAIR ? umma_idesc_bf16_m256(C128) : umma_idesc_bf16(C128);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint64_t desc0 = umma_desc_sw128(sbase);     // + (byte offset >> 4) selects a tile / K slice
+      uint32_t soft_phase = 0;                            // bit per stage: parity of the next software-A fill
       for (int s = 0; s < total_steps; ++s) {
         const int stage = s % STAGES, it = s / STAGES;
         const bool is_gdn = s >= nsteps;
         mbar_wait(&full[stage], it & 1);
         if (SOFT_A || is_gdn) {
-          mbar_wait(&afull[stage], soft_uses[stage] & 1);
-          ++soft_uses[stage];
+          if (PAIR) mbar_wait_cluster(&afull[stage], (soft_phase >> stage) & 1u);
+          else mbar_wait(&afull[stage], (soft_phase >> stage) & 1u);
+          soft_phase ^= 1u << stage;
         }
         tcgen05_fence_after();
-        TC_MARK(1);
-        const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + SLOT_BYTES;
-        const uint32_t b_hi = st + (SPLIT3 ? 2 : 1) * SLOT_BYTES, b_lo = b_hi + SLOT_BYTES;
-        const uint32_t d = tmem_base + (is_gdn ? (uint32_t)C128 : 0u);
+        if (lane == 0) TC_MARK(1);
+        const uint32_t off = (uint32_t)(stage * STAGE_BYTES);
+        const uint64_t a_hi = desc0 + (off >> 4), a_lo = a_hi + (SLOT_BYTES >> 4);
+        const uint64_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * SLOT_BYTES) >> 4), b_lo = b_hi + (SLOT_BYTES >> 4);
+        const uint32_t d = tb + (is_gdn ? (uint32_t)C128 : 0u);
         const uint32_t idesc = is_gdn ? idesc_gdn : idesc_main;
-        const int first = is_gdn ? nsteps : 0;
+        const uint32_t acc0 = (s > (is_gdn ? nsteps : 0)) ? 1u : 0u;
+        if (elect_one()) {
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {  // 4 x (K = 16) per 64-wide k-block: +32 B inside the swizzle atom
-          const uint64_t da_hi = umma_desc_sw128(a_hi + k4 * 32), db_hi = umma_desc_sw128(b_hi + k4 * 32);
-          umma_bf16(d, da_hi, db_hi, idesc, (s > first || k4 > 0) ? 1u : 0u);
-          if (SPLIT3) {
-            const uint64_t da_lo = umma_desc_sw128(a_lo + k4 * 32), db_lo = umma_desc_sw128(b_lo + k4 * 32);
-            umma_bf16(d, da_hi, db_lo, idesc, 1u);
-            umma_bf16(d, da_lo, db_hi, idesc, 1u);
+          for (int k4 = 0; k4 < 4; ++k4) {  // 4 x (K = 16) per 64-wide k-block: +32 B inside the swizzle atom
+            const uint32_t acc = k4 > 0 ? 1u : acc0;
+            if (PAIR) {
+              umma_bf16_pair(d, a_hi + 2 * k4, b_hi + 2 * k4, idesc, acc);
+              if (SPLIT3) {
+                umma_bf16_pair(d, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1u);
+                umma_bf16_pair(d, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
+              }
+            } else {
+              umma_bf16(d, a_hi + 2 * k4, b_hi + 2 * k4, idesc, acc);
+              if (SPLIT3) {
+                umma_bf16(d, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1u);
+                umma_bf16(d, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1u);
+              }
+            }
+          }
+          if (PAIR) {
+            umma_commit_pair(&empty[stage]);
+            if (s == nsteps - 1) umma_commit_pair(accum_full);
+            if (GDN && s == total_steps - 1) umma_commit_pair(norm_full);
+          } else {
+            umma_commit(&empty[stage]);
+            if (s == nsteps - 1) umma_commit(accum_full);
+            if (GDN && s == total_steps - 1) umma_commit(norm_full);
           }
         }
-        umma_commit(&empty[stage]);
-        if (s == nsteps - 1) umma_commit(accum_full);
-        if (GDN && s == total_steps - 1) umma_commit(norm_full);
+        __syncwarp();
       }
     }
   } else {
@@ -367,7 +417,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           }
           fence_proxy_async_smem();
         }
-        mbar_arrive(&afull[stage]);
+        if (PAIR) mbar_arrive_leader(&afull[stage]);
+        else mbar_arrive(&afull[stage]);
       }
       TC_WMARK();
       mbar_wait(norm_full, 0);
@@ -532,9 +583,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer may still be reading this CTA's shared memory / signalling its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 #undef TC_MARK
 #undef TC_WMARK
@@ -712,10 +765,10 @@ static int make_image_map(CUtensorMap* m, const void* base, int B, int H, int W)
   return B2C_OK;
 }
 
-template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE>
+template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE, bool PAIR = false>
 static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStream_t stream) {
   constexpr size_t SMEM = TcCfg<SPLIT3, KIND>::SMEM;
-  auto kern = igemm_tc_kernel<N_TILE, SPLIT3, KIND, GDN, OUT_MODE>;
+  auto kern = igemm_tc_kernel<N_TILE, SPLIT3, KIND, GDN, OUT_MODE, PAIR>;
   {  // opt in to > 48 KB dynamic shared memory once per (instantiation, device); never during graph capture replays
     static std::mutex mu;
     static bool done[64] = {false};
@@ -743,11 +796,13 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
   }
   const int groups = KIND == B2C_TC_CONV1 ? 4 : (KIND == B2C_TC_DECONV3 ? 9 : 25);
   const int wcols = KIND == B2C_TC_CONV1 ? 64 : 128;
-  if ((rc = make_mat_map(&mB_hi, L->w_hi, groups * N_TILE, wcols, N_TILE))) return rc;
-  if (SPLIT3 && (rc = make_mat_map(&mB_lo, L->w_lo, groups * N_TILE, wcols, N_TILE))) return rc;
+  constexpr int BROWS = PAIR ? N_TILE / 2 : N_TILE;     // a CTA pair stages half of the weight rows per CTA
+  if ((rc = make_mat_map(&mB_hi, L->w_hi, groups * N_TILE, wcols, BROWS))) return rc;
+  if (SPLIT3 && (rc = make_mat_map(&mB_lo, L->w_lo, groups * N_TILE, wcols, BROWS))) return rc;
   if (GDN) {
-    if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C128, C128, C128))) return rc;
-    if (SPLIT3 && (rc = make_mat_map(&mG_lo, L->gamma_lo, C128, C128, C128))) return rc;
+    constexpr int GROWS = PAIR ? C128 / 2 : C128;
+    if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C128, C128, GROWS))) return rc;
+    if (SPLIT3 && (rc = make_mat_map(&mG_lo, L->gamma_lo, C128, C128, GROWS))) return rc;
   }
   TcOutMaps mO;
   memset(&mO, 0, sizeof(mO));
@@ -760,6 +815,24 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
       if (L->out_lo && (rc = make_out_map(&mO.m[4 + ph], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, ps, ry, rx)))
         return rc;
     }
+  }
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((grid.x + 1) & ~1u, grid.y, grid.z);     // an odd tile count gets one fully masked tile
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(pair): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+    count_launch();
+    return check_launch("tc_layer_run(pair)");
   }
   kern<<<grid, NTHREADS, SMEM, stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
   count_launch();
@@ -890,6 +963,20 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   dim3 grid(p.tiles_x * tiles_y, phases, L->B);
 
   const int key = L->kind * 1000 + (L->split3 ? 100 : 0) + L->gdn * 10 + (L->out_f32_nchw ? 1 : 0);
+  static const int use_pairs = [] {   // 0: off, 1: bf16x3 5x5 convs (default), 2: also the bf16 transposed convs
+    const char* e = getenv("B2C_TC_PAIRS");
+    return e ? atoi(e) : B2C_TC_PAIRS_DEFAULT;
+  }();
+  if (use_pairs) {
+    switch (key) {
+      case B2C_TC_CONV5S2 * 1000 + 100 + 10 + 0: return launch<128, true, B2C_TC_CONV5S2, 1, OUT_BF16, true>(L, p, grid, stream);
+      case B2C_TC_CONV5S2 * 1000 + 100 + 0 + 1: return launch<128, true, B2C_TC_CONV5S2, 0, OUT_F32_NCHW, true>(L, p, grid, stream);
+      case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 0:
+        if (use_pairs > 1) return launch<128, false, B2C_TC_DECONV5S2, 2, OUT_BF16, true>(L, p, grid, stream);
+        break;   // measured slower than two independent CTAs per SM for the bf16 kinds: opt-in only (B2C_TC_PAIRS=2)
+      default: break;
+    }
+  }
   switch (key) {
     // analysis transform (error-compensated)
     case B2C_TC_CONV1 * 1000 + 100 + 10 + 0: return launch<128, true, B2C_TC_CONV1, 1, OUT_BF16>(L, p, grid, stream);
