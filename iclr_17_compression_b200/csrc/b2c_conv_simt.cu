@@ -395,17 +395,25 @@ __global__ void __launch_bounds__(TG_THREADS) conv_wgrad_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------- channel sum
+// grid (C, splits): each block reduces a slice of the B*HW elements of one channel; with few channels
+// (deconv3 bias: C = 3) a single block per channel would serialise hundreds of thousands of loads.
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ t, float* __restrict__ out,
                                                           int B, int C, int HW) {
   __shared__ float red[32];
   const int c = blockIdx.x;
+  const size_t total = (size_t)B * HW;
+  const size_t per = (total + gridDim.y - 1) / gridDim.y;
+  const size_t i0 = blockIdx.y * per, i1 = min(total, i0 + per);
   float s = 0.f;
-  for (int n = 0; n < B; ++n) {
-    const float* p = t + ((size_t)n * C + c) * HW;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += __ldg(p + i);
+  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const size_t n = i / HW, r = i - n * HW;
+    s += __ldg(t + (n * C + c) * HW + r);
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) out[c] = s;
+  if (threadIdx.x == 0) {
+    if (gridDim.y == 1) out[c] = s;
+    else atomicAdd(out + c, s);
+  }
 }
 
 }  // namespace b2c
@@ -493,7 +501,16 @@ int b2c_conv_wgrad(const float* small_t, const float* big_t, float* dW, int B, i
 
 int b2c_channel_sum(const float* t, float* out, int B, int C, int HW, void* stream) {
   B2C_REQUIRE(t && out && B > 0 && C > 0 && HW > 0, "channel_sum: bad arguments");
-  channel_sum_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(t, out, B, C, HW);
+  const size_t total = (size_t)B * HW;
+  int splits = (int)((total + 8191) / 8192);                 // >= 8192 elements per block
+  const int max_splits = (148 * 4 + C - 1) / C;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 1) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("channel_sum: memset: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+  }
+  channel_sum_kernel<<<dim3(C, splits), 256, 0, (cudaStream_t)stream>>>(t, out, B, C, HW);
   count_launch();
   return check_launch("channel_sum");
 }
