@@ -75,6 +75,14 @@ class _Fork:
         self.used = []
         self.outs = []
 
+    @staticmethod
+    def _side(dev):
+        """a dedicated side stream for operand packing"""
+        key = (dev.index, "pack")
+        if key not in _Fork._streams:
+            _Fork._streams[key] = [torch.cuda.Stream(device=dev)]
+        return _Fork._streams[key][0]
+
     def run(self, fn, *inputs):
         s = self.sides[self.i % len(self.sides)]
         self.i += 1
@@ -114,16 +122,43 @@ class TrainStepTC(torch.autograd.Function):
         dev = x.device
         W1, W2, W3 = prm["Encoder.conv1.weight"], prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
         D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
+        # ---- operand packing: only conv1 / gdn1 are needed immediately; every other pack of the step (forward and
+        # dgrad forms, gamma and gamma^T) only depends on the parameters and runs on a side stream
+        main = torch.cuda.current_stream(dev)
+        w1p = T.pack_weights(T.TC_CONV1, W1, False)
         gp1 = T.pack_gdn(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], False)
-        gp2 = T.pack_gdn(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], False)
-        gi1 = T.pack_gdn(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], False)
-        gi2 = T.pack_gdn(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], False)
+        side = _Fork._side(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            pk = {
+                "w2": T.pack_weights(T.TC_CONV5S2, W2, False), "gp2": T.pack_gdn(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], False),
+                "w3": T.pack_weights(T.TC_CONV5S2, W3, False),
+                "d1": T.pack_weights(T.TC_DECONV5S2, D1, False), "gi1": T.pack_gdn(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], False),
+                "d2": T.pack_weights(T.TC_DECONV5S2, D2, False), "gi2": T.pack_gdn(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], False),
+                "d3": T.pack_weights(T.TC_DECONV3, D3, False),
+            }
+            ev_fwd = torch.cuda.Event()
+            ev_fwd.record(side)
+            pk.update({     # backward forms
+                "d3_dg": T.pack_weights(T.TC_CONV1, D3, False), "gi2_t": T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"]),
+                "d2_dg": T.pack_weights(T.TC_CONV5S2, D2, False), "gi1_t": T.pack_gdn_t(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"]),
+                "d1_dg": T.pack_weights(T.TC_CONV5S2, D1, False),
+                "w3_dg": T.pack_weights(T.TC_DECONV5S2, W3, False), "gp2_t": T.pack_gdn_t(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"]),
+                "w2_dg": T.pack_weights(T.TC_DECONV5S2, W2, False), "gp1_t": T.pack_gdn_t(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"]),
+            })
+            ev_bwd = torch.cuda.Event()
+            ev_bwd.record(side)
+        for v in pk.values():
+            for t in v:
+                if t is not None:
+                    t.record_stream(main)
         # ---- analysis transform
-        h1, n1 = T.layer_run(T.TC_CONV1, x, None, T.pack_weights(T.TC_CONV1, W1, False), prm["Encoder.conv1.bias"],
-                             gdn=gp1, gdn_mode=1, second_plane=True)
-        h2, n2 = T.layer_run(T.TC_CONV5S2, h1, None, T.pack_weights(T.TC_CONV5S2, W2, False),
-                             prm["Encoder.conv2.bias"], gdn=gp2, gdn_mode=1, second_plane=True)
-        y = T.layer_run(T.TC_CONV5S2, h2, None, T.pack_weights(T.TC_CONV5S2, W3, False), None, out_f32_nchw=True)
+        h1, n1 = T.layer_run(T.TC_CONV1, x, None, w1p, prm["Encoder.conv1.bias"], gdn=gp1, gdn_mode=1,
+                             second_plane=True)
+        main.wait_event(ev_fwd)
+        h2, n2 = T.layer_run(T.TC_CONV5S2, h1, None, pk["w2"], prm["Encoder.conv2.bias"], gdn=pk["gp2"], gdn_mode=1,
+                             second_plane=True)
+        y = T.layer_run(T.TC_CONV5S2, h2, None, pk["w3"], None, out_f32_nchw=True)
         # ---- quantizer (noise) + bits
         bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
         C, HW = 128, y.shape[2] * y.shape[3]
@@ -137,12 +172,11 @@ class TrainStepTC(torch.autograd.Function):
         total_bits = image_bits.sum()
         # ---- synthesis transform
         zh, _ = T.nchw_to_nhwc(z, False)
-        i1, m1 = T.layer_run(T.TC_DECONV5S2, zh, None, T.pack_weights(T.TC_DECONV5S2, D1, False),
-                             prm["Decoder.deconv1.bias"], gdn=gi1, gdn_mode=2, second_plane=True)
-        i2, m2 = T.layer_run(T.TC_DECONV5S2, i1, None, T.pack_weights(T.TC_DECONV5S2, D2, False),
-                             prm["Decoder.deconv2.bias"], gdn=gi2, gdn_mode=2, second_plane=True)
-        recon = T.layer_run(T.TC_DECONV3, i2, None, T.pack_weights(T.TC_DECONV3, D3, False), prm["Decoder.deconv3.bias"],
-                            out_f32_nchw=True)
+        i1, m1 = T.layer_run(T.TC_DECONV5S2, zh, None, pk["d1"], prm["Decoder.deconv1.bias"], gdn=pk["gi1"], gdn_mode=2,
+                             second_plane=True)
+        i2, m2 = T.layer_run(T.TC_DECONV5S2, i1, None, pk["d2"], prm["Decoder.deconv2.bias"], gdn=pk["gi2"], gdn_mode=2,
+                             second_plane=True)
+        recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
         # ---- distortion
         clipped = torch.empty_like(recon)
         sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
@@ -152,7 +186,9 @@ class TrainStepTC(torch.autograd.Function):
             _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, x[0].numel(), _p(ws), nbytes,
                                              _stream()), "clamp_sse_fwd")
         sse_total = sse[:, 0].sum()
+        main.wait_event(ev_bwd)          # the backward packs are done long before; keeps stream bookkeeping simple
         ctx.prm = prm
+        ctx.pk = pk
         ctx.saved = (x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon)
         ctx.stats = (image_bits, plane_bits, sse)
         ctx.mark_non_differentiable(clipped, z)
@@ -161,7 +197,7 @@ class TrainStepTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _g_clipped, g_sse, g_bits, _g_z):
         lib = _lib.load()
-        prm = ctx.prm
+        prm, pk = ctx.prm, ctx.pk
         x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon = ctx.saved
         dev = x.device
         B = x.shape[0]
@@ -196,39 +232,35 @@ class TrainStepTC(torch.autograd.Function):
         D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
         grads["Decoder.deconv3.weight"] = fork.run(lambda: T.wgrad9(i2, g_recon), g_recon)
         grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon), g_recon)
-        gt = T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"])
-        gp_d2, dn2 = T.layer_run(T.TC_CONV1, g_recon, None, T.pack_weights(T.TC_CONV1, D3, False), None, gdn=gt,
+        gp_d2, dn2 = T.layer_run(T.TC_CONV1, g_recon, None, pk["d3_dg"], None, gdn=pk["gi2_t"],
                                  gdn_mode=4, second_plane=True, saved=(i2, m2))
         grads["Decoder.igdn2.beta"], grads["Decoder.igdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
             prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn2, True), dn2)
         # ---- deconv2
         grads["Decoder.deconv2.weight"] = fork.run(lambda: T.wgrad(i1, gp_d2, 5, 2, 2), gp_d2)
         grads["Decoder.deconv2.bias"] = fork.run(lambda: _colsum(gp_d2), gp_d2)
-        gt = T.pack_gdn_t(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"])
-        gp_d1, dn1 = T.layer_run(T.TC_CONV5S2, gp_d2, None, T.pack_weights(T.TC_CONV5S2, D2, False), None, gdn=gt,
+        gp_d1, dn1 = T.layer_run(T.TC_CONV5S2, gp_d2, None, pk["d2_dg"], None, gdn=pk["gi1_t"],
                                  gdn_mode=4, second_plane=True, saved=(i1, m1))
         grads["Decoder.igdn1.beta"], grads["Decoder.igdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
             prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn1, True), dn1)
         # ---- deconv1
         grads["Decoder.deconv1.weight"] = fork.run(lambda: T.wgrad(zh, gp_d1, 5, 2, 2), gp_d1)
         grads["Decoder.deconv1.bias"] = fork.run(lambda: _colsum(gp_d1), gp_d1)
-        g_z = T.layer_run(T.TC_CONV5S2, gp_d1, None, T.pack_weights(T.TC_CONV5S2, D1, False), None, out_f32_nchw=True)
+        g_z = T.layer_run(T.TC_CONV5S2, gp_d1, None, pk["d1_dg"], None, out_f32_nchw=True)
         fork.main.wait_stream(fork.sides[0])               # dz comes from the entropy backward (first forked task)
         g_y = g_z + dz                                     # z = y + noise -> dz/dy = 1
         gyh, _ = T.nchw_to_nhwc(g_y, False)
         # ---- conv3 (no bias): wgrad, dgrad (= transposed conv) + GDN2 backward fused
         W1, W2, W3 = prm["Encoder.conv1.weight"], prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
         grads["Encoder.conv3.weight"] = fork.run(lambda: T.wgrad(gyh, h2, 5, 2, 2), gyh)
-        gt = T.pack_gdn_t(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"])
-        gp_c2, dng2 = T.layer_run(T.TC_DECONV5S2, gyh, None, T.pack_weights(T.TC_DECONV5S2, W3, False), None, gdn=gt,
+        gp_c2, dng2 = T.layer_run(T.TC_DECONV5S2, gyh, None, pk["w3_dg"], None, gdn=pk["gp2_t"],
                                   gdn_mode=3, second_plane=True, saved=(h2, n2))
         grads["Encoder.gdn2.beta"], grads["Encoder.gdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
             prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dng2, False), dng2)
         # ---- conv2
         grads["Encoder.conv2.weight"] = fork.run(lambda: T.wgrad(gp_c2, h1, 5, 2, 2), gp_c2)
         grads["Encoder.conv2.bias"] = fork.run(lambda: _colsum(gp_c2), gp_c2)
-        gt = T.pack_gdn_t(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"])
-        gp_c1, dng1 = T.layer_run(T.TC_DECONV5S2, gp_c2, None, T.pack_weights(T.TC_DECONV5S2, W2, False), None, gdn=gt,
+        gp_c1, dng1 = T.layer_run(T.TC_DECONV5S2, gp_c2, None, pk["w2_dg"], None, gdn=pk["gp1_t"],
                                   gdn_mode=3, second_plane=True, saved=(h1, n1))
         grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
             prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dng1, False), dng1)
@@ -237,6 +269,7 @@ class TrainStepTC(torch.autograd.Function):
         grads["Encoder.conv1.bias"] = fork.run(lambda: _colsum(gp_c1), gp_c1)
         fork.join()
         ctx.saved = None
+        ctx.pk = None
         return (None, None) + tuple(grads[k].reshape(prm[k].shape) for k in PARAM_ORDER)
 
 
