@@ -284,18 +284,13 @@ def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
     if os.environ.get("B2C_TRAIN_GRAPH", "1") == "1" and getattr(model, "fast_training", False):
         from iclr_17_compression_b200.train_tc import GraphedTrainStep
         if sync is not None:
-            sync.remove()                                      # hooks do not fire inside a graph replay
+            sync.remove()                                      # hooks do not fire inside a graph replay;
+            sync = None                                        # the graphed step all-reduces its flat gradient buffer
         graphed = GraphedTrainStep(model, xb, 8192.0)
-        if sync is not None:
-            from iclr_17_compression_b200.ddp import GradSync
-            sync = GradSync(model, broadcast_parameters=False)
-            sync.remove()
 
     def tstep():
         if graphed is not None:
             graphed(xb)
-            if sync is not None:
-                sync.reduce_now()
             return
         for p in model.parameters():
             p.grad = None
@@ -327,7 +322,7 @@ def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
     return {"metric": "train img/s (batch 8 of 3x256x256 per GPU, fwd+bwd, noise quantizer, lambda=8192)",
             "value": 8 * world / (ms / 1e3), "unit": "img/s", "ms_per_step": ms,
             "allreduce": ("none (1 GPU)" if world == 1 else
-                          "nccl bucketed after the graphed step" if graphed is not None else
+                          "one NCCL all-reduce (mean) of the flat 7 MB gradient buffer after the graphed step" if graphed is not None else
                           "nccl bucketed, overlapped with backward"),
             "path": getattr(model, "last_path", None), "cuda_graph": graphed is not None,
             "ops": {k: round(v["ms_total"] / steps, 4) for k, v in sorted(ops.items(), key=lambda kv: -kv[1]["ms_total"])},

@@ -154,7 +154,7 @@ class ImageCompressor(nn.Module):
             x = B2F._prep(x, "input image")
             clipped_recon_image, mse_loss, bpp_feature, z = train_forward(self, x, self._noise(x))
             self.last_path = "tcgen05-bf16-train"
-            self.last = {"mse_loss": mse_loss}
+            self.last = {"mse_loss": mse_loss.detach()}      # detached: must not keep the autograd graph alive
             if self.return_mode == "mse":
                 return clipped_recon_image, mse_loss, bpp_feature
             return clipped_recon_image, z, bpp_feature
@@ -176,7 +176,7 @@ class ImageCompressor(nn.Module):
             clipped_recon_image, sse_total, sse = B2F.distortion(recon_image, x)
         mse_loss = sse_total / x.numel()                                   # model.py:61
         bpp_feature = total_bits / (x.size(0) * x.size(2) * x.size(3))      # model.py:78
-        self.last = {"image_bits": image_bits, "plane_bits": plane_bits, "sse": sse, "mse_loss": mse_loss}
+        self.last = {"image_bits": image_bits, "plane_bits": plane_bits, "sse": sse, "mse_loss": mse_loss.detach()}
         if self.return_mode == "mse":
             return clipped_recon_image, mse_loss, bpp_feature
         return clipped_recon_image, z, bpp_feature

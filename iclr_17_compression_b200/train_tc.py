@@ -283,29 +283,42 @@ def train_forward(model, x, noise):
 
 
 class GraphedTrainStep:
-    """Whole-step CUDA graph (forward + backward [+ gradient all-reduce hooks are NOT captured]) for a fixed input
-    shape: the ~70 kernel launches and their TMA descriptors replay as one submission, so the step is not host
-    bound.  Usage: step = GraphedTrainStep(model, x_example, lam); loss = step(x, noise) -> grads in p.grad."""
+    """Whole-step CUDA graph (forward + backward + gradient flattening) for a fixed input shape: the ~110 kernel
+    launches and their TMA descriptors replay as one submission, so the step is not host bound.  The gradients of
+    all 30 tensors are gathered into ONE flat fp32 buffer inside the graph and ``p.grad`` are views of it, so data
+    parallel training needs a single NCCL all-reduce (mean) of 7 MB per step and no per-tensor copies.
 
-    def __init__(self, model, x_example, lam=8192.0, warmup=3):
-        self.model, self.lam = model, lam
+        step = GraphedTrainStep(model, x_example, lam)      # after torch.distributed init when multi-GPU
+        loss = step(x)                                       # p.grad holds the (averaged) gradients
+    """
+
+    def __init__(self, model, x_example, lam=8192.0, warmup=3, group=None):
+        import torch.distributed as dist
+        self.model, self.lam, self.group = model, lam, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.x = x_example.clone()
         N = model.out_channel_N
-        self.noise = torch.zeros(x_example.size(0), N, x_example.size(2) // 16, x_example.size(3) // 16,
-                                 device=x_example.device)
+        dev = self.x.device
+        self.noise = torch.zeros(x_example.size(0), N, x_example.size(2) // 16, x_example.size(3) // 16, device=dev)
         self.params = [p for p in model.parameters()]
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        views, o = [], 0
+        for p in self.params:
+            views.append(self.flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+        self.views = views
         prev_override, prev_mode = model.noise_override, model.return_mode
         model.noise_override, model.return_mode = self.noise, "mse"
-        side = torch.cuda.Stream(device=self.x.device)
-        side.wait_stream(torch.cuda.current_stream(self.x.device))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 for p in self.params:
                     p.grad = None
                 _, mse, bpp = model(self.x)
                 (lam * mse + bpp).backward()
-        torch.cuda.current_stream(self.x.device).wait_stream(side)
-        torch.cuda.synchronize(self.x.device)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         for p in self.params:
             p.grad = None
@@ -313,6 +326,9 @@ class GraphedTrainStep:
             _, self.mse, self.bpp = model(self.x)
             self.loss = lam * self.mse + self.bpp
             self.loss.backward()
+            torch._foreach_copy_(self.views, [p.grad for p in self.params])
+        for p, v in zip(self.params, self.views):
+            p.grad = v                                   # optimizers read the flat buffer through these views
         model.noise_override, model.return_mode = prev_override, prev_mode
 
     def __call__(self, x, noise=None):
@@ -322,4 +338,7 @@ class GraphedTrainStep:
         else:
             self.noise.copy_(noise, non_blocking=True)
         self.graph.replay()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
         return self.loss

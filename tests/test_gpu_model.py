@@ -267,3 +267,27 @@ def test_tc_train_step_gradients(name):
     _, mse2, bpp2 = m(c.x.cuda())
     assert m.last_path == "fp32"
     assert abs(mse2.item() - mse.item()) <= 2e-3 * mse2.item()
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (whole-step CUDA graph, flat gradient buffer) reproduces the eager tensor-core step."""
+    from iclr_17_compression_b200.train_tc import GraphedTrainStep
+    c = Case("train_W1_S_n128_64")
+    m = _model(c, return_mode="mse").train()
+    x, noise = c.x.cuda(), c.noise.cuda()
+    m.noise_override = noise
+    _, mse, bpp = m(x)
+    loss_t = c.lam * mse + bpp
+    loss_t.backward()
+    eager_loss = loss_t.item()
+    eager = {k: p.grad.clone() for k, p in m.named_parameters()}
+    del mse, bpp, loss_t, _          # drop the eager autograd graph (its AccumulateGrad nodes live on the legacy stream)
+    m.noise_override = None
+    step = GraphedTrainStep(m, x, c.lam)
+    for _ in range(2):
+        loss = step(x, noise)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - eager_loss) <= 1e-4 * abs(eager_loss)
+    for k, p in m.named_parameters():
+        assert p.grad.data_ptr() >= step.flat.data_ptr()                      # views of the flat buffer
+        assert _rel(p.grad, eager[k]) < 2e-3, (k, _rel(p.grad, eager[k]))      # atomics reorder sums slightly
