@@ -42,17 +42,18 @@ class TcLayer(ctypes.Structure):
                 ("B", _c_i), ("Hin", _c_i), ("Win", _c_i),
                 ("in_hi", _c_f), ("in_lo", _c_f), ("w_hi", _c_f), ("w_lo", _c_f), ("bias", _c_f),
                 ("gamma_hi", _c_f), ("gamma_lo", _c_f), ("beta_eff", _c_f), ("out_hi", _c_f), ("out_lo", _c_f),
-                ("ref_image", _c_f), ("sse_partial", _c_f), ("saved_y", _c_f), ("saved_n", _c_f)]
+                ("ref_image", _c_f), ("sse_partial", _c_f), ("saved_y", _c_f), ("saved_n", _c_f),
+                ("channels", _c_i)]
 
 
 TC_CONV1, TC_CONV5S2, TC_DECONV5S2, TC_DECONV3 = 0, 1, 2, 3
 
 SIGNATURES.update({
-    "b2c_tc_packed_weight_elems": (_c_sz, [_c_i]),
-    "b2c_tc_pack_weights": (_c_i, [_c_i, _c_f, _c_f, _c_f, _c_f]),
-    "b2c_tc_pack_gdn": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_f, _c_f]),
+    "b2c_tc_packed_weight_elems": (_c_sz, [_c_i, _c_i]),
+    "b2c_tc_pack_weights": (_c_i, [_c_i, _c_i, _c_f, _c_f, _c_f, _c_f]),
+    "b2c_tc_pack_gdn": (_c_i, [_c_i, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f]),
     "b2c_tc_layer_run": (_c_i, [ctypes.POINTER(TcLayer), _c_f]),
-    "b2c_tc_pack_gdn_t": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_f]),
+    "b2c_tc_pack_gdn_t": (_c_i, [_c_i, _c_f, _c_f, _c_f, _c_f, _c_f]),
     "b2c_tc_tiles_per_image": (_c_i, [_c_i, _c_i, _c_i]),
     "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
     "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),

@@ -33,9 +33,9 @@ constexpr int TH = 8, TW = 16;            // output tile (pixels)
 constexpr int TILE_M = TH * TW;           // 128
 constexpr int KBLK = 64;                  // bf16 per k-block row (128 B)
 constexpr int SLOT_BYTES = TILE_M * KBLK * 2;  // 16 KB operand slot
-constexpr int NWORKERS = 256;             // 8 row-worker warps
-constexpr int NTHREADS = 64 + NWORKERS;   // + TMA producer warp + MMA warp
-constexpr int C128 = 128;
+// channels C in {128, 192, 256}: C/64 k-blocks per tap, C/64 row workers per tile row (64 channels each)
+constexpr int nworkers(int C) { return 128 * (C / 64); }
+constexpr int nthreads(int C) { return 64 + nworkers(C); }   // + TMA producer warp + MMA warp
 
 enum { OUT_BF16 = 0, OUT_F32_NCHW = 1, OUT_F32_NCHW_PS4 = 2 };
 
@@ -57,32 +57,32 @@ struct TcParams {
   long long* trace;     // debug: clock64 timeline of CTA (0,0,0): [3 roles][64 marks]
 };
 
-template <int KIND>
+template <int KIND, int NCB>
 __device__ __forceinline__ int num_steps(int phase) {
   if (KIND == B2C_TC_CONV1) return 4;
-  if (KIND == B2C_TC_CONV5S2) return 50;
-  if (KIND == B2C_TC_DECONV3) return 18;
-  const int ry = phase >> 1, rx = phase & 1;  // DECONV5S2: (3-ry) x (3-rx) taps x 2 channel blocks
-  return (3 - ry) * (3 - rx) * 2;
+  if (KIND == B2C_TC_CONV5S2) return 25 * NCB;
+  if (KIND == B2C_TC_DECONV3) return 9 * NCB;
+  const int ry = phase >> 1, rx = phase & 1;  // DECONV5S2: (3-ry) x (3-rx) taps x NCB channel blocks
+  return (3 - ry) * (3 - rx) * NCB;
 }
 
 // step -> A box offset (dy, dx in input pixels), channel block, weight-panel group
-template <int KIND>
+template <int KIND, int NCB>
 __device__ __forceinline__ void decode_step(int s, int phase, int& dy, int& dx, int& cb, int& group) {
   if (KIND == B2C_TC_CONV1) {
     dy = dx = 0; cb = 0; group = s;
   } else if (KIND == B2C_TC_CONV5S2) {
-    cb = s & 1;
-    const int t = s >> 1, ky = t / 5, kx = t - ky * 5;
+    cb = s % NCB;
+    const int t = s / NCB, ky = t / 5, kx = t - ky * 5;
     dy = ky - 2; dx = kx - 2; group = t;                 // iy = 2*oy - 2 + ky
   } else if (KIND == B2C_TC_DECONV3) {
-    cb = s & 1;
-    const int t = s >> 1, sy = t / 3, sx = t - sy * 3;
+    cb = s % NCB;
+    const int t = s / NCB, sy = t / 3, sx = t - sy * 3;
     dy = sy - 1; dx = sx - 1; group = t;                 // iy = my + dy
   } else {                                               // DECONV5S2: ky = ry + 2 - 2*dy, dy = 1 - jy
     const int ry = phase >> 1, rx = phase & 1;
-    cb = s & 1;
-    const int t = s >> 1, ntx = 3 - rx, jy = t / ntx, jx = t - jy * ntx;
+    cb = s % NCB;
+    const int t = s / NCB, ntx = 3 - rx, jy = t / ntx, jx = t - jy * ntx;
     dy = 1 - jy; dx = 1 - jx;
     group = (ry + 2 * jy) * 5 + (rx + 2 * jx);
   }
@@ -96,33 +96,50 @@ struct TcOutMaps {
   CUtensorMap m[8];   // [0..3] primary plane (conv: [0]; deconv: per phase), [4..7] second plane (lo / norm / dnorm)
 };
 
-template <bool SPLIT3, int KIND>
+template <int C, bool SPLIT3, int KIND, int GDN>
 struct TcCfg {
-  static constexpr int STAGES = (KIND == B2C_TC_CONV1 && SPLIT3) ? B2C_CONV1_STAGES : 3;
-  // DECONV3's weight tile is 48 rows (6 KB): 24 KB stages, three CTAs per SM keep 9 stages in flight
-  static constexpr int STAGE_BYTES = (KIND == B2C_TC_DECONV3) ? SLOT_BYTES + 8192 : (SPLIT3 ? 4 : 2) * SLOT_BYTES;
+  static constexpr int NCB = C / KBLK;
+  // weight / gamma tile: C rows of 128 B (DECONV3: 48 rows = 6 KB in an 8 KB slot)
+  static constexpr int B_SLOT = (KIND == B2C_TC_DECONV3) ? 8192 : C * 128;
+  static constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (SLOT_BYTES + B_SLOT);
   static constexpr int PATCH = (KIND == B2C_TC_CONV1) ? P1_SLOT : 0;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + PATCH + 1024 /*align*/ + 1024 /*bias, beta*/ + 256 /*barriers*/;
-  static constexpr int MIN_CTAS = (SMEM <= 75 * 1024) ? 3 : (SMEM <= 113 * 1024) ? 2 : 1;
+  static constexpr int EXTRA = 1024 /*align*/ + 2048 /*bias, beta*/ + 256 /*barriers*/;
+  static constexpr int N_TILE = (KIND == B2C_TC_DECONV3) ? 48 : C;
+  static constexpr int TMEM_COLS = GDN ? (2 * C <= 256 ? 256 : 512) : (N_TILE <= 64 ? 64 : (N_TILE <= 128 ? 128 : 256));
+  static constexpr int MAX_SMEM = 227 * 1024;
+  static constexpr int STAGES =
+      (KIND == B2C_TC_CONV1 && SPLIT3 && C == 128) ? B2C_CONV1_STAGES
+                                                   : ((3 * STAGE_BYTES + PATCH + EXTRA <= MAX_SMEM)
+                                                          ? 3
+                                                          : ((2 * STAGE_BYTES + PATCH + EXTRA <= MAX_SMEM) ? 2 : 1));
+  static constexpr int SMEM = STAGES * STAGE_BYTES + PATCH + EXTRA;
+  static_assert(SMEM <= MAX_SMEM, "shared memory budget");
+  static constexpr int BY_SMEM = (SMEM <= 75 * 1024) ? 3 : (SMEM <= 113 * 1024) ? 2 : 1;
+  static constexpr int BY_TMEM = 512 / TMEM_COLS;
+  static constexpr int MIN_CTAS = BY_SMEM < BY_TMEM ? BY_SMEM : BY_TMEM;
 };
 
-template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE, bool PAIR>
-__global__ void __launch_bounds__(NTHREADS, TcCfg<SPLIT3, KIND>::MIN_CTAS)
+template <int C, bool SPLIT3, int KIND, int GDN, int OUT_MODE, bool PAIR>
+__global__ void __launch_bounds__(nthreads(C), TcCfg<C, SPLIT3, KIND, GDN>::MIN_CTAS)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                 const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo,
                 const __grid_constant__ TcOutMaps tmO, const TcParams p) {
-  using Cfg = TcCfg<SPLIT3, KIND>;
+  using Cfg = TcCfg<C, SPLIT3, KIND, GDN>;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NCB = Cfg::NCB;                // 64-channel k-blocks (and row workers per tile row)
+  constexpr int N_TILE = Cfg::N_TILE;
+  constexpr int B_SLOT = Cfg::B_SLOT;
+  constexpr int NWORKERS = nworkers(C);
   constexpr int IN_STRIDE = (KIND == B2C_TC_CONV5S2) ? 2 : 1;
   constexpr bool SOFT_A = (KIND == B2C_TC_CONV1);
-  constexpr uint32_t TMEM_COLS = GDN ? 256 : (N_TILE > 64 ? 128 : 64);
+  constexpr uint32_t TMEM_COLS = Cfg::TMEM_COLS;
   // PAIR: two CTAs (adjacent tiles) form a cta_group::2 pair: one M = 256 MMA per step issued by the leader,
   // each CTA stages its own A tile and HALF of the weight tile, halving B fill and B operand reads per SM.
-  static_assert(!PAIR || (KIND != B2C_TC_CONV1 && N_TILE == 128), "CTA pairs: TMA-fed 128-channel kinds only");
+  static_assert(!PAIR || (KIND != B2C_TC_CONV1 && KIND != B2C_TC_DECONV3), "CTA pairs: TMA-fed C-channel kinds only");
   constexpr uint32_t B_BYTES = N_TILE * KBLK * 2 / (PAIR ? 2 : 1);
-  static_assert(GDN == 0 || N_TILE == 128, "fused GDN needs all 128 channels in the tile");
+  static_assert(GDN == 0 || N_TILE == C, "fused GDN needs all channels in the tile");
   // GDN: 0 none, 1 GDN forward, 2 IGDN forward, 3 GDN backward, 4 IGDN backward (epilogue of the dgrad conv)
   constexpr bool GDN_BWD = (GDN == 3 || GDN == 4);
   static_assert(!GDN_BWD || !SPLIT3, "the GDN backward epilogue is bf16 only");
@@ -131,8 +148,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* patch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);   // CONV1 only
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + Cfg::PATCH);
-  float* s_beta = s_bias + 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+  float* s_beta = s_bias + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 512);
   uint64_t* full = bars;                    // [STAGES] TMA bytes landed
   uint64_t* empty = bars + STAGES;          // [STAGES] MMAs that read the stage completed
   uint64_t* afull = bars + 2 * STAGES;      // [STAGES] software-written A tile ready (NWORKERS arrivals)
@@ -146,8 +163,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int n_img = blockIdx.z;
   const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
   const int oy0 = tile_y * TH, ox0 = tile_x * TW;
-  const int nsteps = num_steps<KIND>(phase);
-  const int total_steps = nsteps + (GDN ? 2 : 0);
+  const int nsteps = num_steps<KIND, NCB>(phase);
+  const int total_steps = nsteps + (GDN ? NCB : 0);
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -177,9 +194,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
     else tmem_alloc(tmem_slot, TMEM_COLS);
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {   // per-channel epilogue constants
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + C) {   // per-channel epilogue constants
     const int c = threadIdx.x - 64;
-    s_bias[c] = (p.bias && c < (KIND == B2C_TC_DECONV3 ? 3 : 128)) ? __ldg(p.bias + c) : 0.f;
+    s_bias[c] = (p.bias && c < (KIND == B2C_TC_DECONV3 ? 3 : C)) ? __ldg(p.bias + c) : 0.f;
     s_beta[c] = (GDN && p.beta_eff) ? __ldg(p.beta_eff + c) : 1.f;
   }
   tcgen05_fence_before();
@@ -204,10 +221,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         uint8_t* a_hi = st;
         uint8_t* a_lo = st + SLOT_BYTES;
         uint8_t* b_hi = st + (SPLIT3 ? 2 : 1) * SLOT_BYTES;
-        uint8_t* b_lo = b_hi + SLOT_BYTES;
+        uint8_t* b_lo = b_hi + B_SLOT;
         if (s < nsteps) {
           int dy, dx, cb, group;
-          decode_step<KIND>(s, phase, dy, dx, cb, group);
+          decode_step<KIND, NCB>(s, phase, dy, dx, cb, group);
           const uint32_t a_bytes = SOFT_A ? 0u : (uint32_t)SLOT_BYTES;
           if (PAIR) {
             // bytes of BOTH CTAs are counted on the leader's barrier
@@ -231,11 +248,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         } else {
           const int g = s - nsteps;  // GDN k-block: gamma[:, g*64 .. g*64+63]
           if (PAIR) {
-            if (leader) mbar_arrive_expect_tx(&full[stage], (uint32_t)(C128 * KBLK * 2) * (SPLIT3 ? 2u : 1u));
-            tma_load_2d_pair(b_hi, &tmG_hi, &full[stage], g * KBLK, (int)cta_rank * (C128 / 2));
-            if (SPLIT3) tma_load_2d_pair(b_lo, &tmG_lo, &full[stage], g * KBLK, (int)cta_rank * (C128 / 2));
+            if (leader) mbar_arrive_expect_tx(&full[stage], (uint32_t)(C * KBLK * 2) * (SPLIT3 ? 2u : 1u));
+            tma_load_2d_pair(b_hi, &tmG_hi, &full[stage], g * KBLK, (int)cta_rank * (C / 2));
+            if (SPLIT3) tma_load_2d_pair(b_lo, &tmG_lo, &full[stage], g * KBLK, (int)cta_rank * (C / 2));
           } else {
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)(C128 * KBLK * 2) * (SPLIT3 ? 2u : 1u));
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)(C * KBLK * 2) * (SPLIT3 ? 2u : 1u));
             tma_load_2d(b_hi, &tmG_hi, &full[stage], g * KBLK, 0);
             if (SPLIT3) tma_load_2d(b_lo, &tmG_lo, &full[stage], g * KBLK, 0);
           }
@@ -249,7 +266,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     // of every UTCHMMA and made the kernel MMA-issue bound at ~100 clk per instruction.)
     if (leader) {
       constexpr uint32_t idesc_main = PAIR ? umma_idesc_bf16_m256(N_TILE) : umma_idesc_bf16(N_TILE);
-      constexpr uint32_t idesc_gdn = PAIR ? umma_idesc_bf16_m256(C128) : umma_idesc_bf16(C128);
+      constexpr uint32_t idesc_gdn = PAIR ? umma_idesc_bf16_m256(C) : umma_idesc_bf16(C);
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint64_t desc0 = umma_desc_sw128(sbase);     // + (byte offset >> 4) selects a tile / K slice
@@ -267,8 +284,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         if (lane == 0) TC_MARK(1);
         const uint32_t off = (uint32_t)(stage * STAGE_BYTES);
         const uint64_t a_hi = desc0 + (off >> 4), a_lo = a_hi + (SLOT_BYTES >> 4);
-        const uint64_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * SLOT_BYTES) >> 4), b_lo = b_hi + (SLOT_BYTES >> 4);
-        const uint32_t d = tb + (is_gdn ? (uint32_t)C128 : 0u);
+        const uint64_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * SLOT_BYTES) >> 4), b_lo = b_hi + (B_SLOT >> 4);
+        const uint32_t d = tb + (is_gdn ? (uint32_t)C : 0u);
         const uint32_t idesc = is_gdn ? idesc_gdn : idesc_main;
         const uint32_t acc0 = (s > (is_gdn ? nsteps : 0)) ? 1u : 0u;
         if (elect_one()) {
@@ -304,7 +321,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else {
     // ================================================================ row workers (8 warps, 256 threads)
-    // two threads per tile row: `half` selects which 64 of the 128 channels (or which k-chunks) it owns
+    // NCB threads per tile row: `half` (0 .. NCB-1) selects which 64 channels (or which k-chunks) it owns
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;            // tile row = pixel
@@ -325,7 +342,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (OUT_MODE == OUT_F32_NCHW_PS4) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) xref[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.ref_image && valid) {
+      if (p.ref_image && valid && half < 2) {
 #pragma unroll
         for (int o = 0; o < 3; ++o)
 #pragma unroll
@@ -345,7 +362,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int stage = s % STAGES, it = s / STAGES;
         mbar_wait(&empty[stage], (it & 1) ^ 1);
         uint8_t* st = smem + stage * STAGE_BYTES;
-        if (half == 0) {
+        if (half >= 2) {
+          // C > 128: the 8 chunks of a k-block are built by the first two workers of the row
+        } else if (half == 0) {
           if (s == 0) conv1_build_row<0, 0, SPLIT3>(pp, st, st + SLOT_BYTES, r);
           else if (s == 1) conv1_build_row<1, 0, SPLIT3>(pp, st, st + SLOT_BYTES, r);
           else if (s == 2) conv1_build_row<2, 0, SPLIT3>(pp, st, st + SLOT_BYTES, r);
@@ -370,7 +389,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       // ---- pass 1: (acc + bias)^2 -> K-major swizzled bf16 A tile for the gamma product.
       // thread (r, half) writes k-block g = half (its 64 channels) and only arrives on the other one.
 #pragma unroll 1
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < NCB; ++g) {
         const int s = nsteps + g;
         const int stage = s % STAGES, it = s / STAGES;
         // every worker waits for the slot (with one stage, k-block 1 reuses k-block 0's slot and barrier:
@@ -385,7 +404,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (GDN_BWD) {
             // acc = dL/dy.  dL/dnorm = -+ 1/2 * g * y / n  (GDN: y = x n^-1/2, IGDN: y = x n^1/2)
             const size_t pixb = (((size_t)n_img * p.Hfull + (oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0))) *
-                                     p.Wfull + (ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0))) * C128 + g * 64;
+                                     p.Wfull + (ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0))) * C + g * 64;
             const uint4* py = reinterpret_cast<const uint4*>(p.saved_y + pixb);
             const uint4* pn = reinterpret_cast<const uint4*>(p.saved_n + pixb);
 #pragma unroll
@@ -434,12 +453,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       // With a reference image the distortion is fused: out = clamp(r, 0, 1) (model.py:59) and the CTA's
       // partial sums of (r - x)^2 (model.py:61) and (clamp(r) - x)^2 (train.py:172) go to sse_partial.
       uint32_t raw[24];
-      tmem_ld8(t_row + (uint32_t)(half * 24), *reinterpret_cast<uint32_t(*)[8]>(&raw[0]));
-      tmem_ld8(t_row + (uint32_t)(half * 24 + 8), *reinterpret_cast<uint32_t(*)[8]>(&raw[8]));
-      tmem_ld8(t_row + (uint32_t)(half * 24 + 16), *reinterpret_cast<uint32_t(*)[8]>(&raw[16]));
+      const int hh = half < 2 ? half : 0;      // warp-uniform; workers beyond the first two per row only reduce
+      tmem_ld8(t_row + (uint32_t)(hh * 24), *reinterpret_cast<uint32_t(*)[8]>(&raw[0]));
+      tmem_ld8(t_row + (uint32_t)(hh * 24 + 8), *reinterpret_cast<uint32_t(*)[8]>(&raw[8]));
+      tmem_ld8(t_row + (uint32_t)(hh * 24 + 16), *reinterpret_cast<uint32_t(*)[8]>(&raw[16]));
       tmem_ld_wait();
       float s0 = 0.f, s1 = 0.f;
-      if (valid) {
+      if (valid && half < 2) {
         float* out = reinterpret_cast<float*>(p.out_hi);
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
@@ -479,7 +499,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         if (warp == 2 && lane == 0) {
           float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) { t0 += red[w * 2]; t1 += red[w * 2 + 1]; }
+          for (int w = 0; w < NWORKERS / 32; ++w) { t0 += red[w * 2]; t1 += red[w * 2 + 1]; }
           float* dst = p.sse_partial + ((size_t)n_img * p.tiles_per_image + blockIdx.x) * 2;
           dst[0] = t0;
           dst[1] = t1;
@@ -491,7 +511,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int c0 = half * 64 + h * 32;
         uint32_t raw[32], rawn[32];
         tmem_ld32(t_row + (uint32_t)c0, raw);
-        if (GDN) tmem_ld32(t_row + (uint32_t)(C128 + c0), rawn);
+        if (GDN) tmem_ld32(t_row + (uint32_t)(C + c0), rawn);
         tmem_ld_wait();
         if (valid) {
           float* out = reinterpret_cast<float*>(p.out_hi);
@@ -514,18 +534,20 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       //   SPLIT3: stage 0 = {hi k-blocks 0,1 ; lo k-blocks 0,1}.
       //   bf16:   primary plane -> both slots of the stage the GDN steps did not touch; second plane (forward:
       //           norm n, for training; backward: dL/dnorm, which already sits in the GDN steps' A slots).
-      const int st_c = SPLIT3 ? 0 : (nsteps + 2) % STAGES;
+      //   C != 128 (inference only): all planes staged from the start of the ring.
+      constexpr bool SIMPLE_STAGING = SPLIT3 || C != 128;
+      const int st_c = SIMPLE_STAGING ? 0 : (nsteps + 2) % STAGES;
       uint8_t* stg_hi = smem + st_c * STAGE_BYTES + half * SLOT_BYTES;
-      uint8_t* stg_lo = smem + (2 + half) * SLOT_BYTES;                                   // SPLIT3 only
-      const bool second_plane = !SPLIT3 && GDN != 0 && p.out_lo != nullptr;
+      uint8_t* stg_lo = smem + (NCB + half) * SLOT_BYTES;                                 // SPLIT3 only
+      const bool second_plane = !SPLIT3 && C == 128 && GDN != 0 && p.out_lo != nullptr;
       uint8_t* stg_n = smem + ((nsteps + half) % STAGES) * STAGE_BYTES + SLOT_BYTES;     // forward norm: B slot
-      const size_t pixb = (((size_t)n_img * p.Hfull + oyf) * p.Wfull + oxf) * C128;
+      const size_t pixb = (((size_t)n_img * p.Hfull + oyf) * p.Wfull + oxf) * C;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {            // 2 x 32 channels of this thread's 64
         const int c0 = half * 64 + h * 32;
         uint32_t raw[32], rawn[32];
         tmem_ld32(t_row + (uint32_t)c0, raw);
-        if (GDN) tmem_ld32(t_row + (uint32_t)(C128 + c0), rawn);
+        if (GDN) tmem_ld32(t_row + (uint32_t)(C + c0), rawn);
         tmem_ld_wait();
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
@@ -564,11 +586,12 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       if (warp == 2 && lane == 0) {
         const int mi = (KIND == B2C_TC_DECONV5S2) ? phase : 0;
         uint8_t* c_base = smem + st_c * STAGE_BYTES;
-        tma_store_4d(&tmO.m[mi], c_base, 0, ox0, oy0, n_img);
-        tma_store_4d(&tmO.m[mi], c_base + SLOT_BYTES, KBLK, ox0, oy0, n_img);
+#pragma unroll
+        for (int j = 0; j < NCB; ++j) tma_store_4d(&tmO.m[mi], c_base + j * SLOT_BYTES, j * KBLK, ox0, oy0, n_img);
         if (SPLIT3) {
-          tma_store_4d(&tmO.m[4 + mi], smem + 2 * SLOT_BYTES, 0, ox0, oy0, n_img);
-          tma_store_4d(&tmO.m[4 + mi], smem + 3 * SLOT_BYTES, KBLK, ox0, oy0, n_img);
+#pragma unroll
+          for (int j = 0; j < NCB; ++j)
+            tma_store_4d(&tmO.m[4 + mi], smem + (NCB + j) * SLOT_BYTES, j * KBLK, ox0, oy0, n_img);
         } else if (second_plane) {
           // forward: norm tiles in the B slots; backward: dnorm tiles still in the A slots of the GDN steps
           const int off = GDN_BWD ? 0 : SLOT_BYTES;
@@ -596,22 +619,22 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 // ------------------------------------------------------------------------------------ packing kernels
 // weights -> bf16 (hi, lo) panels, row = (group, out channel), 128-byte K-major rows
 __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo, int total) {
+                                    __nv_bfloat16* __restrict__ lo, int total, int C) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   float v = 0.f;
-  if (kind == B2C_TC_CONV1) {            // [kb 4][o 128][j 64], k = kb*64 + j, w OIHW [128][3][9][9]
-    const int j = idx & 63, o = (idx >> 6) & 127, kb = idx >> 13;
+  if (kind == B2C_TC_CONV1) {            // [kb 4][o C][j 64], k = kb*64 + j, w OIHW [C][3][9][9]
+    const int j = idx & 63, o = (idx >> 6) % C, kb = idx / (64 * C);
     const int k = kb * 64 + j;
     if (k < 243) v = w[o * 243 + k];
-  } else if (kind == B2C_TC_CONV5S2) {   // [tap 25][o 128][c 128], w OIHW [128][128][5][5]
-    const int c = idx & 127, o = (idx >> 7) & 127, t = idx >> 14;
-    v = w[(o * 128 + c) * 25 + t];
-  } else if (kind == B2C_TC_DECONV5S2) { // [tap 25][o 128][c 128], w IOHW [128 c][128 o][5][5]
-    const int c = idx & 127, o = (idx >> 7) & 127, t = idx >> 14;
-    v = w[(c * 128 + o) * 25 + t];
-  } else {                               // DECONV3: [shift 9][n 48][c 128], n = (ry*4+rx)*3+o, w IOHW [128][3][9][9]
-    const int c = idx & 127, n = (idx >> 7) % 48, sh = idx / (128 * 48);
+  } else if (kind == B2C_TC_CONV5S2) {   // [tap 25][o C][c C], w OIHW [C][C][5][5]
+    const int c = idx % C, o = (idx / C) % C, t = idx / (C * C);
+    v = w[(o * C + c) * 25 + t];
+  } else if (kind == B2C_TC_DECONV5S2) { // [tap 25][o C][c C], w IOHW [C c][C o][5][5]
+    const int c = idx % C, o = (idx / C) % C, t = idx / (C * C);
+    v = w[(c * C + o) * 25 + t];
+  } else {                               // DECONV3: [shift 9][n 48][c C], n = (ry*4+rx)*3+o, w IOHW [C][3][9][9]
+    const int c = idx % C, n = (idx / C) % 48, sh = idx / (C * 48);
     const int o = n % 3, ph = n / 3, ry = ph >> 2, rx = ph & 3;
     const int dy = sh / 3 - 1, dx = sh % 3 - 1;
     const int ky = ry + 4 - 4 * dy, kx = rx + 4 - 4 * dx;
@@ -625,10 +648,10 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
 
 __global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
                                 __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
-                                float* __restrict__ beta_eff, int transpose) {
+                                float* __restrict__ beta_eff, int transpose, int C) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < C128 * C128) {
-    const int src = transpose ? ((idx & 127) * C128 + (idx >> 7)) : idx;
+  if (idx < C * C) {
+    const int src = transpose ? ((idx % C) * C + (idx / C)) : idx;
     const float b = fmaxf(gamma_p[src], 3.814697265625e-06f);
     const float g = b * b - 1.4551915228366852e-11f;
     __nv_bfloat16 h, l;
@@ -636,7 +659,7 @@ __global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* _
     ghi[idx] = h;
     if (glo) glo[idx] = l;
   }
-  if (idx < C128) {
+  if (idx < C) {
     const float b = fmaxf(beta_p[idx], (float)0.0010000072759311445);
     beta_eff[idx] = b * b - 1.4551915228366852e-11f;
   }
@@ -702,11 +725,11 @@ static EncodeTiledFn get_encode() {
 }
 
 // NHWC bf16 activation [B][H][W][128]: box = 64 channels x TW x TH pixels with traversal stride S
-static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int S) {
+static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int S, int C) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)C128, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C128 * 2, (cuuint64_t)W * C128 * 2, (cuuint64_t)H * W * C128 * 2};
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)(TW * S), (cuuint32_t)(TH * S), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)S, (cuuint32_t)S, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -719,13 +742,13 @@ static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, i
 // NHWC bf16 output lattice: pixel (oy*ps + ry, ox*ps + rx) of [B][Hfull][Wfull][128] seen as a dense
 // [B][Hg][Wg][128] tensor with strides; box = 64 channels x TW x TH pixels (TMA clips at the image border)
 static int make_out_map(CUtensorMap* m, const void* base, int B, int Hg, int Wg, int Hfull, int Wfull, int ps, int ry,
-                        int rx) {
+                        int rx, int C) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
-  const char* origin = reinterpret_cast<const char*>(base) + ((size_t)ry * Wfull + rx) * C128 * 2;
-  cuuint64_t dims[4] = {(cuuint64_t)C128, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)ps * C128 * 2, (cuuint64_t)ps * Wfull * C128 * 2,
-                           (cuuint64_t)Hfull * Wfull * C128 * 2};
+  const char* origin = reinterpret_cast<const char*>(base) + ((size_t)ry * Wfull + rx) * C * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ps * C * 2, (cuuint64_t)ps * Wfull * C * 2,
+                           (cuuint64_t)Hfull * Wfull * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(origin), dims, strides, box, estr,
@@ -765,10 +788,12 @@ static int make_image_map(CUtensorMap* m, const void* base, int B, int H, int W)
   return B2C_OK;
 }
 
-template <int N_TILE, bool SPLIT3, int KIND, int GDN, int OUT_MODE, bool PAIR = false>
+template <int C, bool SPLIT3, int KIND, int GDN, int OUT_MODE, bool PAIR = false>
 static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr size_t SMEM = TcCfg<SPLIT3, KIND>::SMEM;
-  auto kern = igemm_tc_kernel<N_TILE, SPLIT3, KIND, GDN, OUT_MODE, PAIR>;
+  constexpr int N_TILE = TcCfg<C, SPLIT3, KIND, GDN>::N_TILE;
+  constexpr int NTHREADS = nthreads(C);
+  constexpr size_t SMEM = TcCfg<C, SPLIT3, KIND, GDN>::SMEM;
+  auto kern = igemm_tc_kernel<C, SPLIT3, KIND, GDN, OUT_MODE, PAIR>;
   {  // opt in to > 48 KB dynamic shared memory once per (instantiation, device); never during graph capture replays
     static std::mutex mu;
     static bool done[64] = {false};
@@ -791,18 +816,18 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
   if (KIND == B2C_TC_CONV1) {
     if ((rc = make_image_map(&mA_hi, L->in_hi, L->B, L->Hin, L->Win))) return rc;
   } else {
-    if ((rc = make_act_map(&mA_hi, L->in_hi, L->B, L->Hin, L->Win, S))) return rc;
-    if (SPLIT3 && (rc = make_act_map(&mA_lo, L->in_lo, L->B, L->Hin, L->Win, S))) return rc;
+    if ((rc = make_act_map(&mA_hi, L->in_hi, L->B, L->Hin, L->Win, S, C))) return rc;
+    if (SPLIT3 && (rc = make_act_map(&mA_lo, L->in_lo, L->B, L->Hin, L->Win, S, C))) return rc;
   }
   const int groups = KIND == B2C_TC_CONV1 ? 4 : (KIND == B2C_TC_DECONV3 ? 9 : 25);
-  const int wcols = KIND == B2C_TC_CONV1 ? 64 : 128;
+  const int wcols = KIND == B2C_TC_CONV1 ? 64 : C;
   constexpr int BROWS = PAIR ? N_TILE / 2 : N_TILE;     // a CTA pair stages half of the weight rows per CTA
   if ((rc = make_mat_map(&mB_hi, L->w_hi, groups * N_TILE, wcols, BROWS))) return rc;
   if (SPLIT3 && (rc = make_mat_map(&mB_lo, L->w_lo, groups * N_TILE, wcols, BROWS))) return rc;
   if (GDN) {
-    constexpr int GROWS = PAIR ? C128 / 2 : C128;
-    if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C128, C128, GROWS))) return rc;
-    if (SPLIT3 && (rc = make_mat_map(&mG_lo, L->gamma_lo, C128, C128, GROWS))) return rc;
+    constexpr int GROWS = PAIR ? C / 2 : C;
+    if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C, C, GROWS))) return rc;
+    if (SPLIT3 && (rc = make_mat_map(&mG_lo, L->gamma_lo, C, C, GROWS))) return rc;
   }
   TcOutMaps mO;
   memset(&mO, 0, sizeof(mO));
@@ -811,8 +836,8 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
     const int ps = (KIND == B2C_TC_DECONV5S2) ? 2 : 1;
     for (int ph = 0; ph < nph; ++ph) {
       const int ry = nph == 4 ? (ph >> 1) : 0, rx = nph == 4 ? (ph & 1) : 0;
-      if ((rc = make_out_map(&mO.m[ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, ps, ry, rx))) return rc;
-      if (L->out_lo && (rc = make_out_map(&mO.m[4 + ph], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, ps, ry, rx)))
+      if ((rc = make_out_map(&mO.m[ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, ps, ry, rx, C))) return rc;
+      if (L->out_lo && (rc = make_out_map(&mO.m[4 + ph], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, ps, ry, rx, C)))
         return rc;
     }
   }
@@ -852,38 +877,43 @@ extern "C" {
 /* debug hook (not part of the stable ABI): device buffer of 3*64 int64 receiving a clock64 timeline */
 void b2c_tc_debug_set_trace(void* device_buffer) { g_tc_trace = (long long*)device_buffer; }
 
-size_t b2c_tc_packed_weight_elems(int kind) {
+static bool tc_channels_ok(int C) { return C == 128 || C == 192 || C == 256; }
+
+size_t b2c_tc_packed_weight_elems(int kind, int channels) {
+  const size_t C = (size_t)channels;
+  if (!tc_channels_ok(channels)) return 0;
   switch (kind) {
-    case B2C_TC_CONV1: return 4 * 128 * 64;
+    case B2C_TC_CONV1: return 4 * C * 64;
     case B2C_TC_CONV5S2:
-    case B2C_TC_DECONV5S2: return 25 * 128 * 128;
-    case B2C_TC_DECONV3: return 9 * 48 * 128;
+    case B2C_TC_DECONV5S2: return 25 * C * C;
+    case B2C_TC_DECONV3: return 9 * 48 * C;
     default: return 0;
   }
 }
 
-int b2c_tc_pack_weights(int kind, const float* w, void* w_hi, void* w_lo, void* stream) {
-  const size_t n = b2c_tc_packed_weight_elems(kind);
-  B2C_REQUIRE(n > 0 && w && w_hi, "tc_pack_weights: bad arguments");
+int b2c_tc_pack_weights(int kind, int channels, const float* w, void* w_hi, void* w_lo, void* stream) {
+  const size_t n = b2c_tc_packed_weight_elems(kind, channels);
+  B2C_REQUIRE(n > 0 && w && w_hi, "tc_pack_weights: bad arguments (channels must be 128, 192 or 256)");
   pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      kind, w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, (int)n);
+      kind, w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, (int)n, channels);
   count_launch();
   return check_launch("tc_pack_weights");
 }
 
-int b2c_tc_pack_gdn(const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo, float* beta_eff,
-                    void* stream) {
-  B2C_REQUIRE(beta_p && gamma_p && gamma_hi && beta_eff, "tc_pack_gdn: bad arguments");
-  pack_gdn_kernel<<<(C128 * C128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      beta_p, gamma_p, (__nv_bfloat16*)gamma_hi, (__nv_bfloat16*)gamma_lo, beta_eff, 0);
+int b2c_tc_pack_gdn(int channels, const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo,
+                    float* beta_eff, void* stream) {
+  B2C_REQUIRE(tc_channels_ok(channels) && beta_p && gamma_p && gamma_hi && beta_eff, "tc_pack_gdn: bad arguments");
+  pack_gdn_kernel<<<(channels * channels + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      beta_p, gamma_p, (__nv_bfloat16*)gamma_hi, (__nv_bfloat16*)gamma_lo, beta_eff, 0, channels);
   count_launch();
   return check_launch("tc_pack_gdn");
 }
 
-int b2c_tc_pack_gdn_t(const float* beta_p, const float* gamma_p, void* gamma_t, float* beta_eff, void* stream) {
-  B2C_REQUIRE(beta_p && gamma_p && gamma_t && beta_eff, "tc_pack_gdn_t: bad arguments");
-  pack_gdn_kernel<<<(C128 * C128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      beta_p, gamma_p, (__nv_bfloat16*)gamma_t, nullptr, beta_eff, 1);
+int b2c_tc_pack_gdn_t(int channels, const float* beta_p, const float* gamma_p, void* gamma_t, float* beta_eff,
+                      void* stream) {
+  B2C_REQUIRE(tc_channels_ok(channels) && beta_p && gamma_p && gamma_t && beta_eff, "tc_pack_gdn_t: bad arguments");
+  pack_gdn_kernel<<<(channels * channels + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      beta_p, gamma_p, (__nv_bfloat16*)gamma_t, nullptr, beta_eff, 1, channels);
   count_launch();
   return check_launch("tc_pack_gdn_t");
 }
@@ -963,6 +993,26 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   dim3 grid(p.tiles_x * tiles_y, phases, L->B);
 
   const int key = L->kind * 1000 + (L->split3 ? 100 : 0) + L->gdn * 10 + (L->out_f32_nchw ? 1 : 0);
+  const int channels = L->channels ? L->channels : 128;
+  B2C_REQUIRE(tc_channels_ok(channels), "tc_layer_run: channels must be 128, 192 or 256 (got %d)", channels);
+  if (channels != 128) {   // wider latents (config 5): inference kinds only
+#define B2C_WIDE(CC)                                                                                                    \
+  switch (key) {                                                                                                       \
+    case B2C_TC_CONV1 * 1000 + 100 + 10 + 0: return launch<CC, true, B2C_TC_CONV1, 1, OUT_BF16>(L, p, grid, stream);   \
+    case B2C_TC_CONV1 * 1000 + 100 + 0 + 1: return launch<CC, true, B2C_TC_CONV1, 0, OUT_F32_NCHW>(L, p, grid, stream); \
+    case B2C_TC_CONV5S2 * 1000 + 100 + 10 + 0: return launch<CC, true, B2C_TC_CONV5S2, 1, OUT_BF16, true>(L, p, grid, stream); \
+    case B2C_TC_CONV5S2 * 1000 + 100 + 0 + 1: return launch<CC, true, B2C_TC_CONV5S2, 0, OUT_F32_NCHW, true>(L, p, grid, stream); \
+    case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 0: return launch<CC, false, B2C_TC_DECONV5S2, 2, OUT_BF16>(L, p, grid, stream); \
+    case B2C_TC_DECONV5S2 * 1000 + 0 + 0 + 1: return launch<CC, false, B2C_TC_DECONV5S2, 0, OUT_F32_NCHW>(L, p, grid, stream); \
+    case B2C_TC_DECONV3 * 1000 + 0 + 0 + 1: return launch<CC, false, B2C_TC_DECONV3, 0, OUT_F32_NCHW_PS4>(L, p, grid, stream); \
+    default: break;                                                                                                    \
+  }
+    if (channels == 192) { B2C_WIDE(192) } else { B2C_WIDE(256) }
+#undef B2C_WIDE
+    set_error("tc_layer_run: unsupported combination for %d channels: kind=%d split3=%d gdn=%d out_f32_nchw=%d", channels,
+              L->kind, L->split3, L->gdn, L->out_f32_nchw);
+    return B2C_EINVAL;
+  }
   static const int use_pairs = [] {   // 0: off, 1: bf16x3 5x5 convs (default), 2: also the bf16 transposed convs
     const char* e = getenv("B2C_TC_PAIRS");
     return e ? atoi(e) : B2C_TC_PAIRS_DEFAULT;
@@ -995,7 +1045,7 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
     case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 0: return launch<128, false, B2C_TC_DECONV5S2, 2, OUT_BF16>(L, p, grid, stream);
     case B2C_TC_DECONV5S2 * 1000 + 0 + 0 + 1: return launch<128, false, B2C_TC_DECONV5S2, 0, OUT_F32_NCHW>(L, p, grid, stream);
     case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 1: return launch<128, false, B2C_TC_DECONV5S2, 2, OUT_F32_NCHW>(L, p, grid, stream);
-    case B2C_TC_DECONV3 * 1000 + 0 + 0 + 1: return launch<48, false, B2C_TC_DECONV3, 0, OUT_F32_NCHW_PS4>(L, p, grid, stream);
+    case B2C_TC_DECONV3 * 1000 + 0 + 0 + 1: return launch<128, false, B2C_TC_DECONV3, 0, OUT_F32_NCHW_PS4>(L, p, grid, stream);
     default:
       set_error("tc_layer_run: unsupported combination kind=%d split3=%d gdn=%d out_f32_nchw=%d", L->kind, L->split3,
                 L->gdn, L->out_f32_nchw);

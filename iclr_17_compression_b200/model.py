@@ -59,8 +59,8 @@ class ImageCompressor(nn.Module):
         self.return_mode = mode
         self.noise_override = None      # test hook: inject the quantization noise
         self.last = {}
-        # eval + no_grad + out_channel_N == 128 runs the tcgen05 pipeline (bf16x3 analysis, bf16 synthesis);
-        # everything else (training, autograd, other widths) runs the exact-fp32 kernels.
+        # eval + no_grad + out_channel_N in {128, 192, 256} runs the tcgen05 pipeline (bf16x3 analysis, bf16
+        # synthesis); everything else (autograd in eval mode, other widths) runs the exact-fp32 kernels.
         self.fast_inference = True
         # training + out_channel_N == 128: bf16 tensor-core forward/backward (train_tc.TrainStepTC); gradients
         # match the fp32 path within 1e-2 relative L2.  Set False for the exact-fp32 kernels.
@@ -130,7 +130,7 @@ class ImageCompressor(nn.Module):
 
     def _use_tc(self, x):
         return (self.fast_inference and not self.training and not torch.is_grad_enabled()
-                and self.out_channel_N == 128 and x.is_cuda)
+                and self.out_channel_N in (128, 192, 256) and x.is_cuda)
 
     def _noise(self, x):
         """model.py:48-49, same torch calls (so the CUDA generator stream matches the reference)."""

@@ -23,25 +23,29 @@ def _stream():
 def pack_weights(kind, w, need_lo):
     """state_dict weight (fp32 OIHW / IOHW) -> (hi, lo) bf16 tap-major panels."""
     lib = _lib.load()
-    n = lib.b2c_tc_packed_weight_elems(kind)
+    C = max(w.shape[0], w.shape[1])               # conv1 [C,3,9,9] / deconv3 [C,3,9,9] / 5x5 [C,C,5,5]
+    n = lib.b2c_tc_packed_weight_elems(kind, C)
+    if n == 0:
+        raise _lib.B2CError(f"tensor-core kernels support 128, 192 or 256 channels, got {C}")
     w = w.detach().contiguous().float()
     hi = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
     lo = torch.empty((n,), device=w.device, dtype=torch.bfloat16) if need_lo else None
     with torch.cuda.device(w.device):
-        _lib.check(lib.b2c_tc_pack_weights(kind, _p(w), _p(hi), _p(lo), _stream()), "tc_pack_weights")
+        _lib.check(lib.b2c_tc_pack_weights(kind, C, _p(w), _p(hi), _p(lo), _stream()), "tc_pack_weights")
     return hi, lo
 
 
 def pack_gdn(beta, gamma, need_lo):
     lib = _lib.load()
     beta, gamma = beta.detach().contiguous().float(), gamma.detach().contiguous().float()
-    if beta.numel() != 128 or gamma.numel() != 128 * 128:
-        raise _lib.B2CError("tensor-core GDN needs 128 channels")
-    ghi = torch.empty((128, 128), device=beta.device, dtype=torch.bfloat16)
-    glo = torch.empty((128, 128), device=beta.device, dtype=torch.bfloat16) if need_lo else None
-    be = torch.empty((128,), device=beta.device, dtype=torch.float32)
+    C = beta.numel()
+    if C not in (128, 192, 256) or gamma.numel() != C * C:
+        raise _lib.B2CError("tensor-core GDN needs 128, 192 or 256 channels")
+    ghi = torch.empty((C, C), device=beta.device, dtype=torch.bfloat16)
+    glo = torch.empty((C, C), device=beta.device, dtype=torch.bfloat16) if need_lo else None
+    be = torch.empty((C,), device=beta.device, dtype=torch.float32)
     with torch.cuda.device(beta.device):
-        _lib.check(lib.b2c_tc_pack_gdn(_p(beta), _p(gamma), _p(ghi), _p(glo), _p(be), _stream()), "tc_pack_gdn")
+        _lib.check(lib.b2c_tc_pack_gdn(C, _p(beta), _p(gamma), _p(ghi), _p(glo), _p(be), _stream()), "tc_pack_gdn")
     return ghi, glo, be
 
 
@@ -64,18 +68,20 @@ def nhwc_to_nchw(hi, lo=None):
     return out
 
 
-_FLOPS_PER_OUT_PIXEL = {TC_CONV1: 2 * 243 * 128, TC_CONV5S2: 2 * 3200 * 128, TC_DECONV5S2: 2 * 3200 * 128 / 4,
-                        TC_DECONV3: 2 * 128 * 243 / 16}
+def _flops_per_out_pixel(kind, C):
+    return {TC_CONV1: 2 * 243 * C, TC_CONV5S2: 2 * 25 * C * C, TC_DECONV5S2: 2 * 25 * C * C / 4,
+            TC_DECONV3: 2 * C * 243 / 16}[kind]
 
 
 def pack_gdn_t(beta, gamma):
     """gamma_eff^T (bf16) and beta_eff, for the GDN backward epilogue"""
     lib = _lib.load()
     beta, gamma = beta.detach().contiguous().float(), gamma.detach().contiguous().float()
-    gt = torch.empty((128, 128), device=beta.device, dtype=torch.bfloat16)
-    be = torch.empty((128,), device=beta.device, dtype=torch.float32)
+    C = beta.numel()
+    gt = torch.empty((C, C), device=beta.device, dtype=torch.bfloat16)
+    be = torch.empty((C,), device=beta.device, dtype=torch.float32)
     with torch.cuda.device(beta.device):
-        _lib.check(lib.b2c_tc_pack_gdn_t(_p(beta), _p(gamma), _p(gt), _p(be), _stream()), "tc_pack_gdn_t")
+        _lib.check(lib.b2c_tc_pack_gdn_t(C, _p(beta), _p(gamma), _p(gt), _p(be), _stream()), "tc_pack_gdn_t")
     return gt, None, be
 
 
@@ -86,13 +92,14 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
     Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
     if kind == TC_CONV1:
         B, _, Hin, Win = x_hi.shape
-        Ho, Wo, Cout = Hin // 4, Win // 4, 128
+        C = w[0].numel() // (4 * 64)
+        Ho, Wo, Cout = Hin // 4, Win // 4, C
     else:
-        B, Hin, Win, _ = x_hi.shape
+        B, Hin, Win, C = x_hi.shape
         if kind == TC_CONV5S2:
-            Ho, Wo, Cout = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1, 128
+            Ho, Wo, Cout = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1, C
         elif kind == TC_DECONV5S2:
-            Ho, Wo, Cout = Hin * 2, Win * 2, 128
+            Ho, Wo, Cout = Hin * 2, Win * 2, C
         else:
             Ho, Wo, Cout = Hin * 4, Win * 4, 3
     dev = x_hi.device
@@ -105,6 +112,7 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
     L = TcLayer()
     L.kind, L.split3, L.gdn, L.out_f32_nchw = kind, int(split3), int(gdn_mode), int(out_f32_nchw)
     L.B, L.Hin, L.Win = B, Hin, Win
+    L.channels = C
     L.in_hi, L.in_lo = x_hi.data_ptr(), (x_lo.data_ptr() if x_lo is not None else 0)
     L.w_hi, L.w_lo = w[0].data_ptr(), (w[1].data_ptr() if w[1] is not None else 0)
     L.bias = bias.data_ptr() if bias is not None else 0
@@ -121,7 +129,7 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         partial = torch.empty((B, tiles, 2), device=dev, dtype=torch.float32)
         sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
         L.ref_image, L.sse_partial = ref_image.data_ptr(), partial.data_ptr()
-    flops = int(_FLOPS_PER_OUT_PIXEL[kind] * B * Ho * Wo) + (2 * 128 * 128 * B * Ho * Wo if gdn_mode else 0)
+    flops = int(_flops_per_out_pixel(kind, C) * B * Ho * Wo) + (2 * C * C * B * Ho * Wo if gdn_mode else 0)
     name = f"tc_layer[kind{kind},{B}x{Hin}x{Win},split{int(split3)},gdn{gdn_mode}]"
     with torch.cuda.device(dev), _timed(name, flops, 0):
         _lib.check(_lib.load().b2c_tc_layer_run(ctypes.byref(L), _stream()), "tc_layer_run")

@@ -150,16 +150,19 @@ int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped
 #define B2C_TC_DECONV3 3   /* 9x9 s4 p4 op3 transposed, 128->3, as a 3x3 conv to 16 phases x 3 channels
                               (models/synthesis_17.py:23) */
 
+/* `channels` = out_channel_N in {128, 192, 256} (model.py:39; 192 / 256 are the wider-latent variants of
+ * BASELINE config 5; the training kinds - gdn 3/4, the norm plane, b2c_tc_wgrad* - exist for 128 only). */
 /* bf16 elements in ONE packed weight plane (hi or lo) of a layer kind. */
-size_t b2c_tc_packed_weight_elems(int kind);
+size_t b2c_tc_packed_weight_elems(int kind, int channels);
 /* fp32 OIHW (conv) / IOHW (deconv) weights as in state_dict -> tap-major bf16 panels; w_lo may be NULL. */
-int b2c_tc_pack_weights(int kind, const float* w, void* w_hi, void* w_lo, void* stream);
-/* GDN parameters (raw, reparametrised) -> gamma_eff as bf16 hi/lo [128][128] and beta_eff fp32 [128]. */
-int b2c_tc_pack_gdn(const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo, float* beta_eff,
-                    void* stream);
+int b2c_tc_pack_weights(int kind, int channels, const float* w, void* w_hi, void* w_lo, void* stream);
+/* GDN parameters (raw, reparametrised) -> gamma_eff as bf16 hi/lo [C][C] and beta_eff fp32 [C]. */
+int b2c_tc_pack_gdn(int channels, const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo,
+                    float* beta_eff, void* stream);
 
-/* gamma_eff transposed (bf16 [128][128]) for the GDN backward epilogue, and beta_eff */
-int b2c_tc_pack_gdn_t(const float* beta_p, const float* gamma_p, void* gamma_t, float* beta_eff, void* stream);
+/* gamma_eff transposed (bf16 [C][C]) for the GDN backward epilogue, and beta_eff */
+int b2c_tc_pack_gdn_t(int channels, const float* beta_p, const float* gamma_p, void* gamma_t, float* beta_eff,
+                      void* stream);
 
 typedef struct b2c_tc_layer {
   int kind;         /* B2C_TC_*                                                                   */
@@ -188,6 +191,7 @@ typedef struct b2c_tc_layer {
    * (a bf16 forward launch with gdn 1 / 2 writes n to out_lo), NHWC bf16 shaped like this launch's output */
   const void* saved_y;
   const void* saved_n;
+  int channels;     /* 0 or 128, 192, 256 (see above)                                               */
 } b2c_tc_layer;
 
 /* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid */

@@ -149,7 +149,7 @@ def test_full_kodak_size_vs_oracle_on_gpu(kind):
 
 
 # ------------------------------------------------------------------------------ tensor-core pipeline
-@pytest.mark.parametrize("name", [n for n in golden_names("eval_") if "_n128_" in n])
+@pytest.mark.parametrize("name", [n for n in golden_names("eval_") if "_n128_" in n or "_n192_" in n])
 def test_tc_eval_matches_reference_golden(name):
     """eval + no_grad + N=128 runs the tcgen05 pipeline: latents bit-exact away from rounding boundaries
     (bf16x3 analysis), bpp / MSE within 1e-3 relative (bf16 synthesis)."""
@@ -291,3 +291,26 @@ def test_graphed_train_step_matches_eager():
     for k, p in m.named_parameters():
         assert p.grad.data_ptr() >= step.flat.data_ptr()                      # views of the flat buffer
         assert _rel(p.grad, eager[k]) < 2e-3, (k, _rel(p.grad, eager[k]))      # atomics reorder sums slightly
+
+
+@pytest.mark.parametrize("N", [192, 256])
+def test_tc_wide_latents_vs_fp64_oracle(N):
+    """config-5 stand-in: ImageCompressor(192 / 256) on the tensor-core pipeline vs the fp64 oracle (W1-style weights)."""
+    from oracle import balle17_oracle as O
+    import iclr_17_compression_b200 as P
+    sd = O.perturb_state_dict(O.init_state_dict(N, seed=234))
+    m = P.ImageCompressor(N)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = O.synth_images("S", 2, 256, 384, 1003).cuda()
+    sd64 = {k: v.cuda().double() for k, v in sd.items()}
+    with torch.no_grad():
+        clipped, z, bpp = m(x)
+        assert m.last_path == "tcgen05"
+        ref = O.forward(x.double(), sd64)
+    ndiff = check_latents(z, ref["z"].float(), ref["y"])
+    assert ndiff <= 2e-3 * z.numel()
+    assert abs(bpp.item() - ref["bpp"].item()) <= REL_BPP_MSE * ref["bpp"].item()
+    mse = (m.last["sse"][:, 0].sum() / x.numel()).item()
+    assert abs(mse - ref["mse"].item()) <= REL_BPP_MSE * ref["mse"].item(), (mse, ref["mse"].item())
+    assert tuple(z.shape) == (2, N, 16, 24)
