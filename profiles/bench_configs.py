@@ -111,14 +111,21 @@ x2k = O.synth_images("S", 4, 1536, 2048, 1003).cuda()
 with torch.no_grad():
     ms2k = timed(lambda: m(x2k), 5)
 out["cfg5_2k_n128_tc_batch4"] = {"ms": ms2k, "mpix_s": 4 * 1536 * 2048 / 1e6 / ms2k * 1e3}
-m192 = P.ImageCompressor(192).cuda().eval()
-with torch.no_grad():
-    ms192 = timed(lambda: m192(x2k[:1]), 2, warmup=1)
-    sd192 = {k: v.detach() for k, v in m192.state_dict().items()}
-    msr192 = timed(lambda: O.forward(x2k[:1], sd192), 2, warmup=1)
-out["cfg5_2k_n192_fp32_kernels_batch1"] = {"ms": ms192, "mpix_s": 1536 * 2048 / 1e6 / ms192 * 1e3,
-                                           "note": "tensor-core kernels are specialised for N=128; N=192 runs the exact-fp32 kernels"}
-out["cfg5_2k_n192_reference_eager_cuda"] = {"ms": msr192, "mpix_s": 1536 * 2048 / 1e6 / msr192 * 1e3}
+for N in (192, 256):
+    mw = P.ImageCompressor(N).cuda().eval()
+    sdw = {k: v.detach() for k, v in mw.state_dict().items()}
+    with torch.no_grad():
+        ms_tc = timed(lambda: mw(x2k), 5)
+        mw.fast_inference = False
+        ms_fp32 = timed(lambda: mw(x2k[:1]), 2, warmup=1)
+        mw.fast_inference = True
+        torch.backends.cudnn.allow_tf32 = True
+        ms_ref = timed(lambda: O.forward(x2k[:1], sdw), 2, warmup=1)
+        torch.backends.cudnn.allow_tf32 = False
+    out[f"cfg5_2k_n{N}_tc_batch4"] = {"ms": ms_tc, "mpix_s": 4 * 1536 * 2048 / 1e6 / ms_tc * 1e3}
+    out[f"cfg5_2k_n{N}_fp32_kernels_batch1"] = {"ms": ms_fp32, "mpix_s": 1536 * 2048 / 1e6 / ms_fp32 * 1e3}
+    out[f"cfg5_2k_n{N}_reference_eager_cuda_tf32_batch1"] = {"ms": ms_ref, "mpix_s": 1536 * 2048 / 1e6 / ms_ref * 1e3}
+    del mw
 
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "r1_configs.json")
 os.makedirs(os.path.dirname(path), exist_ok=True)
