@@ -103,7 +103,8 @@ struct TcCfg {
   static constexpr int B_SLOT = (KIND == B2C_TC_DECONV3) ? 8192 : C * 128;
   static constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (SLOT_BYTES + B_SLOT);
   static constexpr int PATCH = (KIND == B2C_TC_CONV1) ? P1_SLOT : 0;
-  static constexpr int EXTRA = 1024 /*align*/ + 2048 /*bias, beta*/ + 256 /*barriers*/;
+  static constexpr int CONSTS = (C <= 128) ? 128 : 256;       // floats of bias and of beta kept in smem
+  static constexpr int EXTRA = 1024 /*align*/ + 2 * CONSTS * 4 /*bias, beta*/ + 256 /*barriers*/;
   static constexpr int N_TILE = (KIND == B2C_TC_DECONV3) ? 48 : C;
   static constexpr int TMEM_COLS = GDN ? (2 * C <= 256 ? 256 : 512) : (N_TILE <= 64 ? 64 : (N_TILE <= 128 ? 128 : 256));
   static constexpr int MAX_SMEM = 227 * 1024;
@@ -148,8 +149,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* patch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);   // CONV1 only
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + Cfg::PATCH);
-  float* s_beta = s_bias + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 512);
+  float* s_beta = s_bias + Cfg::CONSTS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * Cfg::CONSTS);
   uint64_t* full = bars;                    // [STAGES] TMA bytes landed
   uint64_t* empty = bars + STAGES;          // [STAGES] MMAs that read the stage completed
   uint64_t* afull = bars + 2 * STAGES;      // [STAGES] software-written A tile ready (NWORKERS arrivals)
