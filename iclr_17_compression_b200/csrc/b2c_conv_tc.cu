@@ -138,7 +138,22 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   constexpr uint32_t TMEM_COLS = Cfg::TMEM_COLS;
   // PAIR: two CTAs (adjacent tiles) form a cta_group::2 pair: one M = 256 MMA per step issued by the leader,
   // each CTA stages its own A tile and HALF of the weight tile, halving B fill and B operand reads per SM.
-  static_assert(!PAIR || (KIND != B2C_TC_CONV1 && KIND != B2C_TC_DECONV3), "CTA pairs: TMA-fed C-channel kinds only");
+  static_assert(!PAIR || KIND != B2C_TC_DECONV3, "CTA pairs: C-channel output kinds only");
+  // DEC (CONV1 as a CTA pair): the stage is re-cut into ONE software A slot and a ring of TWO half-size weight
+  // slots (each CTA of the pair stages half of the weight rows), so the next k-block's weights are prefetched
+  // while the current one is built and multiplied - same shared-memory footprint, two CTAs per SM.
+  constexpr bool DEC = SOFT_A && PAIR;
+  static_assert(!DEC || (STAGES == 1 && SPLIT3), "decoupled rings are the single-stage bf16x3 CONV1 layout");
+  constexpr int NA = DEC ? 1 : STAGES;                  // A ring depth
+  constexpr int NB = DEC ? 2 : STAGES;                  // B ring depth
+  constexpr int NBAR = NA > NB ? NA : NB;
+  constexpr uint32_t B_HALF = B_SLOT / 2;
+  constexpr uint32_t B_LO = DEC ? B_HALF : (uint32_t)B_SLOT;   // offset of the lo weight tile from the hi one
+  auto a_off = [](int s) -> uint32_t { return DEC ? 0u : (uint32_t)((s % STAGES) * STAGE_BYTES); };
+  auto b_off = [](int s) -> uint32_t {
+    return DEC ? (uint32_t)(2 * SLOT_BYTES) + (uint32_t)(s % 2) * 2u * B_HALF
+               : (uint32_t)((s % STAGES) * STAGE_BYTES) + (uint32_t)((SPLIT3 ? 2 : 1) * SLOT_BYTES);
+  };
   constexpr uint32_t B_BYTES = N_TILE * KBLK * 2 / (PAIR ? 2 : 1);
   static_assert(GDN == 0 || N_TILE == C, "fused GDN needs all channels in the tile");
   // GDN: 0 none, 1 GDN forward, 2 IGDN forward, 3 GDN backward, 4 IGDN backward (epilogue of the dgrad conv)
@@ -151,13 +166,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + Cfg::PATCH);
   float* s_beta = s_bias + Cfg::CONSTS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * Cfg::CONSTS);
-  uint64_t* full = bars;                    // [STAGES] TMA bytes landed
-  uint64_t* empty = bars + STAGES;          // [STAGES] MMAs that read the stage completed
-  uint64_t* afull = bars + 2 * STAGES;      // [STAGES] software-written A tile ready (NWORKERS arrivals)
-  uint64_t* accum_full = bars + 3 * STAGES;
-  uint64_t* norm_full = bars + 3 * STAGES + 1;
-  uint64_t* patch_full = bars + 3 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 3);
+  uint64_t* full = bars;                    // [NB] TMA bytes landed
+  uint64_t* empty = bars + NBAR;            // [NB] MMAs that read the (B or whole) stage completed
+  uint64_t* afull = bars + 2 * NBAR;        // [NA] software-written A tile ready (NWORKERS arrivals per CTA)
+  uint64_t* aempty = DEC ? bars + 3 * NBAR : empty;   // [NA] A slot released (its own barrier only when decoupled)
+  uint64_t* accum_full = bars + 4 * NBAR;
+  uint64_t* norm_full = bars + 4 * NBAR + 1;
+  uint64_t* patch_full = bars + 4 * NBAR + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * NBAR + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int phase = blockIdx.y;
@@ -176,10 +192,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } while (0)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NBAR; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
       mbar_init(&afull[i], NWORKERS * (PAIR ? 2 : 1));
+      if (DEC) mbar_init(&aempty[i], 1);
     }
     mbar_init(accum_full, 1);
     mbar_init(norm_full, 1);
@@ -215,14 +232,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
       TC_MARK(0);
       for (int s = 0; s < total_steps; ++s) {
-        const int stage = s % STAGES, it = s / STAGES;
+        const int stage = s % NB, it = s / NB;
         mbar_wait(&empty[stage], (it & 1) ^ 1);
         TC_MARK(0);
-        uint8_t* st = smem + stage * STAGE_BYTES;
-        uint8_t* a_hi = st;
-        uint8_t* a_lo = st + SLOT_BYTES;
-        uint8_t* b_hi = st + (SPLIT3 ? 2 : 1) * SLOT_BYTES;
-        uint8_t* b_lo = b_hi + B_SLOT;
+        uint8_t* a_hi = smem + a_off(s);
+        uint8_t* a_lo = a_hi + SLOT_BYTES;
+        uint8_t* b_hi = smem + b_off(s);
+        uint8_t* b_lo = b_hi + B_LO;
         if (s < nsteps) {
           int dy, dx, cb, group;
           decode_step<KIND, NCB>(s, phase, dy, dx, cb, group);
@@ -232,8 +248,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             if (leader) mbar_arrive_expect_tx(&full[stage], 2u * (a_bytes + B_BYTES) * (SPLIT3 ? 2u : 1u));
             const int cx = ox0 * IN_STRIDE + dx, cy = oy0 * IN_STRIDE + dy;
             const int brow = group * N_TILE + (int)cta_rank * (N_TILE / 2);
-            tma_load_4d_pair(a_hi, &tmA_hi, &full[stage], cb * KBLK, cx, cy, n_img);
-            if (SPLIT3) tma_load_4d_pair(a_lo, &tmA_lo, &full[stage], cb * KBLK, cx, cy, n_img);
+            if (!SOFT_A) {
+              tma_load_4d_pair(a_hi, &tmA_hi, &full[stage], cb * KBLK, cx, cy, n_img);
+              if (SPLIT3) tma_load_4d_pair(a_lo, &tmA_lo, &full[stage], cb * KBLK, cx, cy, n_img);
+            }
             tma_load_2d_pair(b_hi, &tmB_hi, &full[stage], cb * KBLK, brow);
             if (SPLIT3) tma_load_2d_pair(b_lo, &tmB_lo, &full[stage], cb * KBLK, brow);
           } else {
@@ -273,19 +291,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint64_t desc0 = umma_desc_sw128(sbase);     // + (byte offset >> 4) selects a tile / K slice
       uint32_t soft_phase = 0;                            // bit per stage: parity of the next software-A fill
       for (int s = 0; s < total_steps; ++s) {
-        const int stage = s % STAGES, it = s / STAGES;
+        const int stage = s % NB, it = s / NB, sa = s % NA;
         const bool is_gdn = s >= nsteps;
         mbar_wait(&full[stage], it & 1);
         if (SOFT_A || is_gdn) {
-          if (PAIR) mbar_wait_cluster(&afull[stage], (soft_phase >> stage) & 1u);
-          else mbar_wait(&afull[stage], (soft_phase >> stage) & 1u);
-          soft_phase ^= 1u << stage;
+          if (PAIR) mbar_wait_cluster(&afull[sa], (soft_phase >> sa) & 1u);
+          else mbar_wait(&afull[sa], (soft_phase >> sa) & 1u);
+          soft_phase ^= 1u << sa;
         }
         tcgen05_fence_after();
         if (lane == 0) TC_MARK(1);
-        const uint32_t off = (uint32_t)(stage * STAGE_BYTES);
-        const uint64_t a_hi = desc0 + (off >> 4), a_lo = a_hi + (SLOT_BYTES >> 4);
-        const uint64_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * SLOT_BYTES) >> 4), b_lo = b_hi + (B_SLOT >> 4);
+        const uint64_t a_hi = desc0 + (a_off(s) >> 4), a_lo = a_hi + (SLOT_BYTES >> 4);
+        const uint64_t b_hi = desc0 + (b_off(s) >> 4), b_lo = b_hi + (B_LO >> 4);
         const uint32_t d = tb + (is_gdn ? (uint32_t)C : 0u);
         const uint32_t idesc = is_gdn ? idesc_gdn : idesc_main;
         const uint32_t acc0 = (s > (is_gdn ? nsteps : 0)) ? 1u : 0u;
@@ -309,6 +326,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           }
           if (PAIR) {
             umma_commit_pair(&empty[stage]);
+            if (DEC) umma_commit_pair(&aempty[sa]);
             if (s == nsteps - 1) umma_commit_pair(accum_full);
             if (GDN && s == total_steps - 1) umma_commit_pair(norm_full);
           } else {
@@ -360,9 +378,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       TC_WMARK();
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        const int stage = s % STAGES, it = s / STAGES;
-        mbar_wait(&empty[stage], (it & 1) ^ 1);
-        uint8_t* st = smem + stage * STAGE_BYTES;
+        const int stage = s % NA, it = s / NA;
+        mbar_wait(&aempty[stage], (it & 1) ^ 1);
+        uint8_t* st = smem + a_off(s);
         if (half >= 2) {
           // C > 128: the 8 chunks of a k-block are built by the first two workers of the row
         } else if (half == 0) {
@@ -377,7 +395,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           else conv1_build_row<3, 1, SPLIT3>(pp, st, st + SLOT_BYTES, r);
         }
         fence_proxy_async_smem();
-        mbar_arrive(&afull[stage]);
+        if (PAIR) mbar_arrive_leader(&afull[stage]);
+        else mbar_arrive(&afull[stage]);
         TC_WMARK();
       }
     }
@@ -392,12 +411,12 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 #pragma unroll 1
       for (int g = 0; g < NCB; ++g) {
         const int s = nsteps + g;
-        const int stage = s % STAGES, it = s / STAGES;
-        // every worker waits for the slot (with one stage, k-block 1 reuses k-block 0's slot and barrier:
+        const int stage = s % NA, it = s / NA;
+        // every worker waits for the slot (with one A slot, k-block 1 reuses k-block 0's slot and barrier:
         // arriving early would be counted in the previous phase)
-        mbar_wait(&empty[stage], (it & 1) ^ 1);
+        mbar_wait(&aempty[stage], (it & 1) ^ 1);
         if (g == half) {
-          uint8_t* st = smem + stage * STAGE_BYTES;
+          uint8_t* st = smem + a_off(s);
           uint32_t raw[64];
           tmem_ld32(t_row + (uint32_t)(g * 64), *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
           tmem_ld32(t_row + (uint32_t)(g * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
@@ -1014,12 +1033,16 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
               L->kind, L->split3, L->gdn, L->out_f32_nchw);
     return B2C_EINVAL;
   }
-  static const int use_pairs = [] {   // 0: off, 1: bf16x3 5x5 convs (default), 2: also the bf16 transposed convs
+  static const int use_pairs = [] {   // 0: off, 1: bf16x3 5x5 convs (default), 2: + bf16 transposed convs, 3: + conv1
     const char* e = getenv("B2C_TC_PAIRS");
     return e ? atoi(e) : B2C_TC_PAIRS_DEFAULT;
   }();
   if (use_pairs) {
     switch (key) {
+      case B2C_TC_CONV1 * 1000 + 100 + 10 + 0:   // measured slower (0.32 vs 0.28 ms at cfg2): both CTAs of a pair build their
+        if (use_pairs > 2 && B2C_CONV1_STAGES == 1)   // A tiles in lock-step and contend for shared memory; opt-in (=3)
+          return launch<128, true, B2C_TC_CONV1, 1, OUT_BF16, true>(L, p, grid, stream);
+        break;
       case B2C_TC_CONV5S2 * 1000 + 100 + 10 + 0: return launch<128, true, B2C_TC_CONV5S2, 1, OUT_BF16, true>(L, p, grid, stream);
       case B2C_TC_CONV5S2 * 1000 + 100 + 0 + 1: return launch<128, true, B2C_TC_CONV5S2, 0, OUT_F32_NCHW, true>(L, p, grid, stream);
       case B2C_TC_DECONV5S2 * 1000 + 0 + 20 + 0:
