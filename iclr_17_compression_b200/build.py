@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "--expt-relaxed-constexpr",
     "-cudart", "static",
-]
+] + os.environ.get("B2C_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DB2C_TCP_FINE_TRACE (debug timelines)
 
 
 def _sources():

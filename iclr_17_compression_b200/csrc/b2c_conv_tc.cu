@@ -804,7 +804,7 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
 
 namespace b2c {
 namespace tcp {
-int try_launch(const b2c_tc_layer* L, cudaStream_t stream);   // b2c_conv_tcp.cu; 1 = not covered
+int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   // b2c_conv_tcp.cu; 1 = not covered
 }
 }  // namespace b2c
 
@@ -897,8 +897,8 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   B2C_REQUIRE(!L->gdn || (L->gamma_hi && L->beta_eff && (!L->split3 || L->gamma_lo)), "tc_layer_run: gdn needs gamma/beta");
   B2C_REQUIRE(L->out_f32_nchw || !L->split3 || L->out_lo, "tc_layer_run: split3 bf16 output needs out_lo");
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!g_tc_trace) {   // persistent kernels for the TMA-fed 128-channel inference layers
-    const int rc = b2c::tcp::try_launch(L, stream);
+  {   // persistent kernels for the TMA-fed 128-channel inference layers
+    const int rc = b2c::tcp::try_launch(L, stream, g_tc_trace);
     if (rc != 1) return rc;
   }
   TcParams p;

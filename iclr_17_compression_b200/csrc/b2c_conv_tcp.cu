@@ -48,6 +48,7 @@ struct PParams {
   float* out_f32;
   const float* ref_image;   // DECONV3 fused distortion
   float* sse_partial;
+  long long* trace;         // debug: clock64 timeline of CTA 0: [3 roles][64 marks]
 };
 
 struct POutMaps {
@@ -116,10 +117,57 @@ __device__ __forceinline__ void sts128(uint8_t* slot, int r, int cidx, uint32_t 
   const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cidx ^ (r & 7)) << 4);
   *reinterpret_cast<uint4*>(slot + off) = make_uint4(a, b, c, d);
 }
+// packed fp32x2 arithmetic (FADD2 / FMUL2): halves the ALU instruction count of the epilogues
+__device__ __forceinline__ uint64_t pk2(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t pkf2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float rsqrt_fast(float x) {   // MUFU.RSQ without the denormal fix-up code around rsqrtf()
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// Arrive on the mbarrier at the same offset in CTA 0 of the pair with the DEFAULT semantics (release at CTA scope),
+// as CUTLASS' ClusterBarrier::arrive does.  The explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR
+// (~1.1 k clk on the critical path of every x^2 / accumulator hand-off); the data these arrivals publish is this
+// CTA's own shared memory / TMEM, already ordered by fence.proxy.async / tcgen05.fence + the named barrier.
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 rem;\n\t"
+      "mapa.shared::cluster.u32 rem, %0, 0;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// L2 prefetch of one activation box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -144,6 +192,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   constexpr int XS_ROUNDS = SPLIT3 ? 2 : 1;
   constexpr uint32_t NPAIR = PAIR ? 2u : 1u;
   constexpr uint32_t ACC_STRIDE = Cfg::ACC_STRIDE;
+  constexpr bool PREFETCH = false;   // measured slower (TMA queue shared with the demand loads): conv2 0.250 -> 0.258 ms
   static_assert(OUT_MODE != OUT_BF16 || GDN != 0, "bf16 NHWC output stages through the x^2 buffer");
   static_assert(!SPLIT3 || PAIR, "the bf16x3 rings only fit as a CTA pair");
   static_assert(!B_RES || (!PAIR && !SPLIT3 && GDN == 0 && OUT_MODE == OUT_F32_NCHW_PS4), "DECONV3 form");
@@ -174,6 +223,17 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const bool leader = cta_rank == 0;
   const int n_units = (p.n_tiles + (int)NPAIR - 1) / (int)NPAIR;           // tiles, or pairs of adjacent tiles
   const int unit0 = (int)(blockIdx.x / NPAIR), unit_stride = (int)(gridDim.x / NPAIR);
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  int tmark = 0;
+#ifdef B2C_TCP_FINE_TRACE
+#define TCP_FINE() TCP_MARK(2, threadIdx.x == 64)
+#else
+#define TCP_FINE() do {} while (0)
+#endif
+#define TCP_MARK(role, cond)                                                        \
+  do {                                                                              \
+    if (tracing && (cond) && tmark < 64) p.trace[(role) * 64 + tmark++] = clock64(); \
+  } while (0)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -238,13 +298,29 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int trem = tile - n_img * p.tiles_per_image;
         const int tile_y = trem / p.tiles_x, tile_x = trem - tile_y * p.tiles_x;
         const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+        // the next unit's input window -> L2 while this unit is computed (its first boxes would otherwise pay the
+        // full HBM latency with only NA boxes of run-ahead)
+        int pf_img = -1, pf_x = 0, pf_y = 0;
+        if (PREFETCH && unit + unit_stride < n_units) {
+          const int ntile = (unit + unit_stride) * (int)NPAIR + (int)cta_rank;
+          pf_img = ntile / p.tiles_per_image;
+          const int nrem = ntile - pf_img * p.tiles_per_image;
+          const int nty = nrem / p.tiles_x;
+          pf_y = nty * TH * IN_STRIDE; pf_x = (nrem - nty * p.tiles_x) * TW * IN_STRIDE;
+          if (pf_img >= p.B) pf_img = -1;
+        }
         for (int phase = 0; phase < NPH; ++phase) {
           const int ng = p_ngroups<KIND>(phase);
           for (int gi = 0; gi < ng; ++gi, ++ga) {
             int cb, x_off, y_off, ntaps;
             p_group<KIND>(gi, phase, cb, x_off, y_off, ntaps);
+            if (PREFETCH && pf_img >= 0 && phase == 0) {
+              tma_prefetch_4d(&tmA_hi, cb * KBLK, pf_x + x_off, pf_y + y_off, pf_img);
+              if (SPLIT3) tma_prefetch_4d(&tmA_lo, cb * KBLK, pf_x + x_off, pf_y + y_off, pf_img);
+            }
             const uint32_t as = ga % NA;
             mbar_wait(&a_empty[as], ((ga / NA) & 1) ^ 1);
+            TCP_MARK(0, true);
             uint8_t* a_hi = smem + as * A_SLOT;
             const int cx = ox0 * IN_STRIDE + x_off, cy = oy0 * IN_STRIDE + y_off;
             if (PAIR) {
@@ -367,6 +443,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 if (t < ntaps) mbar_wait(&b_full[(gb + t) % NBX], ((gb + t) / NBX) & 1);
             }
             tcgen05_fence_after();
+            TCP_MARK(1, lane == 0);
             const uint64_t a_box = desc0 + ((as * A_SLOT) >> 4);
             const bool last_group = gi == ng - 1;
             // ONE elected region per group: up to 3 taps x 4 k-slices x (1 | 3) MMAs and their commits back to back
@@ -477,77 +554,67 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int phase = 0; phase < NPH; ++phase, ++st) {
         const uint32_t buf = st & 1u, par = (st >> 1) & 1u;
         const uint32_t t_acc = t_lane + buf * ACC_STRIDE, t_nrm = t_acc + 128u;
+        TCP_MARK(2, threadIdx.x == 64);
         mbar_wait(&accum_full[buf], par);
         tcgen05_fence_after();
+        TCP_MARK(2, threadIdx.x == 64);
 
+        // x = acc + bias of this thread's 64 channels stays in registers between the two passes (TMEM reads are
+        // 64 B/clk per SM: re-reading the accumulator would cost as much as the gamma MMAs)
+        //   SPLIT3: xk[g*16 + i] = channels g*64 + half*32 + 2i, +1     bf16: xk[hh*16 + i] = half*64 + hh*32 + 2i, +1
+        uint64_t xk[GDN ? 32 : 1];
         if (GDN) {
-          // ---- x^2 = (acc + bias)^2 as the K-major swizzled A tile of the gamma product
-          if (SPLIT3) {
-#pragma unroll 1
-            for (int g = 0; g < 2; ++g) {        // round g = k-block g; this thread: channels g*64 + half*32 .. +31
-              uint32_t raw[32];
-              const int c0 = g * 64 + half * 32;
-              tmem_ld32(t_acc + (uint32_t)c0, raw);
-              tmem_ld_wait();
-              if (g == 0) {                      // the previous sub-tile's lo-plane store must have left the buffer
-                if (elected && store_pending) { tma_store_wait_read(); store_pending = false; }
-                WORKER_SYNC();
-              } else {
-                mbar_wait(xs_empty, st & 1u);    // the gamma MMAs of round 0 have read it
+          // ---- x^2 as the K-major swizzled A tile of the gamma product
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint32_t raw[32];
+            const int c0 = SPLIT3 ? g * 64 + half * 32 : half * 64 + g * 32;
+            tmem_ld32(t_acc + (uint32_t)c0, raw);
+            tmem_ld_wait();
+            TCP_FINE();
+            if (g == 0) {                      // the previous sub-tile's (last) store must have left the buffer
+              if (elected && store_pending) { tma_store_wait_read(); store_pending = false; }
+              WORKER_SYNC();
+              TCP_FINE();
+            } else if (SPLIT3) {
+              mbar_wait(xs_empty, st & 1u);    // the gamma MMAs of round 0 have read it
+            }
+            const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + c0);
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t x2 = add2(pk2(raw[ci * 8 + 2 * j], raw[ci * 8 + 2 * j + 1]), bias2[ci * 4 + j]);
+                xk[g * 16 + ci * 4 + j] = x2;
+                float v0, v1;
+                upk2(mul2(x2, x2), v0, v1);
+                h[j] = cvt_bf16x2(v0, v1);
+                if (SPLIT3) l[j] = lo_of(v0, v1, h[j]);
               }
-#pragma unroll
-              for (int ci = 0; ci < 4; ++ci) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float x0 = __uint_as_float(raw[ci * 8 + 2 * j]) + s_bias[c0 + ci * 8 + 2 * j];
-                  const float x1 = __uint_as_float(raw[ci * 8 + 2 * j + 1]) + s_bias[c0 + ci * 8 + 2 * j + 1];
-                  const float v0 = x0 * x0, v1 = x1 * x1;
-                  h[j] = cvt_bf16x2(v0, v1);
-                  l[j] = lo_of(v0, v1, h[j]);
-                }
+              if (SPLIT3) {
                 sts128(xs, r, half * 4 + ci, h[0], h[1], h[2], h[3]);
                 sts128(xs + SLOT_BYTES, r, half * 4 + ci, l[0], l[1], l[2], l[3]);
+              } else {
+                sts128(xs + half * SLOT_BYTES, r, g * 4 + ci, h[0], h[1], h[2], h[3]);
               }
+            }
+            TCP_FINE();
+            if (SPLIT3 || g == 1) {
               fence_proxy_async_smem();
+              TCP_FINE();
               WORKER_SYNC();
+              TCP_FINE();
               if (elected) {
-                if (PAIR) mbar_arrive_leader(xs_full);
+                if (PAIR) mbar_arrive_cta0(xs_full);
                 else mbar_arrive(xs_full);
               }
             }
-          } else {                                // one round: this thread's 64 channels = k-block `half`
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t raw[32];
-              const int c0 = half * 64 + hh * 32;
-              tmem_ld32(t_acc + (uint32_t)c0, raw);
-              tmem_ld_wait();
-              if (hh == 0) {
-                if (elected && store_pending) { tma_store_wait_read(); store_pending = false; }
-                WORKER_SYNC();
-              }
-#pragma unroll
-              for (int ci = 0; ci < 4; ++ci) {
-                uint32_t h[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float x0 = __uint_as_float(raw[ci * 8 + 2 * j]) + s_bias[c0 + ci * 8 + 2 * j];
-                  const float x1 = __uint_as_float(raw[ci * 8 + 2 * j + 1]) + s_bias[c0 + ci * 8 + 2 * j + 1];
-                  h[j] = cvt_bf16x2(x0 * x0, x1 * x1);
-                }
-                sts128(xs + half * SLOT_BYTES, r, hh * 4 + ci, h[0], h[1], h[2], h[3]);
-              }
-            }
-            fence_proxy_async_smem();
-            WORKER_SYNC();
-            if (elected) {
-              if (PAIR) mbar_arrive_leader(xs_full);
-              else mbar_arrive(xs_full);
-            }
           }
+          TCP_MARK(2, threadIdx.x == 64);
           mbar_wait(&norm_full[buf], par);     // also: every gamma MMA has finished reading the x^2 tile
           tcgen05_fence_after();
+          TCP_MARK(2, threadIdx.x == 64);
         }
 
         // ---- final pass: y = (acc + bias) [* or / sqrt(beta + norm)]
@@ -623,7 +690,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               tcgen05_fence_before();
               WORKER_SYNC();
               if (elected) {
-                if (PAIR) mbar_arrive_leader(&acc_empty[buf]);
+                if (PAIR) mbar_arrive_cta0(&acc_empty[buf]);
                 else mbar_arrive(&acc_empty[buf]);
               }
             }
@@ -645,38 +712,39 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           uint32_t lo_pack[SPLIT3 ? 32 : 1];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int c0 = half * 64 + h * 32;
-            uint32_t raw[32], rawn[32];
-            tmem_ld32(t_acc + (uint32_t)c0, raw);
+            const int c0 = SPLIT3 ? h * 64 + half * 32 : half * 64 + h * 32;
+            uint32_t rawn[32];
             tmem_ld32(t_nrm + (uint32_t)c0, rawn);
             tmem_ld_wait();
+            TCP_FINE();
             if (h == 1) tcgen05_fence_before();
+            const uint64_t* beta2 = reinterpret_cast<const uint64_t*>(s_beta + c0);
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
               uint32_t hp[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                float y[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int cc = ci * 8 + 2 * j + e;
-                  const float xv = __uint_as_float(raw[cc]) + s_bias[c0 + cc];
-                  const float nb = __uint_as_float(rawn[cc]) + s_beta[c0 + cc];
-                  const float rs = rsqrt_fast(nb);
-                  y[e] = (GDN == 2) ? xv * (nb * rs) : xv * rs;
-                }
-                hp[j] = cvt_bf16x2(y[0], y[1]);
-                if (SPLIT3) lo_pack[h * 16 + ci * 4 + j] = lo_of(y[0], y[1], hp[j]);
+                float n0, n1, y0, y1;
+                upk2(add2(pk2(rawn[ci * 8 + 2 * j], rawn[ci * 8 + 2 * j + 1]), beta2[ci * 4 + j]), n0, n1);
+                const uint64_t sc = (GDN == 2) ? pkf2(sqrt_fast(n0), sqrt_fast(n1)) : pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
+                upk2(mul2(xk[h * 16 + ci * 4 + j], sc), y0, y1);
+                hp[j] = cvt_bf16x2(y0, y1);
+                if (SPLIT3) lo_pack[h * 16 + ci * 4 + j] = lo_of(y0, y1, hp[j]);
               }
-              sts128(xs + half * SLOT_BYTES, r, h * 4 + ci, hp[0], hp[1], hp[2], hp[3]);
+              if (SPLIT3) sts128(xs + h * SLOT_BYTES, r, half * 4 + ci, hp[0], hp[1], hp[2], hp[3]);
+              else sts128(xs + half * SLOT_BYTES, r, h * 4 + ci, hp[0], hp[1], hp[2], hp[3]);
             }
           }
           const int mi = (KIND == B2C_TC_DECONV5S2) ? phase : 0;
+          TCP_FINE();
           fence_proxy_async_smem();
+          TCP_FINE();
           WORKER_SYNC();                        // staging complete; every worker has finished its TMEM reads
+          TCP_FINE();
           if (elected) {
-            if (PAIR) mbar_arrive_leader(&acc_empty[buf]);
+            if (PAIR) mbar_arrive_cta0(&acc_empty[buf]);
             else mbar_arrive(&acc_empty[buf]);
+            TCP_FINE();
             tma_store_4d(&tmO.m[mi], xs, 0, ox0, oy0, n_img);
             tma_store_4d(&tmO.m[mi], xs + SLOT_BYTES, KBLK, ox0, oy0, n_img);
             tma_store_commit();
@@ -689,7 +757,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             for (int h = 0; h < 2; ++h)
 #pragma unroll
               for (int ci = 0; ci < 4; ++ci)
-                sts128(xs + half * SLOT_BYTES, r, h * 4 + ci, lo_pack[h * 16 + ci * 4 + 0], lo_pack[h * 16 + ci * 4 + 1],
+                sts128(xs + h * SLOT_BYTES, r, half * 4 + ci, lo_pack[h * 16 + ci * 4 + 0], lo_pack[h * 16 + ci * 4 + 1],
                        lo_pack[h * 16 + ci * 4 + 2], lo_pack[h * 16 + ci * 4 + 3]);
             fence_proxy_async_smem();
             WORKER_SYNC();
@@ -704,6 +772,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
     if (elected && store_pending) tma_store_wait_read();
+    TCP_MARK(2, threadIdx.x == 64);
 #undef WORKER_SYNC
   }
 
@@ -734,7 +803,7 @@ static int make_act_box_map(CUtensorMap* m, const void* base, int B, int H, int 
 }
 
 template <int KIND, bool SPLIT3, int GDN, int OUT_MODE, bool PAIR>
-static int launch_p(const b2c_tc_layer* L, cudaStream_t stream) {
+static int launch_p(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   using Cfg = PCfg<KIND, SPLIT3, PAIR, GDN>;
   constexpr size_t SMEM = Cfg::SMEM;
   constexpr int N_TILE = Cfg::N_TILE;
@@ -752,6 +821,7 @@ static int launch_p(const b2c_tc_layer* L, cudaStream_t stream) {
   p.bias = L->bias; p.beta_eff = L->beta_eff;
   p.out_f32 = (float*)L->out_hi;
   p.ref_image = L->ref_image; p.sse_partial = L->sse_partial;
+  p.trace = trace;
 
   // grid: one CTA (pair) per SM, never more than can be co-resident (a persistent CTA that waits for a slot
   // would serialise its whole share of the tiles)
@@ -841,7 +911,7 @@ static int launch_p(const b2c_tc_layer* L, cudaStream_t stream) {
 
 // Returns 1 when the layer is not one the persistent kernels cover (the caller then uses the per-tile kernels),
 // otherwise the launch status.
-int try_launch(const b2c_tc_layer* L, cudaStream_t stream) {
+int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   static const int mode = [] {   // 0: off, 1: on (default); bit 1: transposed 5x5 convs as independent CTAs
     const char* e = getenv("B2C_TC_PERSIST");
     return e ? atoi(e) : 1;
@@ -851,17 +921,17 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream) {
   if (channels != 128 || L->saved_y) return 1;
   if (L->kind == B2C_TC_CONV5S2 && L->split3) {
     if (L->gdn == 1 && !L->out_f32_nchw && L->out_lo)
-      return launch_p<B2C_TC_CONV5S2, true, 1, OUT_BF16, true>(L, stream);
+      return launch_p<B2C_TC_CONV5S2, true, 1, OUT_BF16, true>(L, stream, trace);
     if (L->gdn == 0 && L->out_f32_nchw)
-      return launch_p<B2C_TC_CONV5S2, true, 0, OUT_F32_NCHW, true>(L, stream);
+      return launch_p<B2C_TC_CONV5S2, true, 0, OUT_F32_NCHW, true>(L, stream, trace);
     return 1;
   }
   if (L->kind == B2C_TC_DECONV5S2 && !L->split3 && L->gdn == 2 && !L->out_f32_nchw && !L->out_lo) {
-    if (mode & 2) return launch_p<B2C_TC_DECONV5S2, false, 2, OUT_BF16, false>(L, stream);
-    return launch_p<B2C_TC_DECONV5S2, false, 2, OUT_BF16, true>(L, stream);
+    if (mode & 2) return launch_p<B2C_TC_DECONV5S2, false, 2, OUT_BF16, false>(L, stream, trace);
+    return launch_p<B2C_TC_DECONV5S2, false, 2, OUT_BF16, true>(L, stream, trace);
   }
   if (L->kind == B2C_TC_DECONV3 && !L->split3 && L->gdn == 0 && L->out_f32_nchw && !(mode & 4))
-    return launch_p<B2C_TC_DECONV3, false, 0, OUT_F32_NCHW_PS4, false>(L, stream);
+    return launch_p<B2C_TC_DECONV3, false, 0, OUT_F32_NCHW_PS4, false>(L, stream, trace);
   return 1;
 }
 
