@@ -162,6 +162,24 @@ __device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {
       "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
+// NON-blocking phase test for polling (try_wait may suspend the warp for a system-dependent time when the phase is
+// not complete - that suspended the MMA warp for 2-3.5 k clk at every tile boundary)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity, bool cluster_scope) {
+  uint32_t ok;
+  if (cluster_scope)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
 // L2 prefetch of one activation box (no shared-memory destination, no barrier)
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
@@ -227,8 +245,10 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   int tmark = 0;
 #ifdef B2C_TCP_FINE_TRACE
 #define TCP_FINE() TCP_MARK(2, threadIdx.x == 64)
+#define TCP_FINE_MMA() TCP_MARK(1, lane == 0)
 #else
 #define TCP_FINE() do {} while (0)
+#define TCP_FINE_MMA() do {} while (0)
 #endif
 #define TCP_MARK(role, cond)                                                        \
   do {                                                                              \
@@ -417,7 +437,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (++pend_round == XS_ROUNDS) pend_buf = -1;
       };
       auto xs_ready = [&]() -> bool {
-        uint32_t ok = PAIR ? mbar_try_wait_cluster(xs_full, xs_cnt & 1u) : mbar_try_wait(xs_full, xs_cnt & 1u);
+        uint32_t ok = mbar_test_wait(xs_full, xs_cnt & 1u, PAIR);
         return __shfl_sync(0xffffffffu, ok, 0) != 0;
       };
 
@@ -427,9 +447,11 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const uint32_t buf = st & 1u;
           const int ng = p_ngroups<KIND>(phase);
           // the workers must have drained this accumulator set (sub-tile st-2)
+          TCP_FINE_MMA();
           if (PAIR) mbar_wait_cluster(&acc_empty[buf], ((st >> 1) & 1u) ^ 1u);
           else mbar_wait(&acc_empty[buf], ((st >> 1) & 1u) ^ 1u);
           tcgen05_fence_after();
+          TCP_FINE_MMA();
           const uint32_t d = tb + buf * ACC_STRIDE;
           for (int gi = 0; gi < ng; ++gi, ++ga) {
             int cb, x_off, y_off, ntaps;
@@ -494,6 +516,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
           if (GDN) {
             // the previous sub-tile's gamma product must be out before this one's can be queued
+            TCP_FINE_MMA();
             while (pend_buf >= 0) {
               if (PAIR) mbar_wait_cluster(xs_full, xs_cnt & 1u);
               else mbar_wait(xs_full, xs_cnt & 1u);
@@ -745,8 +768,10 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             if (PAIR) mbar_arrive_cta0(&acc_empty[buf]);
             else mbar_arrive(&acc_empty[buf]);
             TCP_FINE();
+#ifndef B2C_TCP_NO_STORE   /* timing experiment only */
             tma_store_4d(&tmO.m[mi], xs, 0, ox0, oy0, n_img);
             tma_store_4d(&tmO.m[mi], xs + SLOT_BYTES, KBLK, ox0, oy0, n_img);
+#endif
             tma_store_commit();
             if (SPLIT3) tma_store_wait_read();
             else store_pending = true;          // waited for just before the buffer is written again
