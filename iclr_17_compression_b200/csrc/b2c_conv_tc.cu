@@ -806,6 +806,9 @@ namespace b2c {
 namespace tcp {
 int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   // b2c_conv_tcp.cu; 1 = not covered
 }
+namespace tcp1 {
+int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   // b2c_conv1_tcp.cu; 1 = not covered
+}
 }  // namespace b2c
 
 using namespace b2c;
@@ -898,7 +901,9 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   B2C_REQUIRE(L->out_f32_nchw || !L->split3 || L->out_lo, "tc_layer_run: split3 bf16 output needs out_lo");
   cudaStream_t stream = (cudaStream_t)stream_;
   {   // persistent kernels for the TMA-fed 128-channel inference layers
-    const int rc = b2c::tcp::try_launch(L, stream, g_tc_trace);
+    int rc = b2c::tcp::try_launch(L, stream, g_tc_trace);
+    if (rc != 1) return rc;
+    rc = b2c::tcp1::try_launch(L, stream, g_tc_trace);
     if (rc != 1) return rc;
   }
   TcParams p;
