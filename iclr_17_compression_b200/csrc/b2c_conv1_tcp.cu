@@ -12,9 +12,10 @@
 // i+1 in the gaps of tile i's epilogue (where they would otherwise wait for the gamma MMAs), two TMEM
 // accumulator sets let the conv MMAs of tile i+1 run under the epilogue of tile i, and the next patch is
 // fetched while the current tile's epilogue finishes.  Worker order per iteration `it` (B = build tile it,
-// E = epilogue tile it-1):   B.kb0  B.kb1  E.x^2[0]  B.kb2  E.x^2[1]  B.kb3  E.final
+// E = epilogue tile it-1; `|` = fence + worker barrier + signals):
+//                            B.kb0 B.kb1 | E.x^2[0] | B.kb2 E.x^2[1] | B.kb3 | E.final
 // MMA-warp order (static, deadlock-free against the order above):
-//                            conv kb0  conv kb1  gamma[0]  conv kb2  gamma[1]  conv kb3
+//                            conv kb0  conv kb1  gamma[0]  gamma[1]  conv kb2  conv kb3
 #include <mutex>
 
 #include "b2c_common.cuh"
@@ -55,18 +56,12 @@ struct Params {
 
 #define WORKER_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory")
 
-// im2col k-block KB of this CTA's tile -> A slot (KB & 1); signals the leader's a_full
+// im2col k-block KB of this CTA's tile -> A slot (KB & 1); the caller waits for the slot and signals a_full
 template <int KB>
-__device__ __forceinline__ void build_kb(const float* pp, uint8_t* smem, uint64_t* a_full, uint64_t* a_empty, int r,
-                                         int half, bool elected) {
-  constexpr int slot = KB & 1;
-  mbar_wait(&a_empty[slot], ((KB >> 1) & 1) ^ 1);        // use j = 2*it + (KB >> 1) of the slot
-  uint8_t* st = smem + slot * A_SLOT;
+__device__ __forceinline__ void build_rows(const float* pp, uint8_t* smem, int r, int half) {
+  uint8_t* st = smem + (KB & 1) * A_SLOT;
   if (half == 0) conv1_build_row<KB, 0, true>(pp, st, st + A_PLANE, r);
   else conv1_build_row<KB, 1, true>(pp, st, st + A_PLANE, r);
-  fence_proxy_async_smem();
-  WORKER_SYNC();
-  if (elected) mbar_arrive_cta0(&a_full[slot]);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -161,6 +156,13 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
         T1_MARK(0, true);
         mbar_arrive_expect_tx(patch_full, (uint32_t)P1_BYTES);
         tma_load_4d(patch, &tmImg, patch_full, tile_x * TW * 4 - 4, tile_y * TH * 4 - 4, 0, n_img);
+        if (it + 1 < n_it) {    // next tile's patch -> L2 now, so the load issued when the buffer frees skips the HBM latency
+          const int ntile = (unit0 + (it + 1) * unit_stride) * 2 + (int)cta_rank;
+          const int ni = ntile / p.tiles_per_image;
+          const int nrem = ntile - ni * p.tiles_per_image;
+          const int nty = nrem / p.tiles_x;
+          if (ni < p.B) tma_prefetch_4d(&tmImg, (nrem - nty * p.tiles_x) * TW * 4 - 4, nty * TH * 4 - 4, 0, ni);
+        }
       }
     }
   } else if (warp == 1) {
@@ -233,8 +235,8 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
           conv_kb(1, buf, false);
         }
         if (E_) gamma_round(0, ebuf);
+        if (E_) gamma_round(1, ebuf);           // posted together with k-block 2: the workers need the norm first
         if (B_) conv_kb(2, buf, false);
-        if (E_) gamma_round(1, ebuf);
         if (B_) conv_kb(3, buf, true);
       }
     }
@@ -257,18 +259,8 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
       uint64_t xk[32];                          // x = acc + bias: xk[g*16 + i] = channels g*64 + half*32 + 2i, +1
 
       // x^2 (hi, lo) of k-block g as the K-major swizzled A tile of the gamma product
-      auto x2_round = [&](const int g) {
-        uint32_t raw[32];
-        const int c0 = g * 64 + half * 32;
-        tmem_ld32(t_acc + (uint32_t)c0, raw);
-        tmem_ld_wait();
-        if (g == 0) {                           // the previous tile's lo-plane store must have left the buffer
-          if (elected && store_pending) { tma_store_wait_read(); store_pending = false; }
-          WORKER_SYNC();
-        } else {
-          mbar_wait(xs_empty, e & 1u);          // the gamma MMAs of round 0 have read it
-        }
-        const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + c0);
+      auto x2_work = [&](const int g, const uint32_t (&raw)[32]) {
+        const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + g * 64 + half * 32);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           uint32_t h[4], l[4];
@@ -284,37 +276,76 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
           sts128(xs, r, half * 4 + ci, h[0], h[1], h[2], h[3]);
           sts128(xs + SLOT_BYTES, r, half * 4 + ci, l[0], l[1], l[2], l[3]);
         }
+      };
+
+      // Each phase ends in ONE fence + worker barrier, after which the elected thread posts all of its signals
+      // (every fence / barrier / arrival exposes ~200 clk with two warps per scheduler).
+      // ---- phase A: k-blocks 0, 1 of tile `it`
+      if (B_) {
+        mbar_wait(patch_full, (uint32_t)it & 1u);
+        T1_MARK(2, threadIdx.x == 64);             // [0] patch landed
+        mbar_wait(&a_empty[0], 1u);                // uses 2*it of both slots
+        mbar_wait(&a_empty[1], 1u);
+        build_rows<0>(pp, smem, r, half);
+        build_rows<1>(pp, smem, r, half);
+        fence_proxy_async_smem();
+      }
+      // the previous tile's last store must have left the staging buffer before phase B writes x^2 into it
+      if (elected && store_pending) { tma_store_wait_read(); store_pending = false; }
+      WORKER_SYNC();
+      if (B_ && elected) { mbar_arrive_cta0(&a_full[0]); mbar_arrive_cta0(&a_full[1]); }
+      T1_MARK(2, threadIdx.x == 64);               // [1] kb0, kb1 built
+      // ---- phase B: x^2 round 0 of tile it-1
+      if (E_) {
+        mbar_wait(&accum_full[ebuf], epar);
+        tcgen05_fence_after();
+        T1_MARK(2, threadIdx.x == 64);             // [2] conv accumulator ready
+        uint32_t raw[32];
+        tmem_ld32(t_acc + (uint32_t)(half * 32), raw);
+        tmem_ld_wait();
+        x2_work(0, raw);
         fence_proxy_async_smem();
         WORKER_SYNC();
         if (elected) mbar_arrive_cta0(xs_full);
-      };
-
+        T1_MARK(2, threadIdx.x == 64);             // [3] x^2 round 0 written
+      }
+      // ---- phase C: k-block 2 of tile `it` (while the gamma MMAs of round 0 read the x^2 tile), x^2 round 1
+      {
+        uint32_t raw[32];
+        if (E_) tmem_ld32(t_acc + (uint32_t)(64 + half * 32), raw);
+        if (B_) {
+          mbar_wait(&a_empty[0], 0u);              // use 2*it + 1
+          build_rows<2>(pp, smem, r, half);
+        }
+        if (E_) {
+          tmem_ld_wait();
+          mbar_wait(xs_empty, e & 1u);             // the gamma MMAs of round 0 have read the x^2 tile
+          x2_work(1, raw);
+        }
+      }
+      fence_proxy_async_smem();
+      WORKER_SYNC();
+      if (elected) {
+        if (E_) mbar_arrive_cta0(xs_full);
+        if (B_) mbar_arrive_cta0(&a_full[0]);
+      }
+      T1_MARK(2, threadIdx.x == 64);               // [4] kb2 + x^2 round 1 written
+      // ---- phase D: k-block 3 of tile `it` (while the gamma MMAs of round 1 run)
       if (B_) {
-        mbar_wait(patch_full, (uint32_t)it & 1u);
-        T1_MARK(2, threadIdx.x == 64);
-        build_kb<0>(pp, smem, a_full, a_empty, r, half, elected);
-        build_kb<1>(pp, smem, a_full, a_empty, r, half, elected);
+        mbar_wait(&a_empty[1], 0u);
+        build_rows<3>(pp, smem, r, half);
+        fence_proxy_async_smem();
+        WORKER_SYNC();
+        if (elected) { mbar_arrive_cta0(&a_full[1]); mbar_arrive(patch_empty); }   // every worker is done with the patch
+        T1_MARK(2, threadIdx.x == 64);             // [5] kb3 written
       }
+      // ---- phase E: final pass of tile it-1
       if (E_) {
-        T1_MARK(2, threadIdx.x == 64);
-        mbar_wait(&accum_full[ebuf], epar);
-        tcgen05_fence_after();
-        T1_MARK(2, threadIdx.x == 64);
-        x2_round(0);
-      }
-      if (B_) build_kb<2>(pp, smem, a_full, a_empty, r, half, elected);
-      if (E_) x2_round(1);
-      if (B_) {
-        build_kb<3>(pp, smem, a_full, a_empty, r, half, elected);
-        if (elected) mbar_arrive(patch_empty);     // every worker passed build_kb<3>'s barrier: the patch is free
-      }
-      if (E_) {
-        T1_MARK(2, threadIdx.x == 64);
         mbar_wait(&norm_full[ebuf], epar);         // also: every gamma MMA has finished reading the x^2 tile
         tcgen05_fence_after();
-        T1_MARK(2, threadIdx.x == 64);
-        // ---- y = x * rsqrt(beta + norm) -> NHWC bf16 through the x^2 buffer + TMA stores: hi plane, then lo plane
-        uint32_t lo_pack[32];
+        T1_MARK(2, threadIdx.x == 64);             // [6] norm ready
+        // ---- y = x * rsqrt(beta + norm) -> NHWC bf16 through the x^2 buffer + TMA stores, one 64-channel block
+        // (hi plane | lo plane) at a time: block 1 is computed while the TMA unit still reads block 0
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = h * 64 + half * 32;
@@ -323,44 +354,34 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
           tmem_ld_wait();
           if (h == 1) tcgen05_fence_before();
           const uint64_t* beta2 = reinterpret_cast<const uint64_t*>(s_beta + c0);
+          uint32_t hp[16], lp[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float n0, n1, y0, y1;
+            upk2(add2(pk2(rawn[2 * i], rawn[2 * i + 1]), beta2[i]), n0, n1);
+            const uint64_t sc = pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
+            upk2(mul2(xk[h * 16 + i], sc), y0, y1);
+            hp[i] = cvt_bf16x2(y0, y1);
+            lp[i] = lo_of(y0, y1, hp[i]);
+          }
+          if (h == 1) {                          // block 0's stores must have left the staging buffer
+            if (elected) tma_store_wait_read();
+            WORKER_SYNC();
+          }
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
-            uint32_t hp[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float n0, n1, y0, y1;
-              upk2(add2(pk2(rawn[ci * 8 + 2 * j], rawn[ci * 8 + 2 * j + 1]), beta2[ci * 4 + j]), n0, n1);
-              const uint64_t sc = pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
-              upk2(mul2(xk[h * 16 + ci * 4 + j], sc), y0, y1);
-              hp[j] = cvt_bf16x2(y0, y1);
-              lo_pack[h * 16 + ci * 4 + j] = lo_of(y0, y1, hp[j]);
-            }
-            sts128(xs + h * SLOT_BYTES, r, half * 4 + ci, hp[0], hp[1], hp[2], hp[3]);
+            sts128(xs, r, half * 4 + ci, hp[ci * 4 + 0], hp[ci * 4 + 1], hp[ci * 4 + 2], hp[ci * 4 + 3]);
+            sts128(xs + SLOT_BYTES, r, half * 4 + ci, lp[ci * 4 + 0], lp[ci * 4 + 1], lp[ci * 4 + 2], lp[ci * 4 + 3]);
           }
-        }
-        fence_proxy_async_smem();
-        WORKER_SYNC();                          // staging complete; every worker has finished its TMEM reads
-        if (elected) {
-          mbar_arrive_cta0(&acc_empty[ebuf]);
-          tma_store_4d(&tmO_hi, xs, 0, e_ox0, e_oy0, e_img);
-          tma_store_4d(&tmO_hi, xs + SLOT_BYTES, KBLK, e_ox0, e_oy0, e_img);
-          tma_store_commit();
-          tma_store_wait_read();
-        }
-        WORKER_SYNC();
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int ci = 0; ci < 4; ++ci)
-            sts128(xs + h * SLOT_BYTES, r, half * 4 + ci, lo_pack[h * 16 + ci * 4 + 0], lo_pack[h * 16 + ci * 4 + 1],
-                   lo_pack[h * 16 + ci * 4 + 2], lo_pack[h * 16 + ci * 4 + 3]);
-        fence_proxy_async_smem();
-        WORKER_SYNC();
-        if (elected) {
-          tma_store_4d(&tmO_lo, xs, 0, e_ox0, e_oy0, e_img);
-          tma_store_4d(&tmO_lo, xs + SLOT_BYTES, KBLK, e_ox0, e_oy0, e_img);
-          tma_store_commit();
-          store_pending = true;
+          fence_proxy_async_smem();
+          WORKER_SYNC();                        // staging complete (h = 1: every worker has finished its TMEM reads)
+          if (elected) {
+            if (h == 1) mbar_arrive_cta0(&acc_empty[ebuf]);
+            tma_store_4d(&tmO_hi, xs, h * KBLK, e_ox0, e_oy0, e_img);
+            tma_store_4d(&tmO_lo, xs + SLOT_BYTES, h * KBLK, e_ox0, e_oy0, e_img);
+            tma_store_commit();
+            if (h == 1) store_pending = true;
+          }
         }
         T1_MARK(2, threadIdx.x == 64);
       }

@@ -42,8 +42,8 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* slot_hi, uint8_t* slot_
 
 // CONV1: the 32 im2col values k = KB*64 + HALF*32 .. +31 (k = c*81 + ky*9 + kx, zero for k >= 243) of the
 // pixel whose patch origin is `pp` (16-byte aligned), written as four swizzled 16-byte chunks (hi, lo) of the
-// pixel's 128-byte K-major row.  Each (c, ky) patch row is fetched with three conflict-free LDS.128
-// (12 floats, 9 used); every index below is a compile-time constant.
+// pixel's 128-byte K-major row.  Each (c, ky) patch row is fetched with up to two conflict-free LDS.128 and one
+// LDS.32 (9 floats); every index below is a compile-time constant.
 template <int KB, int HALF, bool SPLIT3>
 __device__ __forceinline__ void conv1_build_row(const float* __restrict__ pp, uint8_t* slot_hi, uint8_t* slot_lo,
                                                 int r) {
@@ -56,11 +56,21 @@ __device__ __forceinline__ void conv1_build_row(const float* __restrict__ pp, ui
   for (int gi = 0; gi < NG; ++gi) {
     const int g = G0 + gi;
     if (g < 27) {
-      const float4* row = reinterpret_cast<const float4*>(pp + (g / 9) * P1_PLANE + (g % 9) * P1_W);
-      const float4 a = row[0], b = row[1], c = row[2];
+      // only the 16-byte pieces (kx 0-3, 4-7) and the scalar kx = 8 that this 32-wide k range uses are fetched:
+      // shared-memory wavefronts, not instructions, bound the builders
+      const float* rowf = pp + (g / 9) * P1_PLANE + (g % 9) * P1_W;
+      const float4* row = reinterpret_cast<const float4*>(rowf);
+      const int klo = (K0 > 9 * g ? K0 : 9 * g) - 9 * g;
+      const int kend = K0 + 31 < 242 ? K0 + 31 : 242;
+      const int khi = (kend < 9 * g + 8 ? kend : 9 * g + 8) - 9 * g;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      float c8 = 0.f;
+      if (klo <= 3) a = row[0];
+      if (klo <= 7 && khi >= 4) b = row[1];
+      if (khi >= 8) c8 = rowf[8];
       vals[gi * 12 + 0] = a.x; vals[gi * 12 + 1] = a.y; vals[gi * 12 + 2] = a.z; vals[gi * 12 + 3] = a.w;
       vals[gi * 12 + 4] = b.x; vals[gi * 12 + 5] = b.y; vals[gi * 12 + 6] = b.z; vals[gi * 12 + 7] = b.w;
-      vals[gi * 12 + 8] = c.x; vals[gi * 12 + 9] = c.y; vals[gi * 12 + 10] = c.z; vals[gi * 12 + 11] = c.w;
+      vals[gi * 12 + 8] = c8; vals[gi * 12 + 9] = 0.f; vals[gi * 12 + 10] = 0.f; vals[gi * 12 + 11] = 0.f;
     } else {
 #pragma unroll
       for (int t = 0; t < 12; ++t) vals[gi * 12 + t] = 0.f;
