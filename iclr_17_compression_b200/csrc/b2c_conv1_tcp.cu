@@ -132,6 +132,7 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();       // the next layer's prologue may overlap this kernel's tail
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -147,6 +148,7 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
         tma_load_2d_pair(gam + g * B_BYTES, &tmG_hi, res_full, g * KBLK, (int)cta_rank * (C / 2));
         tma_load_2d_pair(gam + (NCB + g) * B_BYTES, &tmG_lo, res_full, g * KBLK, (int)cta_rank * (C / 2));
       }
+      griddep_wait();             // the image (and the buffers this kernel overwrites) are free from here on
       for (int it = 0; it < n_it; ++it) {
         const int tile = (unit0 + it * unit_stride) * 2 + (int)cta_rank;
         const int n_img = tile / p.tiles_per_image;          // == B for the masked tile of an odd count: all OOB (zeros)
@@ -251,6 +253,7 @@ conv1_gdn_tcp_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_con
     const float* pp = patch + (4 * ty) * P1_W + 4 * tx;
     bool store_pending = false;
     int e_img = 0, e_ox0 = 0, e_oy0 = 0;       // tile whose epilogue runs in the current iteration
+    griddep_wait();
 
     for (int it = 0; it <= n_it; ++it) {
       const bool B_ = it < n_it, E_ = it >= 1;
@@ -485,13 +488,15 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mImg, mB_hi, mB_lo, mG_hi, mG_lo, mO_hi, mO_lo, p);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(conv1 tcp): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
   count_launch();

@@ -208,6 +208,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (PAIR) cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();       // the next layer's prologue may overlap this kernel's tail
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -232,6 +233,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           for (int cb = 0; cb < NCB; ++cb)
             tma_load_2d(wres + (t * NCB + cb) * B_BYTES, &tmB_hi, res_full, cb * KBLK, t * N_TILE);
       }
+      griddep_wait();             // the previous layer's output is complete and visible from here on
       uint32_t ga = 0, gb = 0;    // A boxes / weight tiles issued so far
       for (int unit = unit0; unit < n_units; unit += unit_stride) {
         const int tile = unit * (int)NPAIR + (int)cta_rank;
@@ -469,6 +471,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const bool elected = warp == 2 && lane == 0;
     bool store_pending = false;        // elected thread: a TMA store may still be reading the staging buffer
     uint32_t st = 0;
+    griddep_wait();                    // before any global read / write of activations
 #define WORKER_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory")
     for (int unit = unit0; unit < n_units; unit += unit_stride) {
       const int tile = unit * (int)NPAIR + (int)cta_rank;
@@ -842,13 +845,15 @@ static int launch_p(const b2c_tc_layer* L, cudaStream_t stream, long long* trace
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(tcp): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
   count_launch();

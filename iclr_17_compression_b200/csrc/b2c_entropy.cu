@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* _
   __shared__ float red[32];
   const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
   const int pix0 = chunk * QI_PIX;
+  // programmatic dependent launch: the per-channel constants are set up while the producer of y drains
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const ChanConst k = load_chan(bp, c);
     float* d = kc + c * 12;
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* _
     d[6] = k.sp[2]; d[7] = k.b[2]; d[8] = k.ta[2];
     d[9] = k.sp[3]; d[10] = k.b[3]; d[11] = 0.f;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int pix = pix0 + lane;
@@ -310,6 +313,8 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
                                                              float* __restrict__ out, int per_image, int width) {
   __shared__ float red[32];
   const int n = blockIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // no-ops unless launched as a programmatic dependent
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int j = 0; j < width; ++j) {
     float s = 0.f;
     for (int i = threadIdx.x; i < per_image; i += blockDim.x) s += partial[((size_t)n * per_image + i) * width + j];
@@ -368,9 +373,26 @@ int b2c_quant_entropy_infer(const float* y, const float* const* host_params, flo
   const int chunks = (HW + QI_PIX - 1) / QI_PIX;
   const size_t smem = (size_t)C * 12 * sizeof(float) + (size_t)QI_PIX * C * 2;
   B2C_REQUIRE(smem <= 48 * 1024, "quant_entropy_infer: too many channels");
-  quant_entropy_infer_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(
-      y, bp, z, (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks);
-  partial_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, image_bits, chunks, 1);
+  {   // both kernels are programmatic dependents of their predecessor (B2C_PDL=0: plain stream order)
+    static const bool pdl = [] { const char* e = getenv("B2C_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * chunks));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, quant_entropy_infer_kernel, y, bp, z, (__nv_bfloat16*)z_nhwc_bf16,
+                                       (float*)workspace, C, HW, chunks);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(quant_entropy_infer): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+    cfg.gridDim = dim3((unsigned)B);
+    cfg.dynamicSmemBytes = 0;
+    e = cudaLaunchKernelEx(&cfg, partial_reduce_kernel, (const float*)workspace, image_bits, chunks, 1);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(partial_reduce): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+  }
   count_launch(2);
   return check_launch("quant_entropy_infer");
 }

@@ -15,6 +15,15 @@ constexpr int TILE_M = TH * TW;           // 128
 constexpr int KBLK = 64;                  // bf16 per k-block row (128 B)
 constexpr int SLOT_BYTES = TILE_M * KBLK * 2;  // 16 KB operand slot
 
+// Programmatic dependent launch between consecutive layers of the inference pipeline (B2C_PDL=0 disables it)
+static inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B2C_PDL");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
