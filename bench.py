@@ -299,7 +299,7 @@ def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
         if sync is not None:
             sync.remove()                                      # hooks do not fire inside a graph replay;
             sync = None                                        # the graphed step all-reduces its flat gradient buffer
-        graphed = GraphedTrainStep(model, xb, 8192.0)
+        graphed = GraphedTrainStep(model, xb, 8192.0, direct=os.environ.get("B2C_TRAIN_DIRECT", "1") == "1")
 
     def tstep():
         if graphed is not None:

@@ -27,6 +27,12 @@ namespace tc {
 #ifndef B2C_TC_PAIRS_DEFAULT
 #define B2C_TC_PAIRS_DEFAULT 1
 #endif
+#ifndef B2C_GDNBWD_PREFETCH
+#define B2C_GDNBWD_PREFETCH 1
+#endif
+#ifndef B2C_TC_DEEP_STAGES
+#define B2C_TC_DEEP_STAGES 3
+#endif
 #ifndef B2C_CONV1_STAGES
 #define B2C_CONV1_STAGES 1
 #endif
@@ -105,8 +111,13 @@ struct TcCfg {
   static constexpr int N_TILE = (KIND == B2C_TC_DECONV3) ? 48 : C;
   static constexpr int TMEM_COLS = GDN ? (2 * C <= 256 ? 256 : 512) : (N_TILE <= 64 ? 64 : (N_TILE <= 128 ? 128 : 256));
   static constexpr int MAX_SMEM = 227 * 1024;
+  // B2C_TC_DEEP_STAGES (compile-time experiment, default 3 = off): ring depth of the plain-bf16 128-channel 5x5
+  // kinds.  6 stages (one CTA per SM) measured only -1 % on the training step: the main loop is bound by shared
+  // memory bandwidth (MMA operand reads + TMA fills), not by TMA latency, and 2 CTAs / SM keep 256-CTA grids in one wave.
+  static constexpr bool DEEP = !SPLIT3 && C == 128 && (KIND == B2C_TC_CONV5S2 || KIND == B2C_TC_DECONV5S2);
   static constexpr int STAGES =
       (KIND == B2C_TC_CONV1 && SPLIT3 && C == 128) ? B2C_CONV1_STAGES
+      : (DEEP && B2C_TC_DEEP_STAGES * STAGE_BYTES + PATCH + EXTRA <= MAX_SMEM) ? B2C_TC_DEEP_STAGES
                                                    : ((3 * STAGE_BYTES + PATCH + EXTRA <= MAX_SMEM)
                                                           ? 3
                                                           : ((2 * STAGE_BYTES + PATCH + EXTRA <= MAX_SMEM) ? 2 : 1));
@@ -114,7 +125,9 @@ struct TcCfg {
   static_assert(SMEM <= MAX_SMEM, "shared memory budget");
   static constexpr int BY_SMEM = (SMEM <= 75 * 1024) ? 3 : (SMEM <= 113 * 1024) ? 2 : 1;
   static constexpr int BY_TMEM = 512 / TMEM_COLS;
-  static constexpr int MIN_CTAS = BY_SMEM < BY_TMEM ? BY_SMEM : BY_TMEM;
+  // GDN backward epilogues (GDN 3 / 4) keep this thread's saved (y, n) rows in 64 registers, prefetched under the
+  // main loop: one CTA per SM (register budget), see B2C_GDNBWD_PREFETCH
+  static constexpr int MIN_CTAS = (GDN >= 3 && B2C_GDNBWD_PREFETCH) ? 1 : (BY_SMEM < BY_TMEM ? BY_SMEM : BY_TMEM);
 };
 
 template <int C, bool SPLIT3, int KIND, int GDN, int OUT_MODE, bool PAIR>
@@ -188,6 +201,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (tracing && tmark < 64) p.trace[(role) * 64 + tmark++] = clock64(); \
   } while (0)
 
+  griddep_launch_dependents();       // the next kernel's launch + prologue may overlap this kernel (no-op without PDL)
   if (threadIdx.x == 0) {
     for (int i = 0; i < NBAR; ++i) {
       mbar_init(&full[i], 1);
@@ -209,6 +223,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS);
     else tmem_alloc(tmem_slot, TMEM_COLS);
   }
+  // Programmatic dependent launch: everything above (barrier init, descriptor prefetch, TMEM allocation) overlapped
+  // the predecessor's tail; every global read / write of this kernel happens after this point.
+  griddep_wait();
   if (threadIdx.x >= 64 && threadIdx.x < 64 + C) {   // per-channel epilogue constants
     const int c = threadIdx.x - 64;
     s_bias[c] = (p.bias && c < (KIND == B2C_TC_DECONV3 ? 3 : C)) ? __ldg(p.bias + c) : 0.f;
@@ -398,6 +415,42 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       }
     }
 
+    // GDN backward epilogue: this thread's 64 channels of the saved forward output y and norm n (2 x 128 B) are
+    // fetched NOW, while the main loop runs, and stay in registers for both epilogue passes.
+    uint4 sv_y[GDN_BWD ? 8 : 1], sv_n[GDN_BWD ? 8 : 1];
+    {
+      const size_t pixs = (((size_t)n_img * p.Hfull + (oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0))) *
+                               p.Wfull + (ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0))) * C + half * 64;
+      (void)pixs;
+#if B2C_GDNBWD_PREFETCH
+      if (GDN_BWD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sv_y[i] = make_uint4(0, 0, 0, 0);
+          sv_n[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+          if (valid) {
+            sv_y[i] = __ldg(reinterpret_cast<const uint4*>(p.saved_y + pixs) + i);
+            sv_n[i] = __ldg(reinterpret_cast<const uint4*>(p.saved_n + pixs) + i);
+          }
+        }
+      }
+#endif
+    }
+    const size_t pix_saved = (((size_t)n_img * p.Hfull + (oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0))) *
+                                  p.Wfull + (ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0))) * C + half * 64;
+    auto saved_chunk = [&](int i, uint4& qy, uint4& qn) {      // 8 channels (i = 0..7) of this thread's 64
+#if B2C_GDNBWD_PREFETCH
+      qy = sv_y[i]; qn = sv_n[i];
+#else
+      qy = make_uint4(0, 0, 0, 0);
+      qn = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+      if (valid) {
+        qy = __ldg(reinterpret_cast<const uint4*>(p.saved_y + pix_saved) + i);
+        qn = __ldg(reinterpret_cast<const uint4*>(p.saved_n + pix_saved) + i);
+      }
+#endif
+    };
+
     mbar_wait(accum_full, 0);
     tcgen05_fence_after();
     TC_WMARK();
@@ -420,14 +473,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tmem_ld_wait();
           if (GDN_BWD) {
             // acc = dL/dy.  dL/dnorm = -+ 1/2 * g * y / n  (GDN: y = x n^-1/2, IGDN: y = x n^1/2)
-            const size_t pixb = (((size_t)n_img * p.Hfull + (oy * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase >> 1) : 0))) *
-                                     p.Wfull + (ox * p.ps + (KIND == B2C_TC_DECONV5S2 ? (phase & 1) : 0))) * C + g * 64;
-            const uint4* py = reinterpret_cast<const uint4*>(p.saved_y + pixb);
-            const uint4* pn = reinterpret_cast<const uint4*>(p.saved_n + pixb);
 #pragma unroll
             for (int cidx = 0; cidx < 8; ++cidx) {
-              uint4 qy = make_uint4(0, 0, 0, 0), qn = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
-              if (valid) { qy = __ldg(py + cidx); qn = __ldg(pn + cidx); }
+              uint4 qy, qn;
+              saved_chunk(cidx, qy, qn);
               const uint32_t wy[4] = {qy.x, qy.y, qy.z, qy.w}, wn[4] = {qn.x, qn.y, qn.z, qn.w};
               float v[8];
 #pragma unroll
@@ -435,7 +484,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const float yv = __uint_as_float((j & 1) ? (wy[j >> 1] & 0xffff0000u) : (wy[j >> 1] << 16));
                 const float nv = __uint_as_float((j & 1) ? (wn[j >> 1] & 0xffff0000u) : (wn[j >> 1] << 16));
                 const float gv = __uint_as_float(raw[cidx * 8 + j]);
-                v[j] = (GDN == 3 ? -0.5f : 0.5f) * gv * yv / nv;
+                float rn;                                        // n is a bf16 value >= beta_min > 0: one MUFU op
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nv));
+                v[j] = (GDN == 3 ? -0.5f : 0.5f) * gv * yv * rn;
               }
               store_row_chunk<false>(st, st + SLOT_BYTES, r, cidx, v);
             }
@@ -570,9 +621,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         for (int ci = 0; ci < 4; ++ci) {
           float v[8], vn[8];
           uint32_t wy[4] = {0, 0, 0, 0}, wn[4] = {0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
-          if (GDN_BWD && valid) {
-            const uint4 qy = __ldg(reinterpret_cast<const uint4*>(p.saved_y + pixb + c0) + ci);
-            const uint4 qn = __ldg(reinterpret_cast<const uint4*>(p.saved_n + pixb + c0) + ci);
+          if (GDN_BWD) {
+            // registers prefetched before the main loop; the h loop is rolled, so select with constant indices
+            uint4 qy, qn;
+#if B2C_GDNBWD_PREFETCH
+            uint4 qy1, qn1;              // the h loop is rolled: select between constant register indices
+            saved_chunk(ci, qy, qn);
+            saved_chunk(4 + ci, qy1, qn1);
+            if (h) { qy = qy1; qn = qn1; }
+#else
+            saved_chunk(h * 4 + ci, qy, qn);
+#endif
             wy[0] = qy.x; wy[1] = qy.y; wy[2] = qy.z; wy[3] = qy.w;
             wn[0] = qn.x; wn[1] = qn.y; wn[2] = qn.z; wn[3] = qn.w;
           }
@@ -782,19 +841,34 @@ static int launch(const b2c_tc_layer* L, const TcParams& p, dim3 grid, cudaStrea
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
     if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(pair): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
     count_launch();
     return check_launch("tc_layer_run(pair)");
   }
-  kern<<<grid, NTHREADS, SMEM, stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA_hi, mA_lo, mB_hi, mB_lo, mG_hi, mG_lo, mO, p);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+  }
   count_launch();
   return check_launch("tc_layer_run");
 }

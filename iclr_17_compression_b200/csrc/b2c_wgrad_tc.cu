@@ -12,6 +12,7 @@
 //
 // Covers conv2/conv3/deconv1/deconv2 weight gradients (25 taps, stride 2) and the GDN gamma
 // gradient d gamma[i][j] = sum_pix dn[pix][i] * x^2[pix][j] (1 tap, stride 1).
+#include <cstdlib>
 #include <mutex>
 
 #include "b2c_common.cuh"
@@ -414,7 +415,8 @@ int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int
   int rc;
   if ((rc = make_nhwc_map(&mS, small_t, B, h, w, 1))) return rc;
   if ((rc = make_image_map9(&mI, image, B, 4 * h, 4 * w))) return rc;
-  int ctas = (p.total_tiles + 3) / 4;
+  static const int tiles_per_cta = [] { const char* e = getenv("B2C_WG9_TILES_PER_CTA"); int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
+  int ctas = (p.total_tiles + tiles_per_cta - 1) / tiles_per_cta;
   if (ctas > 148) ctas = 148;
   if (ctas < 1) ctas = 1;
   wgrad9_tc_kernel<<<ctas, W9_THREADS, SMEM, (cudaStream_t)stream>>>(mS, mI, p);

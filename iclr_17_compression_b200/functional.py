@@ -118,9 +118,10 @@ def _wgrad_raw(small, big, k, stride, pad):
     return dW
 
 
-def _channel_sum_raw(t):
+def _channel_sum_raw(t, out=None):
     B, C = t.shape[0], t.shape[1]
-    out = torch.empty((C,), device=t.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((C,), device=t.device, dtype=torch.float32)
     with torch.cuda.device(t.device):
         _lib.check(_lib.load().b2c_channel_sum(_p(t), _p(out), B, C, t[0, 0].numel(), _stream()), "channel_sum")
     return out

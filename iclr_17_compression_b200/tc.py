@@ -140,22 +140,30 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
     return out_hi if out_f32_nchw else (out_hi, out_lo)
 
 
-def wgrad(small, big, k, stride, pad):
-    """dW[m][n][ky][kx] = sum small[.,ys,xs,m] * big[., stride*ys-pad+ky, stride*xs-pad+kx, n]; NHWC bf16 in, fp32 out"""
+def wgrad(small, big, k, stride, pad, tmp=None, out=None):
+    """dW[m][n][ky][kx] = sum small[.,ys,xs,m] * big[., stride*ys-pad+ky, stride*xs-pad+kx, n]; NHWC bf16 in, fp32 out.
+    tmp: zero-filled fp32 [k,k,128,128] scratch (tap-major partial layout, accumulated with red.add); out: optional
+    destination for the [128,128,k,k] result (e.g. a slice of a flat gradient buffer)."""
     B, hs, ws, _ = small.shape
     _, hb, wb, _ = big.shape
-    dW = torch.zeros((k, k, 128, 128), device=small.device, dtype=torch.float32)       # tap-major partial layout
+    dW = tmp if tmp is not None else torch.zeros((k, k, 128, 128), device=small.device, dtype=torch.float32)
     flops = 2 * B * hs * ws * 128 * 128 * k * k
     with torch.cuda.device(small.device), _timed(f"tc_wgrad[{B}x{hs}x{ws},k{k}s{stride}]", flops, 0):
         _lib.check(_lib.load().b2c_tc_wgrad(_p(small), _p(big), _p(dW), B, hs, ws, hb, wb, k, stride, pad, _stream()),
                    "tc_wgrad")
-    return dW.permute(2, 3, 0, 1).contiguous() if k > 1 else dW.view(128, 128, 1, 1)
+    if k == 1:
+        return dW.view(128, 128, 1, 1)
+    if out is not None:
+        out.view(128, 128, k, k).copy_(dW.permute(2, 3, 0, 1))
+        return out
+    return dW.permute(2, 3, 0, 1).contiguous()
 
 
-def wgrad9(small, image):
-    """9x9/4 weight gradient: small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w] -> fp32 [128,3,9,9]"""
+def wgrad9(small, image, out=None):
+    """9x9/4 weight gradient: small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w] -> fp32 [128,3,9,9]
+    (accumulated with red.add into ``out``, which must be zero-filled)"""
     B, h, w, _ = small.shape
-    dW = torch.zeros((128, 3, 9, 9), device=small.device, dtype=torch.float32)
+    dW = out if out is not None else torch.zeros((128, 3, 9, 9), device=small.device, dtype=torch.float32)
     with torch.cuda.device(small.device), _timed(f"tc_wgrad9[{B}x{h}x{w}]", 2 * B * h * w * 128 * 243, 0):
         _lib.check(_lib.load().b2c_tc_wgrad9(_p(small), _p(image), _p(dW), B, h, w, _stream()), "tc_wgrad9")
     return dW

@@ -39,21 +39,46 @@ def _xsq(y, n, inverse):
     return out
 
 
-def _colsum(t):
-    out = torch.zeros((128,), device=t.device, dtype=torch.float32)
+class _Pool:
+    """Zero-initialised fp32 scratch carved out of ONE flat tensor, so that a whole training step needs a single
+    memset instead of one fill kernel per accumulator (weight-gradient partials, column sums, Bitparm gradients)."""
+
+    def __init__(self, flat, offset):
+        self.flat, self.off = flat, offset
+
+    def zeros(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.flat.numel():
+            raise _lib.B2CError("training scratch pool exhausted")
+        t = self.flat[self.off:self.off + n].view(*shape)
+        self.off += (n + 63) // 64 * 64                     # keep 256-byte alignment (vector red.add)
+        return t
+
+
+def _zeros(pool, dev, *shape):
+    return pool.zeros(*shape) if pool is not None else torch.zeros(shape, device=dev, dtype=torch.float32)
+
+
+def _colsum(t, out=None):
+    """out[c] += sum over pixels of an NHWC bf16 tensor; ``out`` must be zero-filled"""
+    if out is None:
+        out = torch.zeros((128,), device=t.device, dtype=torch.float32)
     with torch.cuda.device(t.device), _timed("tc_nhwc_colsum", 0, 2 * t.numel()):
         _lib.check(_lib.load().b2c_tc_nhwc_colsum(_p(t), _p(out), t.numel() // 128, _stream()), "tc_nhwc_colsum")
     return out
 
 
-def _gdn_param_grads(beta_p, gamma_p, y, n, dn, inverse):
+def _gdn_param_grads(beta_p, gamma_p, y, n, dn, inverse, pool=None, out=None):
     """d beta_p, d gamma_p from dL/dnorm: d gamma_eff = sum_pix dn_i x_j^2 (tcgen05 wgrad, 1 tap), d beta_eff = sum dn,
     then the LowerBound / square reparametrisation (models/GDN.py:18-24,73-79)."""
+    dev = y.device
     xsq = _xsq(y, n, inverse)
-    dgamma_eff = T.wgrad(dn, xsq, 1, 1, 0).view(128, 128)
-    dbeta_eff = _colsum(dn)
-    dbeta_p, dgamma_p = torch.empty_like(beta_p), torch.empty_like(gamma_p)
-    with torch.cuda.device(y.device):
+    dgamma_eff = T.wgrad(dn, xsq, 1, 1, 0, tmp=_zeros(pool, dev, 1, 1, 128, 128)).view(128, 128)
+    dbeta_eff = _colsum(dn, _zeros(pool, dev, 128))
+    dbeta_p, dgamma_p = out if out is not None else (torch.empty_like(beta_p), torch.empty_like(gamma_p))
+    with torch.cuda.device(dev):
         _lib.check(_lib.load().b2c_gdn_reparam_bwd(_p(beta_p), _p(gamma_p), _p(dbeta_eff), _p(dgamma_eff), _p(dbeta_p),
                                                    _p(dgamma_p), 128, _stream()), "gdn_reparam_bwd")
     return dbeta_p, dgamma_p
@@ -104,9 +129,170 @@ class _Fork:
             o.record_stream(self.main)
 
 
-def _wgrad_simt(small, big, k, stride, pad):
-    from .functional import _wgrad_raw
-    return _wgrad_raw(small, big, k, stride, pad)
+def step_forward(x, noise, prm):
+    """Forward of the training step on tensor cores (model.py:47-78 with the noise quantizer).  prm: name -> fp32
+    CUDA tensor for the 30 parameters.  Returns the state dict the backward needs plus the per-image statistics."""
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    dev = x.device
+    W2, W3 = prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
+    W1 = prm["Encoder.conv1.weight"]
+    D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
+    # ---- operand packing: only conv1 / gdn1 are needed immediately; every other pack of the step (forward and
+    # dgrad forms, gamma and gamma^T) only depends on the parameters and runs on a side stream
+    main = torch.cuda.current_stream(dev)
+    w1p = T.pack_weights(T.TC_CONV1, W1, False)
+    gp1 = T.pack_gdn(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], False)
+    side = _Fork._side(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        pk = {
+            "w2": T.pack_weights(T.TC_CONV5S2, W2, False), "gp2": T.pack_gdn(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], False),
+            "w3": T.pack_weights(T.TC_CONV5S2, W3, False),
+            "d1": T.pack_weights(T.TC_DECONV5S2, D1, False), "gi1": T.pack_gdn(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], False),
+            "d2": T.pack_weights(T.TC_DECONV5S2, D2, False), "gi2": T.pack_gdn(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], False),
+            "d3": T.pack_weights(T.TC_DECONV3, D3, False),
+        }
+        ev_fwd = torch.cuda.Event()
+        ev_fwd.record(side)
+        pk.update({     # backward forms
+            "d3_dg": T.pack_weights(T.TC_CONV1, D3, False), "gi2_t": T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"]),
+            "d2_dg": T.pack_weights(T.TC_CONV5S2, D2, False), "gi1_t": T.pack_gdn_t(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"]),
+            "d1_dg": T.pack_weights(T.TC_CONV5S2, D1, False),
+            "w3_dg": T.pack_weights(T.TC_DECONV5S2, W3, False), "gp2_t": T.pack_gdn_t(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"]),
+            "w2_dg": T.pack_weights(T.TC_DECONV5S2, W2, False), "gp1_t": T.pack_gdn_t(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"]),
+        })
+        ev_bwd = torch.cuda.Event()
+        ev_bwd.record(side)
+    for v in pk.values():
+        for t in v:
+            if t is not None:
+                t.record_stream(main)
+    # ---- analysis transform
+    h1, n1 = T.layer_run(T.TC_CONV1, x, None, w1p, prm["Encoder.conv1.bias"], gdn=gp1, gdn_mode=1,
+                         second_plane=True)
+    main.wait_event(ev_fwd)
+    h2, n2 = T.layer_run(T.TC_CONV5S2, h1, None, pk["w2"], prm["Encoder.conv2.bias"], gdn=pk["gp2"], gdn_mode=1,
+                         second_plane=True)
+    y = T.layer_run(T.TC_CONV5S2, h2, None, pk["w3"], None, out_f32_nchw=True)
+    # ---- quantizer (noise) + bits
+    bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
+    C, HW = 128, y.shape[2] * y.shape[3]
+    z = torch.empty_like(y)
+    plane_bits = torch.empty((B, C), device=dev, dtype=torch.float32)
+    image_bits = torch.empty((B,), device=dev, dtype=torch.float32)
+    pp, keep = _lib.ptr_array(bitp)
+    with torch.cuda.device(dev), _timed("quant_entropy_fwd[train]", 60 * y.numel(), 12 * y.numel()):
+        _lib.check(lib.b2c_quant_entropy_fwd(_p(y), _p(noise), pp, _p(z), _p(plane_bits), _p(image_bits), B, C, HW,
+                                             _stream()), "quant_entropy_fwd")
+    # ---- synthesis transform
+    zh, _ = T.nchw_to_nhwc(z, False)
+    i1, m1 = T.layer_run(T.TC_DECONV5S2, zh, None, pk["d1"], prm["Decoder.deconv1.bias"], gdn=pk["gi1"], gdn_mode=2,
+                         second_plane=True)
+    i2, m2 = T.layer_run(T.TC_DECONV5S2, i1, None, pk["d2"], prm["Decoder.deconv2.bias"], gdn=pk["gi2"], gdn_mode=2,
+                         second_plane=True)
+    recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
+    # ---- distortion
+    clipped = torch.empty_like(recon)
+    sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
+    nbytes = lib.b2c_clamp_sse_workspace_bytes(B, x[0].numel())
+    ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev), _timed("clamp_sse_fwd[train]", 8 * x.numel(), 12 * x.numel()):
+        _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, x[0].numel(), _p(ws), nbytes,
+                                         _stream()), "clamp_sse_fwd")
+    main.wait_event(ev_bwd)          # the backward packs are done long before; keeps stream bookkeeping simple
+    return {"prm": prm, "pk": pk, "saved": (x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon),
+            "image_bits": image_bits, "plane_bits": plane_bits, "sse": sse, "clipped": clipped, "z": z}
+
+
+def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None):
+    """Backward of the training step: gradients of ``g_sse * sum (recon - x)^2 + g_bits * total_bits`` for the 30
+    parameters (name -> tensor).  ``out`` (name -> zero-filled fp32 tensor of the parameter's shape, e.g. views of one
+    flat buffer) receives the gradients in place; ``pool`` supplies zero-filled scratch.  ``on_decoder_done`` is
+    called (on the main stream, with the fork object) once every Decoder.* and bitEstimator.* gradient kernel has
+    been enqueued - the hook a data-parallel caller uses to start reducing that bucket while the encoder backward runs."""
+    lib = _lib.load()
+    prm, pk = st["prm"], st["pk"]
+    x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon = st["saved"]
+    dev = x.device
+    B = x.shape[0]
+    grads = {}
+
+    def dst(k):
+        return out[k] if out is not None else None
+
+    def gdn_dst(prefix):
+        return (out[prefix + ".beta"], out[prefix + ".gamma"]) if out is not None else None
+
+    fork = _Fork(dev)
+    from .functional import _channel_sum_raw
+    # ---- entropy model: d bits / dz and the 11 parameter vectors (independent of the synthesis chain)
+    bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
+    C, HW = 128, z.shape[2] * z.shape[3]
+
+    def entropy_bwd():
+        dbit = [out[k].view(-1) if out is not None else torch.zeros_like(p) for k, p in zip(PARAM_ORDER[19:], bitp)]
+        dz_ = torch.empty_like(z)
+        pp, k1 = _lib.ptr_array(bitp)
+        dp, k2 = _lib.ptr_array(dbit)
+        with torch.cuda.device(dev):
+            _lib.check(lib.b2c_entropy_bwd(_p(z), pp, _p(g_bits), _p(dz_), dp, B, C, HW, _stream()), "entropy_bwd")
+        return [dz_] + dbit
+    ent = fork.run(entropy_bwd, g_bits)
+    dz, dbit = ent[0], ent[1:]
+    ent_stream = fork.sides[0]
+    for k, g in zip(PARAM_ORDER[19:], dbit):
+        grads[k] = g.view(1, -1, 1, 1)
+    # ---- distortion
+    g_recon = torch.empty_like(recon)
+    with torch.cuda.device(dev):
+        _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _vp(0), _p(g_sse), _p(g_recon), recon.numel(), _stream()),
+                   "clamp_sse_bwd")
+    # ---- deconv3 (9x9/4, 128 -> 3): weight grad (im2col MN-major tcgen05), dgrad (= conv 9x9/4) + IGDN2 backward fused
+    grads["Decoder.deconv3.weight"] = fork.run(lambda: T.wgrad9(i2, g_recon, out=dst("Decoder.deconv3.weight")), g_recon)
+    grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon, dst("Decoder.deconv3.bias")), g_recon)
+    gp_d2, dn2 = T.layer_run(T.TC_CONV1, g_recon, None, pk["d3_dg"], None, gdn=pk["gi2_t"],
+                             gdn_mode=4, second_plane=True, saved=(i2, m2))
+    grads["Decoder.igdn2.beta"], grads["Decoder.igdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
+        prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn2, True, pool, gdn_dst("Decoder.igdn2")), dn2)
+    # ---- deconv2
+    grads["Decoder.deconv2.weight"] = fork.run(lambda: T.wgrad(
+        i1, gp_d2, 5, 2, 2, tmp=_zeros(pool, dev, 5, 5, 128, 128), out=dst("Decoder.deconv2.weight")), gp_d2)
+    grads["Decoder.deconv2.bias"] = fork.run(lambda: _colsum(gp_d2, dst("Decoder.deconv2.bias")), gp_d2)
+    gp_d1, dn1 = T.layer_run(T.TC_CONV5S2, gp_d2, None, pk["d2_dg"], None, gdn=pk["gi1_t"],
+                             gdn_mode=4, second_plane=True, saved=(i1, m1))
+    grads["Decoder.igdn1.beta"], grads["Decoder.igdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
+        prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn1, True, pool, gdn_dst("Decoder.igdn1")), dn1)
+    # ---- deconv1
+    grads["Decoder.deconv1.weight"] = fork.run(lambda: T.wgrad(
+        zh, gp_d1, 5, 2, 2, tmp=_zeros(pool, dev, 5, 5, 128, 128), out=dst("Decoder.deconv1.weight")), gp_d1)
+    grads["Decoder.deconv1.bias"] = fork.run(lambda: _colsum(gp_d1, dst("Decoder.deconv1.bias")), gp_d1)
+    if on_decoder_done is not None:
+        on_decoder_done(fork)
+    g_z = T.layer_run(T.TC_CONV5S2, gp_d1, None, pk["d1_dg"], None, out_f32_nchw=True)
+    fork.main.wait_stream(ent_stream)                  # dz comes from the entropy backward (first forked task)
+    g_y = g_z + dz                                     # z = y + noise -> dz/dy = 1
+    gyh, _ = T.nchw_to_nhwc(g_y, False)
+    # ---- conv3 (no bias): wgrad, dgrad (= transposed conv) + GDN2 backward fused
+    grads["Encoder.conv3.weight"] = fork.run(lambda: T.wgrad(
+        gyh, h2, 5, 2, 2, tmp=_zeros(pool, dev, 5, 5, 128, 128), out=dst("Encoder.conv3.weight")), gyh)
+    gp_c2, dng2 = T.layer_run(T.TC_DECONV5S2, gyh, None, pk["w3_dg"], None, gdn=pk["gp2_t"],
+                              gdn_mode=3, second_plane=True, saved=(h2, n2))
+    grads["Encoder.gdn2.beta"], grads["Encoder.gdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
+        prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dng2, False, pool, gdn_dst("Encoder.gdn2")), dng2)
+    # ---- conv2
+    grads["Encoder.conv2.weight"] = fork.run(lambda: T.wgrad(
+        gp_c2, h1, 5, 2, 2, tmp=_zeros(pool, dev, 5, 5, 128, 128), out=dst("Encoder.conv2.weight")), gp_c2)
+    grads["Encoder.conv2.bias"] = fork.run(lambda: _colsum(gp_c2, dst("Encoder.conv2.bias")), gp_c2)
+    gp_c1, dng1 = T.layer_run(T.TC_DECONV5S2, gp_c2, None, pk["w2_dg"], None, gdn=pk["gp1_t"],
+                              gdn_mode=3, second_plane=True, saved=(h1, n1))
+    grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
+        prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dng1, False, pool, gdn_dst("Encoder.gdn1")), dng1)
+    # ---- conv1 (9x9/4, 3 -> 128): weight grad (im2col MN-major tcgen05); the image needs no gradient
+    grads["Encoder.conv1.weight"] = fork.run(lambda: T.wgrad9(gp_c1, x, out=dst("Encoder.conv1.weight")), gp_c1)
+    grads["Encoder.conv1.bias"] = fork.run(lambda: _colsum(gp_c1, dst("Encoder.conv1.bias")), gp_c1)
+    fork.join()
+    return grads
 
 
 class TrainStepTC(torch.autograd.Function):
@@ -114,162 +300,25 @@ class TrainStepTC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, noise, *params):
-        lib = _lib.load()
         prm = dict(zip(PARAM_ORDER, [p.detach().contiguous().float() for p in params]))
-        x = x.detach().contiguous().float()
-        noise = noise.detach().contiguous().float()
-        B, _, H, W = x.shape
-        dev = x.device
-        W1, W2, W3 = prm["Encoder.conv1.weight"], prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
-        D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
-        # ---- operand packing: only conv1 / gdn1 are needed immediately; every other pack of the step (forward and
-        # dgrad forms, gamma and gamma^T) only depends on the parameters and runs on a side stream
-        main = torch.cuda.current_stream(dev)
-        w1p = T.pack_weights(T.TC_CONV1, W1, False)
-        gp1 = T.pack_gdn(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], False)
-        side = _Fork._side(dev)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            pk = {
-                "w2": T.pack_weights(T.TC_CONV5S2, W2, False), "gp2": T.pack_gdn(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], False),
-                "w3": T.pack_weights(T.TC_CONV5S2, W3, False),
-                "d1": T.pack_weights(T.TC_DECONV5S2, D1, False), "gi1": T.pack_gdn(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], False),
-                "d2": T.pack_weights(T.TC_DECONV5S2, D2, False), "gi2": T.pack_gdn(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], False),
-                "d3": T.pack_weights(T.TC_DECONV3, D3, False),
-            }
-            ev_fwd = torch.cuda.Event()
-            ev_fwd.record(side)
-            pk.update({     # backward forms
-                "d3_dg": T.pack_weights(T.TC_CONV1, D3, False), "gi2_t": T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"]),
-                "d2_dg": T.pack_weights(T.TC_CONV5S2, D2, False), "gi1_t": T.pack_gdn_t(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"]),
-                "d1_dg": T.pack_weights(T.TC_CONV5S2, D1, False),
-                "w3_dg": T.pack_weights(T.TC_DECONV5S2, W3, False), "gp2_t": T.pack_gdn_t(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"]),
-                "w2_dg": T.pack_weights(T.TC_DECONV5S2, W2, False), "gp1_t": T.pack_gdn_t(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"]),
-            })
-            ev_bwd = torch.cuda.Event()
-            ev_bwd.record(side)
-        for v in pk.values():
-            for t in v:
-                if t is not None:
-                    t.record_stream(main)
-        # ---- analysis transform
-        h1, n1 = T.layer_run(T.TC_CONV1, x, None, w1p, prm["Encoder.conv1.bias"], gdn=gp1, gdn_mode=1,
-                             second_plane=True)
-        main.wait_event(ev_fwd)
-        h2, n2 = T.layer_run(T.TC_CONV5S2, h1, None, pk["w2"], prm["Encoder.conv2.bias"], gdn=pk["gp2"], gdn_mode=1,
-                             second_plane=True)
-        y = T.layer_run(T.TC_CONV5S2, h2, None, pk["w3"], None, out_f32_nchw=True)
-        # ---- quantizer (noise) + bits
-        bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
-        C, HW = 128, y.shape[2] * y.shape[3]
-        z = torch.empty_like(y)
-        plane_bits = torch.empty((B, C), device=dev, dtype=torch.float32)
-        image_bits = torch.empty((B,), device=dev, dtype=torch.float32)
-        pp, keep = _lib.ptr_array(bitp)
-        with torch.cuda.device(dev), _timed("quant_entropy_fwd[train]", 60 * y.numel(), 12 * y.numel()):
-            _lib.check(lib.b2c_quant_entropy_fwd(_p(y), _p(noise), pp, _p(z), _p(plane_bits), _p(image_bits), B, C, HW,
-                                                 _stream()), "quant_entropy_fwd")
-        total_bits = image_bits.sum()
-        # ---- synthesis transform
-        zh, _ = T.nchw_to_nhwc(z, False)
-        i1, m1 = T.layer_run(T.TC_DECONV5S2, zh, None, pk["d1"], prm["Decoder.deconv1.bias"], gdn=pk["gi1"], gdn_mode=2,
-                             second_plane=True)
-        i2, m2 = T.layer_run(T.TC_DECONV5S2, i1, None, pk["d2"], prm["Decoder.deconv2.bias"], gdn=pk["gi2"], gdn_mode=2,
-                             second_plane=True)
-        recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
-        # ---- distortion
-        clipped = torch.empty_like(recon)
-        sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
-        nbytes = lib.b2c_clamp_sse_workspace_bytes(B, x[0].numel())
-        ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
-        with torch.cuda.device(dev), _timed("clamp_sse_fwd[train]", 8 * x.numel(), 12 * x.numel()):
-            _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, x[0].numel(), _p(ws), nbytes,
-                                             _stream()), "clamp_sse_fwd")
-        sse_total = sse[:, 0].sum()
-        main.wait_event(ev_bwd)          # the backward packs are done long before; keeps stream bookkeeping simple
-        ctx.prm = prm
-        ctx.pk = pk
-        ctx.saved = (x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon)
-        ctx.stats = (image_bits, plane_bits, sse)
-        ctx.mark_non_differentiable(clipped, z)
-        return clipped, sse_total, total_bits, z
+        st = step_forward(x.detach().contiguous().float(), noise.detach().contiguous().float(), prm)
+        total_bits = st["image_bits"].sum()
+        sse_total = st["sse"][:, 0].sum()
+        ctx.st = st
+        ctx.stats = (st["image_bits"], st["plane_bits"], st["sse"])
+        ctx.mark_non_differentiable(st["clipped"], st["z"])
+        return st["clipped"], sse_total, total_bits, st["z"]
 
     @staticmethod
     def backward(ctx, _g_clipped, g_sse, g_bits, _g_z):
-        lib = _lib.load()
-        prm, pk = ctx.prm, ctx.pk
-        x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon = ctx.saved
-        dev = x.device
-        B = x.shape[0]
-        grads = {}
+        st = ctx.st
+        dev = st["z"].device
         zero = torch.zeros((1,), device=dev, dtype=torch.float32)
         g_sse = g_sse.reshape(1).float().contiguous() if g_sse is not None else zero
         g_bits = g_bits.reshape(1).float().contiguous() if g_bits is not None else zero
-        fork = _Fork(dev)
-        from .functional import _channel_sum_raw
-        # ---- entropy model: d bits / dz and the 11 parameter vectors (independent of the synthesis chain)
-        bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
-        C, HW = 128, z.shape[2] * z.shape[3]
-
-        def entropy_bwd():
-            dbit = [torch.zeros_like(p) for p in bitp]
-            dz_ = torch.empty_like(z)
-            pp, k1 = _lib.ptr_array(bitp)
-            dp, k2 = _lib.ptr_array(dbit)
-            with torch.cuda.device(dev):
-                _lib.check(lib.b2c_entropy_bwd(_p(z), pp, _p(g_bits), _p(dz_), dp, B, C, HW, _stream()), "entropy_bwd")
-            return [dz_] + dbit
-        ent = fork.run(entropy_bwd, g_bits)
-        dz, dbit = ent[0], ent[1:]
-        for k, g in zip(PARAM_ORDER[19:], dbit):
-            grads[k] = g.view(1, -1, 1, 1)
-        # ---- distortion
-        g_recon = torch.empty_like(recon)
-        with torch.cuda.device(dev):
-            _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _vp(0), _p(g_sse), _p(g_recon), recon.numel(), _stream()),
-                       "clamp_sse_bwd")
-        # ---- deconv3 (9x9/4, 128 -> 3): weight grad (im2col MN-major tcgen05), dgrad (= conv 9x9/4) + IGDN2 backward fused
-        D1, D2, D3 = prm["Decoder.deconv1.weight"], prm["Decoder.deconv2.weight"], prm["Decoder.deconv3.weight"]
-        grads["Decoder.deconv3.weight"] = fork.run(lambda: T.wgrad9(i2, g_recon), g_recon)
-        grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon), g_recon)
-        gp_d2, dn2 = T.layer_run(T.TC_CONV1, g_recon, None, pk["d3_dg"], None, gdn=pk["gi2_t"],
-                                 gdn_mode=4, second_plane=True, saved=(i2, m2))
-        grads["Decoder.igdn2.beta"], grads["Decoder.igdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
-            prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn2, True), dn2)
-        # ---- deconv2
-        grads["Decoder.deconv2.weight"] = fork.run(lambda: T.wgrad(i1, gp_d2, 5, 2, 2), gp_d2)
-        grads["Decoder.deconv2.bias"] = fork.run(lambda: _colsum(gp_d2), gp_d2)
-        gp_d1, dn1 = T.layer_run(T.TC_CONV5S2, gp_d2, None, pk["d2_dg"], None, gdn=pk["gi1_t"],
-                                 gdn_mode=4, second_plane=True, saved=(i1, m1))
-        grads["Decoder.igdn1.beta"], grads["Decoder.igdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
-            prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn1, True), dn1)
-        # ---- deconv1
-        grads["Decoder.deconv1.weight"] = fork.run(lambda: T.wgrad(zh, gp_d1, 5, 2, 2), gp_d1)
-        grads["Decoder.deconv1.bias"] = fork.run(lambda: _colsum(gp_d1), gp_d1)
-        g_z = T.layer_run(T.TC_CONV5S2, gp_d1, None, pk["d1_dg"], None, out_f32_nchw=True)
-        fork.main.wait_stream(fork.sides[0])               # dz comes from the entropy backward (first forked task)
-        g_y = g_z + dz                                     # z = y + noise -> dz/dy = 1
-        gyh, _ = T.nchw_to_nhwc(g_y, False)
-        # ---- conv3 (no bias): wgrad, dgrad (= transposed conv) + GDN2 backward fused
-        W1, W2, W3 = prm["Encoder.conv1.weight"], prm["Encoder.conv2.weight"], prm["Encoder.conv3.weight"]
-        grads["Encoder.conv3.weight"] = fork.run(lambda: T.wgrad(gyh, h2, 5, 2, 2), gyh)
-        gp_c2, dng2 = T.layer_run(T.TC_DECONV5S2, gyh, None, pk["w3_dg"], None, gdn=pk["gp2_t"],
-                                  gdn_mode=3, second_plane=True, saved=(h2, n2))
-        grads["Encoder.gdn2.beta"], grads["Encoder.gdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
-            prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dng2, False), dng2)
-        # ---- conv2
-        grads["Encoder.conv2.weight"] = fork.run(lambda: T.wgrad(gp_c2, h1, 5, 2, 2), gp_c2)
-        grads["Encoder.conv2.bias"] = fork.run(lambda: _colsum(gp_c2), gp_c2)
-        gp_c1, dng1 = T.layer_run(T.TC_DECONV5S2, gp_c2, None, pk["w2_dg"], None, gdn=pk["gp1_t"],
-                                  gdn_mode=3, second_plane=True, saved=(h1, n1))
-        grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
-            prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dng1, False), dng1)
-        # ---- conv1 (9x9/4, 3 -> 128): weight grad (im2col MN-major tcgen05); the image needs no gradient
-        grads["Encoder.conv1.weight"] = fork.run(lambda: T.wgrad9(gp_c1, x), gp_c1)
-        grads["Encoder.conv1.bias"] = fork.run(lambda: _colsum(gp_c1), gp_c1)
-        fork.join()
-        ctx.saved = None
-        ctx.pk = None
+        grads = step_backward(st, g_sse, g_bits)
+        prm = st["prm"]
+        ctx.st = None
         return (None, None) + tuple(grads[k].reshape(prm[k].shape) for k in PARAM_ORDER)
 
 
@@ -283,30 +332,118 @@ def train_forward(model, x, noise):
 
 
 class GraphedTrainStep:
-    """Whole-step CUDA graph (forward + backward + gradient flattening) for a fixed input shape: the ~110 kernel
-    launches and their TMA descriptors replay as one submission, so the step is not host bound.  The gradients of
-    all 30 tensors are gathered into ONE flat fp32 buffer inside the graph and ``p.grad`` are views of it, so data
-    parallel training needs a single NCCL all-reduce (mean) of 7 MB per step and no per-tensor copies.
+    """Whole-step CUDA graph (forward + backward) for a fixed input shape: the kernel launches and their TMA
+    descriptors replay as one submission, so the step is not host bound.  The gradients of all 30 tensors live in
+    ONE flat fp32 buffer (``p.grad`` are views of it).
+
+    ``direct=True`` (default) drives ``step_forward`` / ``step_backward`` without autograd: the loss weights
+    d loss / d sse = lam / numel and d loss / d bits = 1 / (B H W) are constants (train.py:102), every gradient
+    kernel writes straight into its slice of the flat buffer, and all accumulators of the step are cleared by a
+    single memset.  With ``world_size > 1`` the gradient all-reduce (mean) is captured INSIDE the graph in two
+    buckets on a communication stream: Decoder + bitEstimator gradients are reduced over NVLink while the encoder
+    backward still runs, the encoder bucket at the end (``allreduce_in_graph=False``: one NCCL call after replay).
 
         step = GraphedTrainStep(model, x_example, lam)      # after torch.distributed init when multi-GPU
         loss = step(x)                                       # p.grad holds the (averaged) gradients
     """
 
-    def __init__(self, model, x_example, lam=8192.0, warmup=3, group=None):
+    def __init__(self, model, x_example, lam=8192.0, warmup=3, group=None, direct=True, allreduce_in_graph=None):
+        import os
         import torch.distributed as dist
         self.model, self.lam, self.group = model, lam, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.x = x_example.clone()
         N = model.out_channel_N
         dev = self.x.device
-        self.noise = torch.zeros(x_example.size(0), N, x_example.size(2) // 16, x_example.size(3) // 16, device=dev)
-        self.params = [p for p in model.parameters()]
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        B, _, H, W = self.x.shape
+        self.noise = torch.zeros(B, N, H // 16, W // 16, device=dev)
+        named = list(model.named_parameters())
+        self.params = [p for _, p in named]
+        n_par = sum(p.numel() for p in self.params)
+        n_par_pad = (n_par + 63) // 64 * 64
+        scratch = 4 * 25 * 128 * 128 + 4 * (128 * 128 + 128) + 1024 if direct else 0
+        self.buf = torch.zeros(n_par_pad + scratch, device=dev, dtype=torch.float32)
+        self.flat = self.buf[:n_par]
         views, o = [], 0
         for p in self.params:
             views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
         self.views = views
+        self.direct = direct
+        if allreduce_in_graph is None:
+            allreduce_in_graph = os.environ.get("B2C_AR_IN_GRAPH", "1") == "1"
+        self.ar_in_graph = bool(allreduce_in_graph and direct and self.world > 1)
+        if direct:
+            if N != 128 or set(k for k, _ in named) != set(PARAM_ORDER):
+                raise _lib.B2CError("the tensor-core training step needs ImageCompressor(out_channel_N=128)")
+            self._capture_direct(named, n_par_pad, warmup)
+        else:
+            self._capture_autograd(warmup)
+        for p, v in zip(self.params, self.views):
+            p.grad = v                                   # optimizers read the flat buffer through these views
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _run_direct(self, prm, gviews, n_par_pad, enc_elems):
+        import torch.distributed as dist
+        dev = self.x.device
+        main = torch.cuda.current_stream(dev)
+        self.buf.zero_()                                              # ONE memset: gradients + all accumulators
+        st = step_forward(self.x, self.noise, prm)
+        stat = self._stat_stream
+        stat.wait_stream(main)
+        with torch.cuda.stream(stat):                                 # reporting only: off the critical path
+            self.mse = st["sse"][:, 0].sum() / self.x.numel()          # model.py:61
+            self.bpp = st["image_bits"].sum() / (self.x.size(0) * self.x.size(2) * self.x.size(3))   # model.py:78
+            self.loss = self.lam * self.mse + self.bpp                # train.py:102
+        comm = self._comm_stream
+
+        def decoder_done(fork):
+            if not self.ar_in_graph:
+                return
+            comm.wait_stream(main)
+            for s in fork.used:
+                comm.wait_stream(s)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(self.flat[enc_elems:], op=dist.ReduceOp.AVG, group=self.group)
+
+        step_backward(st, self._g_sse, self._g_bits, out=gviews, pool=_Pool(self.buf, n_par_pad),
+                      on_decoder_done=decoder_done)
+        if self.ar_in_graph:
+            dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
+            main.wait_stream(comm)
+        main.wait_stream(stat)
+
+    @torch.no_grad()
+    def _capture_direct(self, named, n_par_pad, warmup):
+        dev = self.x.device
+        B, _, H, W = self.x.shape
+        prm = {k: p.detach() for k, p in named}
+        for k, t in prm.items():
+            if not (t.is_contiguous() and t.dtype == torch.float32):
+                raise _lib.B2CError(f"parameter {k} must be contiguous fp32")
+        gviews = {k: v for (k, _), v in zip(named, self.views)}
+        enc_elems = sum(p.numel() for k, p in named if k.startswith("Encoder."))
+        if [k.split(".")[0] for k, _ in named] != sorted([k.split(".")[0] for k, _ in named], key=["Encoder", "Decoder", "bitEstimator"].index):
+            raise _lib.B2CError("unexpected parameter order (Encoder, Decoder, bitEstimator expected)")
+        self._g_sse = torch.full((1,), self.lam / self.x.numel(), device=dev, dtype=torch.float32)
+        self._g_bits = torch.full((1,), 1.0 / (B * H * W), device=dev, dtype=torch.float32)
+        self._stat_stream = torch.cuda.Stream(device=dev)
+        self._comm_stream = torch.cuda.Stream(device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._run_direct(prm, gviews, n_par_pad, enc_elems)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._run_direct(prm, gviews, n_par_pad, enc_elems)
+        self.model.last_path = "tcgen05-bf16-train"
+
+    def _capture_autograd(self, warmup):
+        model, lam = self.model, self.lam
+        dev = self.x.device
         prev_override, prev_mode = model.noise_override, model.return_mode
         model.noise_override, model.return_mode = self.noise, "mse"
         side = torch.cuda.Stream(device=dev)
@@ -327,8 +464,6 @@ class GraphedTrainStep:
             self.loss = lam * self.mse + self.bpp
             self.loss.backward()
             torch._foreach_copy_(self.views, [p.grad for p in self.params])
-        for p, v in zip(self.params, self.views):
-            p.grad = v                                   # optimizers read the flat buffer through these views
         model.noise_override, model.return_mode = prev_override, prev_mode
 
     def __call__(self, x, noise=None):
@@ -338,7 +473,7 @@ class GraphedTrainStep:
         else:
             self.noise.copy_(noise, non_blocking=True)
         self.graph.replay()
-        if self.world > 1:
+        if self.world > 1 and not self.ar_in_graph:
             import torch.distributed as dist
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
         return self.loss

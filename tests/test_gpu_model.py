@@ -269,8 +269,10 @@ def test_tc_train_step_gradients(name):
     assert abs(mse2.item() - mse.item()) <= 2e-3 * mse2.item()
 
 
-def test_graphed_train_step_matches_eager():
-    """GraphedTrainStep (whole-step CUDA graph, flat gradient buffer) reproduces the eager tensor-core step."""
+@pytest.mark.parametrize("direct", [True, False])
+def test_graphed_train_step_matches_eager(direct):
+    """GraphedTrainStep (whole-step CUDA graph, flat gradient buffer; autograd-free ``direct`` form and the captured
+    autograd form) reproduces the eager tensor-core step."""
     from iclr_17_compression_b200.train_tc import GraphedTrainStep
     c = Case("train_W1_S_n128_64")
     m = _model(c, return_mode="mse").train()
@@ -283,7 +285,7 @@ def test_graphed_train_step_matches_eager():
     eager = {k: p.grad.clone() for k, p in m.named_parameters()}
     del mse, bpp, loss_t, _          # drop the eager autograd graph (its AccumulateGrad nodes live on the legacy stream)
     m.noise_override = None
-    step = GraphedTrainStep(m, x, c.lam)
+    step = GraphedTrainStep(m, x, c.lam, direct=direct)
     for _ in range(2):
         loss = step(x, noise)
     torch.cuda.synchronize()
