@@ -43,7 +43,7 @@ class TcLayer(ctypes.Structure):
                 ("in_hi", _c_f), ("in_lo", _c_f), ("w_hi", _c_f), ("w_lo", _c_f), ("bias", _c_f),
                 ("gamma_hi", _c_f), ("gamma_lo", _c_f), ("beta_eff", _c_f), ("out_hi", _c_f), ("out_lo", _c_f),
                 ("ref_image", _c_f), ("sse_partial", _c_f), ("saved_y", _c_f), ("saved_n", _c_f),
-                ("channels", _c_i)]
+                ("channels", _c_i), ("ksplit", _c_i)]
 
 
 TC_CONV1, TC_CONV5S2, TC_DECONV5S2, TC_DECONV3 = 0, 1, 2, 3
@@ -56,7 +56,8 @@ SIGNATURES.update({
     "b2c_tc_pack_gdn_t": (_c_i, [_c_i, _c_f, _c_f, _c_f, _c_f, _c_f]),
     "b2c_tc_tiles_per_image": (_c_i, [_c_i, _c_i, _c_i]),
     "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
-    "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
+    "b2c_tc_wgrad9_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
     "b2c_tc_xsq": (_c_i, [_c_f, _c_f, _c_f, _c_sz, _c_i, _c_f]),
     "b2c_tc_nhwc_colsum": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),
     "b2c_gdn_reparam_bwd": (_c_i, [_c_f] * 6 + [_c_i, _c_f]),

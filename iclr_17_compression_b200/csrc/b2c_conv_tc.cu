@@ -57,6 +57,8 @@ struct TcParams {
   const float* ref_image;  // DECONV3 fused distortion: input image x (fp32 NCHW) or null
   float* sse_partial;      // [B][tiles][2] per-CTA {sum (r-x)^2, sum (clamp(r)-x)^2}
   int tiles_per_image;
+  int ksplit;           // CONV5S2, fp32 NCHW output, no GDN: the 25 taps are split over gridDim.y CTAs that add their
+                        // partial sums into the zero-filled output with red.global (1 = off)
   long long* trace;     // debug: clock64 timeline of CTA (0,0,0): [3 roles][64 marks]
 };
 
@@ -186,11 +188,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * NBAR + 3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int phase = blockIdx.y;
+  const int phase = (KIND == B2C_TC_CONV5S2) ? 0 : blockIdx.y;   // DECONV5S2: sub-pixel phase
+  const int ks = (KIND == B2C_TC_CONV5S2) ? blockIdx.y : 0;       // CONV5S2: split-K slice (taps)
   const int n_img = blockIdx.z;
   const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x - tile_y * p.tiles_x;
   const int oy0 = tile_y * TH, ox0 = tile_x * TW;
-  const int nsteps = num_steps<KIND, NCB>(phase);
+  int nsteps = num_steps<KIND, NCB>(phase);
+  int s_off = 0;                                                  // first global step of this CTA (split-K)
+  if (KIND == B2C_TC_CONV5S2 && !GDN && p.ksplit > 1) {
+    const int t0 = ks * 25 / p.ksplit, t1 = (ks + 1) * 25 / p.ksplit;
+    s_off = t0 * NCB;
+    nsteps = (t1 - t0) * NCB;
+  }
   const int total_steps = nsteps + (GDN ? NCB : 0);
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -255,7 +264,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         uint8_t* b_lo = b_hi + B_LO;
         if (s < nsteps) {
           int dy, dx, cb, group;
-          decode_step<KIND, NCB>(s, phase, dy, dx, cb, group);
+          decode_step<KIND, NCB>(s + s_off, phase, dy, dx, cb, group);
           const uint32_t a_bytes = SOFT_A ? 0u : (uint32_t)SLOT_BYTES;
           if (PAIR) {
             // bytes of BOTH CTAs are counted on the leader's barrier
@@ -583,15 +592,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tmem_ld_wait();
         if (valid) {
           float* out = reinterpret_cast<float*>(p.out_hi);
+          const bool split_k = KIND == B2C_TC_CONV5S2 && !GDN && p.ksplit > 1;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float xv = __uint_as_float(raw[j]) + s_bias[c0 + j];
+            float xv = __uint_as_float(raw[j]) + ((split_k && ks != 0) ? 0.f : s_bias[c0 + j]);
             if (GDN) {
               const float nb = __uint_as_float(rawn[j]) + s_beta[c0 + j];
               const float rs = rsqrtf(nb);
               xv = (GDN == 2) ? xv * (nb * rs) : xv * rs;
             }
-            out[(((size_t)n_img * N_TILE + c0 + j) * p.Hfull + oyf) * p.Wfull + oxf] = xv;
+            float* dst = out + (((size_t)n_img * N_TILE + c0 + j) * p.Hfull + oyf) * p.Wfull + oxf;
+            if (split_k) atomicAdd(dst, xv);      // lanes = consecutive pixels: coalesced red.global.add
+            else *dst = xv;
           }
         }
       }
@@ -1014,6 +1026,13 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   p.tiles_x = (p.Wg + TW - 1) / TW;
   const int tiles_y = (p.Hg + TH - 1) / TH;
   p.tiles_per_image = p.tiles_x * tiles_y;
+  p.ksplit = 1;
+  if (L->ksplit > 1) {
+    B2C_REQUIRE(L->kind == B2C_TC_CONV5S2 && !L->gdn && L->out_f32_nchw && L->ksplit <= 25,
+                "tc_layer_run: ksplit is for CONV5S2 with fp32 NCHW output and no GDN (2..25)");
+    p.ksplit = L->ksplit;
+    phases = L->ksplit;
+  }
   dim3 grid(p.tiles_x * tiles_y, phases, L->B);
 
   const int key = L->kind * 1000 + (L->split3 ? 100 : 0) + L->gdn * 10 + (L->out_f32_nchw ? 1 : 0);

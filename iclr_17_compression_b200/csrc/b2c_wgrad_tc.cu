@@ -210,7 +210,8 @@ constexpr int W9_B_BYTES = 4 * IM_SLOT_BYTES;   // 64 KB
 
 struct Wg9Params {
   int tiles_x, tiles_per_image, total_tiles;
-  float* dW;   // [128][243]
+  float* dW;        // [128][243]
+  float* partial;   // two-stage reduction: [ctas][256 k][128 m] per-CTA sums (no atomics), or nullptr
 };
 
 __global__ void __launch_bounds__(W9_THREADS, 1)
@@ -320,10 +321,16 @@ wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         const int k0 = half * 128 + h * 32;
         tmem_ld32(t_row + (uint32_t)k0, raw);
         tmem_ld_wait();
-        float* dst = p.dW + (size_t)m * 243 + k0;
+        if (p.partial) {     // k-major per-CTA tile: lanes = consecutive m -> every store instruction is one 128-byte line
+          float* dst = p.partial + ((size_t)blockIdx.x * 256 + k0) * 128 + m;
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (k0 + c < 243) atomicAdd(dst + c, __uint_as_float(raw[c]));
+          for (int c = 0; c < 32; ++c) dst[(size_t)c * 128] = __uint_as_float(raw[c]);
+        } else {
+          float* dst = p.dW + (size_t)m * 243 + k0;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (k0 + c < 243) atomicAdd(dst + c, __uint_as_float(raw[c]));
+        }
       }
     }
   }
@@ -348,6 +355,25 @@ static int make_image_map9(CUtensorMap* m, const void* base, int B, int H, int W
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(image) failed: %d", (int)r); return B2C_ECUDA; }
   return B2C_OK;
+}
+
+// second stage of the 9x9 weight gradient: dW[m][k] += sum_j partial[j][k][m] in a fixed order (deterministic);
+// one block per k, thread = m
+__global__ void __launch_bounds__(128) wgrad9_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW,
+                                                            int nparts) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int k = blockIdx.x, m = threadIdx.x;
+  const float* src = partial + (size_t)k * 128 + m;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int j = 0;
+  for (; j + 4 <= nparts; j += 4) {
+    s0 += __ldg(src + (size_t)(j + 0) * 256 * 128);
+    s1 += __ldg(src + (size_t)(j + 1) * 256 * 128);
+    s2 += __ldg(src + (size_t)(j + 2) * 256 * 128);
+    s3 += __ldg(src + (size_t)(j + 3) * 256 * 128);
+  }
+  for (; j < nparts; ++j) s0 += __ldg(src + (size_t)j * 256 * 128);
+  dW[(size_t)m * 243 + k] += (s0 + s1) + (s2 + s3);
 }
 
 // x^2 of the GDN input from the saved (y, n): GDN x^2 = y^2 n, IGDN x^2 = y^2 / n   (bf16, 8 per thread)
@@ -391,7 +417,22 @@ using namespace b2c::tc;
 
 extern "C" {
 
-int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int h, int w, void* stream) {
+static int wgrad9_ctas(int total_tiles) {
+  static const int tiles_per_cta = [] { const char* e = getenv("B2C_WG9_TILES_PER_CTA"); int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
+  int ctas = (total_tiles + tiles_per_cta - 1) / tiles_per_cta;
+  if (ctas > 148) ctas = 148;
+  if (ctas < 1) ctas = 1;
+  return ctas;
+}
+
+size_t b2c_tc_wgrad9_workspace_bytes(int B, int h, int w) {
+  if (B <= 0 || h <= 0 || w <= 0) return 0;
+  const int total_tiles = B * ((w + W_TW - 1) / W_TW) * ((h + W_TH - 1) / W_TH);
+  return (size_t)wgrad9_ctas(total_tiles) * 256 * 128 * sizeof(float);
+}
+
+int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int h, int w, void* workspace,
+                  size_t workspace_bytes, void* stream) {
   B2C_REQUIRE(small_t && image && dW && B > 0 && h > 0 && w > 0, "tc_wgrad9: bad arguments");
   constexpr size_t SMEM = 2 * W9_S_BYTES + 2 * P1_SLOT + W9_B_BYTES + 1024 + 256;
   {
@@ -415,12 +456,37 @@ int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int
   int rc;
   if ((rc = make_nhwc_map(&mS, small_t, B, h, w, 1))) return rc;
   if ((rc = make_image_map9(&mI, image, B, 4 * h, 4 * w))) return rc;
-  static const int tiles_per_cta = [] { const char* e = getenv("B2C_WG9_TILES_PER_CTA"); int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
-  int ctas = (p.total_tiles + tiles_per_cta - 1) / tiles_per_cta;
-  if (ctas > 148) ctas = 148;
-  if (ctas < 1) ctas = 1;
+  int ctas;
+  if (workspace) {
+    // two-stage, atomic-free: per-CTA partial tiles, then a fixed-order reduction (deterministic)
+    ctas = wgrad9_ctas(p.total_tiles);
+    if (workspace_bytes < (size_t)ctas * 256 * 128 * sizeof(float)) {
+      set_error("tc_wgrad9: workspace too small");
+      return B2C_EWORKSPACE;
+    }
+    p.partial = (float*)workspace;
+  } else {
+    ctas = (p.total_tiles + 3) / 4;   // >= 4 tiles per CTA: the scalar red.global.add of the 128 x 243 tile dominate
+    if (ctas > 148) ctas = 148;
+    p.partial = nullptr;
+  }
   wgrad9_tc_kernel<<<ctas, W9_THREADS, SMEM, (cudaStream_t)stream>>>(mS, mI, p);
   count_launch();
+  if (workspace) {
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(243);
+    cfg.blockDim = dim3(128);
+    cfg.stream = (cudaStream_t)stream;
+    cfg.attrs = attr;
+    static const bool pdl = [] { const char* e = getenv("B2C_PDL"); return !e || atoi(e) != 0; }();
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad9_reduce_kernel, (const float*)workspace, dW, ctas);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(wgrad9_reduce): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+    count_launch();
+  }
   return check_launch("tc_wgrad9");
 }
 

@@ -86,7 +86,7 @@ def pack_gdn_t(beta, gamma):
 
 
 def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False, ref_image=None,
-              second_plane=False, saved=None):
+              second_plane=False, saved=None, ksplit=1, out=None):
     """One fused layer.  x_hi/x_lo: NHWC bf16 (CONV1: x_hi = fp32 NCHW image).  w = (w_hi, w_lo);
     gdn = (gamma_hi, gamma_lo, beta_eff) with gdn_mode 1 (GDN) / 2 (IGDN).
     Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
@@ -104,7 +104,12 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
             Ho, Wo, Cout = Hin * 4, Win * 4, 3
     dev = x_hi.device
     if out_f32_nchw:
-        out_hi = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
+        if out is not None:                           # caller-provided (zero-filled when ksplit > 1)
+            out_hi = out.view(B, Cout, Ho, Wo)
+        elif ksplit > 1:
+            out_hi = torch.zeros((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
+        else:
+            out_hi = torch.empty((B, Cout, Ho, Wo), device=dev, dtype=torch.float32)
         out_lo = None
     else:
         out_hi = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.bfloat16)
@@ -113,6 +118,7 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
     L.kind, L.split3, L.gdn, L.out_f32_nchw = kind, int(split3), int(gdn_mode), int(out_f32_nchw)
     L.B, L.Hin, L.Win = B, Hin, Win
     L.channels = C
+    L.ksplit = ksplit
     L.in_hi, L.in_lo = x_hi.data_ptr(), (x_lo.data_ptr() if x_lo is not None else 0)
     L.w_hi, L.w_lo = w[0].data_ptr(), (w[1].data_ptr() if w[1] is not None else 0)
     L.bias = bias.data_ptr() if bias is not None else 0
@@ -161,9 +167,12 @@ def wgrad(small, big, k, stride, pad, tmp=None, out=None):
 
 def wgrad9(small, image, out=None):
     """9x9/4 weight gradient: small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w] -> fp32 [128,3,9,9]
-    (accumulated with red.add into ``out``, which must be zero-filled)"""
+    (added to ``out``, which must be zero-filled).  Per-CTA partial tiles + fixed-order reduction (deterministic)."""
     B, h, w, _ = small.shape
+    lib = _lib.load()
     dW = out if out is not None else torch.zeros((128, 3, 9, 9), device=small.device, dtype=torch.float32)
+    nbytes = lib.b2c_tc_wgrad9_workspace_bytes(B, h, w)
+    ws = torch.empty((nbytes,), device=small.device, dtype=torch.uint8)
     with torch.cuda.device(small.device), _timed(f"tc_wgrad9[{B}x{h}x{w}]", 2 * B * h * w * 128 * 243, 0):
-        _lib.check(_lib.load().b2c_tc_wgrad9(_p(small), _p(image), _p(dW), B, h, w, _stream()), "tc_wgrad9")
+        _lib.check(lib.b2c_tc_wgrad9(_p(small), _p(image), _p(dW), B, h, w, _p(ws), nbytes, _stream()), "tc_wgrad9")
     return dW

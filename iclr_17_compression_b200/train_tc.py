@@ -129,7 +129,14 @@ class _Fork:
             o.record_stream(self.main)
 
 
-def step_forward(x, noise, prm):
+def _ksplit():
+    """split-K factor of the two 16-tile 5x5 convs of a batch-8 step (conv3 forward, deconv1 dgrad): one CTA per
+    output tile would leave 132 of 148 SMs idle, so the 25 taps are spread over KSPLIT CTAs per tile"""
+    import os
+    return max(1, min(25, int(os.environ.get("B2C_TRAIN_KSPLIT", "5"))))
+
+
+def step_forward(x, noise, prm, pool=None):
     """Forward of the training step on tensor cores (model.py:47-78 with the noise quantizer).  prm: name -> fp32
     CUDA tensor for the 30 parameters.  Returns the state dict the backward needs plus the per-image statistics."""
     lib = _lib.load()
@@ -174,7 +181,9 @@ def step_forward(x, noise, prm):
     main.wait_event(ev_fwd)
     h2, n2 = T.layer_run(T.TC_CONV5S2, h1, None, pk["w2"], prm["Encoder.conv2.bias"], gdn=pk["gp2"], gdn_mode=1,
                          second_plane=True)
-    y = T.layer_run(T.TC_CONV5S2, h2, None, pk["w3"], None, out_f32_nchw=True)
+    ks = _ksplit() if h2.shape[0] * h2.shape[1] * h2.shape[2] <= 148 * 128 * 4 else 1      # <= 148 output tiles
+    y = T.layer_run(T.TC_CONV5S2, h2, None, pk["w3"], None, out_f32_nchw=True, ksplit=ks,
+                    out=(pool.zeros(B, 128, H // 16, W // 16) if (pool is not None and ks > 1) else None))
     # ---- quantizer (noise) + bits
     bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
     C, HW = 128, y.shape[2] * y.shape[3]
@@ -269,9 +278,12 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None):
     grads["Decoder.deconv1.bias"] = fork.run(lambda: _colsum(gp_d1, dst("Decoder.deconv1.bias")), gp_d1)
     if on_decoder_done is not None:
         on_decoder_done(fork)
-    g_z = T.layer_run(T.TC_CONV5S2, gp_d1, None, pk["d1_dg"], None, out_f32_nchw=True)
     fork.main.wait_stream(ent_stream)                  # dz comes from the entropy backward (first forked task)
-    g_y = g_z + dz                                     # z = y + noise -> dz/dy = 1
+    ks = _ksplit() if gp_d1.shape[0] * gp_d1.shape[1] * gp_d1.shape[2] <= 148 * 128 * 4 else 1
+    if ks > 1:     # split-K CTAs ADD into their output: accumulate on top of d bits / dz (z = y + noise -> dz/dy = 1)
+        g_y = T.layer_run(T.TC_CONV5S2, gp_d1, None, pk["d1_dg"], None, out_f32_nchw=True, ksplit=ks, out=dz)
+    else:
+        g_y = T.layer_run(T.TC_CONV5S2, gp_d1, None, pk["d1_dg"], None, out_f32_nchw=True) + dz
     gyh, _ = T.nchw_to_nhwc(g_y, False)
     # ---- conv3 (no bias): wgrad, dgrad (= transposed conv) + GDN2 backward fused
     grads["Encoder.conv3.weight"] = fork.run(lambda: T.wgrad(
@@ -361,7 +373,7 @@ class GraphedTrainStep:
         self.params = [p for _, p in named]
         n_par = sum(p.numel() for p in self.params)
         n_par_pad = (n_par + 63) // 64 * 64
-        scratch = 4 * 25 * 128 * 128 + 4 * (128 * 128 + 128) + 1024 if direct else 0
+        scratch = (4 * 25 * 128 * 128 + 4 * (128 * 128 + 128) + B * N * (H // 16) * (W // 16) + 1024) if direct else 0
         self.buf = torch.zeros(n_par_pad + scratch, device=dev, dtype=torch.float32)
         self.flat = self.buf[:n_par]
         views, o = [], 0
@@ -388,7 +400,8 @@ class GraphedTrainStep:
         dev = self.x.device
         main = torch.cuda.current_stream(dev)
         self.buf.zero_()                                              # ONE memset: gradients + all accumulators
-        st = step_forward(self.x, self.noise, prm)
+        pool = _Pool(self.buf, n_par_pad)
+        st = step_forward(self.x, self.noise, prm, pool)
         stat = self._stat_stream
         stat.wait_stream(main)
         with torch.cuda.stream(stat):                                 # reporting only: off the critical path
@@ -406,8 +419,7 @@ class GraphedTrainStep:
             with torch.cuda.stream(comm):
                 dist.all_reduce(self.flat[enc_elems:], op=dist.ReduceOp.AVG, group=self.group)
 
-        step_backward(st, self._g_sse, self._g_bits, out=gviews, pool=_Pool(self.buf, n_par_pad),
-                      on_decoder_done=decoder_done)
+        step_backward(st, self._g_sse, self._g_bits, out=gviews, pool=pool, on_decoder_done=decoder_done)
         if self.ar_in_graph:
             dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
             main.wait_stream(comm)

@@ -192,6 +192,9 @@ typedef struct b2c_tc_layer {
   const void* saved_y;
   const void* saved_n;
   int channels;     /* 0 or 128, 192, 256 (see above)                                               */
+  int ksplit;       /* 0 / 1: off.  2..25 (CONV5S2, out_f32_nchw, gdn == 0 only): the 25 taps are split over
+                       ksplit CTAs per tile which ADD their partial sums into out_hi - the caller zero-fills it.
+                       For small batches where one CTA per tile leaves most SMs idle (training, batch 8).   */
 } b2c_tc_layer;
 
 /* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid */
@@ -211,8 +214,13 @@ int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int h
 
 /* 9x9 / stride-4 / pad-4 weight gradient on tensor cores: dW[m][c][ky][kx] += sum small[img,ys,xs,m] *
  * image[img,c,4ys-4+ky,4xs-4+kx]; small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w], dW fp32 [128][3][9][9]
- * zero-filled by the caller.  conv1 (OIHW): small = grad_out, image = x; deconv3 (IOHW): small = input, image = grad_out. */
-int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int h, int w, void* stream);
+ * zero-filled by the caller.  conv1 (OIHW): small = grad_out, image = x; deconv3 (IOHW): small = input, image = grad_out.
+ * With a workspace of b2c_tc_wgrad9_workspace_bytes() bytes (need not be zeroed) the per-CTA sums are written as
+ * tiles and reduced in a fixed order by a second kernel (deterministic, no atomics); with workspace = NULL they are
+ * accumulated with red.global.add. */
+size_t b2c_tc_wgrad9_workspace_bytes(int B, int h, int w);
+int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int h, int w, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* helpers of the bf16 training path: x^2 of a GDN input from the saved output and norm (GDN: y^2 n, IGDN: y^2/n;
  * count bf16 elements, multiple of 8), and out[c] += sum_rows t[row][c] for a bf16 [P][128] tensor (out zero-filled). */

@@ -241,3 +241,25 @@ def test_wgrad9_im2col(tc, shape):
     (F.conv2d(_bf(img).cpu(), wt, None, stride=4, padding=4) * _bf(s).cpu()).sum().backward()
     d = tc.wgrad9(sh, img)
     assert _rel(d, wt.grad) < 1e-5, _rel(d, wt.grad)
+
+
+@pytest.mark.parametrize("ksplit", [2, 5, 25])
+@pytest.mark.parametrize("shape", [(8, 32, 32), (1, 24, 40)])
+def test_conv5s2_bf16_split_k(tc, shape, ksplit):
+    """split-K form of the plain-bf16 5x5/2 conv (training: conv3 forward, deconv1 dgrad): the taps are spread over
+    ksplit CTAs per tile that add into the zero-filled fp32 output; must match the single-CTA result and add the bias once."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 128, H, W, generator=g).cuda()
+    w = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    xh, _ = tc.nchw_to_nhwc(x, False)
+    wp = tc.pack_weights(tc.TC_CONV5S2, w, False)
+    y1 = tc.layer_run(tc.TC_CONV5S2, xh, None, wp, b, out_f32_nchw=True)
+    yk = tc.layer_run(tc.TC_CONV5S2, xh, None, wp, b, out_f32_nchw=True, ksplit=ksplit)
+    assert _rel(yk, y1) < 1e-5, _rel(yk, y1)
+    ref = F.conv2d(xh.permute(0, 3, 1, 2).double(), w.to(torch.bfloat16).double(), b.double(), stride=2, padding=2)
+    assert _rel(yk, ref) < 1e-4, _rel(yk, ref)
+    base = torch.full_like(y1, 0.25)                                  # accumulate on top of existing contents
+    y2 = tc.layer_run(tc.TC_CONV5S2, xh, None, wp, b, out_f32_nchw=True, ksplit=ksplit, out=base)
+    assert _rel(y2 - 0.25, y1) < 1e-5
