@@ -43,7 +43,7 @@ class TcLayer(ctypes.Structure):
                 ("in_hi", _c_f), ("in_lo", _c_f), ("w_hi", _c_f), ("w_lo", _c_f), ("bias", _c_f),
                 ("gamma_hi", _c_f), ("gamma_lo", _c_f), ("beta_eff", _c_f), ("out_hi", _c_f), ("out_lo", _c_f),
                 ("ref_image", _c_f), ("sse_partial", _c_f), ("saved_y", _c_f), ("saved_n", _c_f),
-                ("channels", _c_i), ("ksplit", _c_i)]
+                ("channels", _c_i), ("grad_out", _c_f), ("grad_scale", ctypes.c_float), ("ksplit", _c_i)]
 
 
 TC_CONV1, TC_CONV5S2, TC_DECONV5S2, TC_DECONV3 = 0, 1, 2, 3

@@ -708,6 +708,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 // weights -> bf16 (hi, lo) panels, row = (group, out channel), 128-byte K-major rows
 __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int total, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   float v = 0.f;
@@ -737,6 +739,8 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
 __global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
                                 __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
                                 float* __restrict__ beta_eff, int transpose, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < C * C) {
     const int src = transpose ? ((idx % C) * C + (idx / C)) : idx;
@@ -756,6 +760,8 @@ __global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* _
 // fp32 NCHW -> NHWC bf16 (hi[,lo]) through a 32x32 shared-memory transpose
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int C, int HW) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float t[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -951,8 +957,8 @@ int b2c_tc_pack_gdn_t(int channels, const float* beta_p, const float* gamma_p, v
 int b2c_tc_nchw_to_nhwc(const float* in, void* out_hi, void* out_lo, int B, int C, int HW, void* stream) {
   B2C_REQUIRE(in && out_hi && B > 0 && C > 0 && HW > 0, "tc_nchw_to_nhwc: bad arguments");
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, C,
-                                                                HW);
+  launch_pdl(PDL_LAYOUT, nchw_to_nhwc_kernel, grid, block, 0, (cudaStream_t)stream, in, (__nv_bfloat16*)out_hi,
+             (__nv_bfloat16*)out_lo, C, HW);
   count_launch();
   return check_launch("tc_nchw_to_nhwc");
 }
@@ -992,6 +998,8 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
     rc = b2c::tcp1::try_launch(L, stream, g_tc_trace);
     if (rc != 1) return rc;
   }
+  B2C_REQUIRE(!L->grad_out, "tc_layer_run: grad_out needs the persistent DECONV3 kernel (ref_image set, 128 channels, "
+                            "B2C_TC_PERSIST on)");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.B = L->B; p.Hin = L->Hin; p.Win = L->Win;

@@ -49,6 +49,8 @@ struct PParams {
   float* out_f32;
   const float* ref_image;   // DECONV3 fused distortion
   float* sse_partial;
+  float* grad_out;          // DECONV3 + ref_image (training): grad_scale * (recon - x), fp32 NCHW, or nullptr
+  float grad_scale;
   long long* trace;         // debug: clock64 timeline of CTA 0: [3 roles][64 marks]
 };
 
@@ -601,6 +603,10 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                   dd = v4.z - x4.z; s0 = fmaf(dd, dd, s0); dd = v4.w - x4.w; s0 = fmaf(dd, dd, s0);
                   dd = c4.x - x4.x; s1 = fmaf(dd, dd, s1); dd = c4.y - x4.y; s1 = fmaf(dd, dd, s1);
                   dd = c4.z - x4.z; s1 = fmaf(dd, dd, s1); dd = c4.w - x4.w; s1 = fmaf(dd, dd, s1);
+                  if (p.grad_out)   // d/d recon of (grad_scale / 2) * sum (recon - x)^2: the distortion backward, fused
+                    *reinterpret_cast<float4*>(p.grad_out + off) =
+                        make_float4(p.grad_scale * (v4.x - x4.x), p.grad_scale * (v4.y - x4.y),
+                                    p.grad_scale * (v4.z - x4.z), p.grad_scale * (v4.w - x4.w));
                   v4 = c4;
                 }
                 *reinterpret_cast<float4*>(p.out_f32 + off) = v4;
@@ -770,6 +776,7 @@ static int launch_p(const b2c_tc_layer* L, cudaStream_t stream, long long* trace
   p.bias = L->bias; p.beta_eff = L->beta_eff;
   p.out_f32 = (float*)L->out_hi;
   p.ref_image = L->ref_image; p.sse_partial = L->sse_partial;
+  p.grad_out = L->ref_image ? L->grad_out : nullptr; p.grad_scale = L->grad_scale;
   p.trace = trace;
 
   // grid: one CTA (pair) per SM, never more than can be co-resident (a persistent CTA that waits for a slot

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(256) quant_entropy_fwd_kernel(const float* __r
                                                                 BitPtrs bp, float* __restrict__ z,
                                                                 float* __restrict__ plane_bits, int C, int HW) {
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int plane = blockIdx.x;  // n*C + c
   const int c = plane % C;
   const ChanConst k = load_chan(bp, c);
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256) quant_entropy_fwd_kernel(const float* __r
 __global__ void __launch_bounds__(256) plane_reduce_kernel(const float* __restrict__ plane_vals,
                                                            float* __restrict__ out, int per_image) {
   __shared__ float red[32];
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x;
   float s = 0.f;
   for (int i = threadIdx.x; i < per_image; i += blockDim.x) s += plane_vals[(size_t)n * per_image + i];
@@ -346,8 +350,8 @@ int b2c_quant_entropy_fwd(const float* y, const float* noise, const float* const
     B2C_REQUIRE(host_params[i], "quant_entropy_fwd: null parameter pointer %d", i);
     bp.p[i] = host_params[i];
   }
-  quant_entropy_fwd_kernel<<<B * C, 256, 0, (cudaStream_t)stream>>>(y, noise, bp, z, plane_bits, C, HW);
-  plane_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(plane_bits, image_bits, C);
+  launch_pdl(PDL_ENTROPY, quant_entropy_fwd_kernel, dim3(B * C), dim3(256), 0, (cudaStream_t)stream, y, noise, bp, z, plane_bits, C, HW);
+  launch_pdl(PDL_ENTROPY, plane_reduce_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, (const float*)plane_bits, image_bits, C);
   count_launch(2);
   return check_launch("quant_entropy_fwd");
 }

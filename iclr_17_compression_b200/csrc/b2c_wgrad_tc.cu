@@ -244,6 +244,8 @@ wgrad9_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     tma_prefetch_desc(&tmI);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
+  pdl_trigger();
+  pdl_wait();              // the prologue above overlapped the predecessor's tail (programmatic dependent launch)
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -470,7 +472,10 @@ int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int
     if (ctas > 148) ctas = 148;
     p.partial = nullptr;
   }
-  wgrad9_tc_kernel<<<ctas, W9_THREADS, SMEM, (cudaStream_t)stream>>>(mS, mI, p);
+  {
+    cudaError_t e = launch_pdl(PDL_WGRAD9, wgrad9_tc_kernel, dim3(ctas), dim3(W9_THREADS), SMEM, (cudaStream_t)stream, mS, mI, p);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(wgrad9): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+  }
   count_launch();
   if (workspace) {
     cudaLaunchAttribute attr[1];
@@ -481,8 +486,7 @@ int b2c_tc_wgrad9(const void* small_t, const float* image, float* dW, int B, int
     cfg.blockDim = dim3(128);
     cfg.stream = (cudaStream_t)stream;
     cfg.attrs = attr;
-    static const bool pdl = [] { const char* e = getenv("B2C_PDL"); return !e || atoi(e) != 0; }();
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = pdl_small_enabled(PDL_WGRAD9) ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad9_reduce_kernel, (const float*)workspace, dW, ctas);
     if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(wgrad9_reduce): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
     count_launch();

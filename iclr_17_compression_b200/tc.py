@@ -85,8 +85,17 @@ def pack_gdn_t(beta, gamma):
     return gt, None, be
 
 
+def reduce_partial_sse(partial):
+    """[B, tiles, 2] per-tile squared-error sums of a DECONV3 launch -> [B, 2] (fixed order)"""
+    B, tiles, _ = partial.shape
+    sse = torch.empty((B, 2), device=partial.device, dtype=torch.float32)
+    with torch.cuda.device(partial.device):
+        _lib.check(_lib.load().b2c_partial_reduce(_p(partial), _p(sse), B, tiles, 2, _stream()), "partial_reduce")
+    return sse
+
+
 def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False, ref_image=None,
-              second_plane=False, saved=None, ksplit=1, out=None):
+              second_plane=False, saved=None, ksplit=1, out=None, grad_scale=None, reduce_sse=True):
     """One fused layer.  x_hi/x_lo: NHWC bf16 (CONV1: x_hi = fp32 NCHW image).  w = (w_hi, w_lo);
     gdn = (gamma_hi, gamma_lo, beta_eff) with gdn_mode 1 (GDN) / 2 (IGDN).
     Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
@@ -135,14 +144,19 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         partial = torch.empty((B, tiles, 2), device=dev, dtype=torch.float32)
         sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
         L.ref_image, L.sse_partial = ref_image.data_ptr(), partial.data_ptr()
+        if grad_scale is not None:                 # training: distortion backward fused into the same epilogue
+            grad_out = torch.empty_like(out_hi)
+            L.grad_out, L.grad_scale = grad_out.data_ptr(), float(grad_scale)
     flops = int(_flops_per_out_pixel(kind, C) * B * Ho * Wo) + (2 * C * C * B * Ho * Wo if gdn_mode else 0)
     name = f"tc_layer[kind{kind},{B}x{Hin}x{Win},split{int(split3)},gdn{gdn_mode}]"
     with torch.cuda.device(dev), _timed(name, flops, 0):
         _lib.check(_lib.load().b2c_tc_layer_run(ctypes.byref(L), _stream()), "tc_layer_run")
-        if sse is not None:
+        if sse is not None and reduce_sse:
             _lib.check(_lib.load().b2c_partial_reduce(_p(partial), _p(sse), B, tiles, 2, _stream()), "partial_reduce")
     if sse is not None:
-        return out_hi, sse
+        if grad_scale is not None:
+            return out_hi, (sse if reduce_sse else partial), grad_out
+        return out_hi, (sse if reduce_sse else partial)
     return out_hi if out_f32_nchw else (out_hi, out_lo)
 
 

@@ -136,7 +136,7 @@ def _ksplit():
     return max(1, min(25, int(os.environ.get("B2C_TRAIN_KSPLIT", "5"))))
 
 
-def step_forward(x, noise, prm, pool=None):
+def step_forward(x, noise, prm, pool=None, grad_scale=None):
     """Forward of the training step on tensor cores (model.py:47-78 with the noise quantizer).  prm: name -> fp32
     CUDA tensor for the 30 parameters.  Returns the state dict the backward needs plus the per-image statistics."""
     lib = _lib.load()
@@ -200,18 +200,28 @@ def step_forward(x, noise, prm, pool=None):
                          second_plane=True)
     i2, m2 = T.layer_run(T.TC_DECONV5S2, i1, None, pk["d2"], prm["Decoder.deconv2.bias"], gdn=pk["gi2"], gdn_mode=2,
                          second_plane=True)
-    recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
-    # ---- distortion
-    clipped = torch.empty_like(recon)
-    sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
-    nbytes = lib.b2c_clamp_sse_workspace_bytes(B, x[0].numel())
-    ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
-    with torch.cuda.device(dev), _timed("clamp_sse_fwd[train]", 8 * x.numel(), 12 * x.numel()):
-        _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, x[0].numel(), _p(ws), nbytes,
-                                         _stream()), "clamp_sse_fwd")
+    if grad_scale is not None:
+        # distortion forward AND backward fused into the last layer's epilogue: clamp, both squared-error sums and
+        # d loss / d recon = grad_scale * (recon - x) leave the kernel together (grad_scale = 2 lambda / numel)
+        clipped, sse_partial, g_recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"],
+                                                    out_f32_nchw=True, ref_image=x, grad_scale=grad_scale,
+                                                    reduce_sse=False)
+        recon, sse = None, None
+    else:
+        recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
+        # ---- distortion
+        clipped = torch.empty_like(recon)
+        sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
+        nbytes = lib.b2c_clamp_sse_workspace_bytes(B, x[0].numel())
+        ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev), _timed("clamp_sse_fwd[train]", 8 * x.numel(), 12 * x.numel()):
+            _lib.check(lib.b2c_clamp_sse_fwd(_p(recon), _p(x), _p(clipped), _p(sse), B, x[0].numel(), _p(ws), nbytes,
+                                             _stream()), "clamp_sse_fwd")
+        sse_partial, g_recon = None, None
     main.wait_event(ev_bwd)          # the backward packs are done long before; keeps stream bookkeeping simple
     return {"prm": prm, "pk": pk, "saved": (x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon),
-            "image_bits": image_bits, "plane_bits": plane_bits, "sse": sse, "clipped": clipped, "z": z}
+            "image_bits": image_bits, "plane_bits": plane_bits, "sse": sse, "clipped": clipped, "z": z,
+            "sse_partial": sse_partial, "g_recon": g_recon}
 
 
 def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None):
@@ -253,10 +263,12 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None):
     for k, g in zip(PARAM_ORDER[19:], dbit):
         grads[k] = g.view(1, -1, 1, 1)
     # ---- distortion
-    g_recon = torch.empty_like(recon)
-    with torch.cuda.device(dev):
-        _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _vp(0), _p(g_sse), _p(g_recon), recon.numel(), _stream()),
-                   "clamp_sse_bwd")
+    g_recon = st.get("g_recon")
+    if g_recon is None:
+        g_recon = torch.empty_like(recon)
+        with torch.cuda.device(dev):
+            _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _vp(0), _p(g_sse), _p(g_recon), recon.numel(), _stream()),
+                       "clamp_sse_bwd")
     # ---- deconv3 (9x9/4, 128 -> 3): weight grad (im2col MN-major tcgen05), dgrad (= conv 9x9/4) + IGDN2 backward fused
     grads["Decoder.deconv3.weight"] = fork.run(lambda: T.wgrad9(i2, g_recon, out=dst("Decoder.deconv3.weight")), g_recon)
     grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon, dst("Decoder.deconv3.bias")), g_recon)
@@ -401,11 +413,14 @@ class GraphedTrainStep:
         main = torch.cuda.current_stream(dev)
         self.buf.zero_()                                              # ONE memset: gradients + all accumulators
         pool = _Pool(self.buf, n_par_pad)
-        st = step_forward(self.x, self.noise, prm, pool)
+        import os
+        fused = os.environ.get("B2C_TRAIN_FUSED_DISTORTION", "1") == "1"
+        st = step_forward(self.x, self.noise, prm, pool, grad_scale=(2.0 * self.lam / self.x.numel()) if fused else None)
         stat = self._stat_stream
         stat.wait_stream(main)
         with torch.cuda.stream(stat):                                 # reporting only: off the critical path
-            self.mse = st["sse"][:, 0].sum() / self.x.numel()          # model.py:61
+            self.sse = T.reduce_partial_sse(st["sse_partial"]) if st["sse_partial"] is not None else st["sse"]
+            self.mse = self.sse[:, 0].sum() / self.x.numel()           # model.py:61
             self.bpp = st["image_bits"].sum() / (self.x.size(0) * self.x.size(2) * self.x.size(3))   # model.py:78
             self.loss = self.lam * self.mse + self.bpp                # train.py:102
         comm = self._comm_stream

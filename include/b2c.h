@@ -192,6 +192,10 @@ typedef struct b2c_tc_layer {
   const void* saved_y;
   const void* saved_n;
   int channels;     /* 0 or 128, 192, 256 (see above)                                               */
+  float* grad_out;  /* DECONV3 with ref_image (training): also write grad_scale * (recon - x), fp32 NCHW - the
+                       gradient of (grad_scale / 2) * sum (recon - x)^2 w.r.t. the unclamped reconstruction
+                       (model.py:61 through train.py:102), so no separate distortion forward / backward pass runs */
+  float grad_scale;
   int ksplit;       /* 0 / 1: off.  2..25 (CONV5S2, out_f32_nchw, gdn == 0 only): the 25 taps are split over
                        ksplit CTAs per tile which ADD their partial sums into out_hi - the caller zero-fills it.
                        For small batches where one CTA per tile leaves most SMs idle (training, batch 8).   */
