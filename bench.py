@@ -139,6 +139,13 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # exactly ONE line may reach stdout: libraries (NCCL prints its version banner there) write to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     import torch.distributed as dist
     import iclr_17_compression_b200 as P
     from iclr_17_compression_b200 import _lib, functional as B2F
@@ -220,6 +227,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item()
     e2e_val = IMAGES * world * MPIX_PER_IMAGE / (e2e_ms / 1e3)
+    # the bound of that call: one pinned-host -> device copy of the step's input alone (PCIe), same CUDA-event timing
+    xd = torch.empty_like(x)
+    xd.copy_(x_host, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        xd.copy_(x_host, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_ms = c0.elapsed_time(c1) / 3
+    del xd
 
     # ---- roofline of the dominant kernel (largest share of the step), from the in-region event pairs
     pk, pk_kind = peaks()
@@ -231,6 +250,12 @@ def main():
         achieved = top["flops"] / (top["ms_avg"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak}
+        if "split1" in top_name:
+            # the analysis transform runs error-compensated bf16x3 (hi*hi + hi*lo + lo*hi): 3 MMAs per algorithmic
+            # product, needed for bit-exact rounded latents - the tensor pipe executes 3x `achieved`
+            roof["executed_tflops"] = 3 * achieved
+            roof["executed_frac_of_peak"] = 3 * achieved / peak
+            roof["executed_frac_of_burst_peak"] = 3 * achieved / pk.get("bf16_tflops", peak)
     else:
         achieved = top["bytes"] / (top["ms_avg"] * 1e-3) / 1e9
         peak = pk["hbm_gbs"]
@@ -262,7 +287,9 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
-                    "call": f"inference.HostPipeline.compress ({IMAGES // E2E_CHUNK} chunks of {E2E_CHUNK} images, copy/compute overlap)"},
+                    "call": f"inference.HostPipeline.compress ({IMAGES // E2E_CHUNK} chunks of {E2E_CHUNK} images, copy/compute overlap)",
+                    "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gbs": x.numel() * 4 / (h2d_ms * 1e-3) / 1e9,
+                    "bound": "PCIe host->device copy of the fp32 input"},
             "roofline": roof,
             "ops": {k: {"ms_avg": round(v["ms_avg"], 4), "calls": v["calls"]} for k, v in ops.items()}}
 
@@ -277,7 +304,7 @@ def main():
         val, cores, sample, _ = cpu_reference_throughput(args.cpu_budget, 4)
         line["cpu_baseline"] = {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -335,9 +362,12 @@ def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
     return {"metric": "train img/s (batch 8 of 3x256x256 per GPU, fwd+bwd, noise quantizer, lambda=8192)",
             "value": 8 * world / (ms / 1e3), "unit": "img/s", "ms_per_step": ms,
             "allreduce": ("none (1 GPU)" if world == 1 else
-                          "one NCCL all-reduce (mean) of the flat 7 MB gradient buffer after the graphed step" if graphed is not None else
+                          ("two-bucket NCCL all-reduce captured inside the step graph" if getattr(graphed, "ar_in_graph", False)
+                           else "one NCCL all-reduce (mean) of the flat 7 MB gradient buffer after the graphed step")
+                          if graphed is not None else
                           "nccl bucketed, overlapped with backward"),
             "path": getattr(model, "last_path", None), "cuda_graph": graphed is not None,
+            "direct": bool(getattr(graphed, "direct", False)),
             "ops": {k: round(v["ms_total"] / steps, 4) for k, v in sorted(ops.items(), key=lambda kv: -kv[1]["ms_total"])},
             "flop_per_step": 68.7e9, "frac_of_tensor_roofline": 68.7e9 / (ms * 1e-3) / 1e12 / peaks()[0]["bf16_tflops_sustained"]}
 

@@ -1,0 +1,79 @@
+// Fused training-step tail: element-wise gradient clamp (train.py:106-111) + torch.optim.Adam update
+// (train.py:112,233: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad) for ALL parameter tensors in one
+// launch.  Gradients, first and second moments live in flat fp32 buffers (concatenated in parameter order); the
+// parameters stay the reference's separate tensors, addressed through a pointer table.  Step count and learning
+// rate are read from device memory so the launch can be replayed inside a CUDA graph.
+#include "b2c_common.cuh"
+
+namespace b2c {
+
+constexpr int ADAM_MAX_TENSORS = 32;
+
+struct AdamTable {
+  float* p[ADAM_MAX_TENSORS];
+  unsigned start[ADAM_MAX_TENSORS + 1];   // flat offset of tensor i; start[n] = total
+  int n;
+};
+
+__global__ void __launch_bounds__(256) adam_clamp_kernel(const AdamTable T, const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         const int* __restrict__ step_dev,
+                                                         const float* __restrict__ lr_dev, float beta1, float beta2,
+                                                         float eps, float clip) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  __shared__ unsigned s_start[ADAM_MAX_TENSORS + 1];
+  if (threadIdx.x <= T.n) s_start[threadIdx.x] = T.start[threadIdx.x];
+  if (threadIdx.x == 0) {
+    const double step = (double)step_dev[0];
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    s_step_size = (float)((double)lr_dev[0] / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const unsigned total = s_start[T.n];
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = T.n;                       // tensor t with start[t] <= i < start[t+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_start[mid] <= i) lo = mid; else hi = mid;
+    }
+    float gi = g[i];
+    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);                 // p.grad.data.clamp_(-5, 5)
+    const float mi = fmaf(1.f - beta1, gi - m[i], m[i]);                 // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(1.f - beta2, gi * gi, v[i] * beta2);           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    float* pp = T.p[lo] + (i - s_start[lo]);
+    *pp = *pp - step_size * (mi / denom);                                // param.addcdiv_(exp_avg, denom, -step_size)
+  }
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_adam_clamp_step(float* const* params, const size_t* numel, int n_tensors, const float* grads_flat,
+                                   float* exp_avg, float* exp_avg_sq, const int* step_dev, const float* lr_dev,
+                                   float beta1, float beta2, float eps, float grad_clip, void* stream) {
+  B2C_REQUIRE(params && numel && grads_flat && exp_avg && exp_avg_sq && step_dev && lr_dev, "adam_clamp_step: null pointer");
+  B2C_REQUIRE(n_tensors > 0 && n_tensors <= ADAM_MAX_TENSORS, "adam_clamp_step: 1..%d tensors", ADAM_MAX_TENSORS);
+  AdamTable T;
+  size_t off = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    B2C_REQUIRE(params[i] && numel[i] > 0, "adam_clamp_step: bad tensor %d", i);
+    T.p[i] = params[i];
+    T.start[i] = (unsigned)off;
+    off += numel[i];
+    B2C_REQUIRE(off < (1ull << 32), "adam_clamp_step: too many elements");
+  }
+  T.start[n_tensors] = (unsigned)off;
+  T.n = n_tensors;
+  unsigned blocks = (unsigned)((off + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_clamp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(T, grads_flat, exp_avg, exp_avg_sq, step_dev, lr_dev, beta1,
+                                                             beta2, eps, grad_clip);
+  count_launch();
+  return check_launch("adam_clamp_step");
+}

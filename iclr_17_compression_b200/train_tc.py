@@ -371,7 +371,8 @@ class GraphedTrainStep:
         loss = step(x)                                       # p.grad holds the (averaged) gradients
     """
 
-    def __init__(self, model, x_example, lam=8192.0, warmup=3, group=None, direct=True, allreduce_in_graph=None):
+    def __init__(self, model, x_example, lam=8192.0, warmup=3, group=None, direct=True, allreduce_in_graph=None,
+                 optimizer=None):
         import os
         import torch.distributed as dist
         self.model, self.lam, self.group = model, lam, group
@@ -394,9 +395,21 @@ class GraphedTrainStep:
             o += p.numel()
         self.views = views
         self.direct = direct
+        # optimizer="adam": train.py:106-112 (gradient clamp +-5, Adam) as one fused launch over the flat buffers -
+        # captured at the end of the step graph on one GPU, launched after the all-reduce otherwise
+        self.optimizer = None
+        if optimizer is not None:
+            from .optim import FusedAdamClamp
+            if optimizer == "adam":
+                optimizer = FusedAdamClamp(self.params, flat_grads=self.flat)
+            elif not isinstance(optimizer, FusedAdamClamp) or optimizer._flat is not None:
+                raise ValueError("optimizer must be 'adam' or a FusedAdamClamp created without flat_grads")
+            optimizer._flat = self.flat
+            self.optimizer = optimizer
         if allreduce_in_graph is None:
-            allreduce_in_graph = os.environ.get("B2C_AR_IN_GRAPH", "1") == "1"
+            allreduce_in_graph = os.environ.get("B2C_AR_IN_GRAPH", "0") == "1"
         self.ar_in_graph = bool(allreduce_in_graph and direct and self.world > 1)
+        self._opt_in_graph = self.optimizer is not None and direct and (self.world == 1 or self.ar_in_graph)
         if direct:
             if N != 128 or set(k for k, _ in named) != set(PARAM_ORDER):
                 raise _lib.B2CError("the tensor-core training step needs ImageCompressor(out_channel_N=128)")
@@ -407,7 +420,7 @@ class GraphedTrainStep:
             p.grad = v                                   # optimizers read the flat buffer through these views
 
     # -------------------------------------------------------------------------------------------------------------
-    def _run_direct(self, prm, gviews, n_par_pad, enc_elems):
+    def _run_direct(self, prm, gviews, n_par_pad, enc_elems, with_optimizer=False):
         import torch.distributed as dist
         dev = self.x.device
         main = torch.cuda.current_stream(dev)
@@ -436,9 +449,15 @@ class GraphedTrainStep:
 
         step_backward(st, self._g_sse, self._g_bits, out=gviews, pool=pool, on_decoder_done=decoder_done)
         if self.ar_in_graph:
-            dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
+            # both buckets go through the SAME stream: collectives of one communicator must be issued in the same
+            # order on every rank, and two unordered graph branches would let each rank's replay pick its own order
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
             main.wait_stream(comm)
         main.wait_stream(stat)
+        if with_optimizer and self._opt_in_graph:
+            self.optimizer.step(capturing=True)                      # inside the graph: gradients are final here
 
     @torch.no_grad()
     def _capture_direct(self, named, n_par_pad, warmup):
@@ -465,7 +484,7 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._run_direct(prm, gviews, n_par_pad, enc_elems)
+            self._run_direct(prm, gviews, n_par_pad, enc_elems, with_optimizer=True)   # (warm-ups must not update)
         self.model.last_path = "tcgen05-bf16-train"
 
     def _capture_autograd(self, warmup):
@@ -494,6 +513,8 @@ class GraphedTrainStep:
         model.noise_override, model.return_mode = prev_override, prev_mode
 
     def __call__(self, x, noise=None):
+        if self.optimizer is not None:
+            self.optimizer.sync_lr()
         self.x.copy_(x, non_blocking=True)
         if noise is None:
             torch.nn.init.uniform_(self.noise, -0.5, 0.5)        # model.py:49
@@ -503,4 +524,6 @@ class GraphedTrainStep:
         if self.world > 1 and not self.ar_in_graph:
             import torch.distributed as dist
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        if self.optimizer is not None and not self._opt_in_graph:
+            self.optimizer.step()
         return self.loss

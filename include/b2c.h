@@ -235,6 +235,17 @@ int b2c_tc_nhwc_colsum(const void* t, float* out, size_t P, void* stream);
 int b2c_tc_nchw_to_nhwc(const float* in, void* out_hi, void* out_lo, int B, int C, int HW, void* stream);
 int b2c_tc_nhwc_to_nchw(const void* in_hi, const void* in_lo, float* out, int B, int C, int HW, void* stream);
 
+/* ---- fused training-step tail (next row N2): gradient clamp + Adam for all parameter tensors in one launch ----------
+ * Replaces train.py:106-112 (`p.grad.data.clamp_(-5, 5)` per tensor, then `optim.Adam(...).step()`: betas (0.9,
+ * 0.999), eps 1e-8, no weight decay, train.py:233).  params[i] / numel[i]: the n_tensors (<= 32) fp32 parameter tensors
+ * (host arrays of device pointers / element counts); grads_flat, exp_avg, exp_avg_sq: flat fp32 device buffers holding
+ * the gradients and both moments concatenated in the same order; step_dev: device int32 holding the 1-based step number
+ * of THIS update; lr_dev: device float learning rate (both read on the device, so a CUDA graph can replay the launch
+ * while the host advances them).  grad_clip <= 0 disables the clamp. */
+int b2c_adam_clamp_step(float* const* params, const size_t* numel, int n_tensors, const float* grads_flat,
+                        float* exp_avg, float* exp_avg_sq, const int* step_dev, const float* lr_dev, float beta1,
+                        float beta2, float eps, float grad_clip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
