@@ -7,10 +7,18 @@ import torch
 class HostPipeline:
     """compress(x_host) for a fixed batch shape; buffers are allocated once."""
 
-    def __init__(self, model, batch, height, width, chunk=8, device=None, use_graphs=True):
+    def __init__(self, model, batch, height, width, chunk=8, device=None, use_graphs=True, ramp=True):
+        """chunk: images per copy/compute slice.  ramp: the first and the last slice are half-size, so the first
+        kernels start (and the last ones finish) sooner next to the PCIe copy that bounds the call."""
         if batch % chunk:
             raise ValueError("batch must be a multiple of chunk")
-        self.model, self.chunk, self.n_chunks = model, chunk, batch // chunk
+        sizes = [chunk] * (batch // chunk)
+        if ramp and chunk >= 2 and len(sizes) >= 2:
+            h = chunk // 2
+            sizes = [h] + [chunk] * (batch // chunk - 1) + [chunk - h]
+        self.sizes = sizes
+        self.offsets = [sum(sizes[:i]) for i in range(len(sizes))]
+        self.model, self.chunk, self.n_chunks = model, chunk, len(sizes)
         self.dev = device or next(model.parameters()).device
         N = model.out_channel_N
         self.lat_host = torch.empty((batch, N, height // 16, width // 16), dtype=torch.float32).pin_memory()
@@ -30,50 +38,54 @@ class HostPipeline:
 
     @torch.no_grad()
     def _capture(self):
-        """one CUDA graph per input buffer: the ~14 launches (and their TMA descriptors) of a chunk replay as
-        a single submission, so small chunks are not host-bound"""
+        """one CUDA graph per (input buffer, slice size): the ~14 launches (and their TMA descriptors) of a slice
+        replay as a single submission, so small slices are not host-bound"""
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
             for b in range(2):
                 self.x_dev[b].uniform_(0, 1)
-                self.model(self.x_dev[b])                      # warm-up: packs weights, sizes the allocator
+                for n in sorted(set(self.sizes)):
+                    self.model(self.x_dev[b][:n])              # warm-up: packs weights, sizes the allocator
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        self.graphs = []
-        for b in range(2):
+        self.graphs = {}
+        for i, n in enumerate(self.sizes):
+            b = i & 1
+            if (b, n) in self.graphs:
+                continue
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                _, z, _ = self.model(self.x_dev[b])
+                _, z, _ = self.model(self.x_dev[b][:n])
                 stats = torch.cat([self.model.last["image_bits"][:, None], self.model.last["sse"]], dim=1)
-            self.graphs.append((g, z, stats))
+            self.graphs[(b, n)] = (g, z, stats)
 
     @torch.no_grad()
     def compress(self, x_host):
         """x_host: pinned fp32 [batch,3,H,W].  Returns (latents_host, stats_host) after a full sync."""
-        c, main = self.chunk, torch.cuda.current_stream(self.dev)
+        main = torch.cuda.current_stream(self.dev)
         for i in range(self.n_chunks):
-            b = i & 1
+            b, n, o = i & 1, self.sizes[i], self.offsets[i]
             with torch.cuda.stream(self.copy_stream):
                 if i >= 2:
-                    self.copy_stream.wait_event(self.buf_free[b])      # kernels of chunk i-2 are done with it
-                self.x_dev[b].copy_(x_host[i * c:(i + 1) * c], non_blocking=True)
+                    self.copy_stream.wait_event(self.buf_free[b])      # kernels of slice i-2 are done with it
+                self.x_dev[b][:n].copy_(x_host[o:o + n], non_blocking=True)
                 self.h2d_done[b].record(self.copy_stream)
             main.wait_event(self.h2d_done[b])
             if self.graphs is not None:
                 if i >= 2:
-                    main.wait_event(self.d2h_done[b])                  # outputs of chunk i-2 have left the device
-                g, z, stats = self.graphs[b]
+                    main.wait_event(self.d2h_done[b])                  # outputs of slice i-2 have left the device
+                g, z, stats = self.graphs[(b, n)]
                 g.replay()
             else:
-                _, z, _ = self.model(self.x_dev[b])
+                _, z, _ = self.model(self.x_dev[b][:n])
                 stats = torch.cat([self.model.last["image_bits"][:, None], self.model.last["sse"]], dim=1)
             self.buf_free[b].record(main)
             self.out_ready.record(main)
             with torch.cuda.stream(self.out_stream):               # D2H on its own stream (other PCIe direction)
                 self.out_stream.wait_event(self.out_ready)
-                self.lat_host[i * c:(i + 1) * c].copy_(z, non_blocking=True)
-                self.stat_host[i * c:(i + 1) * c].copy_(stats, non_blocking=True)
+                self.lat_host[o:o + n].copy_(z, non_blocking=True)
+                self.stat_host[o:o + n].copy_(stats, non_blocking=True)
                 self.d2h_done[b].record(self.out_stream)
                 if self.graphs is None:
                     z.record_stream(self.out_stream)
