@@ -3,7 +3,9 @@
 hand-written sm_100a CUDA kernels behind a C ABI (include/b2c.h, libb2c.so)."""
 from . import _lib  # noqa: F401
 from .model import ImageCompressor, load_model, save_model  # noqa: F401
-from .models import GDN, Analysis_net_17, BitEstimator, Bitparm, Synthesis_net_17  # noqa: F401
+from .model_new import ImageCompressor_new  # noqa: F401
+from .model_twoSteps import ImageCompressor_twoSteps  # noqa: F401
+from .models import GDN, Analysis_net_17, Analysis_net_17_new, BitEstimator, Bitparm, Synthesis_net_17  # noqa: F401
 
-__all__ = ["ImageCompressor", "load_model", "save_model", "GDN", "Analysis_net_17", "Synthesis_net_17",
-           "BitEstimator", "Bitparm"]
+__all__ = ["ImageCompressor", "ImageCompressor_new", "ImageCompressor_twoSteps", "load_model", "save_model", "GDN",
+           "Analysis_net_17", "Analysis_net_17_new", "Synthesis_net_17", "BitEstimator", "Bitparm"]

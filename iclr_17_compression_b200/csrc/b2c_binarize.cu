@@ -1,0 +1,78 @@
+// Sigmoid + straight-through binarizer of the ImageCompressor_new encoder:
+//   models/analysis_17_new.py:35-37  x = sigmoid(conv3(...)); code = Binarizer(x) = (x > 0.5).float()
+//   models/binarizer.py:19-27        backward: identity (straight-through estimator)
+// Forward is one pass: fp32 NCHW conv3 output -> sigmoid (fp32 NCHW), code (fp32 NCHW) and, for the tensor-core
+// synthesis transform, the code as NHWC bf16 (0 / 1 are exact in bf16).  Backward: dL/dy = (g_code + g_sig) s (1 - s).
+#include <cuda_bf16.h>
+
+#include "b2c_common.cuh"
+
+namespace b2c {
+
+// one block = 32 pixels x all channels of one image (like quant_entropy_infer): coalesced NCHW reads along pixels,
+// NHWC bf16 rows written through a shared-memory transpose
+constexpr int SB_PIX = 32;
+
+__global__ void __launch_bounds__(256) sigmoid_binarize_fwd_kernel(const float* __restrict__ y, float* __restrict__ sig,
+                                                                   float* __restrict__ code,
+                                                                   __nv_bfloat16* __restrict__ code_nhwc, int C, int HW,
+                                                                   int chunks) {
+  extern __shared__ __nv_bfloat16 tile[];   // [SB_PIX][C]
+  const int n = blockIdx.x / chunks, p0 = (blockIdx.x % chunks) * SB_PIX;
+  const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;    // 8 channel groups
+  const int pix = p0 + px;
+  for (int c = cg; c < C; c += 8) {
+    float b = 0.f;
+    if (pix < HW) {
+      const size_t a = ((size_t)n * C + c) * HW + pix;
+      const float s = 1.f / (1.f + expf(-__ldg(y + a)));       // torch.sigmoid in fp32
+      b = s > 0.5f ? 1.f : 0.f;                                // models/binarizer.py:20
+      sig[a] = s;
+      code[a] = b;
+    }
+    tile[px * C + c] = __float2bfloat16_rn(b);
+  }
+  if (!code_nhwc) return;
+  __syncthreads();
+  const int rows = min(SB_PIX, HW - p0);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(code_nhwc + ((size_t)n * HW + p0) * C);
+  for (int i = threadIdx.x; i < rows * C / 2; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) sigmoid_binarize_bwd_kernel(const float* __restrict__ sig,
+                                                                   const float* __restrict__ g_code,
+                                                                   const float* __restrict__ g_sig,
+                                                                   float* __restrict__ g_y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float s = sig[i];
+    const float g = (g_code ? g_code[i] : 0.f) + (g_sig ? g_sig[i] : 0.f);
+    g_y[i] = g * s * (1.f - s);
+  }
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_sigmoid_binarize_fwd(const float* y, float* sig, float* code, void* code_nhwc_bf16, int B, int C, int HW,
+                                        void* stream) {
+  B2C_REQUIRE(y && sig && code && B > 0 && C > 0 && C % 2 == 0 && HW > 0, "sigmoid_binarize_fwd: bad arguments");
+  const int chunks = (HW + SB_PIX - 1) / SB_PIX;
+  const size_t smem = (size_t)SB_PIX * C * sizeof(__nv_bfloat16);
+  B2C_REQUIRE(smem <= 48 * 1024, "sigmoid_binarize_fwd: too many channels");
+  sigmoid_binarize_fwd_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(y, sig, code, (__nv_bfloat16*)code_nhwc_bf16, C,
+                                                                              HW, chunks);
+  count_launch();
+  return check_launch("sigmoid_binarize_fwd");
+}
+
+extern "C" int b2c_sigmoid_binarize_bwd(const float* sig, const float* g_code, const float* g_sig, float* g_y, size_t count,
+                                        void* stream) {
+  B2C_REQUIRE(sig && g_y && count > 0, "sigmoid_binarize_bwd: bad arguments");
+  size_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sigmoid_binarize_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sig, g_code, g_sig, g_y, count);
+  count_launch();
+  return check_launch("sigmoid_binarize_bwd");
+}

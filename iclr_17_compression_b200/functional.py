@@ -334,6 +334,50 @@ def quant_entropy_infer(y, params):
     return z, zh, image_bits
 
 
+class _SigmoidBinarize(torch.autograd.Function):
+    """models/analysis_17_new.py:35-37 + models/binarizer.py:7-27: (code, sigmoid) with the straight-through gradient"""
+
+    @staticmethod
+    def forward(ctx, y):
+        y = _prep(y, "conv3 output")
+        B, C = y.shape[0], y.shape[1]
+        HW = y[0, 0].numel()
+        sig, code = torch.empty_like(y), torch.empty_like(y)
+        with torch.cuda.device(y.device), _timed(f"sigmoid_binarize_fwd[{B}x{C}x{HW}]", 8 * y.numel(), 12 * y.numel()):
+            _lib.check(_lib.load().b2c_sigmoid_binarize_fwd(_p(y), _p(sig), _p(code), _vp(0), B, C, HW, _stream()),
+                       "sigmoid_binarize_fwd")
+        ctx.save_for_backward(sig)
+        return code, sig
+
+    @staticmethod
+    def backward(ctx, g_code, g_sig):
+        (sig,) = ctx.saved_tensors
+        g_code = _prep(g_code, "grad") if g_code is not None else None
+        g_sig = _prep(g_sig, "grad") if g_sig is not None else None
+        gy = torch.empty_like(sig)
+        with torch.cuda.device(sig.device):
+            _lib.check(_lib.load().b2c_sigmoid_binarize_bwd(_p(sig), _p(g_code), _p(g_sig), _p(gy), sig.numel(), _stream()),
+                       "sigmoid_binarize_bwd")
+        return gy
+
+
+def sigmoid_binarize(y):
+    """(code, sigmoid(y)); differentiable (straight-through binarizer)"""
+    return _SigmoidBinarize.apply(y)
+
+
+def sigmoid_binarize_infer(y):
+    """eval, no autograd: (code fp32 NCHW, sigmoid fp32 NCHW, code NHWC bf16 for the tensor-core decoder)"""
+    y = _prep(y, "conv3 output")
+    B, C, H, W = y.shape
+    sig, code = torch.empty_like(y), torch.empty_like(y)
+    ch = torch.empty((B, H, W, C), device=y.device, dtype=torch.bfloat16)
+    with torch.cuda.device(y.device), _timed(f"sigmoid_binarize_fwd[{B}x{C}x{H * W}]", 8 * y.numel(), 14 * y.numel()):
+        _lib.check(_lib.load().b2c_sigmoid_binarize_fwd(_p(y), _p(sig), _p(code), _p(ch), B, C, H * W, _stream()),
+                   "sigmoid_binarize_fwd")
+    return code, sig, ch
+
+
 # ------------------------------------------------------------------------------ public ops
 def conv2d(x, weight, bias, stride, padding):
     return _Conv2d.apply(x, weight, bias, stride, padding)

@@ -47,10 +47,36 @@ class ImageCompressor(nn.Module):
     After every forward, ``self.last`` holds per-image statistics (bits, unclamped / clamped SSE).
     """
 
+    # attribute (and state_dict key) names of the two transforms: model_twoSteps.py:41-42 calls them Encoder1 / Decoder1
+    _ENC, _DEC = "Encoder", "Decoder"
+
+    def _make_encoder(self, out_channel_N):
+        return Analysis_net_17(out_channel_N=out_channel_N)
+
+    @property
+    def _enc(self):
+        return getattr(self, self._ENC)
+
+    @property
+    def _dec(self):
+        return getattr(self, self._DEC)
+
+    def canonical_named_parameters(self):
+        """named_parameters() with the transforms' prefixes normalised to Encoder. / Decoder. (the names the
+        tensor-core training step is written against)"""
+        out = []
+        for k, p in self.named_parameters():
+            if k.startswith(self._ENC + "."):
+                k = "Encoder." + k[len(self._ENC) + 1:]
+            elif k.startswith(self._DEC + "."):
+                k = "Decoder." + k[len(self._DEC) + 1:]
+            out.append((k, p))
+        return out
+
     def __init__(self, out_channel_N=128, return_mode=None):
         super().__init__()
-        self.Encoder = Analysis_net_17(out_channel_N=out_channel_N)
-        self.Decoder = Synthesis_net_17(out_channel_N=out_channel_N)
+        setattr(self, self._ENC, self._make_encoder(out_channel_N))
+        setattr(self, self._DEC, Synthesis_net_17(out_channel_N=out_channel_N))
         self.bitEstimator = BitEstimator(channel=out_channel_N)
         self.out_channel_N = out_channel_N
         mode = return_mode or os.environ.get("IMAGECOMPRESSOR_RETURN", "latent")
@@ -94,7 +120,7 @@ class ImageCompressor(nn.Module):
         nn.DataParallel replicas and optimizer steps are handled)."""
         key = self._pack_key()
         if self._packed is None or key != self._packed_key:
-            E, D = self.Encoder, self.Decoder
+            E, D = self._enc, self._dec
             self._packed = {
                 "conv1": B2TC.pack_weights(B2TC.TC_CONV1, E.conv1.weight, True),
                 "conv2": B2TC.pack_weights(B2TC.TC_CONV5S2, E.conv2.weight, True),
@@ -112,7 +138,7 @@ class ImageCompressor(nn.Module):
 
     def encode_tc(self, x):
         """analysis transform on tensor cores (error-compensated bf16x3) -> y, fp32 NCHW"""
-        P, E = self._packed_weights(), self.Encoder
+        P, E = self._packed_weights(), self._enc
         h = B2TC.layer_run(B2TC.TC_CONV1, x, None, P["conv1"], E.conv1.bias, gdn=P["gdn1"], gdn_mode=1, split3=True)
         h = B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv2"], E.conv2.bias, gdn=P["gdn2"], gdn_mode=1,
                            split3=True)
@@ -121,7 +147,7 @@ class ImageCompressor(nn.Module):
     def decode_tc(self, z, ref_image=None, z_nhwc=None):
         """synthesis transform on tensor cores (bf16) -> unclamped reconstruction, fp32 NCHW; with ref_image
         the distortion is fused into the last layer: returns (clamped reconstruction, sse[B,2])"""
-        P, D = self._packed_weights(), self.Decoder
+        P, D = self._packed_weights(), self._dec
         zh = z_nhwc if z_nhwc is not None else B2TC.nchw_to_nhwc(z, False)[0]   # integer |z| <= 256: exact in bf16
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, zh, None, P["deconv1"], D.deconv1.bias, gdn=P["igdn1"], gdn_mode=2)
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, h[0], None, P["deconv2"], D.deconv2.bias, gdn=P["igdn2"], gdn_mode=2)
@@ -169,10 +195,10 @@ class ImageCompressor(nn.Module):
             clipped_recon_image, sse = self.decode_tc(z, ref_image=x, z_nhwc=zh)
             sse_total = sse[:, 0].sum()
         else:
-            feature = self.Encoder(x)
+            feature = self._enc(x)
             noise = self._noise(x) if self.training else None
             z, total_bits, image_bits, plane_bits = self.bitEstimator.bits(feature, noise)
-            recon_image = self.Decoder(z)
+            recon_image = self._dec(z)
             clipped_recon_image, sse_total, sse = B2F.distortion(recon_image, x)
         mse_loss = sse_total / x.numel()                                   # model.py:61
         bpp_feature = total_bits / (x.size(0) * x.size(2) * x.size(3))      # model.py:78

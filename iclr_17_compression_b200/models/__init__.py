@@ -3,5 +3,8 @@ from .GDN import GDN
 from .bitEstimator import BitEstimator, Bitparm
 from .analysis_17 import Analysis_net_17
 from .synthesis_17 import Synthesis_net_17
+from .analysis_17_new import Analysis_net_17_new
+from .binarizer import Binarizer, Lambda, bin_values
 
-__all__ = ["GDN", "BitEstimator", "Bitparm", "Analysis_net_17", "Synthesis_net_17"]
+__all__ = ["GDN", "BitEstimator", "Bitparm", "Analysis_net_17", "Synthesis_net_17", "Analysis_net_17_new",
+           "Binarizer", "Lambda", "bin_values"]

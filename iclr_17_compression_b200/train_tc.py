@@ -348,7 +348,8 @@ class TrainStepTC(torch.autograd.Function):
 
 def train_forward(model, x, noise):
     """ImageCompressor training forward on tensor cores: returns (clipped, mse_loss, bpp, z) and fills model.last"""
-    params = dict(model.named_parameters())
+    params = dict(model.canonical_named_parameters() if hasattr(model, "canonical_named_parameters")
+                  else model.named_parameters())
     clipped, sse_total, total_bits, z = TrainStepTC.apply(x, noise, *[params[k] for k in PARAM_ORDER])
     mse = sse_total / x.numel()
     bpp = total_bits / (x.size(0) * x.size(2) * x.size(3))
@@ -382,7 +383,8 @@ class GraphedTrainStep:
         dev = self.x.device
         B, _, H, W = self.x.shape
         self.noise = torch.zeros(B, N, H // 16, W // 16, device=dev)
-        named = list(model.named_parameters())
+        named = (model.canonical_named_parameters() if hasattr(model, "canonical_named_parameters")
+                 else list(model.named_parameters()))
         self.params = [p for _, p in named]
         n_par = sum(p.numel() for p in self.params)
         n_par_pad = (n_par + 63) // 64 * 64
@@ -411,6 +413,9 @@ class GraphedTrainStep:
         self.ar_in_graph = bool(allreduce_in_graph and direct and self.world > 1)
         self._opt_in_graph = self.optimizer is not None and direct and (self.world == 1 or self.ar_in_graph)
         if direct:
+            from .models import Analysis_net_17
+            if type(getattr(model, "_enc", None)) is not Analysis_net_17:
+                raise _lib.B2CError("the tensor-core training step implements ImageCompressor / ImageCompressor_twoSteps")
             if N != 128 or set(k for k, _ in named) != set(PARAM_ORDER):
                 raise _lib.B2CError("the tensor-core training step needs ImageCompressor(out_channel_N=128)")
             self._capture_direct(named, n_par_pad, warmup)
@@ -483,7 +488,13 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # the dgrad chain is captured from a HIGH-priority stream, the parameter-gradient branches from default-
+        # priority side streams: kernel nodes inherit the priority, so the block scheduler serves the critical path
+        # first when both have CTAs pending (B2C_TRAIN_PRIORITY=0: everything at default priority)
+        import os
+        prio = -1 if os.environ.get("B2C_TRAIN_PRIORITY", "1") == "1" else 0
+        cap = torch.cuda.Stream(device=dev, priority=prio)
+        with torch.cuda.graph(self.graph, stream=cap):
             self._run_direct(prm, gviews, n_par_pad, enc_elems, with_optimizer=True)   # (warm-ups must not update)
         self.model.last_path = "tcgen05-bf16-train"
 

@@ -246,6 +246,16 @@ int b2c_adam_clamp_step(float* const* params, const size_t* numel, int n_tensors
                         float* exp_avg, float* exp_avg_sq, const int* step_dev, const float* lr_dev, float beta1,
                         float beta2, float eps, float grad_clip, void* stream);
 
+/* ---- ImageCompressor_new encoder tail (next row N1): sigmoid + straight-through binarizer --------------------------
+ * models/analysis_17_new.py:35-37 + models/binarizer.py:19-27.  y: conv3 output, fp32 NCHW [B,C,HW]; sig = sigmoid(y),
+ * code = (sig > 0.5) as 0.0 / 1.0 (both fp32 NCHW); code_nhwc_bf16 (optional, may be NULL): the code as NHWC bf16 for
+ * the tensor-core synthesis transform.  Backward (straight-through): g_y = (g_code + g_sig) * sig * (1 - sig); either
+ * incoming gradient may be NULL. */
+int b2c_sigmoid_binarize_fwd(const float* y, float* sig, float* code, void* code_nhwc_bf16, int B, int C, int HW,
+                             void* stream);
+int b2c_sigmoid_binarize_bwd(const float* sig, const float* g_code, const float* g_sig, float* g_y, size_t count,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

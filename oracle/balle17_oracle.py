@@ -134,6 +134,41 @@ def forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], training: bool = False
     return {"y": y, "z": z, "recon": recon, "clipped": clipped, "mse": mse, "bits": bits, "bpp": bpp}
 
 
+class _Binarizer(torch.autograd.Function):
+    """models/binarizer.py:7-27: (i > 0.5).float(), straight-through gradient."""
+
+    @staticmethod
+    def forward(ctx, i):
+        return (i > 0.5).to(i.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output
+
+
+def forward_new(x: torch.Tensor, sd: Dict[str, torch.Tensor], training: bool = False) -> Dict[str, torch.Tensor]:
+    """model_new.py:47-61 (ImageCompressor_new) over models/analysis_17_new.py:32-38: the analysis transform, sigmoid,
+    binarizer; z = code (training) / round(code) (eval); synthesis; clamp.  Returns the HEAD tuple members
+    (clipped, z, pre_threshold) plus the intermediates."""
+    y = analysis(x, sd)
+    pre = torch.sigmoid(y)
+    code = _Binarizer.apply(pre)
+    z = code if training else torch.round(code)
+    recon = synthesis(z, sd)
+    return {"y": y, "pre_threshold": pre, "z": z, "recon": recon, "clipped": recon.clamp(0.0, 1.0)}
+
+
+def new_loss_and_grads(x, sd, target):
+    """a loss touching all three outputs of ImageCompressor_new the way train_new.py:161-180 combines them (image MSE
+    + code MSE against another code) : mean((clipped - x)^2) + 0.5 mean((z - target)^2) + 0.1 mean(pre_threshold)"""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if not k.startswith("bitEstimator.")}
+    out = forward_new(x, leaf, training=True)
+    loss = torch.mean((out["clipped"] - x) ** 2) + 0.5 * torch.mean((out["z"] - target) ** 2) + 0.1 * out["pre_threshold"].mean()
+    keys = list(leaf.keys())
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys])
+    return out, loss.detach(), dict(zip(keys, grads))
+
+
 def rd_loss_and_grads(x, sd, noise, lam: float = 8192.0):
     """train.py:102-105: rd_loss = lambda*mse + bpp; grads for all 30 tensors."""
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}

@@ -116,7 +116,75 @@ def run_case(name, N, weights, kind, B, H, W, xseed, training, nseed=None, lam=8
     print(f"{name}: bpp={out['bpp']:.6f} mse={out['mse']:.6f} -> {os.path.getsize(path)/1024:.0f} KB")
 
 
+def run_case_new(name, N, kind, B, H, W, xseed, tseed):
+    """ImageCompressor_new (model_new.py): eval outputs and the gradients of a three-output loss (W1 weights)."""
+    import model_new as refnew
+    torch.manual_seed(234)
+    net = refnew.ImageCompressor_new(out_channel_N=N)
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in net.state_dict().items()})
+    net.load_state_dict(sd)
+    x = O.synth_images(kind, B, H, W, xseed)
+    out = {"N": N, "kind": kind, "B": B, "H": H, "W": W, "xseed": xseed, "tseed": tseed}
+    for k, v in net.state_dict().items():
+        s_, smp = tensor_digest(v)
+        out["w_sum/" + k] = s_
+        out["w_smp/" + k] = smp
+    net.eval()
+    with torch.no_grad():
+        clipped, z, pre = net(x)
+    out["code_u8"] = z.numpy().astype(np.uint8)
+    out["pre_threshold"] = pre.numpy()
+    out["clipped_sum"] = tensor_digest(clipped)[0]
+    step = max(1, H // 64)
+    out["clipped_sub"] = clipped[:, :, ::step, ::step].numpy()
+    out["clipped_step"] = step
+    out["mse_clipped"] = np.float64(torch.mean((clipped - x).pow(2)).item())
+    net.train()
+    g = torch.Generator().manual_seed(tseed)
+    target = (torch.rand(B, N, H // 16, W // 16, generator=g) > 0.5).float()
+    clipped, z, pre = net(x)
+    loss = torch.mean((clipped - x) ** 2) + 0.5 * torch.mean((z - target) ** 2) + 0.1 * pre.mean()
+    net.zero_grad()
+    loss.backward()
+    out["loss"] = np.float64(loss.item())
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        s_, smp = tensor_digest(p.grad)
+        out["g_sum/" + k] = s_
+        out["g_smp/" + k] = smp
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: ones={z.mean().item():.4f} loss={out['loss']:.6f} -> {os.path.getsize(path)/1024:.0f} KB")
+
+
+def run_case_twosteps(name, N, kind, B, H, W, xseed):
+    """ImageCompressor_twoSteps (model_twoSteps.py): eval outputs with W1 weights under the Encoder1/Decoder1 keys."""
+    import model_twoSteps as ref2
+    torch.manual_seed(234)
+    net = ref2.ImageCompressor_twoSteps(out_channel_N=N)
+    sd = O.perturb_state_dict({k.replace("Encoder1.", "Encoder.").replace("Decoder1.", "Decoder."): v.detach().clone()
+                               for k, v in net.state_dict().items()})
+    net.load_state_dict({k.replace("Encoder.", "Encoder1.").replace("Decoder.", "Decoder1."): v for k, v in sd.items()})
+    x = O.synth_images(kind, B, H, W, xseed)
+    net.eval()
+    with torch.no_grad():
+        clipped, z, bpp = net(x)
+        y = net.Encoder1(x)
+    out = {"N": N, "kind": kind, "B": B, "H": H, "W": W, "xseed": xseed, "keys": np.array(sorted(net.state_dict().keys())),
+           "z_i8": z.numpy().astype(np.int8), "y": y.numpy(), "bpp": np.float64(bpp.item()),
+           "mse_clipped": np.float64(torch.mean((clipped - x).pow(2)).item())}
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: bpp={out['bpp']:.6f} -> {os.path.getsize(path)/1024:.0f} KB")
+
+
 if __name__ == "__main__":
+    if "--next-rows" in sys.argv:      # SURVEY 8f N1 fixtures only (the base fixtures above stay untouched)
+        run_case_new("new_W1_S_n128_64", 128, "S", 2, 64, 96, 1003, 4004)
+        run_case_new("new_W1_U_n32_64", 32, "U", 1, 64, 64, 1002, 4004)
+        run_case_twosteps("twosteps_W1_U_n128_64", 128, "U", 2, 64, 96, 1002)
+        sys.exit(0)
     # (name, N, weights, kind, B, H, W, xseed, training, nseed)
     run_case("eval_W0_U_n128_64", 128, "W0", "U", 2, 64, 96, 1002, False)
     run_case("eval_W1_U_n128_64", 128, "W1", "U", 2, 64, 96, 1002, False)

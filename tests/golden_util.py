@@ -51,3 +51,18 @@ class Case:
             s, smp = digest(v)
             np.testing.assert_allclose(s, self.g["w_sum/" + k], rtol=1e-12, atol=0, err_msg=k)
             np.testing.assert_array_equal(smp, self.g["w_smp/" + k], err_msg=k)
+
+
+class NewCase:
+    """fixtures of the 'next' rows: ImageCompressor_new / ImageCompressor_twoSteps, W1 weights"""
+
+    def __init__(self, name):
+        self.name = name
+        self.g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+        g = self.g
+        self.N, self.B, self.H, self.W = int(g["N"]), int(g["B"]), int(g["H"]), int(g["W"])
+        self.sd = weights(self.N, "W1")
+        self.x = O.synth_images(str(g["kind"]), self.B, self.H, self.W, int(g["xseed"]))
+        if "tseed" in g.files:
+            gen = torch.Generator().manual_seed(int(g["tseed"]))
+            self.target = (torch.rand(self.B, self.N, self.H // 16, self.W // 16, generator=gen) > 0.5).float()

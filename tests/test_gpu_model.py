@@ -399,3 +399,90 @@ def test_graphed_train_step_with_fused_optimizer():
         assert (pb - pa).abs().max().item() <= 6.5e-4, k              # never more than the 3 steps of 1e-4, both ways
         moved = max(moved, ub.abs().max().item())
     assert moved > 1e-4
+
+
+# ------------------------------------------------------------------------------ next rows N1: _new and _twoSteps
+def _check_code(code_gpu, code_ref, y64):
+    """binary code bit-exact except where the fp64 conv3 output is within 1e-4 of the threshold (sigmoid(y) = 0.5 <=> y = 0)"""
+    diff = code_gpu.cpu() != code_ref
+    far = diff & (y64.cpu().abs() > LATENT_BOUNDARY_TOL)
+    assert not far.any(), f"{int(far.sum())} code bits differ away from the threshold"
+    return int(diff.sum())
+
+
+@pytest.mark.parametrize("name", golden_names("new_"))
+@pytest.mark.parametrize("fast", [True, False])
+def test_new_model_eval_matches_reference_golden(name, fast):
+    """ImageCompressor_new (model_new.py:39-63): tensor-core pipeline (N = 128) and exact-fp32 kernels vs the real
+    reference's outputs"""
+    from golden_util import NewCase
+    from oracle import balle17_oracle as O
+    import iclr_17_compression_b200 as P
+    c = NewCase(name)
+    m = P.ImageCompressor_new(c.N)
+    m.load_state_dict(c.sd)
+    m = m.cuda().eval()
+    m.fast_inference = fast
+    with torch.no_grad():
+        clipped, code, pre = m(c.x.cuda())
+        y64 = O.analysis(c.x.double(), O.to_dtype(c.sd, torch.float64))
+    assert m.last_path == ("tcgen05" if (fast and c.N in (128, 192, 256)) else "fp32")
+    g = c.g
+    _check_code(code, torch.from_numpy(g["code_u8"].astype(np.float32)), y64)
+    assert (pre.cpu() - torch.from_numpy(g["pre_threshold"])).abs().max().item() < 2e-5
+    mse_c = torch.mean((clipped.cpu() - c.x) ** 2).item()
+    assert abs(mse_c - float(g["mse_clipped"])) <= (2e-3 if fast else 1e-4) * float(g["mse_clipped"])
+    assert set(code.unique().tolist()) <= {0.0, 1.0} and tuple(code.shape) == (c.B, c.N, c.H // 16, c.W // 16)
+
+
+@pytest.mark.parametrize("name", golden_names("new_"))
+def test_new_model_gradients_match_reference_golden(name):
+    """training forward/backward of ImageCompressor_new through the straight-through binarizer (exact-fp32 kernels)"""
+    from golden_util import NewCase
+    from oracle import balle17_oracle as O
+    import iclr_17_compression_b200 as P
+    c = NewCase(name)
+    m = P.ImageCompressor_new(c.N)
+    m.load_state_dict(c.sd)
+    m = m.cuda().train()
+    x = c.x.cuda()
+    clipped, z, pre = m(x)
+    loss = torch.mean((clipped - x) ** 2) + 0.5 * torch.mean((z - c.target.cuda()) ** 2) + 0.1 * pre.mean()
+    loss.backward()
+    assert abs(loss.item() - float(c.g["loss"])) <= 1e-4 * float(c.g["loss"])
+    _, _, grads = O.new_loss_and_grads(c.x, c.sd, c.target)
+    for k, p in m.named_parameters():
+        if k.startswith("bitEstimator."):
+            assert p.grad is None
+            continue
+        assert _rel(p.grad, grads[k]) < 1e-3, (k, _rel(p.grad, grads[k]))
+        ref_norm = float(c.g["g_sum/" + k][2])
+        assert abs(p.grad.double().norm().item() - ref_norm) <= 1e-3 * ref_norm + 1e-12, k
+
+
+def test_twosteps_model_matches_reference_golden(tmp_path):
+    """ImageCompressor_twoSteps: Encoder1 / Decoder1 attribute + state_dict names, same results, step-parsing load_model"""
+    from golden_util import NewCase
+    from oracle import balle17_oracle as O
+    from iclr_17_compression_b200 import model_twoSteps as M2
+    c = NewCase("twosteps_W1_U_n128_64")
+    m = M2.ImageCompressor_twoSteps(c.N)
+    assert sorted(m.state_dict().keys()) == [str(k) for k in c.g["keys"]]
+    sd1 = {k.replace("Encoder.", "Encoder1.").replace("Decoder.", "Decoder1."): v for k, v in c.sd.items()}
+    f = tmp_path / "iter_1234.pth.tar"
+    torch.save(sd1, f)
+    assert M2.load_model(m, str(f)) == 1234                           # model_twoSteps.py:30-33
+    m = m.cuda().eval()
+    with torch.no_grad():
+        clipped, z, bpp = m(c.x.cuda())
+        y64 = O.analysis(c.x.double(), O.to_dtype(c.sd, torch.float64))
+    assert m.last_path == "tcgen05"
+    check_latents(z, torch.from_numpy(c.g["z_i8"].astype(np.float32)), y64)
+    assert abs(bpp.item() - float(c.g["bpp"])) <= REL_BPP_MSE * float(c.g["bpp"])
+    assert torch.equal(m.Encoder1.conv1.weight.cpu(), c.sd["Encoder.conv1.weight"])
+    # and one tensor-core training step through the renamed modules
+    m.train()
+    m.return_mode = "mse"
+    _, mse, bpp_t = m(c.x.cuda())
+    (8192.0 * mse + bpp_t).backward()
+    assert m.last_path == "tcgen05-bf16-train" and m.Encoder1.conv1.weight.grad is not None

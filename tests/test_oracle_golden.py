@@ -66,3 +66,39 @@ def test_entropy_floor_in_the_tails():
     z = torch.full((1, 8, 2, 2), 1.0e7)
     bits = O.estimate_bits(z, sd).item()
     assert abs(bits - 32 * 33.219280948) < 1e-2
+
+
+# ------------------------------------------------------------------------------ next rows
+@pytest.mark.parametrize("name", golden_names("new_"))
+def test_new_model_matches_reference(name):
+    """oracle.forward_new / new_loss_and_grads vs the real model_new.ImageCompressor_new (binary code bit-exact)"""
+    from golden_util import NewCase
+    c = NewCase(name)
+    g = c.g
+    for k, v in c.sd.items():
+        s, smp = digest(v)
+        np.testing.assert_allclose(s, g["w_sum/" + k], rtol=1e-12, atol=0, err_msg=k)
+    with torch.no_grad():
+        out = O.forward_new(c.x, c.sd, training=False)
+    np.testing.assert_array_equal(out["z"].numpy(), g["code_u8"].astype(np.float32))
+    np.testing.assert_allclose(out["pre_threshold"].numpy(), g["pre_threshold"], rtol=0, atol=1e-6)
+    step = int(g["clipped_step"])
+    np.testing.assert_allclose(out["clipped"][:, :, ::step, ::step].numpy(), g["clipped_sub"], rtol=1e-4, atol=1e-5)
+    _, loss, grads = O.new_loss_and_grads(c.x, c.sd, c.target)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for k, gr in grads.items():
+        s, smp = digest(gr)
+        ref_norm = float(g["g_sum/" + k][2])
+        assert abs(s[2] - ref_norm) <= 1e-4 * ref_norm + 1e-12, (k, s[2], ref_norm)
+
+
+def test_twosteps_matches_reference():
+    """model_twoSteps.ImageCompressor_twoSteps == ImageCompressor under Encoder1 / Decoder1 keys"""
+    from golden_util import NewCase
+    c = NewCase("twosteps_W1_U_n128_64")
+    with torch.no_grad():
+        out = O.forward(c.x, c.sd, training=False)
+    np.testing.assert_array_equal(out["z"].numpy(), c.g["z_i8"].astype(np.float32))
+    assert abs(out["bpp"].item() - float(c.g["bpp"])) <= 1e-6 * float(c.g["bpp"])
+    keys = sorted(k.replace("Encoder.", "Encoder1.").replace("Decoder.", "Decoder1.") for k in c.sd)
+    assert keys == [str(k) for k in c.g["keys"]]
