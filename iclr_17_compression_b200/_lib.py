@@ -28,6 +28,8 @@ SIGNATURES = {
     "b2c_quant_entropy_fwd": (_c_i, [_c_f, _c_f, _PP, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_quant_entropy_infer_workspace_bytes": (_c_sz, [_c_i, _c_i]),
     "b2c_quant_entropy_infer": (_c_i, [_c_f, _PP, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
+    "b2c_entropy_lut_build": (_c_i, [_PP, _c_f, _c_i, _c_i, _c_f]),
+    "b2c_quant_entropy_infer_lut": (_c_i, [_c_f, _PP, _c_f, _c_i, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_entropy_bwd": (_c_i, [_c_f, _PP, _c_f, _c_f, _PP, _c_i, _c_i, _c_i, _c_f]),
     "b2c_clamp_sse_workspace_bytes": (_c_sz, [_c_i, _c_i]),
     "b2c_clamp_sse_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_f, _c_sz, _c_f]),

@@ -17,10 +17,11 @@ __global__ void __launch_bounds__(256) sigmoid_binarize_fwd_kernel(const float* 
                                                                    float* __restrict__ code,
                                                                    __nv_bfloat16* __restrict__ code_nhwc, int C, int HW,
                                                                    int chunks) {
-  extern __shared__ __nv_bfloat16 tile[];   // [SB_PIX][C]
+  extern __shared__ __nv_bfloat16 tile[];   // [SB_PIX][C + 2]
   const int n = blockIdx.x / chunks, p0 = (blockIdx.x % chunks) * SB_PIX;
   const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;    // 8 channel groups
   const int pix = p0 + px;
+  const int TS = C + 2;
   for (int c = cg; c < C; c += 8) {
     float b = 0.f;
     if (pix < HW) {
@@ -30,14 +31,18 @@ __global__ void __launch_bounds__(256) sigmoid_binarize_fwd_kernel(const float* 
       sig[a] = s;
       code[a] = b;
     }
-    tile[px * C + c] = __float2bfloat16_rn(b);
+    tile[px * TS + c] = __float2bfloat16_rn(b);     // padded row stride: lanes (pixels) hit distinct banks
   }
   if (!code_nhwc) return;
   __syncthreads();
   const int rows = min(SB_PIX, HW - p0);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
   uint32_t* dst = reinterpret_cast<uint32_t*>(code_nhwc + ((size_t)n * HW + p0) * C);
-  for (int i = threadIdx.x; i < rows * C / 2; i += blockDim.x) dst[i] = src[i];
+  const int wpr = C / 2;
+  for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+    const int row = i / wpr, col = i - row * wpr;
+    dst[i] = src[row * (TS / 2) + col];
+  }
 }
 
 __global__ void __launch_bounds__(256) sigmoid_binarize_bwd_kernel(const float* __restrict__ sig,
@@ -59,7 +64,7 @@ extern "C" int b2c_sigmoid_binarize_fwd(const float* y, float* sig, float* code,
                                         void* stream) {
   B2C_REQUIRE(y && sig && code && B > 0 && C > 0 && C % 2 == 0 && HW > 0, "sigmoid_binarize_fwd: bad arguments");
   const int chunks = (HW + SB_PIX - 1) / SB_PIX;
-  const size_t smem = (size_t)SB_PIX * C * sizeof(__nv_bfloat16);
+  const size_t smem = (size_t)SB_PIX * (C + 2) * sizeof(__nv_bfloat16);
   B2C_REQUIRE(smem <= 48 * 1024, "sigmoid_binarize_fwd: too many channels");
   sigmoid_binarize_fwd_kernel<<<B * chunks, 256, smem, (cudaStream_t)stream>>>(y, sig, code, (__nv_bfloat16*)code_nhwc_bf16, C,
                                                                               HW, chunks);

@@ -8,6 +8,8 @@
 // softplus(h_k), tanh(a_k), b_k are computed once per CTA; sums are fixed-order (deterministic).
 #include <cuda_bf16.h>
 
+#include <mutex>
+
 #include "b2c_common.cuh"
 
 namespace b2c {
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* _
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int pix = pix0 + lane;
+  const int TS = C + 2;       // padded tile row (bf16 elements); with stride C every lane hit the same bank (ncu:
+                              // 36.6 M store bank conflicts, LSU wavefronts 91 % of peak - that bound the kernel)
   float sum = 0.f;
   for (int c = warp; c < C; c += nwarps) {
     float zv = 0.f;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* _
       const float p = cdf_fast(k, zv + 0.5f) - cdf_fast(k, zv - 0.5f);
       sum += fminf(fmaxf(-__log2f(p + 1e-10f), 0.f), 50.f);
     }
-    tile[lane * C + c] = __float2bfloat16_rn(zv);
+    tile[lane * TS + c] = __float2bfloat16_rn(zv);        // row stride C + 2: lanes (pixels) land in distinct banks
   }
   sum = block_sum(sum, red);                              // also a __syncthreads() for `tile`
   if (threadIdx.x == 0) partial[blockIdx.x] = sum;
@@ -182,7 +186,93 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* _
     const int npix = min(QI_PIX, HW - pix0);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
     uint32_t* dst = reinterpret_cast<uint32_t*>(z_nhwc + ((size_t)n * HW + pix0) * C);
-    for (int i = threadIdx.x; i < npix * C / 2; i += blockDim.x) dst[i] = src[i];
+    const int wpr = C / 2;     // 32-bit words per output row
+    for (int i = threadIdx.x; i < npix * wpr; i += blockDim.x) {
+      const int row = i / wpr, col = i - row * wpr;
+      dst[i] = src[row * (TS / 2) + col];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- table-driven inference variant
+// At inference z = round(y) is an integer, so the bits of an element depend only on (channel, z): a per-channel table
+// bits[c][z + L], |z| <= L, built once per weight version with the SAME per-element formula as the kernel above, turns
+// the pass into pure data movement (read y, write z fp32 + z bf16, one cached table read) - the SFU chain (11 MUFU ops
+// per element, which held the direct kernel at 36 % of HBM peak) only runs for the rare |z| > L.
+__device__ __forceinline__ float elem_bits_fast(const float* k, float zv) {
+  const float p = cdf_fast(k, zv + 0.5f) - cdf_fast(k, zv - 0.5f);
+  return fminf(fmaxf(-__log2f(p + 1e-10f), 0.f), 50.f);
+}
+
+__global__ void entropy_lut_build_kernel(BitPtrs bp, float* __restrict__ lut, int C, int L) {
+  const int c = blockIdx.x;
+  __shared__ float k[12];
+  if (threadIdx.x == 0) {
+    const ChanConst kc = load_chan(bp, c);
+    k[0] = kc.sp[0]; k[1] = kc.b[0]; k[2] = kc.ta[0];
+    k[3] = kc.sp[1]; k[4] = kc.b[1]; k[5] = kc.ta[1];
+    k[6] = kc.sp[2]; k[7] = kc.b[2]; k[8] = kc.ta[2];
+    k[9] = kc.sp[3]; k[10] = kc.b[3]; k[11] = 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * L + 1; i += blockDim.x) lut[(size_t)c * (2 * L + 1) + i] = elem_bits_fast(k, (float)(i - L));
+}
+
+// CTA = LQ_PIX (128) pixels x all channels of one image: 512 contiguous bytes per channel row on the NCHW side (32-pixel
+// chunks = 128-byte pieces ran at 41 % of HBM peak), an 8 KB .. 32 KB contiguous block on the NHWC side.  Warp w handles
+// channels w, w + 8, ...; lane l the pixels l, l + 32, l + 64, l + 96 (four independent coalesced 128-byte accesses).
+constexpr int LQ_PIX = 128;
+
+__global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const float* __restrict__ y, BitPtrs bp,
+                                                                      const float* __restrict__ lut, int L,
+                                                                      float* __restrict__ z,
+                                                                      __nv_bfloat16* __restrict__ z_nhwc,
+                                                                      float* __restrict__ partial, int C, int HW,
+                                                                      int chunks) {
+  extern __shared__ float qi_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(qi_smem);   // [LQ_PIX][C + 2]
+  __shared__ float red[32];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+  const int pix0 = chunk * LQ_PIX;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int TS = C + 2, W = 2 * L + 1;
+  float sum = 0.f;
+  for (int c = warp; c < C; c += nwarps) {
+    const size_t a = ((size_t)n * C + c) * HW + pix0 + lane;
+    const float* row = lut + (size_t)c * W + L;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (pix0 + lane + 32 * j < HW) ? __ldg(y + a + 32 * j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = rintf(v[j]);
+      if (pix0 + lane + 32 * j < HW) {
+        z[a + 32 * j] = v[j];
+        if (fabsf(v[j]) <= (float)L) {
+          sum += __ldg(row + (int)v[j]);
+        } else {                                           // rare: outside the table, same formula evaluated directly
+          const ChanConst kc = load_chan(bp, c);
+          const float k[12] = {kc.sp[0], kc.b[0], kc.ta[0], kc.sp[1], kc.b[1], kc.ta[1], kc.sp[2], kc.b[2], kc.ta[2],
+                               kc.sp[3], kc.b[3], 0.f};
+          sum += elem_bits_fast(k, v[j]);
+        }
+      }
+      tile[(lane + 32 * j) * TS + c] = __float2bfloat16_rn(v[j]);   // row stride C + 2: conflict-free
+    }
+  }
+  sum = block_sum(sum, red);                               // also the __syncthreads() for `tile`
+  if (threadIdx.x == 0) partial[blockIdx.x] = sum;
+  if (z_nhwc) {
+    const int npix = min(LQ_PIX, HW - pix0);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(z_nhwc + ((size_t)n * HW + pix0) * C);
+    const int wpr = C / 2;
+    for (int i = threadIdx.x; i < npix * wpr; i += blockDim.x) {
+      const int r = i / wpr, col = i - r * wpr;
+      dst[i] = src[r * (TS / 2) + col];
+    }
   }
 }
 
@@ -375,7 +465,7 @@ int b2c_quant_entropy_infer(const float* y, const float* const* host_params, flo
     bp.p[i] = host_params[i];
   }
   const int chunks = (HW + QI_PIX - 1) / QI_PIX;
-  const size_t smem = (size_t)C * 12 * sizeof(float) + (size_t)QI_PIX * C * 2;
+  const size_t smem = (size_t)C * 12 * sizeof(float) + (size_t)QI_PIX * (C + 2) * 2;
   B2C_REQUIRE(smem <= 48 * 1024, "quant_entropy_infer: too many channels");
   {   // both kernels are programmatic dependents of their predecessor (B2C_PDL=0: plain stream order)
     static const bool pdl = [] { const char* e = getenv("B2C_PDL"); return !e || atoi(e) != 0; }();
@@ -399,6 +489,71 @@ int b2c_quant_entropy_infer(const float* y, const float* const* host_params, flo
   }
   count_launch(2);
   return check_launch("quant_entropy_infer");
+}
+
+int b2c_entropy_lut_build(const float* const* host_params, float* lut, int C, int half_range, void* stream) {
+  B2C_REQUIRE(host_params && lut && C > 0 && half_range >= 1 && half_range <= 1024, "entropy_lut_build: bad arguments");
+  BitPtrs bp;
+  for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) {
+    B2C_REQUIRE(host_params[i], "entropy_lut_build: null parameter pointer %d", i);
+    bp.p[i] = host_params[i];
+  }
+  entropy_lut_build_kernel<<<C, 128, 0, (cudaStream_t)stream>>>(bp, lut, C, half_range);
+  count_launch();
+  return check_launch("entropy_lut_build");
+}
+
+int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params, const float* lut, int half_range,
+                                float* z, void* z_nhwc_bf16, float* image_bits, int B, int C, int HW, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  B2C_REQUIRE(y && host_params && lut && z && image_bits && workspace && B > 0 && C > 0 && C % 2 == 0 && HW > 0 &&
+                  half_range >= 1,
+              "quant_entropy_infer_lut: bad arguments");
+  if (workspace_bytes < b2c_quant_entropy_infer_workspace_bytes(B, HW)) {
+    set_error("quant_entropy_infer_lut: workspace too small");
+    return B2C_EWORKSPACE;
+  }
+  BitPtrs bp;
+  for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) {
+    B2C_REQUIRE(host_params[i], "quant_entropy_infer_lut: null parameter pointer %d", i);
+    bp.p[i] = host_params[i];
+  }
+  const int chunks = (HW + LQ_PIX - 1) / LQ_PIX;
+  const size_t smem = (size_t)LQ_PIX * (C + 2) * 2;
+  {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(quant_entropy_infer_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           LQ_PIX * (256 + 2) * 2);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+  }
+  B2C_REQUIRE(C <= 256, "quant_entropy_infer_lut: at most 256 channels");
+  static const bool pdl = [] { const char* e = getenv("B2C_PDL"); return !e || atoi(e) != 0; }();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * chunks));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, quant_entropy_infer_lut_kernel, y, bp, lut, half_range, z,
+                                     (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks);
+  if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(quant_entropy_infer_lut): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+  cfg.gridDim = dim3((unsigned)B);
+  cfg.dynamicSmemBytes = 0;
+  e = cudaLaunchKernelEx(&cfg, partial_reduce_kernel, (const float*)workspace, image_bits, chunks, 1);
+  if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(partial_reduce): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+  count_launch(2);
+  return check_launch("quant_entropy_infer_lut");
 }
 
 int b2c_entropy_bwd(const float* z, const float* const* host_params, const float* g_bits, float* dz,

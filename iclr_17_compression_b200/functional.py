@@ -315,8 +315,24 @@ class _Distortion(torch.autograd.Function):
         return g_recon, None
 
 
-def quant_entropy_infer(y, params):
-    """eval quantizer + bits for the tensor-core pipeline (no autograd): (z fp32 NCHW, z NHWC bf16, image_bits[B])"""
+LUT_HALF_RANGE = 32      # table covers z in [-32, 32]; larger |z| are evaluated directly inside the kernel
+
+
+def entropy_lut(params):
+    """bits[c][z + 32] for integer z, the inference entropy table (same formula as the direct kernel); build once per
+    weight version"""
+    params = [_prep(p, "bit-estimator parameter") for p in params]
+    C = params[0].numel()
+    lut = torch.empty((C, 2 * LUT_HALF_RANGE + 1), device=params[0].device, dtype=torch.float32)
+    pp, keep = _lib.ptr_array(params)
+    with torch.cuda.device(lut.device):
+        _lib.check(_lib.load().b2c_entropy_lut_build(pp, _p(lut), C, LUT_HALF_RANGE, _stream()), "entropy_lut_build")
+    return lut
+
+
+def quant_entropy_infer(y, params, lut=None):
+    """eval quantizer + bits for the tensor-core pipeline (no autograd): (z fp32 NCHW, z NHWC bf16, image_bits[B]).
+    With ``lut`` (entropy_lut(params)) the table-driven HBM-bound kernel runs."""
     y = _prep(y, "latent")
     params = [_prep(p, "bit-estimator parameter") for p in params]
     B, C, H, W = y.shape
@@ -329,8 +345,12 @@ def quant_entropy_infer(y, params):
     ws = torch.empty((nbytes,), device=y.device, dtype=torch.uint8)
     pp, keep = _lib.ptr_array(params)
     with torch.cuda.device(y.device), _timed(f"quant_entropy_infer[{B}x{C}x{HW}]", 60 * y.numel(), 10 * y.numel()):
-        _lib.check(lib.b2c_quant_entropy_infer(_p(y), pp, _p(z), _p(zh), _p(image_bits), B, C, HW, _p(ws), nbytes,
-                                               _stream()), "quant_entropy_infer")
+        if lut is not None and C % 2 == 0 and C <= 256:
+            _lib.check(lib.b2c_quant_entropy_infer_lut(_p(y), pp, _p(lut), LUT_HALF_RANGE, _p(z), _p(zh), _p(image_bits),
+                                                       B, C, HW, _p(ws), nbytes, _stream()), "quant_entropy_infer_lut")
+        else:
+            _lib.check(lib.b2c_quant_entropy_infer(_p(y), pp, _p(z), _p(zh), _p(image_bits), B, C, HW, _p(ws), nbytes,
+                                                   _stream()), "quant_entropy_infer")
     return z, zh, image_bits
 
 

@@ -132,6 +132,8 @@ class ImageCompressor(nn.Module):
                 "deconv3": B2TC.pack_weights(B2TC.TC_DECONV3, D.deconv3.weight, False),
                 "igdn1": B2TC.pack_gdn(D.igdn1.beta, D.igdn1.gamma, False),
                 "igdn2": B2TC.pack_gdn(D.igdn2.beta, D.igdn2.gamma, False),
+                # bits[c][z] for integer z: the inference entropy pass becomes a table read (functional.entropy_lut)
+                "bits_lut": B2F.entropy_lut([p.detach().reshape(-1) for p in self.bitEstimator.param_list()]),
             }
             self._packed_key = key
         return self._packed
@@ -190,7 +192,8 @@ class ImageCompressor(nn.Module):
             x = B2F._prep(x.float(), "input image")
             feature = self.encode_tc(x)
             z, zh, image_bits = B2F.quant_entropy_infer(feature, [p.detach().reshape(-1) for p in
-                                                                  self.bitEstimator.param_list()])
+                                                                  self.bitEstimator.param_list()],
+                                                        lut=self._packed_weights()["bits_lut"])
             total_bits, plane_bits = image_bits.sum(), None      # per-plane bits only on the fp32 path
             clipped_recon_image, sse = self.decode_tc(z, ref_image=x, z_nhwc=zh)
             sse_total = sse[:, 0].sum()

@@ -112,6 +112,15 @@ int b2c_quant_entropy_fwd(const float* y, const float* noise, const float* const
  * as NHWC bf16 (z_nhwc_bf16, may be NULL) for the tensor-core synthesis transform.  workspace: one float per
  * (image, 32-pixel chunk). */
 size_t b2c_quant_entropy_infer_workspace_bytes(int B, int HW);
+/* Table-driven form: at inference z = round(y) is an integer, so an element's bits depend only on (channel, z).
+ * b2c_entropy_lut_build fills lut[C][2*half_range + 1] (fp32, entry z + half_range) with the same per-element formula
+ * - once per weight version; b2c_quant_entropy_infer_lut then reads y, writes z (fp32 NCHW, and NHWC bf16 when
+ * z_nhwc_bf16 != NULL) and sums table entries (|z| > half_range falls back to the formula): an HBM-bound pass.
+ * C even, <= 256; same workspace as b2c_quant_entropy_infer. */
+int b2c_entropy_lut_build(const float* const* host_params, float* lut, int C, int half_range, void* stream);
+int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params, const float* lut, int half_range,
+                                float* z, void* z_nhwc_bf16, float* image_bits, int B, int C, int HW, void* workspace,
+                                size_t workspace_bytes, void* stream);
 int b2c_quant_entropy_infer(const float* y, const float* const* host_params, float* z, void* z_nhwc_bf16,
                             float* image_bits, int B, int C, int HW, void* workspace, size_t workspace_bytes,
                             void* stream);

@@ -185,3 +185,23 @@ def test_errors_are_loud(B2F):
         B2F.conv2d(torch.rand(1, 3, 8, 8).cuda(), torch.rand(4, 2, 3, 3).cuda(), None, 1, 1)   # channel mismatch
     with pytest.raises(B2CError):
         B2F.conv2d(torch.rand(1, 3, 8, 8).cuda().half(), torch.rand(4, 3, 3, 3).cuda().half(), None, 1, 1)
+
+
+@pytest.mark.parametrize("scale", [3.0, 30.0])
+def test_entropy_lut_kernel_matches_direct_kernel(scale):
+    """table-driven inference entropy pass == the direct kernel: identical z / NHWC bf16 z, per-image bits equal up to
+    summation order, including |z| beyond the table (scale 30 -> |z| up to ~120) and the fp32 CPU oracle within 1e-5."""
+    from iclr_17_compression_b200 import functional as F
+    from oracle import balle17_oracle as O
+    sd = O.perturb_state_dict(O.init_state_dict(128, seed=234))
+    params = [sd[f"bitEstimator.f{k}.{n}"].reshape(-1).cuda() for k in (1, 2, 3) for n in ("h", "b", "a")] + \
+             [sd["bitEstimator.f4.h"].reshape(-1).cuda(), sd["bitEstimator.f4.b"].reshape(-1).cuda()]
+    g = torch.Generator().manual_seed(3)
+    y = (torch.randn(3, 128, 12, 20, generator=g) * scale).cuda()
+    lut = F.entropy_lut(params)
+    z0, zh0, b0 = F.quant_entropy_infer(y, params)
+    z1, zh1, b1 = F.quant_entropy_infer(y, params, lut=lut)
+    assert torch.equal(z0, z1) and torch.equal(zh0, zh1)
+    assert torch.allclose(b0, b1, rtol=1e-6)
+    ref = torch.stack([O.estimate_bits(torch.round(y[i:i + 1].cpu()), sd) for i in range(3)])
+    assert torch.allclose(b1.cpu(), ref, rtol=2e-5)
