@@ -239,28 +239,54 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int TS = C + 2, W = 2 * L + 1;
   float sum = 0.f;
-  for (int c = warp; c < C; c += nwarps) {
-    const size_t a = ((size_t)n * C + c) * HW + pix0 + lane;
-    const float* row = lut + (size_t)c * W + L;
-    float v[4];
+  // The channel's table row lives in registers, spread over the warp (lane i holds entries i, i + 32, i + 64, ... up to
+  // 4 per lane = 128 entries) and is read with warp shuffles; rows and y values of the NEXT channel are fetched while the
+  // current one is processed (explicit double buffering: no dependent L2 / HBM latency inside the loop).
+  const bool reg_table = W <= 128;
+  bool ok[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (pix0 + lane + 32 * j < HW) ? __ldg(y + a + 32 * j) : 0.f;
+  for (int j = 0; j < 4; ++j) ok[j] = pix0 + lane + 32 * j < HW;
+  float v[4], t[4], vn[4] = {0.f, 0.f, 0.f, 0.f}, tn[4] = {0.f, 0.f, 0.f, 0.f};
+  auto fetch = [&](int c, float* vv, float* tt) {
+    const float* src = y + ((size_t)n * C + c) * HW + pix0 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) vv[j] = ok[j] ? __ldg(src + 32 * j) : 0.f;
+    const float* row = lut + (size_t)c * W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tt[j] = (reg_table && lane + 32 * j < W) ? __ldg(row + lane + 32 * j) : 0.f;
+  };
+  if (warp < C) fetch(warp, v, t);
+  for (int c = warp; c < C; c += nwarps) {
+    if (c + nwarps < C) fetch(c + nwarps, vn, tn);
+    const size_t a = ((size_t)n * C + c) * HW + pix0 + lane;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      v[j] = rintf(v[j]);
-      if (pix0 + lane + 32 * j < HW) {
-        z[a + 32 * j] = v[j];
-        if (fabsf(v[j]) <= (float)L) {
-          sum += __ldg(row + (int)v[j]);
-        } else {                                           // rare: outside the table, same formula evaluated directly
+      const float zv = rintf(v[j]);
+      const bool inside = fabsf(zv) <= (float)L;
+      const int idx = inside ? (int)zv + L : 0;
+      float b;
+      if (reg_table) {                                     // all lanes shuffle (warp-uniform control flow)
+        const float b0 = __shfl_sync(0xffffffffu, t[0], idx & 31), b1 = __shfl_sync(0xffffffffu, t[1], idx & 31);
+        const float b2 = __shfl_sync(0xffffffffu, t[2], idx & 31), b3 = __shfl_sync(0xffffffffu, t[3], idx & 31);
+        const int hi = idx >> 5;
+        b = hi == 0 ? b0 : (hi == 1 ? b1 : (hi == 2 ? b2 : b3));
+      } else {
+        b = __ldg(lut + (size_t)c * W + idx);
+      }
+      if (ok[j]) {
+        z[a + 32 * j] = zv;
+        if (!inside) {                                     // rare: outside the table, same formula evaluated directly
           const ChanConst kc = load_chan(bp, c);
           const float k[12] = {kc.sp[0], kc.b[0], kc.ta[0], kc.sp[1], kc.b[1], kc.ta[1], kc.sp[2], kc.b[2], kc.ta[2],
                                kc.sp[3], kc.b[3], 0.f};
-          sum += elem_bits_fast(k, v[j]);
+          b = elem_bits_fast(k, zv);
         }
+        sum += b;
       }
-      tile[(lane + 32 * j) * TS + c] = __float2bfloat16_rn(v[j]);   // row stride C + 2: conflict-free
+      tile[(lane + 32 * j) * TS + c] = __float2bfloat16_rn(zv);   // row stride C + 2: conflict-free
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[j] = vn[j]; t[j] = tn[j]; }
   }
   sum = block_sum(sum, red);                               // also the __syncthreads() for `tile`
   if (threadIdx.x == 0) partial[blockIdx.x] = sum;
