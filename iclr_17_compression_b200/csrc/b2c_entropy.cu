@@ -219,8 +219,10 @@ __global__ void entropy_lut_build_kernel(BitPtrs bp, float* __restrict__ lut, in
 }
 
 // CTA = LQ_PIX (128) pixels x all channels of one image: 512 contiguous bytes per channel row on the NCHW side (32-pixel
-// chunks = 128-byte pieces ran at 41 % of HBM peak), an 8 KB .. 32 KB contiguous block on the NHWC side.  Warp w handles
-// channels w, w + 8, ...; lane l the pixels l, l + 32, l + 64, l + 96 (four independent coalesced 128-byte accesses).
+// chunks = 128-byte pieces ran at 41 % of HBM peak), a 32 KB contiguous block on the NHWC side.  Thread = 4 consecutive
+// pixels of one channel (LDG.128 / STG.128); lane = (pixel quad 0..7, channel 0..3); warp w covers the 32-pixel group
+// w & 3 and the channel quartet (w >> 2) of every 8-channel pass.  HW % 4 == 0 (16-byte alignment of every row).
+// (Tried: the table row in registers read with warp shuffles - 4 SHFL per element bound the kernel at 2.1 TB/s.)
 constexpr int LQ_PIX = 128;
 
 __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const float* __restrict__ y, BitPtrs bp,
@@ -234,71 +236,54 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
   __shared__ float red[32];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
-  const int pix0 = chunk * LQ_PIX;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int TS = C + 2, W = 2 * L + 1;
+  const unsigned n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+  const unsigned pix0 = chunk * LQ_PIX;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lp = (warp & 3) * 32 + (lane & 7) * 4;      // first of this thread's 4 pixels inside the chunk
+  const unsigned c0 = (warp >> 2) * 4 + (lane >> 3);         // channel inside the 8-channel pass
+  const unsigned TS = C + 2, W = 2 * L + 1;
+  const bool in_image = pix0 + lp < (unsigned)HW;            // whole quads: HW % 4 == 0
+  const float fL = (float)L;
   float sum = 0.f;
-  // The channel's table row lives in registers, spread over the warp (lane i holds entries i, i + 32, i + 64, ... up to
-  // 4 per lane = 128 entries) and is read with warp shuffles; rows and y values of the NEXT channel are fetched while the
-  // current one is processed (explicit double buffering: no dependent L2 / HBM latency inside the loop).
-  const bool reg_table = W <= 128;
-  bool ok[4];
+  const float* yp = y + ((size_t)n * C + c0) * HW + pix0 + lp;
+  float* zp = z + ((size_t)n * C + c0) * HW + pix0 + lp;
+  const float* row = lut + (size_t)c0 * W + L;
+  __nv_bfloat16* tp = tile + lp * TS + c0;
+  const size_t cstep = (size_t)8 * HW;
+#pragma unroll 2
+  for (unsigned c = c0; c < (unsigned)C; c += 8, yp += cstep, zp += cstep, row += 8 * W, tp += 8) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_image) {
+      v = __ldg(reinterpret_cast<const float4*>(yp));
+      v.x = rintf(v.x); v.y = rintf(v.y); v.z = rintf(v.z); v.w = rintf(v.w);
+      *reinterpret_cast<float4*>(zp) = v;
+      const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) ok[j] = pix0 + lane + 32 * j < HW;
-  float v[4], t[4], vn[4] = {0.f, 0.f, 0.f, 0.f}, tn[4] = {0.f, 0.f, 0.f, 0.f};
-  auto fetch = [&](int c, float* vv, float* tt) {
-    const float* src = y + ((size_t)n * C + c) * HW + pix0 + lane;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) vv[j] = ok[j] ? __ldg(src + 32 * j) : 0.f;
-    const float* row = lut + (size_t)c * W;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tt[j] = (reg_table && lane + 32 * j < W) ? __ldg(row + lane + 32 * j) : 0.f;
-  };
-  if (warp < C) fetch(warp, v, t);
-  for (int c = warp; c < C; c += nwarps) {
-    if (c + nwarps < C) fetch(c + nwarps, vn, tn);
-    const size_t a = ((size_t)n * C + c) * HW + pix0 + lane;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float zv = rintf(v[j]);
-      const bool inside = fabsf(zv) <= (float)L;
-      const int idx = inside ? (int)zv + L : 0;
-      float b;
-      if (reg_table) {                                     // all lanes shuffle (warp-uniform control flow)
-        const float b0 = __shfl_sync(0xffffffffu, t[0], idx & 31), b1 = __shfl_sync(0xffffffffu, t[1], idx & 31);
-        const float b2 = __shfl_sync(0xffffffffu, t[2], idx & 31), b3 = __shfl_sync(0xffffffffu, t[3], idx & 31);
-        const int hi = idx >> 5;
-        b = hi == 0 ? b0 : (hi == 1 ? b1 : (hi == 2 ? b2 : b3));
-      } else {
-        b = __ldg(lut + (size_t)c * W + idx);
-      }
-      if (ok[j]) {
-        z[a + 32 * j] = zv;
-        if (!inside) {                                     // rare: outside the table, same formula evaluated directly
+      for (int j = 0; j < 4; ++j) {
+        if (fabsf(e[j]) <= fL) {
+          sum += __ldg(row + (int)e[j]);
+        } else {                                           // rare: outside the table, same formula evaluated directly
           const ChanConst kc = load_chan(bp, c);
           const float k[12] = {kc.sp[0], kc.b[0], kc.ta[0], kc.sp[1], kc.b[1], kc.ta[1], kc.sp[2], kc.b[2], kc.ta[2],
                                kc.sp[3], kc.b[3], 0.f};
-          b = elem_bits_fast(k, zv);
+          sum += elem_bits_fast(k, e[j]);
         }
-        sum += b;
       }
-      tile[(lane + 32 * j) * TS + c] = __float2bfloat16_rn(zv);   // row stride C + 2: conflict-free
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { v[j] = vn[j]; t[j] = tn[j]; }
+    tp[0] = __float2bfloat16_rn(v.x);                      // rows 4q .. 4q+3, row stride C + 2: conflict-free
+    tp[TS] = __float2bfloat16_rn(v.y);
+    tp[2 * TS] = __float2bfloat16_rn(v.z);
+    tp[3 * TS] = __float2bfloat16_rn(v.w);
   }
   sum = block_sum(sum, red);                               // also the __syncthreads() for `tile`
   if (threadIdx.x == 0) partial[blockIdx.x] = sum;
   if (z_nhwc) {
-    const int npix = min(LQ_PIX, HW - pix0);
+    const unsigned npix = min((unsigned)LQ_PIX, (unsigned)HW - pix0);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
     uint32_t* dst = reinterpret_cast<uint32_t*>(z_nhwc + ((size_t)n * HW + pix0) * C);
-    const int wpr = C / 2;
-    for (int i = threadIdx.x; i < npix * wpr; i += blockDim.x) {
-      const int r = i / wpr, col = i - r * wpr;
-      dst[i] = src[r * (TS / 2) + col];
-    }
+    const unsigned wpr = C / 2, tsw = TS / 2;
+    for (unsigned r = warp; r < npix; r += 8)              // one warp per output row: coalesced, no divisions
+      for (unsigned col = lane; col < wpr; col += 32) dst[r * wpr + col] = src[r * tsw + col];
   }
 }
 
@@ -532,9 +517,9 @@ int b2c_entropy_lut_build(const float* const* host_params, float* lut, int C, in
 int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params, const float* lut, int half_range,
                                 float* z, void* z_nhwc_bf16, float* image_bits, int B, int C, int HW, void* workspace,
                                 size_t workspace_bytes, void* stream) {
-  B2C_REQUIRE(y && host_params && lut && z && image_bits && workspace && B > 0 && C > 0 && C % 2 == 0 && HW > 0 &&
-                  half_range >= 1,
-              "quant_entropy_infer_lut: bad arguments");
+  B2C_REQUIRE(y && host_params && lut && z && image_bits && workspace && B > 0 && C > 0 && C % 8 == 0 && HW > 0 &&
+                  HW % 4 == 0 && half_range >= 1,
+              "quant_entropy_infer_lut: bad arguments (C %% 8 == 0 and HW %% 4 == 0 required)");
   if (workspace_bytes < b2c_quant_entropy_infer_workspace_bytes(B, HW)) {
     set_error("quant_entropy_infer_lut: workspace too small");
     return B2C_EWORKSPACE;

@@ -345,7 +345,7 @@ def quant_entropy_infer(y, params, lut=None):
     ws = torch.empty((nbytes,), device=y.device, dtype=torch.uint8)
     pp, keep = _lib.ptr_array(params)
     with torch.cuda.device(y.device), _timed(f"quant_entropy_infer[{B}x{C}x{HW}]", 60 * y.numel(), 10 * y.numel()):
-        if lut is not None and C % 2 == 0 and C <= 256:
+        if lut is not None and C % 8 == 0 and C <= 256 and HW % 4 == 0:
             _lib.check(lib.b2c_quant_entropy_infer_lut(_p(y), pp, _p(lut), LUT_HALF_RANGE, _p(z), _p(zh), _p(image_bits),
                                                        B, C, HW, _p(ws), nbytes, _stream()), "quant_entropy_infer_lut")
         else:

@@ -116,7 +116,7 @@ size_t b2c_quant_entropy_infer_workspace_bytes(int B, int HW);
  * b2c_entropy_lut_build fills lut[C][2*half_range + 1] (fp32, entry z + half_range) with the same per-element formula
  * - once per weight version; b2c_quant_entropy_infer_lut then reads y, writes z (fp32 NCHW, and NHWC bf16 when
  * z_nhwc_bf16 != NULL) and sums table entries (|z| > half_range falls back to the formula): an HBM-bound pass.
- * C even, <= 256; same workspace as b2c_quant_entropy_infer. */
+ * Requires C % 8 == 0, C <= 256 and HW % 4 == 0; same workspace as b2c_quant_entropy_infer. */
 int b2c_entropy_lut_build(const float* const* host_params, float* lut, int C, int half_range, void* stream);
 int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params, const float* lut, int half_range,
                                 float* z, void* z_nhwc_bf16, float* image_bits, int B, int C, int HW, void* workspace,
