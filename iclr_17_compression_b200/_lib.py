@@ -60,6 +60,10 @@ SIGNATURES.update({
     "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
     "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_tc_wgrad9_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
+    "b2c_ssim_workspace_bytes": (_c_sz, [_c_i] * 5),
+    "b2c_ssim_level": (_c_i, [_c_f, _c_f, _c_f, _c_i, ctypes.c_float, ctypes.c_float, _c_f, _c_i, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
+    "b2c_avgpool2": (_c_i, [_c_f, _c_f, _c_i, _c_i, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_msssim_combine": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_f]),
     "b2c_sigmoid_binarize_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_sigmoid_binarize_bwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_sz, _c_f]),
     "b2c_adam_clamp_step": (_c_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t), _c_i, _c_f, _c_f, _c_f,

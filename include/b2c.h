@@ -265,6 +265,21 @@ int b2c_sigmoid_binarize_fwd(const float* y, float* sig, float* code, void* code
 int b2c_sigmoid_binarize_bwd(const float* sig, const float* g_code, const float* g_sig, float* g_y, size_t count,
                              void* stream);
 
+/* ---- SSIM / MS-SSIM on the GPU (next row N3; models/ms_ssim_torch.py, used by train.py:178 on CPU copies) -----------
+ * b2c_ssim_level: X, Y fp32 NCHW [B,C,H,W]; win: device array of win_size (odd, <= 33) 1-D Gaussian taps
+ * (ms_ssim_torch.py:6-18); valid padding; sums[b*2 + 0] = sum over (C, H-win+1, W-win+1) of the ssim map,
+ * sums[b*2 + 1] = the same for the cs map (ms_ssim_torch.py:59-71); C1 = (0.01 data_range)^2, C2 = (0.03 data_range)^2.
+ * b2c_avgpool2: F.avg_pool2d(x, 2, padding=(pad_h, pad_w)) over `planes` HxW planes (ms_ssim_torch.py:164-166).
+ * b2c_msssim_combine: out[b] = prod_{l<levels-1} (cs_l[b])^w_l * (ssim_last[b])^((levels-1) w_last) with
+ * sums[levels][B][2] and the per-level element counts (device float[levels]).  The (levels-1) exponent is the
+ * reference's: ms_ssim_torch.py:169-170 broadcasts the ssim factor inside the product over the first levels-1 rows. */
+size_t b2c_ssim_workspace_bytes(int B, int C, int H, int W, int win_size);
+int b2c_ssim_level(const float* X, const float* Y, const float* win, int win_size, float C1, float C2, float* sums, int B,
+                   int C, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+int b2c_avgpool2(const float* in, float* out, int planes, int H, int W, int pad_h, int pad_w, void* stream);
+int b2c_msssim_combine(const float* sums, const float* counts, const float* weights, float* out, int levels, int B,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,6 +180,63 @@ def rd_loss_and_grads(x, sd, noise, lam: float = 8192.0):
 
 
 # --------------------------------------------------------------------------------------
+# SSIM / MS-SSIM (models/ms_ssim_torch.py), used by the validation loop train.py:178
+# --------------------------------------------------------------------------------------
+def _gauss_1d(size: int, sigma: float) -> torch.Tensor:
+    """models/ms_ssim_torch.py:6-18."""
+    coords = torch.arange(size).to(dtype=torch.float)
+    coords -= size // 2
+    g = torch.exp(-(coords ** 2) / (2 * sigma ** 2))
+    return g / g.sum()
+
+
+def _gaussian_filter(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """models/ms_ssim_torch.py:21-35: depth-wise 1 x k then k x 1 convolution, valid padding."""
+    C = x.shape[1]
+    w = g.to(x.dtype).view(1, 1, 1, -1).repeat(C, 1, 1, 1)
+    out = F.conv2d(x, w, stride=1, padding=0, groups=C)
+    return F.conv2d(out, w.transpose(2, 3), stride=1, padding=0, groups=C)
+
+
+def ssim_per_image(X, Y, g, data_range):
+    """models/ms_ssim_torch.py:38-75 with size_average=False, full=True: (ssim[B], cs[B])."""
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    mu1, mu2 = _gaussian_filter(X, g), _gaussian_filter(Y, g)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = _gaussian_filter(X * X, g) - mu1_sq
+    sigma2_sq = _gaussian_filter(Y * Y, g) - mu2_sq
+    sigma12 = _gaussian_filter(X * Y, g) - mu1_mu2
+    cs_map = (2 * sigma12 + C2) / (sigma1_sq + sigma2_sq + C2)
+    ssim_map = ((2 * mu1_mu2 + C1) / (mu1_sq + mu2_sq + C1)) * cs_map
+    return ssim_map.mean(-1).mean(-1).mean(-1), cs_map.mean(-1).mean(-1).mean(-1)
+
+
+def ms_ssim_per_image(X, Y, data_range=1.0, win_size=11, win_sigma=1.5,
+                      weights=(0.0448, 0.2856, 0.3001, 0.2363, 0.1333)):
+    """models/ms_ssim_torch.py:124-178 with size_average=False: ms-ssim[B]."""
+    g = _gauss_1d(win_size, win_sigma)
+    w = torch.tensor(weights, dtype=X.dtype)
+    mcs = []
+    for _ in range(len(weights)):
+        ssim_val, cs = ssim_per_image(X, Y, g, data_range)
+        mcs.append(cs)
+        padding = (X.shape[2] % 2, X.shape[3] % 2)
+        X = F.avg_pool2d(X, kernel_size=2, padding=padding)
+        Y = F.avg_pool2d(Y, kernel_size=2, padding=padding)
+    mcs = torch.stack(mcs, dim=0)
+    return torch.prod((mcs[:-1] ** w[:-1].unsqueeze(1)) * (ssim_val ** w[-1]), dim=0)
+
+
+def synth_pair(B, H, W, seed, noise=0.05):
+    """an image and a degraded copy for the SSIM tests: smooth image + clamped Gaussian noise"""
+    Hp, Wp = (H + 7) // 8 * 8, (W + 7) // 8 * 8
+    x = synth_images("S", B, Hp, Wp, seed)[:, :, :H, :W].contiguous()
+    g = torch.Generator().manual_seed(seed + 17)
+    y = (x + noise * torch.randn(x.shape, generator=g)).clamp(0, 1)
+    return x, y
+
+
+# --------------------------------------------------------------------------------------
 # weights: the reference's constructor order and init (so the RNG stream matches)
 # --------------------------------------------------------------------------------------
 def init_state_dict(out_channel_N: int = 128, seed: Optional[int] = 234) -> Dict[str, torch.Tensor]:

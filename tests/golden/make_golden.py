@@ -180,6 +180,24 @@ def run_case_twosteps(name, N, kind, B, H, W, xseed):
 
 
 if __name__ == "__main__":
+    if "--msssim" in sys.argv:          # SURVEY 8f N3 fixture: the reference's own models/ms_ssim_torch.py on seeded pairs
+        from models.ms_ssim_torch import ms_ssim as ref_ms_ssim, ssim as ref_ssim
+        out = {}
+        for tag, (B, H, W, seed) in {"a": (2, 256, 384, 7001), "b": (1, 250, 391, 7002), "c": (3, 176, 176, 7003)}.items():
+            x, y = O.synth_pair(B, H, W, seed)
+            out[f"{tag}/shape"] = np.array([B, H, W, seed])
+            # (size_average=False with B > 1 raises inside the reference - its NaN check `if not v == v` is ambiguous
+            #  for a vector - so per-image values are taken one image at a time)
+            out[f"{tag}/ms_ssim"] = np.array([ref_ms_ssim(y[i:i + 1], x[i:i + 1], data_range=1.0, size_average=False).item()
+                                              for i in range(B)], dtype=np.float32)
+            out[f"{tag}/ms_ssim_mean"] = np.float64(ref_ms_ssim(y, x, data_range=1.0, size_average=True).item())   # train.py:178
+            sv, cs = ref_ssim(y, x, data_range=1.0, size_average=False, full=True)
+            out[f"{tag}/ssim"], out[f"{tag}/cs"] = sv.numpy(), cs.numpy()
+            out[f"{tag}/ms_ssim_255"] = np.array([ref_ms_ssim(y[i:i + 1] * 255, x[i:i + 1] * 255, data_range=255,
+                                                              size_average=False).item() for i in range(B)], dtype=np.float32)
+        np.savez_compressed(os.path.join(HERE, "msssim_ref.npz"), **out)
+        print({k: v for k, v in out.items() if "ms_ssim" in k and "mean" in k})
+        sys.exit(0)
     if "--next-rows" in sys.argv:      # SURVEY 8f N1 fixtures only (the base fixtures above stay untouched)
         run_case_new("new_W1_S_n128_64", 128, "S", 2, 64, 96, 1003, 4004)
         run_case_new("new_W1_U_n32_64", 32, "U", 1, 64, 64, 1002, 4004)

@@ -205,3 +205,30 @@ def test_entropy_lut_kernel_matches_direct_kernel(scale):
     assert torch.allclose(b0, b1, rtol=1e-6)
     ref = torch.stack([O.estimate_bits(torch.round(y[i:i + 1].cpu()), sd) for i in range(3)])
     assert torch.allclose(b1.cpu(), ref, rtol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_msssim_matches_reference_golden(tag):
+    """GPU ssim / ms_ssim (models/ms_ssim_torch.py mirror) vs values produced by the reference's implementation:
+    even and odd sizes (the avg_pool padding rule), data_range 1 and 255, per-image and averaged, CPU-tensor inputs."""
+    import os
+    import numpy as np
+    from golden_util import GOLDEN_DIR
+    from oracle import balle17_oracle as O
+    from iclr_17_compression_b200.models import ms_ssim, ssim, MS_SSIM
+    g = np.load(os.path.join(GOLDEN_DIR, "msssim_ref.npz"))
+    B, H, W, seed = [int(v) for v in g[f"{tag}/shape"]]
+    x, y = O.synth_pair(B, H, W, seed)
+    xc, yc = x.cuda(), y.cuda()
+    v = ms_ssim(yc, xc, data_range=1.0, size_average=False)
+    assert v.is_cuda and tuple(v.shape) == (B,)
+    np.testing.assert_allclose(v.cpu().numpy(), g[f"{tag}/ms_ssim"], rtol=2e-5)
+    m = ms_ssim(y, x, data_range=1.0, size_average=True)                 # train.py:178 passes CPU tensors
+    assert not m.is_cuda and abs(m.item() - float(g[f"{tag}/ms_ssim_mean"])) <= 2e-5 * float(g[f"{tag}/ms_ssim_mean"])
+    sv, cs = ssim(yc, xc, data_range=1.0, size_average=False, full=True)
+    np.testing.assert_allclose(sv.cpu().numpy(), g[f"{tag}/ssim"], rtol=2e-5)
+    np.testing.assert_allclose(cs.cpu().numpy(), g[f"{tag}/cs"], rtol=2e-5)
+    v255 = MS_SSIM(data_range=255, size_average=False)(yc * 255, xc * 255)
+    np.testing.assert_allclose(v255.cpu().numpy(), g[f"{tag}/ms_ssim_255"], rtol=5e-5)
+    with pytest.raises(Exception):
+        ms_ssim(yc[:, :, :40, :40], xc[:, :, :40, :40], data_range=1.0)       # 40 -> 20 -> 10 < 11-tap window (the reference fails too)

@@ -102,3 +102,17 @@ def test_twosteps_matches_reference():
     assert abs(out["bpp"].item() - float(c.g["bpp"])) <= 1e-6 * float(c.g["bpp"])
     keys = sorted(k.replace("Encoder.", "Encoder1.").replace("Decoder.", "Decoder1.") for k in c.sd)
     assert keys == [str(k) for k in c.g["keys"]]
+
+
+def test_msssim_oracle_matches_reference():
+    """oracle.ms_ssim_per_image / ssim_per_image vs the reference's models/ms_ssim_torch.py (tests/golden/msssim_ref.npz)"""
+    import os
+    from golden_util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "msssim_ref.npz"))
+    for tag in ("a", "b", "c"):
+        B, H, W, seed = [int(v) for v in g[f"{tag}/shape"]]
+        x, y = O.synth_pair(B, H, W, seed)
+        np.testing.assert_allclose(O.ms_ssim_per_image(y, x, 1.0).numpy(), g[f"{tag}/ms_ssim"], rtol=1e-6)
+        sv, cs = O.ssim_per_image(y, x, O._gauss_1d(11, 1.5), 1.0)
+        np.testing.assert_allclose(sv.numpy(), g[f"{tag}/ssim"], rtol=1e-6)
+        np.testing.assert_allclose(cs.numpy(), g[f"{tag}/cs"], rtol=1e-6)
