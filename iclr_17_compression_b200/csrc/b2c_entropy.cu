@@ -218,6 +218,14 @@ __global__ void entropy_lut_build_kernel(BitPtrs bp, float* __restrict__ lut, in
   for (int i = threadIdx.x; i < 2 * L + 1; i += blockDim.x) lut[(size_t)c * (2 * L + 1) + i] = elem_bits_fast(k, (float)(i - L));
 }
 
+// |z| beyond the table: the direct formula, kept out of line so the hot loop stays small (registers -> occupancy)
+__device__ __noinline__ float bits_outside_table(const BitPtrs& bp, int c, float zv) {
+  const ChanConst kc = load_chan(bp, c);
+  const float k[12] = {kc.sp[0], kc.b[0], kc.ta[0], kc.sp[1], kc.b[1], kc.ta[1], kc.sp[2], kc.b[2], kc.ta[2],
+                       kc.sp[3], kc.b[3], 0.f};
+  return elem_bits_fast(k, zv);
+}
+
 // CTA = LQ_PIX (128) pixels x all channels of one image: 512 contiguous bytes per channel row on the NCHW side (32-pixel
 // chunks = 128-byte pieces ran at 41 % of HBM peak), a 32 KB contiguous block on the NHWC side.  Thread = 4 consecutive
 // pixels of one channel (LDG.128 / STG.128); lane = (pixel quad 0..7, channel 0..3); warp w covers the 32-pixel group
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
   const float* row = lut + (size_t)c0 * W + L;
   __nv_bfloat16* tp = tile + lp * TS + c0;
   const size_t cstep = (size_t)8 * HW;
-#pragma unroll 2
+#pragma unroll 4
   for (unsigned c = c0; c < (unsigned)C; c += 8, yp += cstep, zp += cstep, row += 8 * W, tp += 8) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_image) {
@@ -263,10 +271,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
         if (fabsf(e[j]) <= fL) {
           sum += __ldg(row + (int)e[j]);
         } else {                                           // rare: outside the table, same formula evaluated directly
-          const ChanConst kc = load_chan(bp, c);
-          const float k[12] = {kc.sp[0], kc.b[0], kc.ta[0], kc.sp[1], kc.b[1], kc.ta[1], kc.sp[2], kc.b[2], kc.ta[2],
-                               kc.sp[3], kc.b[3], 0.f};
-          sum += elem_bits_fast(k, e[j]);
+          sum += bits_outside_table(bp, (int)c, e[j]);
         }
       }
     }
