@@ -227,6 +227,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item()
     e2e_val = IMAGES * world * MPIX_PER_IMAGE / (e2e_ms / 1e3)
+    # the same call fed with the 8-bit images the fp32 tensors are made from (ToTensor's / 255 done on the device):
+    # reported next to e2e, not instead of it - the reference's API takes fp32 tensors
+    u8_host = (x_host * 255).round().to(torch.uint8).pin_memory()
+    pipe_u8 = HostPipeline(model, IMAGES, H, W, chunk=int(os.environ.get("B2C_E2E_U8_CHUNK", "12")), device=dev)
+    for _ in range(2):
+        pipe_u8.compress_u8(u8_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe_u8.compress_u8(u8_host)
+    barrier()
+    u8_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    t = torch.tensor([u8_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    u8_ms = t.item()
     # the bound of that call: one pinned-host -> device copy of the step's input alone (PCIe), same CUDA-event timing
     xd = torch.empty_like(x)
     xd.copy_(x_host, non_blocking=True)
@@ -290,6 +306,10 @@ def main():
                     "call": f"inference.HostPipeline.compress (slices of {pipe.sizes} images, copy/compute overlap)",
                     "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gbs": x.numel() * 4 / (h2d_ms * 1e-3) / 1e9,
                     "bound": "PCIe host->device copy of the fp32 input"},
+            "e2e_u8_input": {"value": IMAGES * world * MPIX_PER_IMAGE / (u8_ms / 1e3), "unit": "Mpix/s", "ms_per_step": u8_ms,
+                             "h2d_bytes_per_step": int(pipe.h2d_bytes // 4), "d2h_bytes_per_step": int(pipe.d2h_bytes),
+                             "call": f"inference.HostPipeline.compress_u8 (uint8 images from pinned host memory, slices of "
+                                     f"{pipe_u8.sizes}, x / 255 on the device; identical results)"},
             "roofline": roof,
             "ops": {k: {"ms_avg": round(v["ms_avg"], 4), "calls": v["calls"]} for k, v in ops.items()}}
 

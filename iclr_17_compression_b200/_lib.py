@@ -60,6 +60,7 @@ SIGNATURES.update({
     "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
     "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_tc_wgrad9_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
+    "b2c_u8_to_f32": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),
     "b2c_ssim_workspace_bytes": (_c_sz, [_c_i] * 5),
     "b2c_ssim_level": (_c_i, [_c_f, _c_f, _c_f, _c_i, ctypes.c_float, ctypes.c_float, _c_f, _c_i, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_avgpool2": (_c_i, [_c_f, _c_f, _c_i, _c_i, _c_i, _c_i, _c_i, _c_f]),

@@ -56,9 +56,31 @@ __global__ void __launch_bounds__(256) sigmoid_binarize_bwd_kernel(const float* 
   }
 }
 
+// 8-bit image -> fp32 in [0, 1]: torchvision's ToTensor (img.to(float32).div(255)), IEEE division so the result is
+// bit-identical to the host-side conversion the reference's data loader performs (datasets.py:24-34)
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uchar4* __restrict__ in, float4* __restrict__ out, size_t n4) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const uchar4 v = in[i];
+    out[i] = make_float4(__fdiv_rn((float)v.x, 255.f), __fdiv_rn((float)v.y, 255.f), __fdiv_rn((float)v.z, 255.f),
+                         __fdiv_rn((float)v.w, 255.f));
+  }
+}
+
 }  // namespace b2c
 
 using namespace b2c;
+
+extern "C" int b2c_u8_to_f32(const void* in_u8, float* out, size_t count, void* stream) {
+  B2C_REQUIRE(in_u8 && out && count > 0 && count % 4 == 0, "u8_to_f32: bad arguments (count must be a multiple of 4)");
+  B2C_REQUIRE(((uintptr_t)in_u8 & 3) == 0 && ((uintptr_t)out & 15) == 0, "u8_to_f32: misaligned buffers");
+  const size_t n4 = count / 4;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  u8_to_f32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uchar4*)in_u8, (float4*)out, n4);
+  count_launch();
+  return check_launch("u8_to_f32");
+}
 
 extern "C" int b2c_sigmoid_binarize_fwd(const float* y, float* sig, float* code, void* code_nhwc_bf16, int B, int C, int HW,
                                         void* stream) {

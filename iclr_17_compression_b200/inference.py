@@ -1,7 +1,14 @@
 """Host-facing inference helper: images in pinned host memory -> latents + per-image statistics back on
 the host, with the host<->device copies of one chunk overlapped with the kernels of the previous one
-(two CUDA streams, events; no extra threads).  This is the call bench.py times as ``e2e``."""
+(two CUDA streams, events; no extra threads).  This is the call bench.py times as ``e2e``.
+
+``compress`` takes the reference's fp32 [B,3,H,W] tensors; ``compress_u8`` takes the 8-bit images they were made from
+(uint8 [B,3,H,W]) and performs ToTensor's ``/ 255`` on the device - same results bit for bit, a quarter of the PCIe bytes."""
+import ctypes
+
 import torch
+
+from . import _lib
 
 
 class HostPipeline:
@@ -27,6 +34,8 @@ class HostPipeline:
         self.out_stream = torch.cuda.Stream(device=self.dev)
         self.out_ready = torch.cuda.Event()
         self.x_dev = [torch.empty((chunk, 3, height, width), device=self.dev) for _ in range(2)]
+        self.u8_dev = None                        # allocated by the first compress_u8 call
+        self.graphs_u8 = None
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
         self.buf_free = [torch.cuda.Event() for _ in range(2)]
         self.d2h_done = [torch.cuda.Event() for _ in range(2)]
@@ -60,24 +69,62 @@ class HostPipeline:
                 stats = torch.cat([self.model.last["image_bits"][:, None], self.model.last["sse"]], dim=1)
             self.graphs[(b, n)] = (g, z, stats)
 
+    def _to_f32(self, b, n):
+        """device-side ToTensor: u8_dev[b][:n] / 255 -> x_dev[b][:n]"""
+        src, dst = self.u8_dev[b][:n], self.x_dev[b][:n]
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.load().b2c_u8_to_f32(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()),
+                                                 src.numel(), ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
+                       "u8_to_f32")
+
     @torch.no_grad()
-    def compress(self, x_host):
+    def _capture_u8(self):
+        self.u8_dev = [torch.zeros(self.x_dev[0].shape, device=self.dev, dtype=torch.uint8) for _ in range(2)]
+        if self.graphs is None:
+            return
+        torch.cuda.synchronize(self.dev)
+        self.graphs_u8 = {}
+        for i, n in enumerate(self.sizes):
+            b = i & 1
+            if (b, n) in self.graphs_u8:
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._to_f32(b, n)
+                _, z, _ = self.model(self.x_dev[b][:n])
+                stats = torch.cat([self.model.last["image_bits"][:, None], self.model.last["sse"]], dim=1)
+            self.graphs_u8[(b, n)] = (g, z, stats)
+
+    def compress_u8(self, x_host_u8):
+        """x_host_u8: pinned uint8 [batch,3,H,W] (pixel values 0..255).  Same results as compress(x.float() / 255)."""
+        if x_host_u8.dtype != torch.uint8:
+            raise ValueError("compress_u8 expects uint8 images")
+        if self.u8_dev is None:
+            self._capture_u8()
+        return self.compress(x_host_u8, _u8=True)
+
+    @torch.no_grad()
+    def compress(self, x_host, _u8=False):
         """x_host: pinned fp32 [batch,3,H,W].  Returns (latents_host, stats_host) after a full sync."""
         main = torch.cuda.current_stream(self.dev)
+        in_dev = self.u8_dev if _u8 else self.x_dev
+        graphs = self.graphs_u8 if _u8 else self.graphs
         for i in range(self.n_chunks):
             b, n, o = i & 1, self.sizes[i], self.offsets[i]
             with torch.cuda.stream(self.copy_stream):
                 if i >= 2:
                     self.copy_stream.wait_event(self.buf_free[b])      # kernels of slice i-2 are done with it
-                self.x_dev[b][:n].copy_(x_host[o:o + n], non_blocking=True)
+                in_dev[b][:n].copy_(x_host[o:o + n], non_blocking=True)
                 self.h2d_done[b].record(self.copy_stream)
             main.wait_event(self.h2d_done[b])
-            if self.graphs is not None:
+            if graphs is not None:
                 if i >= 2:
                     main.wait_event(self.d2h_done[b])                  # outputs of slice i-2 have left the device
-                g, z, stats = self.graphs[(b, n)]
+                g, z, stats = graphs[(b, n)]
                 g.replay()
             else:
+                if _u8:
+                    self._to_f32(b, n)
                 _, z, _ = self.model(self.x_dev[b][:n])
                 stats = torch.cat([self.model.last["image_bits"][:, None], self.model.last["sse"]], dim=1)
             self.buf_free[b].record(main)

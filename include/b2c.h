@@ -280,6 +280,11 @@ int b2c_avgpool2(const float* in, float* out, int planes, int H, int W, int pad_
 int b2c_msssim_combine(const float* sums, const float* counts, const float* weights, float* out, int levels, int B,
                        void* stream);
 
+/* ---- 8-bit input (host pipelines): out[i] = (float)in[i] / 255, the conversion torchvision's ToTensor performs on the
+ * host in the reference's data loader (datasets.py:24-34), bit-identical (IEEE division); count % 4 == 0.  Lets a
+ * caller ship uint8 images over PCIe (4x fewer bytes than the fp32 tensors of train.py:96,170). */
+int b2c_u8_to_f32(const void* in_u8, float* out, size_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,6 +237,24 @@ def test_host_pipeline_matches_direct_forward():
         assert torch.allclose(stats[:, 0], bits, rtol=1e-6) and torch.allclose(stats[:, 1:], sse, rtol=1e-5)
 
 
+def test_host_pipeline_u8_input_matches_fp32_input():
+    """compress_u8 (8-bit images over PCIe, ToTensor's / 255 on the device) == compress(u8.float() / 255), bit for bit"""
+    from iclr_17_compression_b200.inference import HostPipeline
+    c = Case("eval_W1_U_n128_64")
+    m = _model(c).eval()
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (8, 3, 128, 192), generator=g, dtype=torch.uint8)
+    x = u8.float().div(255)                                             # torchvision ToTensor
+    for graphs in (True, False):
+        pipe = HostPipeline(m, 8, 128, 192, chunk=4, use_graphs=graphs)
+        lat0, st0 = [t.clone() for t in pipe.compress(x.pin_memory())]
+        for _ in range(2):
+            lat1, st1 = pipe.compress_u8(u8.pin_memory())
+        assert torch.equal(lat0, lat1) and torch.equal(st0, st1)
+        lat2, st2 = pipe.compress(x.pin_memory())                      # and the fp32 entry still works afterwards
+        assert torch.equal(lat0, lat2)
+
+
 # ------------------------------------------------------------------------------ bf16 tensor-core training step
 @pytest.mark.parametrize("name", [n for n in golden_names("train_") if "_n128_" in n])
 def test_tc_train_step_gradients(name):
