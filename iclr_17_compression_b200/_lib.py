@@ -57,7 +57,8 @@ SIGNATURES.update({
     "b2c_tc_layer_run": (_c_i, [ctypes.POINTER(TcLayer), _c_f]),
     "b2c_tc_pack_gdn_t": (_c_i, [_c_i, _c_f, _c_f, _c_f, _c_f, _c_f]),
     "b2c_tc_tiles_per_image": (_c_i, [_c_i, _c_i, _c_i]),
-    "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f]),
+    "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f, _c_sz, _c_f]),
+    "b2c_tc_wgrad_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
     "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_tc_wgrad9_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
     "b2c_u8_to_f32": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),

@@ -32,7 +32,8 @@ struct WgParams {
   int B, hs, ws;          // small (tile) grid
   int tiles_x, tiles_per_image, total_tiles;
   int ksz, stride, pad, ntaps;
-  float* dW;              // [ntaps][128][128] (tap-major)
+  float* dW;              // [ntaps][128][128] (tap-major), accumulated with red.global.add when partial == nullptr
+  float* partial;         // two-stage reduction: [nsplit][ntaps][128 n][128 m] per-CTA sums (no atomics), or nullptr
 };
 
 // MN-major SWIZZLE_128B operand: 64 channels (128 B) x 8 pixels per swizzle atom; atoms along the channel
@@ -138,7 +139,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     mbar_wait(done, 0);
     tcgen05_fence_after();
-    if (my_tiles > 0) {
+    if (p.partial) {
+      // two-stage form: this CTA's sums go to its own tile [tap][n][m] (lanes = consecutive m: every store instruction
+      // is one 128-byte line); wgrad_reduce_kernel adds the splits in a fixed order and writes the final layout
+      for (int j = 0; j < ntap; ++j) {
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+          uint32_t raw[32];
+          if (my_tiles > 0) {
+            tmem_ld32(t_row + (uint32_t)(j * 128 + h * 32), raw);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) raw[c] = 0u;
+          }
+          float* dst = p.partial + ((((size_t)split * p.ntaps + tap0 + j) * 128 + h * 32) * 128) + m;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) dst[(size_t)c * 128] = __uint_as_float(raw[c]);
+        }
+      }
+    } else if (my_tiles > 0) {
       for (int j = 0; j < ntap; ++j) {
 #pragma unroll 1
         for (int h = 0; h < 4; ++h) {
@@ -359,6 +379,25 @@ static int make_image_map9(CUtensorMap* m, const void* base, int B, int H, int W
   return B2C_OK;
 }
 
+// second stage of the 5x5 / 1x1 weight gradient: out[m][n][tap] += sum_split partial[split][tap][n][m], fixed order;
+// one block per (tap, n), thread = m.  `out` is the state_dict layout [128][128][k][k].
+__global__ void __launch_bounds__(128) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                           int nsplit, int ntaps) {
+  const int tap = blockIdx.x, n = blockIdx.y, m = threadIdx.x;
+  const size_t stride = (size_t)ntaps * 128 * 128;
+  const float* src = partial + ((size_t)tap * 128 + n) * 128 + m;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int j = 0;
+  for (; j + 4 <= nsplit; j += 4) {
+    s0 += __ldg(src + (size_t)(j + 0) * stride);
+    s1 += __ldg(src + (size_t)(j + 1) * stride);
+    s2 += __ldg(src + (size_t)(j + 2) * stride);
+    s3 += __ldg(src + (size_t)(j + 3) * stride);
+  }
+  for (; j < nsplit; ++j) s0 += __ldg(src + (size_t)j * stride);
+  out[((size_t)m * 128 + n) * ntaps + tap] += (s0 + s1) + (s2 + s3);
+}
+
 // second stage of the 9x9 weight gradient: dW[m][k] += sum_j partial[j][k][m] in a fixed order (deterministic);
 // one block per k, thread = m
 __global__ void __launch_bounds__(128) wgrad9_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW,
@@ -515,8 +554,22 @@ int b2c_tc_nhwc_colsum(const void* t, float* out, size_t P, void* stream) {
   return check_launch("tc_nhwc_colsum");
 }
 
+static int wgrad_splits(int total_tiles, int ntaps) {
+  const int groups = (ntaps + W_TAPS - 1) / W_TAPS;
+  int splits = 148 / groups;
+  if (splits > (total_tiles + 3) / 4) splits = (total_tiles + 3) / 4;   // >= 4 pixel tiles per CTA: fewer reductions
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+size_t b2c_tc_wgrad_workspace_bytes(int B, int hs, int ws, int k) {
+  if (B <= 0 || hs <= 0 || ws <= 0 || (k != 1 && k != 5)) return 0;
+  const int total_tiles = B * ((ws + W_TW - 1) / W_TW) * ((hs + W_TH - 1) / W_TH);
+  return (size_t)wgrad_splits(total_tiles, k * k) * k * k * 128 * 128 * sizeof(float);
+}
+
 int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
-                 int stride, int pad, void* stream) {
+                 int stride, int pad, void* workspace, size_t workspace_bytes, void* stream) {
   B2C_REQUIRE(small_t && big_t && dW, "tc_wgrad: null pointer");
   B2C_REQUIRE(B > 0 && hs > 0 && ws > 0 && hb > 0 && wb > 0 && (k == 1 || k == 5) && (stride == 1 || stride == 2) &&
                   pad >= 0,
@@ -541,17 +594,27 @@ int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int h
   p.total_tiles = B * p.tiles_per_image;
   p.ksz = k; p.stride = stride; p.pad = pad; p.ntaps = k * k;
   p.dW = dW;
+  p.partial = nullptr;
   CUtensorMap mS, mG;
   int rc;
   if ((rc = make_nhwc_map(&mS, small_t, B, hs, ws, 1))) return rc;
   if ((rc = make_nhwc_map(&mG, big_t, B, hb, wb, stride))) return rc;
   const int groups = (p.ntaps + W_TAPS - 1) / W_TAPS;
-  int splits = 148 / groups;
-  if (splits > (p.total_tiles + 3) / 4) splits = (p.total_tiles + 3) / 4;   // >= 4 pixel tiles per CTA: fewer reductions
-  if (splits < 1) splits = 1;
+  const int splits = wgrad_splits(p.total_tiles, p.ntaps);
+  if (workspace) {
+    if (workspace_bytes < (size_t)splits * p.ntaps * 128 * 128 * sizeof(float)) {
+      set_error("tc_wgrad: workspace too small");
+      return B2C_EWORKSPACE;
+    }
+    p.partial = (float*)workspace;
+  }
   dim3 grid(groups, splits);
   wgrad_tc_kernel<<<grid, W_THREADS, SMEM, (cudaStream_t)stream>>>(mS, mG, p);
   count_launch();
+  if (workspace) {
+    wgrad_reduce_kernel<<<dim3(p.ntaps, 128), 128, 0, (cudaStream_t)stream>>>((const float*)workspace, dW, splits, p.ntaps);
+    count_launch();
+  }
   return check_launch("tc_wgrad");
 }
 

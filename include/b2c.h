@@ -216,14 +216,17 @@ int b2c_tc_tiles_per_image(int kind, int Hin, int Win);
 int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
 
 /* Tensor-core weight gradient (bf16 training path):
- *   dW[ky][kx][m][n] += sum_{img,ys,xs} small[img,ys,xs,m] * big[img, stride*ys - pad + ky, stride*xs - pad + kx, n]
- * small [B,hs,ws,128], big [B,hb,wb,128]: NHWC bf16; dW fp32 TAP-MAJOR [k][k][128][128] (permute to
- * [m][n][ky][kx] for the state_dict layout), zero-filled by the caller
- * (partial sums are added with red.global).  k in {1,5}, stride in {1,2}.
+ *   dW[m][n][ky][kx] += sum_{img,ys,xs} small[img,ys,xs,m] * big[img, stride*ys - pad + ky, stride*xs - pad + kx, n]
+ * small [B,hs,ws,128], big [B,hb,wb,128]: NHWC bf16; k in {1,5}, stride in {1,2}.
  *   conv2d weight grad (OIHW): small = grad_out, big = input;  conv_transpose2d (IOHW): small = input, big = grad_out;
- *   GDN gamma grad: k = 1, small = dL/dnorm, big = x^2.                               (autograd of train.py:105) */
+ *   GDN gamma grad: k = 1, small = dL/dnorm, big = x^2.                               (autograd of train.py:105)
+ * With a workspace of b2c_tc_wgrad_workspace_bytes() bytes (need not be zeroed): per-CTA partial tiles + a
+ * fixed-order second kernel (deterministic, no atomics) that ADDS the result to dW in the state_dict layout
+ * [128][128][k][k].  With workspace = NULL (legacy): dW is a zero-filled TAP-MAJOR [k][k][128][128] buffer that the
+ * CTAs accumulate into with red.global.add. */
+size_t b2c_tc_wgrad_workspace_bytes(int B, int hs, int ws, int k);
 int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
-                 int stride, int pad, void* stream);
+                 int stride, int pad, void* workspace, size_t workspace_bytes, void* stream);
 
 /* 9x9 / stride-4 / pad-4 weight gradient on tensor cores: dW[m][c][ky][kx] += sum small[img,ys,xs,m] *
  * image[img,c,4ys-4+ky,4xs-4+kx]; small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w], dW fp32 [128][3][9][9]

@@ -151,6 +151,13 @@ def test_wgrad_5x5s2(tc, shape):
     (F.conv_transpose2d(gq, wt, None, stride=2, padding=2, output_padding=1) * xq).sum().backward()
     dWt = tc.wgrad(gh, xh, 5, 2, 2)                     # convT with input gq, grad_out xq: small = input, big = grad_out
     assert _rel(dWt, wt.grad) < 1e-5
+    # deterministic two-stage form: same values, bit-identical from run to run, accumulates into `out`
+    d1 = tc.wgrad(gh, xh, 5, 2, 2, deterministic=True)
+    d2 = tc.wgrad(gh, xh, 5, 2, 2, deterministic=True)
+    assert torch.equal(d1, d2) and _rel(d1, w.grad) < 1e-5
+    acc = torch.full((128, 128, 5, 5), 0.5, device="cuda")
+    tc.wgrad(gh, xh, 5, 2, 2, out=acc, deterministic=True)
+    assert _rel(acc - 0.5, w.grad) < 1e-4
 
 
 def test_wgrad_1x1_gamma_form(tc):
@@ -162,6 +169,7 @@ def test_wgrad_1x1_gamma_form(tc):
     ref = torch.einsum("nihw,njhw->ij", ah.float().permute(0, 3, 1, 2).double(), bh.float().permute(0, 3, 1, 2).double())
     d = tc.wgrad(ah, bh, 1, 1, 0).view(128, 128)
     assert _rel(d, ref) < 1e-5
+    assert _rel(tc.wgrad(ah, bh, 1, 1, 0, deterministic=True).view(128, 128), ref) < 1e-5
 
 
 def _bf(t):
