@@ -87,6 +87,22 @@ out["cfg3_train_tc_bf16_eager"] = {"ms": timed(step, 10)}
 from iclr_17_compression_b200.train_tc import GraphedTrainStep
 gs = GraphedTrainStep(mt, xb, 8192.0)
 out["cfg3_train_tc_bf16_graphed"] = {"ms": timed(lambda: gs(xb), 20)}
+del gs
+# whole iteration (forward + backward + gradient clamp + Adam) as one graph replay, and larger per-GPU batches: the
+# batch-8 step is a chain of ~20 dependent launches on <= 256 CTAs (latency bound); these show the same kernels with
+# enough tiles to fill the machine
+mo = P.ImageCompressor(128, return_mode="mse").cuda().train()
+go = GraphedTrainStep(mo, xb, 8192.0, optimizer="adam")
+out["cfg3_train_tc_bf16_graphed_with_clamp_adam"] = {"ms": timed(lambda: go(xb), 20)}
+del go, mo
+for bsz in (32, 64):
+    xbig = O.synth_images("U", bsz, 256, 256, 1004).cuda()
+    mb = P.ImageCompressor(128, return_mode="mse").cuda().train()
+    gb = GraphedTrainStep(mb, xbig, 8192.0)
+    ms_big = timed(lambda: gb(xbig), 10)
+    out[f"train_tc_bf16_graphed_batch{bsz}"] = {"ms": ms_big, "img_s": bsz / ms_big * 1e3,
+                                                "frac_of_tensor_roofline": 8.59e9 * bsz / (ms_big * 1e-3) / 1e12 / 1396.4}
+    del gb, mb, xbig
 leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
 noise = O.synth_noise(8, 128, 256, 256, 2002).cuda()
 
