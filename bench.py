@@ -382,6 +382,8 @@ def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
     return {"metric": "train img/s (batch 8 of 3x256x256 per GPU, fwd+bwd, noise quantizer, lambda=8192)",
             "value": 8 * world / (ms / 1e3), "unit": "img/s", "ms_per_step": ms,
             "allreduce": ("none (1 GPU)" if world == 1 else
+                          ("libb2c NVLink kernel over symmetric memory (" + ("NVLS multimem" if graphed._symm.multicast else "peer loads/stores")
+                           + "), bracketed by two cross-rank barriers, after the graphed step") if getattr(graphed, "_symm", None) is not None else
                           ("two-bucket NCCL all-reduce captured inside the step graph" if getattr(graphed, "ar_in_graph", False)
                            else "one NCCL all-reduce (mean) of the flat 7 MB gradient buffer after the graphed step")
                           if graphed is not None else

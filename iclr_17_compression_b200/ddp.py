@@ -134,3 +134,44 @@ class GradSync:
         for h in self._handles:
             h.remove()
         self._handles = []
+
+
+class SymmAllReduce:
+    """In-place mean of a flat fp32 buffer over NVLink / NVSwitch peer memory (libb2c ``b2c_allreduce_symm``).
+
+    The buffer is allocated in torch's symmetric memory (the same allocation is mapped into every rank of the
+    group); ``all_reduce()`` enqueues, on the current stream: cross-rank barrier -> one kernel in which this rank
+    reduces its 1/world slice (NVLS ``multimem.ld_reduce`` + ``multimem.st`` when the switch supports multicast,
+    peer loads / stores otherwise) -> barrier.  For the 7 MB gradient buffer of the training step this replaces a
+    ~58 us NCCL all-reduce (protocol latency bound at this size).  CUDA only; there is no fallback."""
+
+    def __init__(self, numel: int, device, group=None, use_multicast: bool = True):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        if not dist.is_initialized():
+            raise RuntimeError("SymmAllReduce needs an initialised torch.distributed process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        q = 4 * self.world
+        self.count = (numel + q - 1) // q * q
+        self.buf = symm.empty(self.count, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
+        self.multicast = mc != 0
+        self._mc = ctypes.c_void_p(mc)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+        self._ctypes = ctypes
+
+    def all_reduce(self, mean: bool = True):
+        from . import _lib
+        ct = self._ctypes
+        self.hdl.barrier(channel=0)
+        with torch.cuda.device(self.buf.device):
+            _lib.check(_lib.load().b2c_allreduce_symm(ct.cast(self._ptrs, ct.POINTER(ct.c_void_p)), self._mc, self.rank,
+                                                      self.world, self.count, ct.c_float(1.0 / self.world if mean else 1.0),
+                                                      ct.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)),
+                       "allreduce_symm")
+        self.hdl.barrier(channel=1)

@@ -373,7 +373,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, x_example, lam=8192.0, warmup=3, group=None, direct=True, allreduce_in_graph=None,
-                 optimizer=None):
+                 optimizer=None, allreduce=None):
         import os
         import torch.distributed as dist
         self.model, self.lam, self.group = model, lam, group
@@ -389,8 +389,20 @@ class GraphedTrainStep:
         n_par = sum(p.numel() for p in self.params)
         n_par_pad = (n_par + 63) // 64 * 64
         scratch = (4 * 25 * 128 * 128 + 4 * (128 * 128 + 128) + B * N * (H // 16) * (W // 16) + 1024) if direct else 0
-        self.buf = torch.zeros(n_par_pad + scratch, device=dev, dtype=torch.float32)
-        self.flat = self.buf[:n_par]
+        # allreduce="symm" (or B2C_AR=symm): the gradient buffer lives in symmetric memory and the mean over ranks runs as
+        # libb2c's own NVLink / NVLS kernel (ddp.SymmAllReduce) instead of an NCCL call
+        self._symm = None
+        if self.world > 1 and direct and (allreduce or os.environ.get("B2C_AR", "nccl")) == "symm":
+            from .ddp import SymmAllReduce
+            self._symm = SymmAllReduce(n_par_pad, dev, group)
+            self._grads = self._symm.buf
+            self.buf = torch.zeros(scratch + 64, device=dev, dtype=torch.float32)
+            self._scratch_off = 0
+        else:
+            self.buf = torch.zeros(n_par_pad + scratch, device=dev, dtype=torch.float32)
+            self._grads = self.buf
+            self._scratch_off = n_par_pad
+        self.flat = self._grads[:n_par]
         views, o = [], 0
         for p in self.params:
             views.append(self.flat[o:o + p.numel()].view_as(p))
@@ -410,7 +422,7 @@ class GraphedTrainStep:
             self.optimizer = optimizer
         if allreduce_in_graph is None:
             allreduce_in_graph = os.environ.get("B2C_AR_IN_GRAPH", "0") == "1"
-        self.ar_in_graph = bool(allreduce_in_graph and direct and self.world > 1)
+        self.ar_in_graph = bool(allreduce_in_graph and direct and self.world > 1 and self._symm is None)
         self._opt_in_graph = self.optimizer is not None and direct and (self.world == 1 or self.ar_in_graph)
         if direct:
             from .models import Analysis_net_17
@@ -430,7 +442,9 @@ class GraphedTrainStep:
         dev = self.x.device
         main = torch.cuda.current_stream(dev)
         self.buf.zero_()                                              # ONE memset: gradients + all accumulators
-        pool = _Pool(self.buf, n_par_pad)
+        if self._grads is not self.buf:
+            self._grads.zero_()                                       # (symmetric gradient buffer: its own memset)
+        pool = _Pool(self.buf, self._scratch_off)
         import os
         fused = os.environ.get("B2C_TRAIN_FUSED_DISTORTION", "1") == "1"
         st = step_forward(self.x, self.noise, prm, pool, grad_scale=(2.0 * self.lam / self.x.numel()) if fused else None)
@@ -532,7 +546,9 @@ class GraphedTrainStep:
         else:
             self.noise.copy_(noise, non_blocking=True)
         self.graph.replay()
-        if self.world > 1 and not self.ar_in_graph:
+        if self._symm is not None:
+            self._symm.all_reduce()                                  # barrier, NVLink reduce kernel, barrier
+        elif self.world > 1 and not self.ar_in_graph:
             import torch.distributed as dist
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
         if self.optimizer is not None and not self._opt_in_graph:

@@ -288,6 +288,18 @@ int b2c_msssim_combine(const float* sums, const float* counts, const float* weig
  * caller ship uint8 images over PCIe (4x fewer bytes than the fp32 tensors of train.py:96,170). */
 int b2c_u8_to_f32(const void* in_u8, float* out, size_t count, void* stream);
 
+/* ---- gradient all-reduce over NVLink / NVSwitch peer memory (data-parallel training, replaces the reduce of
+ * nn.DataParallel, train.py:228) -------------------------------------------------------------------------------------
+ * In-place mean/sum of a flat fp32 buffer that lives in SYMMETRIC memory (the same allocation mapped into every rank,
+ * e.g. torch.distributed._symmetric_memory): this rank reduces elements [rank * count / world, (rank+1) * count / world)
+ * over all ranks, multiplies by `scale` (1 / world for the mean) and writes the result to every rank's copy.
+ * multicast_ptr != NULL: NVLS form (multimem.ld_reduce / multimem.st on the multicast address; the switch sums);
+ * otherwise peer_ptrs[0..world) (host array of the ranks' buffer addresses as mapped in THIS process) are read and
+ * written directly, sums in rank order (deterministic).  count % (4 * world) == 0.  The caller brackets the launch with
+ * a cross-rank barrier on the same stream (all inputs written before, all results visible after). */
+int b2c_allreduce_symm(void* const* peer_ptrs, void* multicast_ptr, int rank, int world, size_t count, float scale,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

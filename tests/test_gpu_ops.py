@@ -232,3 +232,32 @@ def test_msssim_matches_reference_golden(tag):
     np.testing.assert_allclose(v255.cpu().numpy(), g[f"{tag}/ms_ssim_255"], rtol=5e-5)
     with pytest.raises(Exception):
         ms_ssim(yc[:, :, :40, :40], xc[:, :, :40, :40], data_range=1.0)       # 40 -> 20 -> 10 < 11-tap window (the reference fails too)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_allreduce_symm_peer_form_single_device(world):
+    """b2c_allreduce_symm, peer form (include/b2c.h): `world` buffers on ONE device stand in for the ranks' symmetric
+    copies; each "rank" launches its slice.  Result on every copy == mean in rank order (bit-exact: fixed order)."""
+    import ctypes as ct
+    from iclr_17_compression_b200 import _lib
+    lib = _lib.load()
+    n = 4 * world * 1237
+    g = torch.Generator(device="cuda").manual_seed(7)
+    bufs = [torch.randn(n, device="cuda", generator=g) for _ in range(world)]
+    want = torch.zeros(n, device="cuda")
+    for b in bufs:
+        want = want + b
+    want = want * (1.0 / world)
+    ptrs = (ct.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    st = ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for r in range(world):
+        _lib.check(lib.b2c_allreduce_symm(ct.cast(ptrs, ct.POINTER(ct.c_void_p)), ct.c_void_p(0), r, world, n,
+                                          ct.c_float(1.0 / world), st), "allreduce_symm")
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b, want)
+    # loud errors: count not a multiple of 4 * world, rank out of range
+    assert lib.b2c_allreduce_symm(ct.cast(ptrs, ct.POINTER(ct.c_void_p)), ct.c_void_p(0), 0, world, n + 1,
+                                  ct.c_float(1.0), st) != 0
+    assert lib.b2c_allreduce_symm(ct.cast(ptrs, ct.POINTER(ct.c_void_p)), ct.c_void_p(0), world, world, n,
+                                  ct.c_float(1.0), st) != 0
