@@ -62,6 +62,11 @@ SIGNATURES.update({
     "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_tc_wgrad9_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
     "b2c_allreduce_symm": (_c_i, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_i, _c_i, _c_sz, ctypes.c_float, _c_f]),
+    "b2c_rans_build_tables": (_c_i, [_PP, _c_i, _c_i, _c_i, _c_f, _c_f, _c_f]),
+    "b2c_rans_num_blocks": (_c_i, [_c_i, _c_i, _c_i]),
+    "b2c_rans_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
+    "b2c_rans_encode": (_c_i, [_c_f, _c_f] + [_c_i] * 6 + [_c_f, _c_sz, _c_f, _c_f, _c_f, _c_sz, _c_f, _c_f]),
+    "b2c_rans_decode": (_c_i, [_c_f, _c_f, _c_f, _c_f] + [_c_i] * 6 + [_c_f, _c_f, _c_f]),
     "b2c_u8_to_f32": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),
     "b2c_ssim_workspace_bytes": (_c_sz, [_c_i] * 5),
     "b2c_ssim_level": (_c_i, [_c_f, _c_f, _c_f, _c_i, ctypes.c_float, ctypes.c_float, _c_f, _c_i, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),

@@ -300,6 +300,27 @@ int b2c_u8_to_f32(const void* in_u8, float* out, size_t count, void* stream);
 int b2c_allreduce_symm(void* const* peer_ptrs, void* multicast_ptr, int rank, int world, size_t count, float scale,
                        void* stream);
 
+/* ---- real bitstream for the integer latents (the reference only estimates the size, model.py:71-74, and
+ * approximates files with gzip(np.packbits(latent == 0)), NewTests/testModelRecon.py:80) ----------------------------
+ * Warp-interleaved range-ANS coder over the BitEstimator's per-channel probabilities (format: csrc/b2c_rans.cu).
+ * Tables: freq_cum [C][A] uint32 = f | (start << 16), slot_sym [C][2^prec] uint8, A = 2 * half_range + 2 (last symbol
+ * = escape + 16 raw bits), 1 <= half_range <= 126, 10 <= prec <= 15.  z: fp32 NCHW [B][C][HW] holding integers
+ * (|z| <= 32767).  One warp codes a block of block_symbols (multiple of 32) consecutive latents of one image; blocks
+ * per image = b2c_rans_num_blocks.  Encode writes block_bytes[B * blocks], offsets[B * blocks + 1] (bytes, exclusive
+ * scan) and the concatenated block streams to out; *status (device int, caller zeroes it) gets bit 0 = value out of
+ * range, bit 1 = out_capacity too small (nothing past the capacity is written), bit 2 (decode) = corrupt stream.
+ * Decode reads the same offsets + bytes and writes z.  Nothing synchronises; all buffers are caller-owned. */
+int b2c_rans_build_tables(const float* const* host_params, int C, int half_range, int prec, uint32_t* freq_cum,
+                          uint8_t* slot_sym, void* stream);
+int b2c_rans_num_blocks(int C, int HW, int block_symbols);
+size_t b2c_rans_scratch_bytes(int B, int C, int HW, int block_symbols);
+int b2c_rans_encode(const float* z, const uint32_t* freq_cum, int half_range, int prec, int B, int C, int HW,
+                    int block_symbols, void* scratch, size_t scratch_bytes, uint32_t* block_bytes, uint64_t* offsets,
+                    uint8_t* out, size_t out_capacity, int* status, void* stream);
+int b2c_rans_decode(const uint8_t* in, const uint64_t* offsets, const uint32_t* freq_cum, const uint8_t* slot_sym,
+                    int half_range, int prec, int B, int C, int HW, int block_symbols, float* z, int* status,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif
