@@ -67,6 +67,7 @@ SIGNATURES.update({
     "b2c_rans_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
     "b2c_rans_encode": (_c_i, [_c_f, _c_f] + [_c_i] * 6 + [_c_f, _c_sz, _c_f, _c_f, _c_f, _c_sz, _c_f, _c_f]),
     "b2c_rans_decode": (_c_i, [_c_f, _c_f, _c_f, _c_f] + [_c_i] * 6 + [_c_f, _c_f, _c_f]),
+    "b2c_resized_crop_flip": (_c_i, [_c_f, _c_sz, _c_f, _c_i, _c_i, _c_i, _c_i, _c_f, _c_f, _c_f]),
     "b2c_u8_to_f32": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),
     "b2c_ssim_workspace_bytes": (_c_sz, [_c_i] * 5),
     "b2c_ssim_level": (_c_i, [_c_f, _c_f, _c_f, _c_i, ctypes.c_float, ctypes.c_float, _c_f, _c_i, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),

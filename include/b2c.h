@@ -321,6 +321,19 @@ int b2c_rans_decode(const uint8_t* in, const uint64_t* offsets, const uint32_t* 
                     int half_range, int prec, int B, int C, int HW, int block_symbols, float* z, int* status,
                     void* stream);
 
+/* ---- training input transform on the device ---------------------------------------------------------
+ * Replaces, per batch, the reference's per-image CPU Compose of datasets.py:24-34: RandomResizedCrop(out_size) ->
+ * RandomHorizontalFlip -> RandomVerticalFlip -> ToTensor, i.e. torchvision resized_crop (PIL crop + antialiased BILINEAR
+ * resize, Pillow src/libImaging/Resample.c, 22-bit fixed point, horizontal pass first), flips, uint8 / 255.  The random
+ * draws stay on the host.  src: decoded RGB images, uint8 HWC, packed in one device buffer (16-byte aligned, each image
+ * at a byte offset that is a multiple of 16).  desc: device int64 [B][8] = {byte offset, H, W, top, left, crop_h,
+ * crop_w, flags (bit 0 horizontal flip, bit 1 vertical flip)}.  out: fp32 [B][3][out_size][out_size], bit-identical to
+ * the reference transform.  out_size: multiple of 32 in [32, 512].  max_crop_h / max_crop_w: upper bounds of the crop
+ * sizes in desc (they size the shared memory; B2C_EINVAL if they need more than 227 KB).  *status (device int, caller
+ * zeroes it) gets bit 0 when a descriptor is outside its image / the buffer / the maxima (that image is not written). */
+int b2c_resized_crop_flip(const uint8_t* src, size_t src_bytes, const int64_t* desc, int B, int out_size, int max_crop_h,
+                          int max_crop_w, float* out, int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,81 @@
+"""CPU: the input-transform oracle (oracle/resample_oracle.py) against golden vectors made with the
+real Pillow / torchvision the reference calls (tests/golden/make_augment_golden.py), against the live packages when
+importable, and the host-side draws / packing of iclr_17_compression_b200.datasets."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import resample_oracle as R
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "augment_ref.npz"))
+
+
+def _photo(meta):
+    h, w, seed, crc = (int(v) for v in meta)
+    img = R.synth_photo(h, w, seed)
+    assert zlib.crc32(img.tobytes()) == crc, "synthetic source image drifted: regenerate the goldens"
+    return img
+
+
+@pytest.mark.parametrize("n", range(int(G["nresize"])))
+def test_resize_matches_pillow_golden(n):
+    img = _photo(G[f"rs_in{n}"])
+    oh, ow, crc = (int(v) for v in G[f"rs_outcrc{n}"])
+    out = R.resize_bilinear_u8(img, oh, ow)
+    assert zlib.crc32(np.ascontiguousarray(out).tobytes()) == crc
+    if f"rs_out{n}" in G:
+        assert np.array_equal(out, G[f"rs_out{n}"])
+
+
+@pytest.mark.parametrize("n", range(int(G["n"])))
+def test_transform_matches_torchvision_golden(n):
+    img = _photo(G[f"img{n}"])
+    torch.manual_seed(int(G[f"seed{n}"]))
+    p = R.sample_params(img.shape[0], img.shape[1])
+    assert [int(v) for v in p] == [int(v) for v in G[f"params{n}"]]
+    y = R.resized_crop_flip(img, *p)
+    y8 = y.mul(255).round().to(torch.uint8).numpy()
+    assert torch.equal(torch.from_numpy(y8).float().div(255), y)
+    assert zlib.crc32(y8.tobytes()) == int(G[f"outcrc{n}"])
+    if f"out{n}" in G:
+        assert np.array_equal(y8, G[f"out{n}"])
+
+
+def test_oracle_against_live_packages():
+    Image = pytest.importorskip("PIL.Image")
+    transforms = pytest.importorskip("torchvision.transforms")
+    tf = transforms.Compose([transforms.RandomResizedCrop(64), transforms.RandomHorizontalFlip(),
+                             transforms.RandomVerticalFlip(), transforms.ToTensor()])
+    for seed, (h, w) in enumerate([(50, 70), (200, 130), (64, 64), (333, 517)]):
+        img = R.synth_photo(h, w, 900 + seed)
+        torch.manual_seed(seed)
+        ref = tf(Image.fromarray(img, "RGB"))
+        torch.manual_seed(seed)
+        p = R.sample_params(h, w)
+        assert torch.equal(R.resized_crop_flip(img, *p, size=64), ref)
+
+
+def test_host_draws_match_oracle_and_consume_the_same_stream():
+    from iclr_17_compression_b200 import datasets as D
+    for seed, (h, w) in enumerate([(300, 451), (97, 1031), (2100, 260), (16, 16), (5, 400)]):
+        torch.manual_seed(seed)
+        a = [D.sample_params(h, w) for _ in range(5)] + [torch.rand(1).item()]
+        torch.manual_seed(seed)
+        b = [R.sample_params(h, w) for _ in range(5)] + [torch.rand(1).item()]
+        assert a == b
+
+
+def test_pack_images_layout():
+    from iclr_17_compression_b200 import datasets as D
+    imgs = [R.synth_photo(7, 5, 1), R.synth_photo(33, 21, 2)]
+    buf, desc, mh, mw = D.pack_images(imgs, [(1, 0, 5, 4, True, False), (0, 3, 33, 10, False, True)])
+    assert desc.tolist() == [[0, 7, 5, 1, 0, 5, 4, 1], [112, 33, 21, 0, 3, 33, 10, 2]]
+    assert (mh, mw) == (33, 10) and buf.numel() == 112 + (33 * 21 * 3 + 15) // 16 * 16
+    assert np.array_equal(buf[112:112 + 33 * 21 * 3].numpy().reshape(33, 21, 3), imgs[1])
+    with pytest.raises(ValueError):
+        D.pack_images(imgs, [(1, 0, 7, 4, False, False), (0, 0, 1, 1, False, False)])
+    with pytest.raises(ValueError):
+        D.pack_images([np.zeros((4, 4, 3), np.float32)], [(0, 0, 1, 1, False, False)])
