@@ -106,7 +106,7 @@ def cpu_reference_throughput(budget_s, images_per_step, steps=None, warmup=1):
             el = time.perf_counter() - t0
             if (steps is not None and nsteps >= steps) or (steps is None and el >= budget_s):
                 break
-    return done * MPIX_PER_IMAGE / el, cores, f"{done} of the {IMAGES} 3x{H}x{W} images, batch 1, eval forward", el / nsteps * 1e3
+    return done * MPIX_PER_IMAGE / el, cores, f"{done} eval forwards of single 3x{H}x{W} images (batch 1, cycling through {images_per_step} of the {IMAGES} images)", el / nsteps * 1e3
 
 
 def run_reference(args):

@@ -97,6 +97,7 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // status bits
+constexpr int RANS_U = 4;        // encoder: steps per software-pipeline group
 constexpr int RS_RANGE = 1;      // |z| > 32767 (clamped) or non-finite
 constexpr int RS_CAPACITY = 2;   // output buffer too small
 constexpr int RS_CORRUPT = 4;    // decoder: final state / length mismatch or read past the block
@@ -113,15 +114,21 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const float* __restrict
   uint32_t ptr = cap_words, x = RANS_LOW;
   const uint32_t lt = lanemask_lt();
   bool bad = false;
-  // software prefetch: the value of the NEXT (lower) step is in flight while this one is coded
-  unsigned i = begin + (unsigned)(steps - 1) * 32 + lane;
-  float v_next = (steps > 0 && i < end) ? __ldg(zp + i) : 0.f;
-  for (int j = steps - 1; j >= 0; --j) {
-    i = begin + (unsigned)j * 32 + lane;
+  // Software pipeline over groups of RANS_U steps (the steps run downwards).  Nothing a step LOADS depends on the coder
+  // state: the latent, and through its symbol the table entry, are known ahead.  While group g is coded, the table
+  // entries of group g+1 and the latents of group g+2 are in flight, so the serial chain per step is ALU only (ncu of
+  // the unpipelined loop: 56 % of all stall samples waiting on the table entry, one L2 latency per step).
+  auto load_v = [&](int j) -> float {
+    if (j < 0) return 0.f;
+    const unsigned i = begin + (unsigned)j * 32 + lane;
+    return i < end ? __ldg(zp + i) : 0.f;
+  };
+  // latent of step j -> (value, flags bit 0 valid, bit 1 escape), table entry load issued
+  auto classify = [&](int j, float v, int& zi, uint32_t& flags, uint32_t& fc) {
+    zi = 0; flags = 0; fc = 1;
+    if (j < 0) return;
+    const unsigned i = begin + (unsigned)j * 32 + lane;
     const bool valid = i < end;
-    const float v = v_next;
-    if (j > 0) v_next = __ldg(zp + i - 32);                   // step j-1 is always full
-    int zi = 0;
     if (valid) {
       const float r = rintf(v);
       if (!(fabsf(r) <= 32767.f)) { bad = true; zi = (r > 0.f) ? 32767 : -32767; if (r != r) zi = 0; }
@@ -130,34 +137,60 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const float* __restrict
     const bool esc = valid && (zi > L || zi < -L);
     const int sym = esc ? A - 1 : zi + L;
     const unsigned c = valid ? i / (unsigned)HW : 0;
-    const uint32_t fc = __ldg(freq_cum + (size_t)c * A + sym);
-    // (B') raw 16 bits of an escaped value: always exactly one word out, then x = (x >> 16) << 16 | raw
-    uint32_t m = __ballot_sync(0xffffffffu, esc);
-    if (m) {
-      const uint32_t cnt = __popc(m);
-      if (esc) {
-        out[ptr - cnt + __popc(m & lt)] = (uint16_t)x;
-        x = (x & 0xffff0000u) | (uint32_t)(zi + 32768);
+    fc = __ldg(freq_cum + (size_t)c * A + sym);
+    flags = (valid ? 1u : 0u) | (esc ? 2u : 0u);
+  };
+  float vn[RANS_U];
+  int zi_c[RANS_U], zi_n[RANS_U];
+  uint32_t fl_c[RANS_U], fl_n[RANS_U], fc_c[RANS_U], fc_n[RANS_U];
+  int jg = steps - 1;
+#pragma unroll
+  for (int u = 0; u < RANS_U; ++u) vn[u] = load_v(jg - u);
+#pragma unroll
+  for (int u = 0; u < RANS_U; ++u) classify(jg - u, vn[u], zi_c[u], fl_c[u], fc_c[u]);
+#pragma unroll
+  for (int u = 0; u < RANS_U; ++u) vn[u] = load_v(jg - RANS_U - u);
+  for (; jg >= 0; jg -= RANS_U) {
+#pragma unroll
+    for (int u = 0; u < RANS_U; ++u) classify(jg - RANS_U - u, vn[u], zi_n[u], fl_n[u], fc_n[u]);
+#pragma unroll
+    for (int u = 0; u < RANS_U; ++u) vn[u] = load_v(jg - 2 * RANS_U - u);
+#pragma unroll
+    for (int u = 0; u < RANS_U; ++u) {
+      if (jg - u < 0) break;                                  // warp-uniform
+      const bool valid = fl_c[u] & 1u, esc = fl_c[u] & 2u;
+      const int zi = zi_c[u];
+      const uint32_t fc = fc_c[u];
+      // (B') raw 16 bits of an escaped value: always exactly one word out, then x = (x >> 16) << 16 | raw
+      uint32_t m = __ballot_sync(0xffffffffu, esc);
+      if (m) {
+        const uint32_t cnt = __popc(m);
+        if (esc) {
+          out[ptr - cnt + __popc(m & lt)] = (uint16_t)x;
+          x = (x & 0xffff0000u) | (uint32_t)(zi + 32768);
+        }
+        ptr -= cnt;
       }
-      ptr -= cnt;
-    }
-    // (A') renormalise, then code the symbol
-    const uint32_t f = fc & 0xffffu, st = fc >> 16;
-    const uint32_t xmax = ((RANS_LOW >> prec) << 16) * f;     // f <= 2^prec - A + 1: no overflow
-    const bool emit = valid && x >= xmax;
-    m = __ballot_sync(0xffffffffu, emit);
-    if (m) {
-      const uint32_t cnt = __popc(m);
-      if (emit) {
-        out[ptr - cnt + __popc(m & lt)] = (uint16_t)x;
-        x >>= 16;
+      // (A') renormalise, then code the symbol
+      const uint32_t f = fc & 0xffffu, st = fc >> 16;
+      const uint32_t xmax = ((RANS_LOW >> prec) << 16) * f;   // f <= 2^prec - A + 1: no overflow
+      const bool emit = valid && x >= xmax;
+      m = __ballot_sync(0xffffffffu, emit);
+      if (m) {
+        const uint32_t cnt = __popc(m);
+        if (emit) {
+          out[ptr - cnt + __popc(m & lt)] = (uint16_t)x;
+          x >>= 16;
+        }
+        ptr -= cnt;
       }
-      ptr -= cnt;
+      if (valid) {
+        const uint32_t q = x / f;
+        x = (q << prec) + (x - q * f) + st;
+      }
     }
-    if (valid) {
-      const uint32_t q = x / f;
-      x = (q << prec) + (x - q * f) + st;
-    }
+#pragma unroll
+    for (int u = 0; u < RANS_U; ++u) { zi_c[u] = zi_n[u]; fl_c[u] = fl_n[u]; fc_c[u] = fc_n[u]; }
   }
   ptr -= 64;
   out[ptr + 2 * lane] = (uint16_t)x;
@@ -223,6 +256,25 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(const uint16_t* __restr
   bool bad = len < 64;
   uint32_t x = bad ? RANS_LOW : ((uint32_t)w[2 * lane] | ((uint32_t)w[2 * lane + 1] << 16));
   uint32_t rp = 64;
+  // Register window over the word stream: wa = w[base + lane], wb = w[base + 32 + lane] with base <= rp < base + 32, so
+  // a renormalising lane takes its word with a shuffle instead of a dependent global load; the refill (one coalesced
+  // 64-byte load per 32 consumed words) is issued many steps before its words are needed.
+  uint32_t base = 64;
+  auto load_w = [&](uint32_t at) -> uint32_t { return at < len ? (uint32_t)w[at] : 0u; };
+  uint32_t wa = load_w(base + lane), wb = load_w(base + 32 + lane);
+  auto fetch = [&](uint32_t at) -> uint32_t {                 // called by all lanes; base <= at < base + 64
+    const uint32_t idx = at - base;
+    const uint32_t a = __shfl_sync(0xffffffffu, wa, idx & 31), b2 = __shfl_sync(0xffffffffu, wb, idx & 31);
+    return idx < 32 ? a : b2;
+  };
+  auto consume = [&](uint32_t cnt) {                          // warp-uniform; cnt <= 32
+    rp += cnt;
+    if (rp - base >= 32) {
+      wa = wb;
+      base += 32;
+      wb = load_w(base + 32 + lane);
+    }
+  };
   for (int j = 0; j < steps; ++j) {
     const unsigned i = begin + (unsigned)j * 32 + lane;
     const bool valid = i < end;
@@ -237,26 +289,26 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(const uint16_t* __restr
     const bool need = valid && x < RANS_LOW;
     uint32_t m = __ballot_sync(0xffffffffu, need);
     if (m) {
+      const uint32_t at = rp + __popc(m & lt);
+      const uint32_t word = fetch(at);
       if (need) {
-        const uint32_t at = rp + __popc(m & lt);
-        uint32_t word = 0;
-        if (at < len) word = w[at]; else bad = true;
+        if (at >= len) bad = true;
         x = (x << 16) | word;
       }
-      rp += __popc(m);
+      consume(__popc(m));
     }
     const bool esc = valid && s == A - 1;
     int zi = s - L;
     m = __ballot_sync(0xffffffffu, esc);
     if (m) {
+      const uint32_t at = rp + __popc(m & lt);
+      const uint32_t word = fetch(at);
       if (esc) {
         zi = (int)(x & 0xffffu) - 32768;
-        const uint32_t at = rp + __popc(m & lt);
-        uint32_t word = 0;
-        if (at < len) word = w[at]; else bad = true;
+        if (at >= len) bad = true;
         x = (x & 0xffff0000u) | word;
       }
-      rp += __popc(m);
+      consume(__popc(m));
     }
     if (valid) zp[i] = (float)zi;
   }

@@ -65,27 +65,52 @@ def _as_u8_hwc(img):
     return t.contiguous()
 
 
-def pack_images(images, params):
+_staging = {}                                    # device index -> (pinned uint8 buffer, event of its last copy)
+
+
+def _staging_buffer(nbytes, key):
+    """grow-only pinned staging buffer; waits for the copy that last read it before handing it out again"""
+    buf, ev = _staging.get(key, (None, None))
+    if ev is not None:
+        ev.synchronize()
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(nbytes, 1 << 20) * 5 // 4,), dtype=torch.uint8, pin_memory=True)
+    _staging[key] = (buf, None)
+    return buf
+
+
+def pack_images(images, params, crop_only=True, staging_key=None):
     """decoded images + their draws -> (pinned uint8 buffer, int64 descriptors [B, 8], max crop_h, max crop_w).
-    Every image starts at a multiple of 16 bytes; descriptor layout as in include/b2c.h (b2c_resized_crop_flip)."""
+    With crop_only (default) only each image's crop rectangle is staged (the descriptor then describes a crop_h x crop_w
+    image cropped in full), so the host->device copy moves the bytes the transform reads and nothing else.  Every image
+    starts at a multiple of 16 bytes; descriptor layout as in include/b2c.h (b2c_resized_crop_flip)."""
     if len(images) != len(params) or not images:
         raise ValueError("need one (top, left, h, w, hflip, vflip) per image and at least one image")
     imgs = [_as_u8_hwc(i) for i in images]
-    desc = torch.empty((len(imgs), 8), dtype=torch.int64)
+    rows = []
     total = 0
     for n, (t, p) in enumerate(zip(imgs, params)):
         H, W = t.shape[0], t.shape[1]
         top, left, h, w, hf, vf = (int(v) for v in p)
         if not (0 <= top and 0 <= left and 0 < h and 0 < w and top + h <= H and left + w <= W):
             raise ValueError(f"crop box {(top, left, h, w)} outside image {n} of size {(H, W)}")
-        desc[n] = torch.tensor([total, H, W, top, left, h, w, (1 if hf else 0) | (2 if vf else 0)])
-        total += (H * W * 3 + 15) // 16 * 16
-    pin = torch.cuda.is_available()
-    buf = torch.empty((total,), dtype=torch.uint8, pin_memory=pin)
-    for n, t in enumerate(imgs):
-        o = int(desc[n, 0])
-        buf[o:o + t.numel()] = t.reshape(-1)
-    return buf, (desc.pin_memory() if pin else desc), int(desc[:, 5].max()), int(desc[:, 6].max())
+        flags = (1 if hf else 0) | (2 if vf else 0)
+        if crop_only:
+            imgs[n] = t[top:top + h, left:left + w]
+            rows.append([total, h, w, 0, 0, h, w, flags])
+            total += (h * w * 3 + 15) // 16 * 16
+        else:
+            rows.append([total, H, W, top, left, h, w, flags])
+            total += (H * W * 3 + 15) // 16 * 16
+    desc = torch.tensor(rows, dtype=torch.int64)
+    if torch.cuda.is_available():
+        buf = _staging_buffer(total, staging_key)[:total]
+        desc = desc.pin_memory()
+    else:
+        buf = torch.empty((total,), dtype=torch.uint8)
+    for r, t in zip(rows, imgs):
+        buf[r[0]:r[0] + r[1] * r[2] * 3].view(r[1], r[2], 3).copy_(t)
+    return buf, desc, int(desc[:, 5].max()), int(desc[:, 6].max())
 
 
 def resized_crop_flip_packed(src, desc, size, max_crop_h, max_crop_w, check=True):
@@ -109,9 +134,15 @@ def resized_crop_flip_packed(src, desc, size, max_crop_h, max_crop_w, check=True
 
 def resized_crop_flip(images, params, size=256, device=None):
     """list of decoded uint8 [H, W, 3] images (numpy / CPU tensors) + their draws -> CUDA fp32 [B, 3, size, size]"""
-    buf, desc, mh, mw = pack_images(images, params)
     dev = torch.device(device if device is not None else "cuda")
-    return resized_crop_flip_packed(buf.to(dev, non_blocking=True), desc.to(dev, non_blocking=True), size, mh, mw)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    buf, desc, mh, mw = pack_images(images, params, staging_key=key)
+    with torch.cuda.device(key):
+        src, dd = buf.to(dev, non_blocking=True), desc.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _staging[key] = (_staging[key][0], ev)
+        return resized_crop_flip_packed(src, dd, size, mh, mw)
 
 
 def _decode(path):

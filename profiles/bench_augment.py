@@ -43,7 +43,7 @@ for name, B, (h, w) in (("8x375x500", 8, (375, 500)), ("64x375x500", 64, (375, 5
     imgs = [base[n % 4] for n in range(B)]
     torch.manual_seed(5)
     params = [D.sample_params(h, w) for _ in range(B)]
-    buf, desc, mh, mw = D.pack_images(imgs, params)
+    buf, desc, mh, mw = D.pack_images(imgs, params, crop_only=False)
     src, dd = buf.cuda(), desc.cuda()
     y = D.resized_crop_flip_packed(src, dd, 256, mh, mw)
     assert torch.equal(y[0].cpu(), R.resized_crop_flip(imgs[0], *params[0]))

@@ -70,6 +70,9 @@ def test_against_oracle_ragged(D, size):
     imgs.append(R.synth_photo(size, size, 7))                      # identity: both passes skipped by Pillow
     params.append((0, 0, size, size, True, True))
     y = D.resized_crop_flip(imgs, params, size).cpu()
+    buf, desc, mh, mw = D.pack_images(imgs, params, crop_only=False)          # whole images resident, crop on the device
+    y2 = D.resized_crop_flip_packed(buf.cuda(), desc.cuda(), size, mh, mw).cpu()
+    assert torch.equal(y, y2)
     for n, (img, p) in enumerate(zip(imgs, params)):
         assert torch.equal(y[n], R.resized_crop_flip(img, *p, size=size)), (n, img.shape, p)
 
@@ -86,7 +89,7 @@ def test_large_downscale_and_full_size_property(D):
 def test_bad_descriptors_fail_loudly(D):
     from iclr_17_compression_b200._lib import B2CError
     img = R.synth_photo(40, 40, 1)
-    buf, desc, mh, mw = D.pack_images([img], [(0, 0, 40, 40, False, False)])
+    buf, desc, mh, mw = D.pack_images([img], [(0, 0, 40, 40, False, False)], crop_only=False)
     desc = desc.clone()
     desc[0, 5] = 41                                               # crop taller than the image
     with pytest.raises(B2CError):

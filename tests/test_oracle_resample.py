@@ -71,10 +71,13 @@ def test_host_draws_match_oracle_and_consume_the_same_stream():
 def test_pack_images_layout():
     from iclr_17_compression_b200 import datasets as D
     imgs = [R.synth_photo(7, 5, 1), R.synth_photo(33, 21, 2)]
-    buf, desc, mh, mw = D.pack_images(imgs, [(1, 0, 5, 4, True, False), (0, 3, 33, 10, False, True)])
+    buf, desc, mh, mw = D.pack_images(imgs, [(1, 0, 5, 4, True, False), (0, 3, 33, 10, False, True)], crop_only=False)
     assert desc.tolist() == [[0, 7, 5, 1, 0, 5, 4, 1], [112, 33, 21, 0, 3, 33, 10, 2]]
     assert (mh, mw) == (33, 10) and buf.numel() == 112 + (33 * 21 * 3 + 15) // 16 * 16
     assert np.array_equal(buf[112:112 + 33 * 21 * 3].numpy().reshape(33, 21, 3), imgs[1])
+    buf, desc, mh, mw = D.pack_images(imgs, [(1, 0, 5, 4, True, False), (0, 3, 33, 10, False, True)])     # crops only
+    assert desc.tolist() == [[0, 5, 4, 0, 0, 5, 4, 1], [64, 33, 10, 0, 0, 33, 10, 2]] and buf.numel() == 64 + 992
+    assert np.array_equal(buf[64:64 + 990].numpy().reshape(33, 10, 3), imgs[1][:, 3:13])
     with pytest.raises(ValueError):
         D.pack_images(imgs, [(1, 0, 7, 4, False, False), (0, 0, 1, 1, False, False)])
     with pytest.raises(ValueError):
