@@ -130,9 +130,11 @@ def encode_latents(z, tables, block_symbols=32768):
     """z [B, C, h, w] (integers in fp32, CUDA) -> list of B byte strings (container in the module docstring)"""
     B, C, h, w = z.shape
     out, offsets, block_bytes, status = encode_latents_raw(z, tables, block_symbols)
-    _status(status, "rans_encode")
-    off = offsets.cpu().numpy()
-    bb = block_bytes.cpu().numpy().astype("<u4")
+    nb = block_bytes.numel()
+    meta = torch.cat([offsets, block_bytes.to(torch.int64), status.to(torch.int64)]).cpu().numpy()   # one small D2H
+    if int(meta[-1]):
+        _status(status, "rans_encode")
+    off, bb = meta[:nb + 1], meta[nb + 1:2 * nb + 1].astype("<u4")
     payload = out[:int(off[-1])].cpu().numpy().tobytes()
     nblk = bb.size // B
     streams = []

@@ -70,5 +70,24 @@ for name, (B, H, Wd), kind in (("cfg2_24x512x768_S", (24, 512, 768), "S"), ("cfg
             t2 = time.perf_counter()
             r["cpu_oracle_1core"] = {"latents": zc.size, "encode_Msym_s": zc.size / (t1 - t0) / 1e6,
                                       "decode_Msym_s": zc.size / (t2 - t1) / 1e6}
+        if bs == 8192:
+            # the public calls, host clock, everything included: network + coder + device->host copy of the bytes, and back
+            def wall(fn, n=5):
+                fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    o = fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / n * 1e3, o
+            t_c, (streams, _) = wall(lambda: BS.compress(m, x, tables, bs))
+            t_d, rec = wall(lambda: BS.decompress(m, streams, tables))
+            with torch.no_grad():
+                assert torch.equal(rec, m(x)[0])
+            r["public_compress_ms"] = t_c
+            r["public_decompress_ms"] = t_d
+            r["public_compress_Mpix_s"] = B * H * Wd / t_c / 1e3
+            r["public_decompress_Mpix_s"] = B * H * Wd / t_d / 1e3
+            r["file_bytes"] = sum(len(s_) for s_ in streams)
         res[f"{name}_bs{bs}"] = r
 print(json.dumps(res, indent=1))
