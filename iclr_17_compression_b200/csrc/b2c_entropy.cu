@@ -292,6 +292,90 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
   }
 }
 
+// Second version of the table-driven pass, for C % 64 == 0 (ncu source view of the first: ~70 issued instructions per
+// 4 elements - a compare + branch + reconvergence point around EVERY table read, which also serialised the four reads
+// behind each other's FADD; 2-byte shared-memory stores; 4-byte copy-out).  Here a thread owns 4 consecutive pixels of
+// TWO adjacent channels: all 8 table reads are issued unconditionally on clamped indices (one rare fix-up branch per 8
+// elements), the two channels of a pixel are packed into one bf16x2 word (4 STS.32 per 8 elements), and the NHWC tile
+// is XOR-swizzled at 16-byte granularity (chunk ^ ((row >> 2) & 7)) instead of padded, so both the 4-byte writes and
+// the 16-byte row reads of the copy-out are bank-conflict free and the copy-out is LDS.128 / STG.128.
+// lane = (pixel quad q 0..7, pair k 0..3); warp w: pixel group w & 3, 8-channel chunk half w >> 2; a pass = 16 channels.
+__global__ void __launch_bounds__(256) quant_entropy_infer_lut2_kernel(const float* __restrict__ y, BitPtrs bp,
+                                                                       const float* __restrict__ lut, int L,
+                                                                       float* __restrict__ z,
+                                                                       __nv_bfloat16* __restrict__ z_nhwc,
+                                                                       float* __restrict__ partial, int C, int HW,
+                                                                       int chunks) {
+  extern __shared__ float qi_smem[];
+  uint32_t* tile = reinterpret_cast<uint32_t*>(qi_smem);     // [LQ_PIX][C / 2] bf16x2 words, 16-byte chunks swizzled
+  __shared__ float red[32];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const unsigned n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
+  const unsigned pix0 = chunk * LQ_PIX;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned q = lane & 7, k = lane >> 3;
+  const unsigned lp = (warp & 3) * 32 + q * 4;               // first of this thread's 4 pixels inside the chunk
+  const unsigned half = warp >> 2;
+  const unsigned wpr = C / 2, W = 2 * L + 1;                 // words per tile row; table row length
+  const bool in_image = pix0 + lp < (unsigned)HW;            // whole quads: HW % 4 == 0
+  const float fL = (float)L;
+  float sum = 0.f;
+  unsigned c = (half * 4 + k) * 2;                           // first channel of the pair, pass 0
+  const float* yp = y + ((size_t)n * C + c) * HW + pix0 + lp;
+  float* zp = z + ((size_t)n * C + c) * HW + pix0 + lp;
+  const float* row = lut + (size_t)c * W + L;
+  const size_t cstep = (size_t)16 * HW;
+  uint32_t* tp = tile + lp * wpr + k;                        // + ((chunk ^ q) * 4) per pass; rows lp .. lp+3 share q
+#pragma unroll 2
+  for (unsigned pass = 0; pass < (unsigned)C / 16; ++pass, c += 16, yp += cstep, zp += cstep, row += 16 * W) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (in_image) {
+      a = __ldg(reinterpret_cast<const float4*>(yp));
+      b = __ldg(reinterpret_cast<const float4*>(yp + HW));
+      a.x = rintf(a.x); a.y = rintf(a.y); a.z = rintf(a.z); a.w = rintf(a.w);
+      b.x = rintf(b.x); b.y = rintf(b.y); b.z = rintf(b.z); b.w = rintf(b.w);
+      *reinterpret_cast<float4*>(zp) = a;
+      *reinterpret_cast<float4*>(zp + HW) = b;
+      const float e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const float* row1 = row + W;
+      float bits[8];
+      float amax = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        amax = fmaxf(amax, fabsf(e[j]));
+        const int idx = (int)fminf(fmaxf(e[j], -fL), fL);
+        bits[j] = __ldg((j < 4 ? row : row1) + idx);
+      }
+      if (!(amax <= fL)) {                                   // rare: outside the table (or NaN), same formula directly
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(fabsf(e[j]) <= fL)) bits[j] = bits_outside_table(bp, (int)c + (j >> 2), e[j]);
+      }
+      sum += ((bits[0] + bits[1]) + (bits[2] + bits[3])) + ((bits[4] + bits[5]) + (bits[6] + bits[7]));
+    }
+    uint32_t* t0 = tp + (((pass * 2 + half) ^ q) << 2);
+    __nv_bfloat162 w0 = __floats2bfloat162_rn(a.x, b.x), w1 = __floats2bfloat162_rn(a.y, b.y);
+    __nv_bfloat162 w2 = __floats2bfloat162_rn(a.z, b.z), w3 = __floats2bfloat162_rn(a.w, b.w);
+    t0[0] = *reinterpret_cast<uint32_t*>(&w0);
+    t0[wpr] = *reinterpret_cast<uint32_t*>(&w1);
+    t0[2 * wpr] = *reinterpret_cast<uint32_t*>(&w2);
+    t0[3 * wpr] = *reinterpret_cast<uint32_t*>(&w3);
+  }
+  sum = block_sum(sum, red);                                 // also the __syncthreads() for `tile`
+  if (threadIdx.x == 0) partial[blockIdx.x] = sum;
+  if (z_nhwc) {
+    const unsigned npix = min((unsigned)LQ_PIX, (unsigned)HW - pix0);
+    const unsigned cpr = C / 8;                              // 16-byte chunks per row
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+    uint4* dst = reinterpret_cast<uint4*>(z_nhwc + ((size_t)n * HW + pix0) * C);
+    for (unsigned i = threadIdx.x; i < npix * cpr; i += 256) {
+      const unsigned r = i / cpr, ch = i - r * cpr;
+      dst[i] = src[r * cpr + (ch ^ ((r >> 2) & 7))];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- backward
 // For each branch u = z +- 1/2:  lambda_4 = sgn * dL/dp * F(1-F) ... chain back through the 3 layers.
 struct Grad11 {
@@ -535,7 +619,9 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
     bp.p[i] = host_params[i];
   }
   const int chunks = (HW + LQ_PIX - 1) / LQ_PIX;
-  const size_t smem = (size_t)LQ_PIX * (C + 2) * 2;
+  static const bool allow_v2 = [] { const char* e = getenv("B2C_ENTROPY_LUT_V1"); return !e || atoi(e) == 0; }();
+  const bool v2 = allow_v2 && C % 64 == 0 && ((uintptr_t)z_nhwc_bf16 & 15) == 0;
+  const size_t smem = v2 ? (size_t)LQ_PIX * C * 2 : (size_t)LQ_PIX * (C + 2) * 2;
   {
     static std::mutex mu;
     static bool done[64] = {false};
@@ -545,6 +631,9 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
     if (dev < 0 || dev >= 64 || !done[dev]) {
       cudaError_t e = cudaFuncSetAttribute(quant_entropy_infer_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            LQ_PIX * (256 + 2) * 2);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+      e = cudaFuncSetAttribute(quant_entropy_infer_lut2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               LQ_PIX * 256 * 2);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
       if (dev >= 0 && dev < 64) done[dev] = true;
     }
@@ -561,8 +650,8 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
   cfg.stream = (cudaStream_t)stream;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, quant_entropy_infer_lut_kernel, y, bp, lut, half_range, z,
-                                     (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, v2 ? quant_entropy_infer_lut2_kernel : quant_entropy_infer_lut_kernel, y, bp, lut,
+                                     half_range, z, (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(quant_entropy_infer_lut): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
   cfg.gridDim = dim3((unsigned)B);
   cfg.dynamicSmemBytes = 0;
