@@ -39,6 +39,9 @@ cases = {
     "sigmoid_binarize_fwd (read y, write sig, code, code bf16)": (14, lambda: lib.b2c_sigmoid_binarize_fwd(p_(y), p_(sig), p_(code), p_(zh), B, C, H * W, cs())),
     "copy (torch, read + write fp32)": (8, lambda: z.copy_(y)),
 }
+only = os.environ.get("B2C_PASSES_ONLY")
+if only:
+    cases = {k: v for k, v in cases.items() if only in k}
 out = {"elements": n, "hbm_peak_gbs": peak}
 R = 10
 for name, (bpe, fn) in cases.items():
