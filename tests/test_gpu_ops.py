@@ -207,6 +207,20 @@ def test_entropy_lut_kernel_matches_direct_kernel(scale):
     assert torch.allclose(b1.cpu(), ref, rtol=2e-5)
 
 
+@pytest.mark.parametrize("C,H,W", [(128, 12, 20), (192, 8, 36), (256, 4, 4), (32, 6, 10), (64, 5, 7)])
+def test_sigmoid_binarize_infer_layouts(C, H, W):
+    """both kernel versions (C % 64 == 0 and HW % 4 == 0 -> 128-pixel swizzled tile; else 32-pixel padded tile):
+    sigmoid within 1 ulp of torch, code = (sigmoid > 0.5) of the kernel's own sigmoid, NHWC bf16 copy == NCHW code"""
+    from iclr_17_compression_b200 import functional as F
+    g = torch.Generator().manual_seed(C + H)
+    y = (torch.randn(3, C, H, W, generator=g) * 2).cuda()
+    y.view(-1)[:7] = torch.tensor([0.0, -0.0, 1e-8, -1e-8, 50.0, -50.0, 3e-4])
+    code, sig, ch = F.sigmoid_binarize_infer(y)
+    assert torch.allclose(sig, torch.sigmoid(y), rtol=3e-7, atol=1e-30)
+    assert torch.equal(code, (sig > 0.5).float())
+    assert torch.equal(ch, code.permute(0, 2, 3, 1).to(torch.bfloat16))
+
+
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_msssim_matches_reference_golden(tag):
     """GPU ssim / ms_ssim (models/ms_ssim_torch.py mirror) vs values produced by the reference's implementation:
