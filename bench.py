@@ -36,7 +36,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons sampled under the load of the timed region (B200_PROFILING.md).  The K
+    timed steps last only a few ms and nvidia-smi answers every ~50-100 ms (later still when 8 ranks start at once), so
+    the sampler is started BEFORE the warm-up, every row is time-stamped, and the caller keeps the SAME step loop
+    running right after the timed steps until rows have arrived; only rows inside that load window are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -47,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -56,12 +59,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def count_since(self, t0):
+        return sum(1 for t, _ in list(self.rows) if t >= t0)
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -69,10 +74,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
             try:
-                sm.append(float(r[0]))
                 smax = float(r[1])
+                if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                    continue
+                sm.append(float(r[0]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
@@ -80,7 +87,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": "timed steps + the same step loop kept running until >= 3 samples"}
 
 
 # ------------------------------------------------------------------------------------------ reference / CPU arm
@@ -173,17 +180,19 @@ def main():
         with torch.no_grad():
             return model(inp)
 
+    sampler = ClockSampler(local)
+    if rank == 0:                                 # the line reports rank 0's GPU; 8 concurrent nvidia-smi loops only slow each other
+        sampler.start()                           # before the warm-up: nvidia-smi is answering by the time the load starts
     for _ in range(args.warmup):
         step(x)
     barrier()
 
     # ---- timed region: K steps, device time, inputs resident in HBM.  No per-launch event records in here: an
     # event between two kernels defeats the programmatic dependent launch of the next layer (and costs ~1 us each).
-    sampler = ClockSampler(local)
-    sampler.start()
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_load0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         step(x)
@@ -207,7 +216,12 @@ def main():
     ev3.record()
     barrier()
     B2F.stop_timing()
-    clocks = sampler.stop()
+    while (sampler.proc is not None and sampler.proc.poll() is None and sampler.count_since(t_load0) < 3
+           and time.perf_counter() - t_load0 < 4.0):
+        for _ in range(args.steps):               # the same load, untimed, until the sampler has seen it
+            step(x)
+        torch.cuda.synchronize()
+    clocks = sampler.stop(t_load0, time.perf_counter())
     ms_instrumented = ev2.elapsed_time(ev3) / args.steps
 
     # ---- end to end: pinned host input -> H2D -> forward -> D2H of latents + per-image (bits, sse, sse_clipped),
