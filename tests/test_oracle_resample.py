@@ -82,3 +82,25 @@ def test_pack_images_layout():
         D.pack_images(imgs, [(1, 0, 7, 4, False, False), (0, 0, 1, 1, False, False)])
     with pytest.raises(ValueError):
         D.pack_images([np.zeros((4, 4, 3), np.float32)], [(0, 0, 1, 1, False, False)])
+
+
+def test_datasets_mirror_on_cpu(tmp_path):
+    """host side of the loader mirror without a GPU: items are (decoded uint8 image, draws in torchvision's RNG order);
+    the device call refuses CPU tensors (no CPU path)"""
+    Image = pytest.importorskip("PIL.Image")
+    from iclr_17_compression_b200 import datasets as D
+    from iclr_17_compression_b200._lib import B2CError
+    for n, (h, w) in enumerate([(40, 60), (33, 33)]):
+        Image.fromarray(R.synth_photo(h, w, n), "RGB").save(tmp_path / f"im{n}.png")
+    ds = D.Datasets(str(tmp_path), 32)
+    assert len(ds) == 2 and len(D.TestKodakDataset(str(tmp_path))) == 2
+    torch.manual_seed(5)
+    img, p = ds[0]
+    torch.manual_seed(5)
+    assert p == R.sample_params(40, 60) and img.dtype == torch.uint8 and tuple(img.shape) == (40, 60, 3)
+    assert np.array_equal(img.numpy(), R.synth_photo(40, 60, 0))
+    with pytest.raises(Exception):
+        D.Datasets(str(tmp_path / "missing"))
+    buf, desc, mh, mw = D.pack_images([img], [p])
+    with pytest.raises(B2CError):
+        D.resized_crop_flip_packed(buf, desc, 32, mh, mw)
