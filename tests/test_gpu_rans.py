@@ -160,3 +160,28 @@ def test_fp32_path_model_and_small_width():
     m.train()
     with pytest.raises(RuntimeError):
         BS.compress(m, c.x.cuda())
+
+
+def test_codec_files_round_trip(tmp_path):
+    """codec.py: image file -> .b2c file -> image file, through the command-line entry; the decoded image equals the
+    model's own clipped reconstruction of the padded input (model.py:57-59), cropped and rounded to 8 bits"""
+    Image = pytest.importorskip("PIL.Image")
+    from iclr_17_compression_b200 import codec
+    from oracle import resample_oracle as RS
+    img = RS.synth_photo(50, 70, 3)
+    Image.fromarray(img, "RGB").save(tmp_path / "a.png")
+    codec.main(["encode", str(tmp_path / "a.png"), str(tmp_path / "a.b2c")])
+    codec.main(["decode", str(tmp_path / "a.b2c"), str(tmp_path / "a_rec.png")])
+    rec = np.asarray(Image.open(tmp_path / "a_rec.png"))
+    assert rec.shape == (50, 70, 3)
+    model = codec.build_model(128)
+    x = torch.from_numpy(codec.pad_to_16(img)).cuda().permute(2, 0, 1).unsqueeze(0).float().div(255).contiguous()
+    with torch.no_grad():
+        ref, z, bpp = model(x)
+    want = ref[0, :, :50, :70].mul(255).round().clamp(0, 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+    assert np.array_equal(rec, want)
+    nbytes = (tmp_path / "a.b2c").stat().st_size
+    est = bpp.item() * 64 * 80 / 8
+    assert 0.95 * est < nbytes < est * 1.15 + 16 + 44 + 128 + 8  # estimate, + coder slack, headers, one state flush
+    with pytest.raises(ValueError):
+        codec.decode_image(codec.build_model(192), (tmp_path / "a.b2c").read_bytes())

@@ -95,3 +95,23 @@ def test_container_parse_rejects_malformed():
     for bad in (good[:10], b"XXXX" + good[4:], good[:-1], head):
         with pytest.raises(ValueError):
             BS.parse_stream(bad)
+
+
+def test_codec_file_container_and_padding():
+    """host side of codec.py: file header round trip, consistency with the embedded stream, edge padding"""
+    import struct
+    from iclr_17_compression_b200 import bitstream as BS
+    from iclr_17_compression_b200 import codec
+    nblk = 2
+    stream = BS._HEAD.pack(BS.MAGIC, BS.VERSION, 14, 31, 0, 128, 4, 5, 8192, nblk) + struct.pack("<II", 3, 1) + b"abcd"
+    data = codec.pack_file(stream, 128, 50, 70)
+    assert codec.unpack_file(data) == (128, 50, 70, stream)
+    for bad in (data[:10], b"XXXX" + data[4:], codec.pack_file(stream, 64, 50, 70), codec.pack_file(stream, 128, 65, 70),
+                codec.pack_file(stream, 128, 48, 70), codec.pack_file(stream[:-1], 128, 50, 70)):
+        with pytest.raises(ValueError):
+            codec.unpack_file(bad)
+    img = np.arange(5 * 7 * 3, dtype=np.uint8).reshape(5, 7, 3)
+    p = codec.pad_to_16(img)
+    assert p.shape == (16, 16, 3) and np.array_equal(p[:5, :7], img)
+    assert np.array_equal(p[5:, :7], np.broadcast_to(img[4:5], (11, 7, 3))) and np.array_equal(p[:, 7:], np.broadcast_to(p[:, 6:7], (16, 9, 3)))
+    assert codec.pad_to_16(np.zeros((32, 48, 3), np.uint8)).shape == (32, 48, 3)
