@@ -15,6 +15,7 @@ import ctypes
 import glob
 import math
 import os
+import threading
 
 import numpy as np
 import torch
@@ -65,7 +66,7 @@ def _as_u8_hwc(img):
     return t.contiguous()
 
 
-_staging = {}                                    # device index -> (pinned uint8 buffer, event of its last copy)
+_staging = {}                                    # (device index, thread) -> (pinned uint8 buffer, event of its last copy)
 
 
 def _staging_buffer(nbytes, key):
@@ -135,9 +136,10 @@ def resized_crop_flip_packed(src, desc, size, max_crop_h, max_crop_w, check=True
 def resized_crop_flip(images, params, size=256, device=None):
     """list of decoded uint8 [H, W, 3] images (numpy / CPU tensors) + their draws -> CUDA fp32 [B, 3, size, size]"""
     dev = torch.device(device if device is not None else "cuda")
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (index, threading.get_ident())         # one staging buffer per calling thread (nn.DataParallel-style callers)
     buf, desc, mh, mw = pack_images(images, params, staging_key=key)
-    with torch.cuda.device(key):
+    with torch.cuda.device(index):
         src, dd = buf.to(dev, non_blocking=True), desc.to(dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
