@@ -217,7 +217,7 @@ def main():
     barrier()
     B2F.stop_timing()
     while (sampler.proc is not None and sampler.proc.poll() is None and sampler.count_since(t_load0) < 3
-           and time.perf_counter() - t_load0 < 4.0):
+           and time.perf_counter() - t_load0 < 8.0):
         for _ in range(args.steps):               # the same load, untimed, until the sampler has seen it
             step(x)
         torch.cuda.synchronize()
