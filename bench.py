@@ -28,6 +28,15 @@ METRIC = "Mpix/s encode+decode (768x512) per B200"
 E2E_CHUNK = int(os.environ.get("B2C_E2E_CHUNK", "3"))
 
 
+def workload_config(world):
+    """the `config` object of the JSON line - the SAME for both arms (the reference arm times a bounded sample of this
+    workload; what the sample was is in its cpu_baseline.sample)"""
+    return {"workload": f"kodak-shape inference, {IMAGES}x3x{H}x{W} per GPU, N={N_CH}, eval, one batch "
+                        f"of {IMAGES} (configs[1])",
+            "weights": "seed-234 random init", "parallelism": f"per-image sharding x{world}, no collective",
+            "l2": "per-step working set (226 MB in/out + >600 MB intermediates) exceeds the 126 MB L2"}
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -113,7 +122,9 @@ def cpu_reference_throughput(budget_s, images_per_step, steps=None, warmup=1):
             el = time.perf_counter() - t0
             if (steps is not None and nsteps >= steps) or (steps is None and el >= budget_s):
                 break
-    return done * MPIX_PER_IMAGE / el, cores, f"{done} eval forwards of single 3x{H}x{W} images (batch 1, cycling through {images_per_step} of the {IMAGES} images)", el / nsteps * 1e3
+    return (done * MPIX_PER_IMAGE / el, cores,
+            f"{done} eval forwards of single 3x{H}x{W} images (batch 1 as train.py:162 does, {images_per_step} images per "
+            f"step, cycling through {images_per_step} of the {IMAGES} images)", el / nsteps * 1e3)
 
 
 def run_reference(args):
@@ -125,8 +136,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"kodak-shape inference, {IMAGES}x3x{H}x{W}, N={N_CH}, eval (configs[1])",
-                       "step": f"bounded sample: {per_step} images per step, batch 1"},
+            "config": workload_config(args.gpus),
             "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -310,10 +320,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"kodak-shape inference, {IMAGES}x3x{H}x{W} per GPU, N={N_CH}, eval, one batch "
-                                   f"of {IMAGES} (configs[1])",
-                       "weights": "seed-234 random init", "parallelism": f"per-image sharding x{world}, no collective",
-                       "l2": "per-step working set (226 MB in/out + >600 MB intermediates) exceeds the 126 MB L2"},
+            "config": workload_config(world),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),

@@ -27,10 +27,13 @@ SIGNATURES = {
     "b2c_gdn_bwd": (_c_i, [_c_f] * 7 + [_c_i] * 4 + [_c_f, _c_sz, _c_f]),
     "b2c_quant_entropy_fwd": (_c_i, [_c_f, _c_f, _PP, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_quant_entropy_infer_workspace_bytes": (_c_sz, [_c_i, _c_i]),
-    "b2c_quant_entropy_infer": (_c_i, [_c_f, _PP, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
+    "b2c_quant_entropy_infer": (_c_i, [_c_f, _PP, _c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_entropy_lut_build": (_c_i, [_PP, _c_f, _c_i, _c_i, _c_f]),
-    "b2c_quant_entropy_infer_lut": (_c_i, [_c_f, _PP, _c_f, _c_i, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
+    "b2c_quant_entropy_infer_lut": (_c_i, [_c_f, _PP, _c_f, _c_i, _c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_entropy_bwd": (_c_i, [_c_f, _PP, _c_f, _c_f, _PP, _c_i, _c_i, _c_i, _c_f]),
+    "b2c_bitparm_fwd": (_c_i, [_c_f] * 5 + [_c_i] * 3 + [_c_f]),
+    "b2c_bitparm_bwd_workspace_bytes": (_c_sz, [_c_i, _c_i]),
+    "b2c_bitparm_bwd": (_c_i, [_c_f] * 9 + [_c_i] * 3 + [_c_f, _c_sz, _c_f]),
     "b2c_clamp_sse_workspace_bytes": (_c_sz, [_c_i, _c_i]),
     "b2c_clamp_sse_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_clamp_sse_bwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_f, _c_sz, _c_f]),
@@ -132,6 +135,22 @@ def require_device(dev_index):
 
 def launch_count():
     return int(load().b2c_launch_count())
+
+
+# Parameters updated through raw device pointers (the fused clamp + Adam launch, also when replayed inside a CUDA
+# graph) do not bump the tensors' autograd ``_version``; every cache keyed on parameter versions (packed bf16 weight
+# panels, GDN packs, the entropy table, rANS tables) also keys on this counter, which those updates increment.
+_weights_epoch = 0
+
+
+def weights_epoch():
+    return _weights_epoch
+
+
+def bump_weights_epoch():
+    global _weights_epoch
+    _weights_epoch += 1
+    return _weights_epoch
 
 
 def ptr_array(tensors):

@@ -139,12 +139,15 @@ __device__ __forceinline__ float cdf_fast(const float* k, float v) {   // k: sp1
 }
 
 constexpr int QI_PIX = 32;
+// integers up to 256 are exact in bf16 (8 significand bits); the NHWC bf16 latent the tensor-core synthesis transform
+// reads is only valid below that.  The inference kernels raise *range_flag (sticky, never cleared here) otherwise.
+constexpr float BF16_EXACT_INT = 256.f;
 
 __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* __restrict__ y, BitPtrs bp,
                                                                   float* __restrict__ z,
                                                                   __nv_bfloat16* __restrict__ z_nhwc,
                                                                   float* __restrict__ partial, int C, int HW,
-                                                                  int chunks) {
+                                                                  int chunks, int* __restrict__ range_flag) {
   extern __shared__ float qi_smem[];
   float* kc = qi_smem;                                   // [C][12]
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(qi_smem + (size_t)C * 12);   // [QI_PIX][C]
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* _
       const size_t a = ((size_t)n * C + c) * HW + pix;
       zv = rintf(__ldg(y + a));
       z[a] = zv;
+      if (range_flag && !(fabsf(zv) <= BF16_EXACT_INT)) *range_flag = 1;     // bf16 copy of z is no longer exact
       const float* k = kc + c * 12;
       const float p = cdf_fast(k, zv + 0.5f) - cdf_fast(k, zv - 0.5f);
       sum += fminf(fmaxf(-__log2f(p + 1e-10f), 0.f), 50.f);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
                                                                       float* __restrict__ z,
                                                                       __nv_bfloat16* __restrict__ z_nhwc,
                                                                       float* __restrict__ partial, int C, int HW,
-                                                                      int chunks) {
+                                                                      int chunks, int* __restrict__ range_flag) {
   extern __shared__ float qi_smem[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(qi_smem);   // [LQ_PIX][C + 2]
   __shared__ float red[32];
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
           sum += __ldg(row + (int)e[j]);
         } else {                                           // rare: outside the table, same formula evaluated directly
           sum += bits_outside_table(bp, (int)c, e[j]);
+          if (range_flag && !(fabsf(e[j]) <= BF16_EXACT_INT)) *range_flag = 1;
         }
       }
     }
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut2_kernel(const flo
                                                                        float* __restrict__ z,
                                                                        __nv_bfloat16* __restrict__ z_nhwc,
                                                                        float* __restrict__ partial, int C, int HW,
-                                                                       int chunks) {
+                                                                       int chunks, int* __restrict__ range_flag) {
   extern __shared__ float qi_smem[];
   uint32_t* tile = reinterpret_cast<uint32_t*>(qi_smem);     // [LQ_PIX][C / 2] bf16x2 words, 16-byte chunks swizzled
   __shared__ float red[32];
@@ -348,6 +353,7 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut2_kernel(const flo
         bits[j] = __ldg((j < 4 ? row : row1) + idx);
       }
       if (!(amax <= fL)) {                                   // rare: outside the table (or NaN), same formula directly
+        if (range_flag && !(amax <= BF16_EXACT_INT)) *range_flag = 1;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (!(fabsf(e[j]) <= fL)) bits[j] = bits_outside_table(bp, (int)c + (j >> 2), e[j]);
@@ -517,6 +523,79 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
   }
 }
 
+
+// ---------------------------------------------------------------------------- Bitparm as a module call
+// models/bitEstimator.py:20-25 for callers that evaluate the CDF themselves (model.py:71-72 pattern
+// bitEstimator(z + .5) - bitEstimator(z - .5), per-channel tables for an entropy coder).  Exact fp32 formula, one CTA
+// per (image, channel) plane; the backward writes per-plane parameter-gradient partials that a fixed-order second
+// kernel sums over the batch (deterministic).
+__global__ void __launch_bounds__(256) bitparm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                          const float* __restrict__ b, const float* __restrict__ a,
+                                                          float* __restrict__ out, int C, int HW) {
+  const int plane = blockIdx.x, c = plane % C;
+  const float sp = softplus_t(__ldg(h + c)), bb = __ldg(b + c);
+  const float ta = a ? tanhf(__ldg(a + c)) : 0.f;
+  const size_t base = (size_t)plane * HW;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float t = fmaf(__ldg(x + base + i), sp, bb);
+    out[base + i] = a ? fmaf(tanhf(t), ta, t) : sigmoid_t(t);
+  }
+}
+
+__global__ void __launch_bounds__(256) bitparm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                          const float* __restrict__ b, const float* __restrict__ a,
+                                                          const float* __restrict__ g, float* __restrict__ dx,
+                                                          float* __restrict__ part, int C, int HW, int planes) {
+  __shared__ float red[32];
+  const int plane = blockIdx.x, c = plane % C;
+  const float hh = __ldg(h + c);
+  const float sp = softplus_t(hh), bb = __ldg(b + c), sg = sigmoid_t(hh);      // d softplus(h) / dh = sigmoid(h)
+  const float ta = a ? tanhf(__ldg(a + c)) : 0.f;
+  const size_t base = (size_t)plane * HW;
+  float sh = 0.f, sb = 0.f, sa = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float xv = __ldg(x + base + i), gv = __ldg(g + base + i);
+    const float t = fmaf(xv, sp, bb);
+    float gt;                                                                  // d loss / d t
+    if (a) {
+      const float th = tanhf(t);
+      gt = gv * fmaf(1.f - th * th, ta, 1.f);
+      sa += gv * th;
+    } else {
+      const float s = sigmoid_t(t);
+      gt = gv * s * (1.f - s);
+    }
+    dx[base + i] = gt * sp;
+    sb += gt;
+    sh += gt * xv;
+  }
+  sh = block_sum(sh, red);
+  sb = block_sum(sb, red);
+  sa = block_sum(sa, red);
+  if (threadIdx.x == 0) {
+    part[plane] = sh * sg;
+    part[planes + plane] = sb;
+    part[2 * planes + plane] = sa * (1.f - ta * ta);
+  }
+}
+
+// out_k[c] = sum_n part[k][n*C + c], k = h, b, a (fixed order)
+__global__ void bitparm_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dh,
+                                            float* __restrict__ db, float* __restrict__ da, int B, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int planes = B * C;
+  float sh = 0.f, sb = 0.f, sa = 0.f;
+  for (int n = 0; n < B; ++n) {
+    sh += part[n * C + c];
+    sb += part[planes + n * C + c];
+    sa += part[2 * planes + n * C + c];
+  }
+  dh[c] = sh;
+  db[c] = sb;
+  if (da) da[c] = sa;
+}
+
 static int clamp_blocks_per_image(int B, int CHW) {
   int bpi = (CHW + 256 * 8 - 1) / (256 * 8);
   const int cap = (148 * 8 + B - 1) / B;
@@ -551,8 +630,8 @@ size_t b2c_quant_entropy_infer_workspace_bytes(int B, int HW) {
 }
 
 int b2c_quant_entropy_infer(const float* y, const float* const* host_params, float* z, void* z_nhwc_bf16,
-                            float* image_bits, int B, int C, int HW, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            float* image_bits, int* range_flag, int B, int C, int HW, void* workspace,
+                            size_t workspace_bytes, void* stream) {
   B2C_REQUIRE(y && host_params && z && image_bits && workspace && B > 0 && C > 0 && C % 2 == 0 && HW > 0,
               "quant_entropy_infer: bad arguments");
   if (workspace_bytes < b2c_quant_entropy_infer_workspace_bytes(B, HW)) {
@@ -580,7 +659,7 @@ int b2c_quant_entropy_infer(const float* y, const float* const* host_params, flo
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, quant_entropy_infer_kernel, y, bp, z, (__nv_bfloat16*)z_nhwc_bf16,
-                                       (float*)workspace, C, HW, chunks);
+                                       (float*)workspace, C, HW, chunks, range_flag);
     if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(quant_entropy_infer): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
     cfg.gridDim = dim3((unsigned)B);
     cfg.dynamicSmemBytes = 0;
@@ -604,8 +683,8 @@ int b2c_entropy_lut_build(const float* const* host_params, float* lut, int C, in
 }
 
 int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params, const float* lut, int half_range,
-                                float* z, void* z_nhwc_bf16, float* image_bits, int B, int C, int HW, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                float* z, void* z_nhwc_bf16, float* image_bits, int* range_flag, int B, int C, int HW,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   B2C_REQUIRE(y && host_params && lut && z && image_bits && workspace && B > 0 && C > 0 && C % 8 == 0 && HW > 0 &&
                   HW % 4 == 0 && half_range >= 1,
               "quant_entropy_infer_lut: bad arguments (C %% 8 == 0 and HW %% 4 == 0 required)");
@@ -651,7 +730,8 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, v2 ? quant_entropy_infer_lut2_kernel : quant_entropy_infer_lut_kernel, y, bp, lut,
-                                     half_range, z, (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks);
+                                     half_range, z, (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks,
+                                     range_flag);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(quant_entropy_infer_lut): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
   cfg.gridDim = dim3((unsigned)B);
   cfg.dynamicSmemBytes = 0;
@@ -710,6 +790,32 @@ int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped
   clamp_sse_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(recon, x, g_clipped, g_sse, g_recon, n);
   count_launch();
   return check_launch("clamp_sse_bwd");
+}
+
+int b2c_bitparm_fwd(const float* x, const float* h, const float* b, const float* a, float* out, int B, int C, int HW,
+                    void* stream) {
+  B2C_REQUIRE(x && h && b && out && B > 0 && C > 0 && HW > 0, "bitparm_fwd: bad arguments");
+  bitparm_fwd_kernel<<<B * C, 256, 0, (cudaStream_t)stream>>>(x, h, b, a, out, C, HW);
+  count_launch();
+  return check_launch("bitparm_fwd");
+}
+
+size_t b2c_bitparm_bwd_workspace_bytes(int B, int C) { return (size_t)3 * B * C * sizeof(float); }
+
+int b2c_bitparm_bwd(const float* x, const float* h, const float* b, const float* a, const float* g, float* dx,
+                    float* dh, float* db, float* da, int B, int C, int HW, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  B2C_REQUIRE(x && h && b && g && dx && dh && db && B > 0 && C > 0 && HW > 0, "bitparm_bwd: bad arguments");
+  B2C_REQUIRE((a == nullptr) == (da == nullptr), "bitparm_bwd: a and da must both be given (or both NULL for the final layer)");
+  if (!workspace || workspace_bytes < b2c_bitparm_bwd_workspace_bytes(B, C)) {
+    set_error("bitparm_bwd: workspace too small");
+    return B2C_EWORKSPACE;
+  }
+  float* part = static_cast<float*>(workspace);
+  bitparm_bwd_kernel<<<B * C, 256, 0, (cudaStream_t)stream>>>(x, h, b, a, g, dx, part, C, HW, B * C);
+  bitparm_param_reduce_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, dh, db, da, B, C);
+  count_launch(2);
+  return check_launch("bitparm_bwd");
 }
 
 }  // extern "C"

@@ -171,17 +171,22 @@ class Datasets(Dataset):
 
 
 class TestKodakDataset(Dataset):
-    """datasets.py:63-80: ToTensor only; items are decoded uint8 images with the identity 'crop' so that the same
-    kernel does the uint8 -> fp32 CHW conversion when the sizes match `image_size`, else use inference.HostPipeline"""
+    """datasets.py:63-80: ``ToTensor()`` only, so items are fp32 ``[3, H, W]`` tensors in [0, 1] exactly as the
+    reference returns them (a default DataLoader over this dataset feeds the model the reference's dtype and layout;
+    ``x / 255`` below is ToTensor's own arithmetic, bit for bit).  ``raw=True`` returns uint8 ``[3, H, W]`` instead,
+    for device-side conversion: ``inference.HostPipeline.compress_u8`` moves a quarter of the bytes over PCIe and
+    divides on the GPU with identical results."""
 
-    def __init__(self, data_dir):
+    def __init__(self, data_dir, raw=False):
         self.data_dir = data_dir
+        self.raw = raw
         if not os.path.exists(data_dir):
             raise Exception(f"[!] {self.data_dir} not exitd")
         self.image_path = sorted(glob.glob(os.path.join(self.data_dir, "*.*")))
 
     def __getitem__(self, item):
-        return _decode(self.image_path[item])
+        chw = _decode(self.image_path[item]).permute(2, 0, 1).contiguous()
+        return chw if self.raw else chw.to(torch.float32).div(255)
 
     def __len__(self):
         return len(self.image_path)

@@ -54,7 +54,11 @@ class GradSync:
         # auto_finish: finish() runs inside the hook that launches the last bucket, so an unmodified training
         # loop (train.py:105-112: backward(); clip; optimizer.step()) sees averaged gradients.
         self.auto_finish = auto_finish
-        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        # bucket prefixes are written against the canonical Encoder. / Decoder. names (ImageCompressor_twoSteps
+        # stores the transforms as Encoder1 / Decoder1, model_twoSteps.py:41-42)
+        named_all = (module.canonical_named_parameters() if hasattr(module, "canonical_named_parameters")
+                     else list(module.named_parameters()))
+        named = [(n, p) for n, p in named_all if p.requires_grad]
         prefixes = buckets if buckets is not None else DEFAULT_BUCKETS
         assigned = {}
         self.buckets = []
@@ -72,6 +76,7 @@ class GradSync:
                 for _, b in module.named_buffers():
                     dist.broadcast(b.data, src=0, group=group)
         self._handles = []
+        self._armed = False
         for bi, b in enumerate(self.buckets):
             for j, (n, p) in enumerate(b["members"]):
                 self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi, j)))
@@ -87,26 +92,47 @@ class GradSync:
             assigned[n] = len(self.buckets)
         self.buckets.append({"members": members, "flat": flat, "offsets": offs, "ready": 0, "work": None})
 
+    def _arm_backward_callback(self):
+        """run ``_backward_done`` when the autograd pass that fired this hook ends, however many gradients it
+        produced: a step in which some parameter gets no gradient (a loss without the rate term leaves
+        bitEstimator.* untouched) must still wait for, average and hand back the buckets that were launched, and
+        must reset the per-step counters"""
+        if self._armed:
+            return
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(self._backward_done)
+            self._armed = True
+        except RuntimeError:            # hook fired outside an autograd pass: the caller finishes explicitly
+            self._armed = False
+
+    def _backward_done(self):
+        self._armed = False
+        if self.auto_finish:
+            self.finish()
+
     def _make_hook(self, bi, j):
         def hook(p):
+            self._arm_backward_callback()
             b = self.buckets[bi]
             o = b["offsets"][j]
             b["flat"][o:o + p.numel()].copy_(p.grad.reshape(-1))
             b["ready"] += 1
-            if b["ready"] == len(b["members"]):
+            if b["ready"] == len(b["members"]) and b["work"] is None:
                 b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-                if self.auto_finish and all(x["work"] is not None for x in self.buckets):
-                    self.finish()
         return hook
 
     def finish(self):
-        """wait for every bucket, average, write the reduced gradients back into .grad"""
+        """wait for every bucket, average, write the reduced gradients back into .grad; resets the step state.
+        Buckets that did not fill up (some member got no gradient) are reduced now with zeros in the gaps.  EVERY
+        bucket is reduced in every step that produced any gradient, in bucket order, so all ranks issue the same
+        sequence of collectives whatever subset of parameters their graph touched.  A second call in the same step
+        (explicit finish() after an auto-finished backward) is a no-op."""
+        if all(b["ready"] == 0 and b["work"] is None for b in self.buckets):
+            return
         for b in self.buckets:
-            if b["ready"] == 0:
-                continue
-            if b["ready"] != len(b["members"]):
-                # some parameter received no gradient this step: reduce what we have (zeros for the rest)
+            if b["work"] is None:
                 b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        for b in self.buckets:
             b["work"].wait()
             b["flat"].div_(self.world)
             for (n, p), o in zip(b["members"], b["offsets"]):
@@ -124,7 +150,8 @@ class GradSync:
                 if p.grad is not None:
                     b["flat"][o:o + p.numel()].copy_(p.grad.reshape(-1))
             b["ready"] = len(b["members"])
-            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if b["work"] is None:
+                b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.finish()
 
     def bucket_bytes(self):

@@ -277,6 +277,54 @@ class _QuantEntropy(torch.autograd.Function):
         return (gy, None, *dparams)
 
 
+class _Bitparm(torch.autograd.Function):
+    """models/bitEstimator.py:20-25 as a module call: non-final ``t + tanh(t) * tanh(a)``, final ``sigmoid(t)`` with
+    ``t = x * softplus(h) + b``; h, b, a are the [1,C,1,1] parameters, x is [B,C,H,W]."""
+
+    @staticmethod
+    def forward(ctx, x, h, b, a):
+        x = _prep(x, "input")
+        if x.dim() != 4:
+            raise _lib.B2CError(f"Bitparm expects a [B,C,H,W] tensor, got {tuple(x.shape)}")
+        B, C = x.shape[0], x.shape[1]
+        HW = x[0, 0].numel()
+        h, b = _prep(h, "h").reshape(-1), _prep(b, "b").reshape(-1)
+        a = _prep(a, "a").reshape(-1) if a is not None else None
+        if h.numel() != C or b.numel() != C or (a is not None and a.numel() != C):
+            raise _lib.B2CError(f"Bitparm parameters do not match {C} channels")
+        out = torch.empty_like(x)
+        if x.numel():
+            with torch.cuda.device(x.device), _timed(f"bitparm_fwd[{B}x{C}x{HW}]", 10 * x.numel(), 8 * x.numel()):
+                _lib.check(_lib.load().b2c_bitparm_fwd(_p(x), _p(h), _p(b), _p(a), _p(out), B, C, HW, _stream()),
+                           "bitparm_fwd")
+        ctx.save_for_backward(x, h, b, a)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, h, b, a = ctx.saved_tensors
+        B, C = x.shape[0], x.shape[1]
+        HW = x[0, 0].numel()
+        g = _prep(g, "grad")
+        lib = _lib.load()
+        dx = torch.empty_like(x)
+        dh, db = torch.zeros_like(h), torch.zeros_like(b)
+        da = torch.zeros_like(a) if a is not None else None
+        if x.numel():
+            nbytes = lib.b2c_bitparm_bwd_workspace_bytes(B, C)
+            ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
+            with torch.cuda.device(x.device), _timed(f"bitparm_bwd[{B}x{C}x{HW}]", 20 * x.numel(), 12 * x.numel()):
+                _lib.check(lib.b2c_bitparm_bwd(_p(x), _p(h), _p(b), _p(a), _p(g), _p(dx), _p(dh), _p(db), _p(da), B, C, HW,
+                                               _p(ws), nbytes, _stream()), "bitparm_bwd")
+        shape = (1, C, 1, 1)
+        return dx, dh.view(shape), db.view(shape), (da.view(shape) if da is not None else None)
+
+
+def bitparm(x, h, b, a=None):
+    """one Bitparm layer (bitEstimator.py:20-25); ``a=None`` selects the final (sigmoid) form.  Differentiable."""
+    return _Bitparm.apply(x, h, b, a)
+
+
 class _Distortion(torch.autograd.Function):
     """model.py:59 (clamp) + model.py:61 (squared error on the unclamped reconstruction)."""
 
@@ -330,9 +378,29 @@ def entropy_lut(params):
     return lut
 
 
-def quant_entropy_infer(y, params, lut=None):
+class RangeFlag:
+    """Sticky 'some |z| > 256' flag of the inference quantizer, living in mapped pinned host memory: the kernel
+    writes it through the device's view of the page, the host reads it WITHOUT synchronising.  Beyond 256 the NHWC
+    bf16 latent the tensor-core synthesis transform consumes is inexact; callers check the flag wherever they
+    synchronise anyway (HostPipeline.compress, bitstream.compress) and ImageCompressor re-checks it at the start of
+    every tensor-core forward."""
+
+    def __init__(self):
+        self.host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+
+    def ptr(self):
+        return _vp(self.host.data_ptr())          # unified addressing: pinned host pointers are valid on the device
+
+    def raised(self):
+        return bool(int(self.host[0]))
+
+    def clear(self):
+        self.host.zero_()
+
+
+def quant_entropy_infer(y, params, lut=None, range_flag=None):
     """eval quantizer + bits for the tensor-core pipeline (no autograd): (z fp32 NCHW, z NHWC bf16, image_bits[B]).
-    With ``lut`` (entropy_lut(params)) the table-driven HBM-bound kernel runs."""
+    With ``lut`` (entropy_lut(params)) the table-driven HBM-bound kernel runs.  ``range_flag``: a RangeFlag."""
     y = _prep(y, "latent")
     params = [_prep(p, "bit-estimator parameter") for p in params]
     B, C, H, W = y.shape
@@ -344,13 +412,14 @@ def quant_entropy_infer(y, params, lut=None):
     nbytes = lib.b2c_quant_entropy_infer_workspace_bytes(B, HW)
     ws = torch.empty((nbytes,), device=y.device, dtype=torch.uint8)
     pp, keep = _lib.ptr_array(params)
+    rf = range_flag.ptr() if range_flag is not None else _vp(0)
     with torch.cuda.device(y.device), _timed(f"quant_entropy_infer[{B}x{C}x{HW}]", 60 * y.numel(), 10 * y.numel()):
         if lut is not None and C % 8 == 0 and C <= 256 and HW % 4 == 0:
             _lib.check(lib.b2c_quant_entropy_infer_lut(_p(y), pp, _p(lut), LUT_HALF_RANGE, _p(z), _p(zh), _p(image_bits),
-                                                       B, C, HW, _p(ws), nbytes, _stream()), "quant_entropy_infer_lut")
+                                                       rf, B, C, HW, _p(ws), nbytes, _stream()), "quant_entropy_infer_lut")
         else:
-            _lib.check(lib.b2c_quant_entropy_infer(_p(y), pp, _p(z), _p(zh), _p(image_bits), B, C, HW, _p(ws), nbytes,
-                                                   _stream()), "quant_entropy_infer")
+            _lib.check(lib.b2c_quant_entropy_infer(_p(y), pp, _p(z), _p(zh), _p(image_bits), rf, B, C, HW, _p(ws),
+                                                   nbytes, _stream()), "quant_entropy_infer")
     return z, zh, image_bits
 
 

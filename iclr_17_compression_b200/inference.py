@@ -139,4 +139,5 @@ class HostPipeline:
                     stats.record_stream(self.out_stream)
         self.out_stream.synchronize()
         main.synchronize()
+        self.model.check_latent_range()          # |z| > 256 guard of the bf16 synthesis path (free: we just synchronised)
         return self.lat_host, self.stat_host

@@ -16,6 +16,7 @@ import torch.optim as optim  # noqa: F401
 from torch.nn.parameter import Parameter  # noqa: F401
 from torch.utils.data import DataLoader  # noqa: F401
 
+from . import _lib
 from . import functional as B2F
 from . import tc as B2TC
 from .models import *  # noqa: F401,F403
@@ -95,6 +96,7 @@ class ImageCompressor(nn.Module):
         self._packed = None
         self._packed_key = None
         self._grad_sync = None
+        self._zflag = None              # functional.RangeFlag of the tensor-core forward (|z| > 256 guard)
 
     def _maybe_join_process_group(self):
         """multi-process data parallel without touching train.py: when the launcher
@@ -112,7 +114,8 @@ class ImageCompressor(nn.Module):
 
     # ------------------------------------------------------------------ tensor-core inference path
     def _pack_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # _version does not move when the fused optimizer writes through raw pointers: weights_epoch() does
+        return (_lib.weights_epoch(),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _packed_weights(self):
         """bf16 (hi, lo) tap-major weight panels and effective GDN parameters, re-packed whenever a
@@ -146,10 +149,31 @@ class ImageCompressor(nn.Module):
                            split3=True)
         return B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv3"], None, split3=True, out_f32_nchw=True)
 
+    def check_latent_range(self):
+        """The tensor-core synthesis transform reads the rounded latent as bf16, exact only for |z| <= 256.  The
+        inference quantizer raises a sticky flag in mapped pinned memory when a latent exceeds that; it is polled
+        here without synchronising - at the start of every tensor-core forward and wherever a caller has synchronised
+        anyway (HostPipeline.compress).  On overflow the model switches itself to the exact-fp32 kernels and raises,
+        so a wrong reconstruction cannot pass silently."""
+        if self._zflag is not None and self._zflag.raised():
+            self._zflag.clear()
+            self.fast_inference = False
+            raise _lib.B2CError("a tensor-core forward of this model produced latents beyond +-256, which the bf16 "
+                                "synthesis path cannot represent exactly: its reconstruction is invalid.  "
+                                "fast_inference is now off (exact-fp32 kernels); run the batch again.")
+
     def decode_tc(self, z, ref_image=None, z_nhwc=None):
         """synthesis transform on tensor cores (bf16) -> unclamped reconstruction, fp32 NCHW; with ref_image
-        the distortion is fused into the last layer: returns (clamped reconstruction, sse[B,2])"""
+        the distortion is fused into the last layer: returns (clamped reconstruction, sse[B,2]).
+        A caller-supplied ``z`` without its bf16 copy is range-checked (one host sync): beyond +-256 the exact-fp32
+        synthesis transform runs instead."""
         P, D = self._packed_weights(), self._dec
+        if z_nhwc is None and float(z.abs().max()) > 256.0:
+            recon = self._dec(z)
+            if ref_image is None:
+                return recon
+            clipped, _, sse = B2F.distortion(recon, ref_image)
+            return clipped, sse
         zh = z_nhwc if z_nhwc is not None else B2TC.nchw_to_nhwc(z, False)[0]   # integer |z| <= 256: exact in bf16
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, zh, None, P["deconv1"], D.deconv1.bias, gdn=P["igdn1"], gdn_mode=2)
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, h[0], None, P["deconv2"], D.deconv2.bias, gdn=P["igdn2"], gdn_mode=2)
@@ -189,11 +213,15 @@ class ImageCompressor(nn.Module):
         tc_path = self._use_tc(x)
         self.last_path = "tcgen05" if tc_path else "fp32"
         if tc_path:
+            self.check_latent_range()
+            if self._zflag is None:
+                self._zflag = B2F.RangeFlag()
             x = B2F._prep(x.float(), "input image")
             feature = self.encode_tc(x)
             z, zh, image_bits = B2F.quant_entropy_infer(feature, [p.detach().reshape(-1) for p in
                                                                   self.bitEstimator.param_list()],
-                                                        lut=self._packed_weights()["bits_lut"])
+                                                        lut=self._packed_weights()["bits_lut"],
+                                                        range_flag=self._zflag)
             total_bits, plane_bits = image_bits.sum(), None      # per-plane bits only on the fp32 path
             clipped_recon_image, sse = self.decode_tc(z, ref_image=x, z_nhwc=zh)
             sse_total = sse[:, 0].sum()

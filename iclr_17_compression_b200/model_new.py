@@ -27,6 +27,8 @@ class ImageCompressor_new(ImageCompressor):
             raise ValueError(f"expected [B,3,H,W] input, got {tuple(x.shape)}")
         if x.size(2) % 16 or x.size(3) % 16:
             raise RuntimeError(f"H and W must be multiples of 16, got {x.size(2)}x{x.size(3)}")
+        if self.training:
+            self._maybe_join_process_group()       # multi-process data parallel under the launcher
         if self._use_tc(x):
             self.last_path = "tcgen05"
             x = B2F._prep(x.float(), "input image")

@@ -1,7 +1,8 @@
 """Mirror of the reference's models/bitEstimator.py: Bitparm / BitEstimator hold the same parameters
-(h, b, a of shape [1,C,1,1], N(0,0.01) init, bitEstimator.py:13-18).  ``BitEstimator.forward(x)``
-returns the factorized CDF like the reference (bitEstimator.py:38-42); ImageCompressor uses the fused
-quantize+bits kernel instead of calling it twice."""
+(h, b, a of shape [1,C,1,1], N(0,0.01) init, bitEstimator.py:13-18).  ``Bitparm.forward`` (bitEstimator.py:20-25) and
+``BitEstimator.forward(x)`` (the factorized CDF, bitEstimator.py:38-42) run libb2c's ``b2c_bitparm_fwd/bwd`` with
+autograd, for callers that evaluate the CDF themselves (model.py:71-72 pattern, entropy-coder tables);
+ImageCompressor uses the fused quantize+bits kernel instead of calling the chain twice."""
 import torch
 import torch.nn as nn
 
@@ -19,6 +20,10 @@ class Bitparm(nn.Module):
         else:
             self.a = None
 
+    def forward(self, x):
+        """bitEstimator.py:20-25"""
+        return B2F.bitparm(x, self.h, self.b, None if self.final else self.a)
+
 
 class BitEstimator(nn.Module):
     def __init__(self, channel):
@@ -27,6 +32,10 @@ class BitEstimator(nn.Module):
         self.f2 = Bitparm(channel)
         self.f3 = Bitparm(channel)
         self.f4 = Bitparm(channel, True)
+
+    def forward(self, x):
+        """bitEstimator.py:38-42: CDF = f4(f3(f2(f1(x))))"""
+        return self.f4(self.f3(self.f2(self.f1(x))))
 
     def param_list(self):
         """the 11 per-channel vectors in libb2c order (include/b2c.h)."""

@@ -15,7 +15,13 @@ class FusedAdamClamp(torch.optim.Optimizer):
 
     ``flat_grads``: optional flat fp32 tensor of which every ``p.grad`` is a view, in parameter order (e.g.
     ``GraphedTrainStep.flat``); without it the gradients are gathered into an internal flat buffer first.
-    ``param_groups[0]['lr']`` may be changed between steps (train.py:69-81 does)."""
+    ``param_groups[0]['lr']`` may be changed between steps (train.py:69-81 does).
+
+    ``state_dict()`` / ``load_state_dict()`` carry the moments and the step count in torch.optim.Adam's own layout
+    (``state[i] = {step, exp_avg, exp_avg_sq}`` per parameter), so a run can resume - also from / into a checkpoint of
+    ``torch.optim.Adam`` itself.  Without ``flat_grads``, parameters whose ``.grad`` is None are skipped like Adam
+    skips them (no decay of their moments, no update); one step counter is shared by all parameters, so a parameter
+    that skipped steps uses the global count in its bias correction (torch keeps one count per parameter)."""
 
     def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_clip=5.0, flat_grads=None):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, grad_clip=grad_clip))
@@ -50,17 +56,58 @@ class FusedAdamClamp(torch.optim.Optimizer):
             self._lr_host = lr
 
     def _grads(self):
+        """-> (flat gradient buffer, list of (first, last+1) index runs of parameters that have a gradient)"""
         if self._flat is not None:
-            return self._flat
+            return self._flat, [(0, len(self._ps))]
         if self._own_flat is None:
             self._own_flat = torch.zeros_like(self.exp_avg)
             o, self._views = 0, []
             for p in self._ps:
                 self._views.append(self._own_flat[o:o + p.numel()].view_as(p))
                 o += p.numel()
-        gs = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self._ps]
-        torch._foreach_copy_(self._views, gs)
-        return self._own_flat
+        have = [i for i, p in enumerate(self._ps) if p.grad is not None]
+        if have:
+            torch._foreach_copy_([self._views[i] for i in have], [self._ps[i].grad for i in have])
+        runs = []
+        for i in have:
+            if runs and runs[-1][1] == i:
+                runs[-1][1] = i + 1
+            else:
+                runs.append([i, i + 1])
+        return self._own_flat, [tuple(r) for r in runs]
+
+    # ---- checkpointing in torch.optim.Adam's layout (train.py saves only the weights; a resumed run needs these)
+    def state_dict(self):
+        sd = super().state_dict()
+        step = self.step_t.detach().cpu().to(torch.float32).reshape(())
+        o, state = 0, {}
+        for i, p in enumerate(self._ps):
+            n = p.numel()
+            state[i] = {"step": step.clone(), "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+            o += n
+        sd["state"] = state
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        state = state_dict.get("state", {})
+        super().load_state_dict({"state": {}, "param_groups": state_dict["param_groups"]})
+        o, steps = 0, []
+        for i, p in enumerate(self._ps):
+            n = p.numel()
+            st = state.get(i, state.get(str(i)))
+            if st is not None:
+                self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.append(int(float(st["step"])))
+            else:
+                self.exp_avg[o:o + n].zero_()
+                self.exp_avg_sq[o:o + n].zero_()
+            o += n
+        self.step_t.fill_(max(steps) if steps else 0)
+        self._lr_host = None                      # force the next sync_lr() to push param_groups[0]['lr']
+        self.sync_lr()
 
     @torch.no_grad()
     def step(self, closure=None, capturing=False):
@@ -69,13 +116,23 @@ class FusedAdamClamp(torch.optim.Optimizer):
         if not capturing:
             self.sync_lr()
         g = self.param_groups[0]
-        flat = self._grads()
+        flat, runs = self._grads()
+        if not runs:
+            return None                                                # no parameter has a gradient: Adam does nothing
         self.step_t.add_(1)
         lib = _lib.load()
+        vp, sz = ctypes.c_void_p, ctypes.sizeof(ctypes.c_void_p)
         with torch.cuda.device(flat.device):
-            _lib.check(lib.b2c_adam_clamp_step(ctypes.cast(self._ptrs, ctypes.POINTER(ctypes.c_void_p)),
-                                               ctypes.cast(self._sizes, ctypes.POINTER(ctypes.c_size_t)), len(self._ps),
-                                               _p(flat), _p(self.exp_avg), _p(self.exp_avg_sq), _p(self.step_t),
-                                               _p(self.lr_t), float(g["betas"][0]), float(g["betas"][1]),
-                                               float(g["eps"]), float(g["grad_clip"]), _stream()), "adam_clamp_step")
+            for first, last in runs:             # one launch per run of consecutive parameters that have a gradient
+                off = sum(p.numel() for p in self._ps[:first]) * 4
+                _lib.check(lib.b2c_adam_clamp_step(
+                    ctypes.cast(ctypes.byref(self._ptrs, first * sz), ctypes.POINTER(vp)),
+                    ctypes.cast(ctypes.byref(self._sizes, first * ctypes.sizeof(ctypes.c_size_t)),
+                                ctypes.POINTER(ctypes.c_size_t)), last - first,
+                    vp(flat.data_ptr() + off), vp(self.exp_avg.data_ptr() + off), vp(self.exp_avg_sq.data_ptr() + off),
+                    _p(self.step_t), _p(self.lr_t), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                    float(g["grad_clip"]), _stream()), "adam_clamp_step")
+        # the parameters changed underneath their tensors (no _version bump): invalidate packed-weight caches.  When
+        # this call is being captured into a graph the replaying caller bumps once per replay (GraphedTrainStep).
+        _lib.bump_weights_epoch()
         return None

@@ -224,9 +224,12 @@ def step_forward(x, noise, prm, pool=None, grad_scale=None):
             "sse_partial": sse_partial, "g_recon": g_recon}
 
 
-def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None):
+def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, g_clipped=None, g_z=None):
     """Backward of the training step: gradients of ``g_sse * sum (recon - x)^2 + g_bits * total_bits`` for the 30
-    parameters (name -> tensor).  ``out`` (name -> zero-filled fp32 tensor of the parameter's shape, e.g. views of one
+    parameters (name -> tensor).  ``g_clipped`` / ``g_z``: optional cotangents of the clamped reconstruction and of
+    the noisy latent - the route a caller takes who builds the loss from the HEAD return tuple (model.py:80:
+    ``lam * mse(clipped, x) + bpp``); clamp passes its gradient where 0 <= recon <= 1, and z = y + noise feeds both
+    the synthesis transform and the entropy model, so ``g_z`` simply adds to d loss / d z.  ``out`` (name -> zero-filled fp32 tensor of the parameter's shape, e.g. views of one
     flat buffer) receives the gradients in place; ``pool`` supplies zero-filled scratch.  ``on_decoder_done`` is
     called (on the main stream, with the fork object) once every Decoder.* and bitEstimator.* gradient kernel has
     been enqueued - the hook a data-parallel caller uses to start reducing that bucket while the encoder backward runs."""
@@ -267,8 +270,11 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None):
     if g_recon is None:
         g_recon = torch.empty_like(recon)
         with torch.cuda.device(dev):
-            _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _vp(0), _p(g_sse), _p(g_recon), recon.numel(), _stream()),
-                       "clamp_sse_bwd")
+            _lib.check(lib.b2c_clamp_sse_bwd(_p(recon), _p(x), _p(g_clipped), _p(g_sse), _p(g_recon), recon.numel(),
+                                             _stream()), "clamp_sse_bwd")
+    elif g_clipped is not None:
+        raise _lib.B2CError("the fused distortion epilogue (grad_scale) has no cotangent input for the clamped "
+                            "reconstruction; run step_forward without grad_scale")
     # ---- deconv3 (9x9/4, 128 -> 3): weight grad (im2col MN-major tcgen05), dgrad (= conv 9x9/4) + IGDN2 backward fused
     grads["Decoder.deconv3.weight"] = fork.run(lambda: T.wgrad9(i2, g_recon, out=dst("Decoder.deconv3.weight")), g_recon)
     grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon, dst("Decoder.deconv3.bias")), g_recon)
@@ -291,6 +297,8 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None):
     if on_decoder_done is not None:
         on_decoder_done(fork)
     fork.main.wait_stream(ent_stream)                  # dz comes from the entropy backward (first forked task)
+    if g_z is not None:
+        dz.add_(g_z)                                   # external cotangent of the noisy latent
     ks = _ksplit() if gp_d1.shape[0] * gp_d1.shape[1] * gp_d1.shape[2] <= 148 * 128 * 4 else 1
     if ks > 1:     # split-K CTAs ADD into their output: accumulate on top of d bits / dz (z = y + noise -> dz/dy = 1)
         g_y = T.layer_run(T.TC_CONV5S2, gp_d1, None, pk["d1_dg"], None, out_f32_nchw=True, ksplit=ks, out=dz)
@@ -330,17 +338,23 @@ class TrainStepTC(torch.autograd.Function):
         sse_total = st["sse"][:, 0].sum()
         ctx.st = st
         ctx.stats = (st["image_bits"], st["plane_bits"], st["sse"])
-        ctx.mark_non_differentiable(st["clipped"], st["z"])
+        # all four outputs are differentiable (model.py:80 hands clipped and z to the caller); unused ones arrive
+        # as None in backward instead of materialised zero tensors
+        ctx.set_materialize_grads(False)
         return st["clipped"], sse_total, total_bits, st["z"]
 
     @staticmethod
-    def backward(ctx, _g_clipped, g_sse, g_bits, _g_z):
+    def backward(ctx, g_clipped, g_sse, g_bits, g_z):
         st = ctx.st
+        if st is None:
+            raise _lib.B2CError("TrainStepTC: backward called twice (the saved activations were released)")
         dev = st["z"].device
         zero = torch.zeros((1,), device=dev, dtype=torch.float32)
         g_sse = g_sse.reshape(1).float().contiguous() if g_sse is not None else zero
         g_bits = g_bits.reshape(1).float().contiguous() if g_bits is not None else zero
-        grads = step_backward(st, g_sse, g_bits)
+        g_clipped = g_clipped.float().contiguous() if g_clipped is not None else None
+        g_z = g_z.float().contiguous() if g_z is not None else None
+        grads = step_backward(st, g_sse, g_bits, g_clipped=g_clipped, g_z=g_z)
         prm = st["prm"]
         ctx.st = None
         return (None, None) + tuple(grads[k].reshape(prm[k].shape) for k in PARAM_ORDER)
@@ -551,6 +565,9 @@ class GraphedTrainStep:
         elif self.world > 1 and not self.ar_in_graph:
             import torch.distributed as dist
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
-        if self.optimizer is not None and not self._opt_in_graph:
-            self.optimizer.step()
+        if self.optimizer is not None:
+            if self._opt_in_graph:
+                _lib.bump_weights_epoch()                            # the replay updated the parameters in place
+            else:
+                self.optimizer.step()
         return self.loss

@@ -118,17 +118,33 @@ size_t b2c_quant_entropy_infer_workspace_bytes(int B, int HW);
  * z_nhwc_bf16 != NULL) and sums table entries (|z| > half_range falls back to the formula): an HBM-bound pass.
  * Requires C % 8 == 0, C <= 256 and HW % 4 == 0; same workspace as b2c_quant_entropy_infer. */
 int b2c_entropy_lut_build(const float* const* host_params, float* lut, int C, int half_range, void* stream);
+/* range_flag (both forms; may be NULL): a device-accessible int (device memory, or mapped pinned host memory so the
+ * host can poll it without synchronising) that the kernel sets to 1 when some |z| > 256 - beyond that the bf16 copy
+ * z_nhwc_bf16 is no longer exact and the tensor-core synthesis transform must not consume it.  Sticky: never cleared
+ * by the library. */
 int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params, const float* lut, int half_range,
-                                float* z, void* z_nhwc_bf16, float* image_bits, int B, int C, int HW, void* workspace,
-                                size_t workspace_bytes, void* stream);
+                                float* z, void* z_nhwc_bf16, float* image_bits, int* range_flag, int B, int C, int HW,
+                                void* workspace, size_t workspace_bytes, void* stream);
 int b2c_quant_entropy_infer(const float* y, const float* const* host_params, float* z, void* z_nhwc_bf16,
-                            float* image_bits, int B, int C, int HW, void* workspace, size_t workspace_bytes,
-                            void* stream);
+                            float* image_bits, int* range_flag, int B, int C, int HW, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* backward of total_bits = sum(image_bits): g_bits is a DEVICE scalar (dL/dtotal_bits).
  * dz[B,C,HW] out (assigned); host_dparams: HOST array of 11 device pointers [C], must be
  * zero-filled by the caller (atomically accumulated). */
 int b2c_entropy_bwd(const float* z, const float* const* host_params, const float* g_bits,
                     float* dz, float* const* host_dparams, int B, int C, int HW, void* stream);
+
+/* One Bitparm layer as a stand-alone call: models/bitEstimator.py:20-25 (non-final: t = x*softplus(h)+b,
+ * out = t + tanh(t)*tanh(a); final (a == NULL): out = sigmoid(t)).  Four of them chained are BitEstimator.forward
+ * (bitEstimator.py:38-42), the CDF a caller evaluates itself (model.py:71-72).  x, out [B,C,HW]; h, b, a [C].
+ * Exact fp32 formula.  Backward: dx assigned, dh/db/da[C] assigned (deterministic fixed-order sums);
+ * workspace: 3*B*C floats. */
+int b2c_bitparm_fwd(const float* x, const float* h, const float* b, const float* a, float* out,
+                    int B, int C, int HW, void* stream);
+size_t b2c_bitparm_bwd_workspace_bytes(int B, int C);
+int b2c_bitparm_bwd(const float* x, const float* h, const float* b, const float* a, const float* g,
+                    float* dx, float* dh, float* db, float* da, int B, int C, int HW,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Distortion: model.py:59 (clamp) and :61 (mse on the UNclamped reconstruction),

@@ -28,9 +28,10 @@ class Toy(torch.nn.Module):
         self.bitEstimator = torch.nn.ModuleDict({"f1": torch.nn.Linear(4, 1)})
         self.unused = torch.nn.Linear(2, 2)              # never gets a gradient
 
-    def forward(self, x):
+    def forward(self, x, rate=True):
         h = self.Encoder["conv3"](self.Encoder["conv2"](self.Encoder["conv1"](x)))
-        return self.Decoder["deconv3"](self.Decoder["deconv1"](h)).pow(2).mean() + self.bitEstimator["f1"](h).mean()
+        d = self.Decoder["deconv3"](self.Decoder["deconv1"](h)).pow(2).mean()
+        return d + self.bitEstimator["f1"](h).mean() if rate else d
 
 
 def _worker(rank, world, port, q):
@@ -69,6 +70,37 @@ def _worker(rank, world, port, q):
                 ok &= p.grad is None
             else:
                 ok &= torch.allclose(p.grad, e / world, rtol=1e-6, atol=1e-7)
+        # a step in which some parameters get NO gradient (loss without the rate term) must still be
+        # finished and averaged, and must not poison the following steps
+        def expected(rate, scale):
+            acc = None
+            for r in range(world):
+                ref.zero_grad(set_to_none=True)
+                ref(xs[r] * scale, rate=rate).backward()
+                g = [p.grad.clone() if p.grad is not None else None for p in ref.parameters()]
+                acc = g if acc is None else [a + b if a is not None else None for a, b in zip(acc, g)]
+            return acc
+        ok_partial = True
+        for rate, scale in ((False, 3.0), (True, 4.0), (False, 5.0)):
+            for p in m.parameters():
+                p.grad = None
+            m(xs[rank] * scale, rate=rate).backward()
+            if not sync.auto_finish:
+                sync.finish()
+            for p, e in zip(m.parameters(), expected(rate, scale)):
+                if e is None:
+                    ok_partial &= p.grad is None
+                else:
+                    ok_partial &= torch.allclose(p.grad, e / world, rtol=1e-6, atol=1e-7)
+            ok_partial &= all(b["ready"] == 0 and b["work"] is None for b in sync.buckets)
+        ok &= ok_partial
+        # bucket prefixes are canonical: ImageCompressor_twoSteps (Encoder1 / Decoder1) gets the same three buckets
+        from iclr_17_compression_b200.model_twoSteps import ImageCompressor_twoSteps
+        m2 = ImageCompressor_twoSteps(8)
+        s2 = GradSync(m2, broadcast_parameters=False)
+        ok &= len(s2.buckets) == 3 and all(n.startswith("Decoder.") for n, _ in s2.buckets[0]["members"])
+        ok &= sum(len(b["members"]) for b in s2.buckets) == 30
+        s2.remove()
         s, e = shard_range(24, rank, world)
         stats = gather_stats(torch.arange(s, e, dtype=torch.float32)[:, None])
         q.put((rank, same, ok, len(sync.buckets), (s, e), stats.flatten().tolist()))

@@ -504,3 +504,151 @@ def test_twosteps_model_matches_reference_golden(tmp_path):
     _, mse, bpp_t = m(c.x.cuda())
     (8192.0 * mse + bpp_t).backward()
     assert m.last_path == "tcgen05-bf16-train" and m.Encoder1.conv1.weight.grad is not None
+
+
+# ------------------------------------------------------------------------------ round-1 advisor findings
+def test_tc_train_step_latent_mode_cotangents():
+    """HEAD return tuple (model.py:80) on the bf16 tensor-core training path: a loss built from the clamped
+    reconstruction and the noisy latent must reach every parameter - compared against the exact-fp32 kernels."""
+    c = Case("train_W1_S_n128_64")
+    x, noise = c.x.cuda(), c.noise.cuda()
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    wz = torch.randn(noise.shape, device="cuda", generator=gen) * 1e-3
+    grads = {}
+    for fast in (True, False):
+        m = _model(c, return_mode="latent").train()
+        m.fast_training = fast
+        m.noise_override = noise
+        clipped, z, bpp = m(x)
+        assert m.last_path == ("tcgen05-bf16-train" if fast else "fp32")
+        assert clipped.requires_grad and z.requires_grad
+        loss = c.lam * torch.mean((clipped - x) ** 2) + bpp + (z * wz).sum()
+        loss.backward()
+        grads[fast] = {k: p.grad.clone() for k, p in m.named_parameters()}
+        assert all(p.grad is not None for p in m.parameters())
+    for k in grads[True]:
+        r = _rel(grads[True][k], grads[False][k])
+        assert r <= REL_GRAD, (k, r)
+    # distortion only, through the clamped reconstruction alone: the rate model gets no gradient, the transforms do
+    m = _model(c, return_mode="latent").train()
+    m.noise_override = noise
+    clipped, z, bpp = m(x)
+    torch.mean((clipped - x) ** 2).backward()
+    assert float(m.Decoder.deconv3.weight.grad.abs().max()) > 0 and float(m.Encoder.conv1.weight.grad.abs().max()) > 0
+    assert float(m.bitEstimator.f1.h.grad.abs().max()) == 0.0
+
+
+def test_eval_after_fused_optimizer_uses_fresh_weights():
+    """eval -> fused clamp + Adam steps (raw-pointer updates: tensor versions do not move) -> eval must re-pack the
+    tensor-core weight panels, GDN packs and the entropy table: same outputs as a freshly built model."""
+    import iclr_17_compression_b200 as P
+    from iclr_17_compression_b200.train_tc import GraphedTrainStep
+    from iclr_17_compression_b200.optim import FusedAdamClamp
+    c = Case("train_W1_S_n128_64")
+    x, noise = c.x.cuda(), c.noise.cuda()
+    for in_graph in (True, False):
+        m = _model(c, return_mode="latent").eval()
+        with torch.no_grad():
+            _, z0, bpp0 = m(x)                                   # packs the weights
+        m.train()
+        if in_graph:
+            step = GraphedTrainStep(m, x, c.lam, optimizer="adam")
+            step.optimizer.param_groups[0]["lr"] = 1e-2
+            for _ in range(3):
+                step(x, noise)
+        else:
+            opt = FusedAdamClamp(m.parameters(), lr=1e-2)
+            for _ in range(3):
+                m.zero_grad()
+                _, _, bpp = m(x)
+                bpp.backward()
+                opt.step()
+        m.eval()
+        fresh = P.ImageCompressor(c.N)
+        fresh.load_state_dict(m.state_dict())
+        fresh = fresh.cuda().eval()
+        with torch.no_grad():
+            c1, z1, bpp1 = m(x)
+            c2, z2, bpp2 = fresh(x)
+        assert m.last_path == "tcgen05"
+        assert torch.equal(z1, z2) and torch.equal(c1, c2) and bpp1.item() == bpp2.item()
+        assert abs(bpp1.item() - bpp0.item()) > 1e-6 * bpp0.item(), "the optimizer steps should have changed the rate"
+
+
+def test_fused_adam_state_dict_and_missing_grads():
+    """optimizer.state_dict() / load_state_dict() carry the moments in torch.optim.Adam's layout (interchangeable with
+    it); parameters without a gradient are skipped as torch skips them."""
+    from iclr_17_compression_b200.optim import FusedAdamClamp
+    torch.manual_seed(3)
+    shapes = [(5, 7), (16,), (3, 2, 2)]
+    pa = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    pc = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ref, opt = torch.optim.Adam(pa, lr=1e-2), FusedAdamClamp(pb, lr=1e-2, grad_clip=0.0)
+    g = torch.Generator(device="cuda").manual_seed(1)
+
+    def grads(skip=None):
+        out = []
+        for i, s in enumerate(shapes):
+            out.append(None if i == skip else torch.randn(s, device="cuda", generator=g))
+        return out
+
+    def apply(params, gs):
+        for p, gr in zip(params, gs):
+            p.grad = None if gr is None else gr.clone()
+
+    for it in range(3):
+        gs = grads()
+        apply(pa, gs), apply(pb, gs)
+        ref.step(), opt.step()
+    sd = opt.state_dict()
+    assert set(sd["state"]) == {0, 1, 2} and float(sd["state"][0]["step"]) == 3.0
+    for i in range(3):
+        assert _rel(sd["state"][i]["exp_avg"], ref.state_dict()["state"][i]["exp_avg"]) < 1e-6
+        assert _rel(sd["state"][i]["exp_avg_sq"], ref.state_dict()["state"][i]["exp_avg_sq"]) < 1e-6
+    # resume a NEW fused optimizer from torch Adam's own checkpoint, continue both
+    for p, q in zip(pc, pa):
+        p.data.copy_(q.data)
+    opt2 = FusedAdamClamp(pc, lr=5e-2, grad_clip=0.0)
+    opt2.load_state_dict(ref.state_dict())
+    assert opt2.param_groups[0]["lr"] == 1e-2
+    gs = grads()
+    apply(pa, gs), apply(pc, gs)
+    ref.step(), opt2.step()
+    for a, cpar in zip(pa, pc):
+        assert _rel(cpar, a) < 1e-6
+    # a parameter without a gradient: untouched, moments untouched (torch.optim.Adam skips it)
+    before = pb[1].detach().clone()
+    m_before = opt.exp_avg.clone()
+    apply(pb, grads(skip=1))
+    opt.step()
+    assert torch.equal(pb[1], before)
+    o = shapes[0][0] * shapes[0][1]
+    assert torch.equal(opt.exp_avg[o:o + 16], m_before[o:o + 16]) and not torch.equal(opt.exp_avg[:o], m_before[:o])
+
+
+def test_latent_range_guard_of_the_bf16_synthesis_path():
+    """|z| > 256 is not exact in bf16: the tensor-core forward raises its sticky flag, the next call fails loudly and
+    the model falls back to the exact-fp32 kernels; decode_tc on caller-supplied latents routes by range."""
+    from iclr_17_compression_b200._lib import B2CError
+    c = Case("eval_W1_U_n128_64")
+    m = _model(c).eval()
+    x = c.x.cuda()
+    with torch.no_grad():
+        m(x)
+        torch.cuda.synchronize()
+        m.check_latent_range()                                   # normal latents: nothing raised
+        m.Encoder.conv3.weight.mul_(400.0)                        # latents far beyond +-256
+        _, z, _ = m(x)
+        assert m.last_path == "tcgen05" and float(z.abs().max()) > 256
+        torch.cuda.synchronize()
+        with pytest.raises(B2CError):
+            m(x)
+        assert m.fast_inference is False
+        c_ok, z_ok, _ = m(x)                                     # exact-fp32 kernels now
+        assert m.last_path == "fp32" and torch.equal(z_ok, z)
+        # caller-supplied latents: beyond the range the fp32 synthesis transform runs, below it the tensor-core one
+        r_big = m.decode_tc(z)
+        assert _rel(r_big, m.Decoder(z)) < 1e-6
+        z_small = torch.round(z / 400.0)
+        assert _rel(m.decode_tc(z_small), m.Decoder(z_small)) < 2e-2

@@ -275,3 +275,35 @@ def test_allreduce_symm_peer_form_single_device(world):
                                   ct.c_float(1.0), st) != 0
     assert lib.b2c_allreduce_symm(ct.cast(ptrs, ct.POINTER(ct.c_void_p)), ct.c_void_p(0), world, world, n,
                                   ct.c_float(1.0), st) != 0
+
+
+def test_bit_estimator_module_forward_matches_reference_golden():
+    """model.bitEstimator(x) and Bitparm(x) are module calls in the reference (bitEstimator.py:20-42,
+    model.py:71-72); values and gradients against the real reference classes (tests/golden/cdf_W1_n32.npz)."""
+    import os
+    import numpy as np
+    import iclr_17_compression_b200 as P
+    from golden_util import GOLDEN_DIR, weights
+    g = np.load(os.path.join(GOLDEN_DIR, "cdf_W1_n32.npz"))
+    N = int(g["N"])
+    be = P.BitEstimator(N)
+    be.load_state_dict({k[len("bitEstimator."):]: v for k, v in weights(N, "W1").items() if k.startswith("bitEstimator.")})
+    be = be.cuda()
+    gen = torch.Generator().manual_seed(4004)
+    x = ((torch.rand(2, N, 5, 7, generator=gen) - 0.5) * 16.0).cuda().requires_grad_(True)
+    w = torch.randn(2, N, 5, 7, generator=gen).cuda()
+    cdf = be(x)
+    np.testing.assert_allclose(cdf.detach().cpu().numpy(), g["cdf"], rtol=2e-6, atol=2e-7)
+    np.testing.assert_allclose(be.f1(x).detach().cpu().numpy(), g["f1"], rtol=2e-6, atol=2e-7)
+    (cdf * w).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["dx"], rtol=1e-4, atol=1e-7)
+    for k, p in be.named_parameters():
+        assert _rel(p.grad, torch.from_numpy(g["d/" + k])) < 1e-5, k
+    # the reference's own usage pattern (model.py:71-73) agrees with the fused kernel's bit count
+    m = P.ImageCompressor(N).cuda().eval()
+    m.bitEstimator.load_state_dict(be.state_dict())
+    z = torch.round((torch.rand(2, N, 4, 6, generator=gen) - 0.5) * 10.0).cuda()
+    prob = m.bitEstimator(z + 0.5) - m.bitEstimator(z - 0.5)
+    bits = torch.sum(torch.clamp(-1.0 * torch.log(prob + 1e-10) / 0.6931471805599453, 0, 50))
+    _, total, _, _ = m.bitEstimator.bits(z, None)
+    assert abs(bits.item() - total.item()) <= 1e-5 * total.item()

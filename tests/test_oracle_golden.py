@@ -116,3 +116,27 @@ def test_msssim_oracle_matches_reference():
         sv, cs = O.ssim_per_image(y, x, O._gauss_1d(11, 1.5), 1.0)
         np.testing.assert_allclose(sv.numpy(), g[f"{tag}/ssim"], rtol=1e-6)
         np.testing.assert_allclose(cs.numpy(), g[f"{tag}/cs"], rtol=1e-6)
+
+
+def test_cdf_oracle_matches_reference_module():
+    """BitEstimator.forward / Bitparm.forward as module calls (bitEstimator.py:20-42): the oracle's bit_estimator /
+    bitparm against values and gradients produced by the real reference classes (tests/golden/make_cdf_golden.py)."""
+    import os
+    import numpy as np
+    import torch
+    from golden_util import GOLDEN_DIR, weights
+    from oracle import balle17_oracle as O
+    g = np.load(os.path.join(GOLDEN_DIR, "cdf_W1_n32.npz"))
+    N = int(g["N"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in weights(N, "W1").items() if k.startswith("bitEstimator.")}
+    gen = torch.Generator().manual_seed(4004)
+    x = ((torch.rand(2, N, 5, 7, generator=gen) - 0.5) * 16.0).requires_grad_(True)
+    w = torch.randn(2, N, 5, 7, generator=gen)
+    cdf = O.bit_estimator(x, sd)
+    np.testing.assert_allclose(cdf.detach().numpy(), g["cdf"], rtol=1e-6, atol=1e-7)
+    f1 = O.bitparm(x, sd["bitEstimator.f1.h"], sd["bitEstimator.f1.b"], sd["bitEstimator.f1.a"])
+    np.testing.assert_allclose(f1.detach().numpy(), g["f1"], rtol=1e-6, atol=1e-7)
+    (cdf * w).sum().backward()
+    np.testing.assert_allclose(x.grad.numpy(), g["dx"], rtol=1e-5, atol=1e-7)
+    for k, p in sd.items():
+        np.testing.assert_allclose(p.grad.numpy(), g["d/" + k[len("bitEstimator."):]], rtol=1e-4, atol=1e-6, err_msg=k)

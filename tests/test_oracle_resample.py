@@ -94,6 +94,15 @@ def test_datasets_mirror_on_cpu(tmp_path):
         Image.fromarray(R.synth_photo(h, w, n), "RGB").save(tmp_path / f"im{n}.png")
     ds = D.Datasets(str(tmp_path), 32)
     assert len(ds) == 2 and len(D.TestKodakDataset(str(tmp_path))) == 2
+    # datasets.py:63-80: TestKodakDataset items are ToTensor() outputs - fp32 [3, H, W] in [0, 1]
+    from torchvision import transforms
+    kd = D.TestKodakDataset(str(tmp_path))
+    ref_item = transforms.ToTensor()(Image.open(tmp_path / "im0.png").convert("RGB"))
+    assert kd[0].dtype == torch.float32 and tuple(kd[0].shape) == (3, 40, 60) and torch.equal(kd[0], ref_item)
+    raw = D.TestKodakDataset(str(tmp_path), raw=True)[0]
+    assert raw.dtype == torch.uint8 and torch.equal(raw.float().div(255), ref_item)
+    batch = next(iter(torch.utils.data.DataLoader(D.TestKodakDataset(str(tmp_path)), batch_size=1)))
+    assert tuple(batch.shape) == (1, 3, 40, 60) and batch.dtype == torch.float32
     torch.manual_seed(5)
     img, p = ds[0]
     torch.manual_seed(5)
