@@ -93,6 +93,9 @@ class FusedAdamClamp(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         state = state_dict.get("state", {})
         super().load_state_dict({"state": {}, "param_groups": state_dict["param_groups"]})
+        for g in self.param_groups:               # a torch.optim.Adam checkpoint has no grad_clip entry
+            for k, v in self.defaults.items():
+                g.setdefault(k, v)
         o, steps = 0, []
         for i, p in enumerate(self._ps):
             n = p.numel()

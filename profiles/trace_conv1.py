@@ -1,5 +1,5 @@
 """Debug: clock64 timeline of CTA 0 of the persistent CONV1+GDN1 kernel (b2c_tc_debug_set_trace).
-Worker marks per steady-state iteration: patch, kb0+1 built, acc ready, x2[0], kb2, x2[1], kb3, norm ready, stored."""
+Worker marks per steady-state iteration: patch, kb0+1 built, acc ready, x2[0], kb2 + x2[1], kb3, norm ready, stored."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -509,33 +509,55 @@ def test_twosteps_model_matches_reference_golden(tmp_path):
 # ------------------------------------------------------------------------------ round-1 advisor findings
 def test_tc_train_step_latent_mode_cotangents():
     """HEAD return tuple (model.py:80) on the bf16 tensor-core training path: a loss built from the clamped
-    reconstruction and the noisy latent must reach every parameter - compared against the exact-fp32 kernels."""
+    reconstruction and the noisy latent must reach every parameter - compared against the exact-fp32 kernels.
+    clamp's gradient is discontinuous at 0 and 1 (a bf16-sized change of the reconstruction flips the mask of a pixel
+    next to a bound), so the comparison runs with the last layer scaled so that the reconstruction stays inside (0, 1);
+    the mask itself is checked with a reconstruction that lies entirely above 1."""
     c = Case("train_W1_S_n128_64")
     x, noise = c.x.cuda(), c.noise.cuda()
     gen = torch.Generator(device="cuda").manual_seed(11)
     wz = torch.randn(noise.shape, device="cuda", generator=gen) * 1e-3
+
+    def model(bias, scale):
+        m = _model(c, return_mode="latent").train()
+        with torch.no_grad():
+            m.Decoder.deconv3.weight.mul_(scale)
+            m.Decoder.deconv3.bias.fill_(bias)
+        m.noise_override = noise
+        return m
+
+    with torch.no_grad():
+        probe = model(0.5, 1.0)
+        probe.fast_training = False
+        r = probe.Decoder(probe.Encoder(x) + noise) - 0.5
+        scale = 0.25 / float(r.abs().max())                      # reconstruction within 0.5 +- 0.25
     grads = {}
     for fast in (True, False):
-        m = _model(c, return_mode="latent").train()
+        m = model(0.5, scale)
         m.fast_training = fast
-        m.noise_override = noise
         clipped, z, bpp = m(x)
         assert m.last_path == ("tcgen05-bf16-train" if fast else "fp32")
         assert clipped.requires_grad and z.requires_grad
+        assert float(clipped.min()) > 0.0 and float(clipped.max()) < 1.0
         loss = c.lam * torch.mean((clipped - x) ** 2) + bpp + (z * wz).sum()
         loss.backward()
-        grads[fast] = {k: p.grad.clone() for k, p in m.named_parameters()}
         assert all(p.grad is not None for p in m.parameters())
-    for k in grads[True]:
-        r = _rel(grads[True][k], grads[False][k])
-        assert r <= REL_GRAD, (k, r)
-    # distortion only, through the clamped reconstruction alone: the rate model gets no gradient, the transforms do
-    m = _model(c, return_mode="latent").train()
-    m.noise_override = noise
+        grads[fast] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    worst = {k: _rel(grads[True][k], grads[False][k]) for k in grads[True]}
+    bad = {k: v for k, v in worst.items() if v > REL_GRAD}
+    assert not bad, bad
+    # distortion through the clamped reconstruction alone: the rate model gets no gradient, the transforms do
+    m = model(0.5, scale)
     clipped, z, bpp = m(x)
     torch.mean((clipped - x) ** 2).backward()
     assert float(m.Decoder.deconv3.weight.grad.abs().max()) > 0 and float(m.Encoder.conv1.weight.grad.abs().max()) > 0
     assert float(m.bitEstimator.f1.h.grad.abs().max()) == 0.0
+    # reconstruction entirely above 1: clamp passes no gradient at all
+    m = model(5.0, scale)
+    clipped, z, bpp = m(x)
+    assert float(clipped.min()) == 1.0
+    torch.mean((clipped - x) ** 2).backward()
+    assert float(m.Decoder.deconv3.weight.grad.abs().max()) == 0.0 and float(m.Encoder.conv2.weight.grad.abs().max()) == 0.0
 
 
 def test_eval_after_fused_optimizer_uses_fresh_weights():
@@ -646,7 +668,7 @@ def test_latent_range_guard_of_the_bf16_synthesis_path():
             m(x)
         assert m.fast_inference is False
         c_ok, z_ok, _ = m(x)                                     # exact-fp32 kernels now
-        assert m.last_path == "fp32" and torch.equal(z_ok, z)
+        assert m.last_path == "fp32" and float((z_ok - z).abs().max()) <= 1.0   # x400 latents: bf16x3 vs fp32 may flip a rounding
         # caller-supplied latents: beyond the range the fp32 synthesis transform runs, below it the tensor-core one
         r_big = m.decode_tc(z)
         assert _rel(r_big, m.Decoder(z)) < 1e-6
