@@ -79,7 +79,7 @@ SIGNATURES.update({
     "b2c_sigmoid_binarize_fwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_sigmoid_binarize_bwd": (_c_i, [_c_f, _c_f, _c_f, _c_f, _c_sz, _c_f]),
     "b2c_adam_clamp_step": (_c_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t), _c_i, _c_f, _c_f, _c_f,
-                                   _c_f, _c_f, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_f]),
+                                   _c_f, _c_f, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_float, _c_f]),
     "b2c_tc_xsq": (_c_i, [_c_f, _c_f, _c_f, _c_sz, _c_i, _c_f]),
     "b2c_tc_nhwc_colsum": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),
     "b2c_gdn_reparam_bwd": (_c_i, [_c_f] * 6 + [_c_i, _c_f]),

@@ -42,16 +42,25 @@ using namespace b2c::tc;
 constexpr int C = 128;
 constexpr int NCB = 2;                               // gamma k-blocks
 constexpr int NKB = 4;                               // conv k-blocks (K = 243 -> 256)
-constexpr int NWORKERS = 256;
-constexpr int NTHREADS = 64 + NWORKERS;
 constexpr int NP = 2;                                // patch slots (the producer runs one tile ahead)
 constexpr uint32_t B_BYTES = (C / 2) * 128;          // this CTA's half of a 128-row weight / gamma tile
 constexpr uint32_t W_RES = NKB * 2 * B_BYTES;        // 64 KB
 constexpr uint32_t GAMMA_BYTES = NCB * 2 * B_BYTES;  // 32 KB
-constexpr int NWARPS_W = NWORKERS / 32;              // worker warps per CTA
-constexpr uint32_t STG_PLANE = 32 * 64;              // per-warp staging: 32 pixels x 32 channels bf16 of one plane
-constexpr uint32_t STG_WARP = 2 /*blocks*/ * 2 /*hi, lo*/ * STG_PLANE;   // 8 KB: both 64-channel blocks in flight
-constexpr uint32_t STG_BYTES = NWARPS_W * STG_WARP;  // 64 KB
+// NPART worker warps share a TMEM lane quadrant (32 pixel rows), each owning CHP = 64 / NPART of the 64 channels /
+// k values of a block.  NPART = 2 (8 worker warps) is the default; NPART = 4 (16 worker warps, 4 per scheduler) was
+// tried for latency hiding and measured slower (0.171 vs 0.158 ms per 24 images).
+template <int NPART>
+struct Cfg {
+  static_assert(NPART == 2 || NPART == 4, "2 or 4 column parts");
+  static constexpr int NWORKERS = 128 * NPART;
+  static constexpr int NTHREADS = 64 + NWORKERS;
+  static constexpr int NWARPS_W = 4 * NPART;                 // worker warps per CTA
+  static constexpr int CHP = 64 / NPART;                     // channels (= k values, = TMEM columns) per thread and block
+  static constexpr int NW = CHP / 2;                         // packed bf16x2 words per plane
+  static constexpr uint32_t STG_PLANE = 32 * CHP * 2;        // per-warp staging: 32 pixels x CHP channels of one plane
+  static constexpr uint32_t STG_WARP = 2 /*blocks*/ * 2 /*hi, lo*/ * STG_PLANE;
+};
+constexpr uint32_t STG_BYTES = 64 * 1024;            // = NWARPS_W * STG_WARP for either NPART
 constexpr uint32_t SMEM = W_RES + GAMMA_BYTES + STG_BYTES + NP * P1_SLOT + 1024 /*align*/ + 1024 /*bias, beta*/ +
                           512 /*barriers*/;
 static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -80,6 +89,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
+__device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T over the CTA pair (M = 256: each CTA supplies the 128 rows held in its own TMEM
@@ -94,15 +115,15 @@ __device__ __forceinline__ void umma_bf16_pair_ts(uint32_t d_tmem, uint32_t a_tm
       : "memory");
 }
 
-// CONV1 im2col: the 32 values k = KB*64 + HALF*32 .. +31 (k = c*81 + ky*9 + kx, zero for k >= 243) of the pixel whose
-// patch origin is `pp` (16-byte aligned), as 16 packed bf16x2 hi words (w[0..15], pair i = k0+2i, k0+2i+1) followed by
-// the 16 lo words (w[16..31]).  Same fetch pattern as tc::conv1_build_row (two conflict-free LDS.128 + one LDS.32 per
-// (c, ky) patch row, only the pieces this k range uses); every index is a compile-time constant.
-template <int KB, int HALF>
-__device__ __forceinline__ void conv1_build_regs(const float* __restrict__ pp, uint32_t (&w)[32]) {
-  constexpr int K0 = KB * 64 + HALF * 32;
+// CONV1 im2col: the CHP values k = KB*64 + PART*CHP .. (k = c*81 + ky*9 + kx, zero for k >= 243) of the pixel whose
+// patch origin is `pp` (16-byte aligned), as CHP/2 packed bf16x2 hi words (pair i = k0+2i, k0+2i+1) followed by the
+// CHP/2 lo words.  Same fetch pattern as tc::conv1_build_row (two conflict-free LDS.128 + one LDS.32 per (c, ky) patch
+// row, only the pieces this k range uses); every index is a compile-time constant.
+template <int KB, int PART, int CHP>
+__device__ __forceinline__ void conv1_build_regs(const float* __restrict__ pp, uint32_t (&w)[CHP]) {
+  constexpr int K0 = KB * 64 + PART * CHP;
   constexpr int G0 = K0 / 9;
-  constexpr int G1 = (K0 + 31) / 9;
+  constexpr int G1 = (K0 + CHP - 1) / 9;
   constexpr int NG = G1 - G0 + 1;
   float vals[NG * 12];
 #pragma unroll
@@ -112,7 +133,7 @@ __device__ __forceinline__ void conv1_build_regs(const float* __restrict__ pp, u
       const float* rowf = pp + (g / 9) * P1_PLANE + (g % 9) * P1_W;
       const float4* row = reinterpret_cast<const float4*>(rowf);
       const int klo = (K0 > 9 * g ? K0 : 9 * g) - 9 * g;
-      const int kend = K0 + 31 < 242 ? K0 + 31 : 242;
+      const int kend = K0 + CHP - 1 < 242 ? K0 + CHP - 1 : 242;
       const int khi = (kend < 9 * g + 8 ? kend : 9 * g + 8) - 9 * g;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
       float c8 = 0.f;
@@ -128,20 +149,34 @@ __device__ __forceinline__ void conv1_build_regs(const float* __restrict__ pp, u
     }
   }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < CHP / 2; ++i) {
     const int k = K0 + 2 * i;
     const float v0 = (k < 243) ? vals[(k / 9 - G0) * 12 + (k % 9)] : 0.f;
     const float v1 = (k + 1 < 243) ? vals[((k + 1) / 9 - G0) * 12 + ((k + 1) % 9)] : 0.f;
     w[i] = cvt_bf16x2(v0, v1);
-    w[16 + i] = lo_of(v0, v1, w[i]);
+    w[CHP / 2 + i] = lo_of(v0, v1, w[i]);
   }
 }
+template <int KB, int NPART>
+__device__ __forceinline__ void conv1_build_part(const float* __restrict__ pp, int part, uint32_t (&w)[64 / NPART]) {
+  if (part == 0) conv1_build_regs<KB, 0, 64 / NPART>(pp, w);
+  else if (part == 1) conv1_build_regs<KB, 1, 64 / NPART>(pp, w);
+  else if (NPART == 4 && part == 2) conv1_build_regs<KB, 2 % NPART, 64 / NPART>(pp, w);
+  else conv1_build_regs<KB, 3 % NPART, 64 / NPART>(pp, w);
+}
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// (NPART = 4: 18 warps are allocated as 20 - warp allocation granularity 4 - so the register cap is 96 per thread;
+// ptxas spills ~150 bytes per thread, all in the cold paths.  112 x 576 threads would fit the file but not the allocator.)
+template <int NPART>
+__global__ void __launch_bounds__(Cfg<NPART>::NTHREADS, 1)
 conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_constant__ CUtensorMap tmB_hi,
                     const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmG_hi,
                     const __grid_constant__ CUtensorMap tmG_lo, const __grid_constant__ CUtensorMap tmO_hi,
                     const __grid_constant__ CUtensorMap tmO_lo, const Params p) {
+  using K = Cfg<NPART>;
+  constexpr int NWARPS_W = K::NWARPS_W, CHP = K::CHP, NW = K::NW;
+  constexpr uint32_t STG_PLANE = K::STG_PLANE, STG_WARP = K::STG_WARP;
+  static_assert(NWARPS_W * STG_WARP == STG_BYTES, "staging budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wres = smem;                                // [hi kb0..3][lo kb0..3], 64 rows each
@@ -193,7 +228,7 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
     tma_prefetch_desc(&tmO_hi); tma_prefetch_desc(&tmO_lo);
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, T_COLS);
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + C) {
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + C) {   // (NWORKERS >= 128)
     const int c = threadIdx.x - 64;
     s_bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
     s_beta[c] = p.beta_eff ? __ldg(p.beta_eff + c) : 1.f;
@@ -243,8 +278,9 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
       const uint64_t gam_d = wres_d + (W_RES >> 4);
       uint32_t tile_cnt = 0;                    // epilogue tiles seen so far (phase of the x^2 barriers)
 
-      // conv k-block kb of the tile being accumulated into set `buf`; k16 step k4 = 2h + s lives in the columns of
-      // worker half h: hi words at 32h + 8s, lo words 16 columns further
+      // conv k-block kb of the tile being accumulated into set `buf`; k16 step k4 lives in the columns of worker part
+      // k4 / (4 / NPART): hi words at part * CHP + 8 * (k4 % (4 / NPART)), lo words CHP / 2 columns further
+      constexpr int SPP = 4 / NPART;             // k16 steps per part
       auto conv_kb = [&](int kb, uint32_t buf, bool last) {
         const uint32_t d = tb + T_ACC + buf * 128u;
         const int slot = kb & 1;
@@ -258,7 +294,7 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
-            const uint32_t a_hi = a0 + (uint32_t)((k4 >> 1) * 32 + (k4 & 1) * 8), a_lo = a_hi + 16u;
+            const uint32_t a_hi = a0 + (uint32_t)((k4 / SPP) * CHP + (k4 % SPP) * 8), a_lo = a_hi + (uint32_t)NW;
             umma_bf16_pair_ts(d, a_hi, b_hi + 2 * k4, idesc, acc);
             umma_bf16_pair_ts(d, a_hi, b_lo + 2 * k4, idesc, 1u);
             umma_bf16_pair_ts(d, a_lo, b_hi + 2 * k4, idesc, 1u);
@@ -283,7 +319,7 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint32_t acc = (round > 0 || k4 > 0) ? 1u : 0u;
-            const uint32_t a_hi = a0 + (uint32_t)((k4 >> 1) * 32 + (k4 & 1) * 8), a_lo = a_hi + 16u;
+            const uint32_t a_hi = a0 + (uint32_t)((k4 / SPP) * CHP + (k4 % SPP) * 8), a_lo = a_hi + (uint32_t)NW;
             umma_bf16_pair_ts(d, a_hi, b_hi + 2 * k4, idesc, acc);
             umma_bf16_pair_ts(d, a_hi, b_lo + 2 * k4, idesc, 1u);
             umma_bf16_pair_ts(d, a_lo, b_hi + 2 * k4, idesc, 1u);
@@ -310,53 +346,53 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
       }
     }
   } else {
-    // ================================================================ row workers (8 warps): thread = (pixel r, half)
+    // ================================================================ row workers: thread = (pixel r, column part)
     // No block-level barrier below: a warp's hand-offs are its own (tcgen05 fence, __syncwarp, one mbarrier arrival).
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int ty = r / TW, tx = r - ty * TW;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_ring = t_lane + T_A + (uint32_t)(half * 32);
+    const uint32_t t_ring = t_lane + T_A + (uint32_t)(part * CHP);
     const bool mark = threadIdx.x == 64;
     const int pp_off = (4 * ty) * P1_W + 4 * tx;
     int e_img = 0, e_ox0 = 0, e_oy0 = 0;       // tile whose epilogue runs in the current iteration
-    // this warp's staging slice: [block 0 hi | block 0 lo | block 1 hi | block 1 lo], rows of 64 bytes (32 channels),
-    // 16-byte chunk index XORed with (row >> 1) & 3 = SWIZZLE_64B: the lanes' STS.128 hit 8 distinct bank groups
+    // this warp's staging slice: [block 0 hi | block 0 lo | block 1 hi | block 1 lo], rows of CHP * 2 bytes, 16-byte
+    // chunk index XORed as TMA's SWIZZLE_64B (CHP = 32) / SWIZZLE_32B (CHP = 16) does: conflict-free STS.128
     uint8_t* my_stg = stg + (uint32_t)(warp - 2) * STG_WARP;
-    const uint32_t st_row = (uint32_t)lane * 64u, st_x = ((uint32_t)lane >> 1) & 3u;
+    const uint32_t st_row = (uint32_t)lane * (uint32_t)(CHP * 2);
+    const uint32_t st_x = CHP == 32 ? (((uint32_t)lane >> 1) & 3u) : (((uint32_t)lane >> 2) & 1u);
     int stores = 0;                            // lane 0: bulk store groups committed so far
     griddep_wait();
 
     for (int it = 0; it <= n_it; ++it) {
       const bool B_ = it < n_it, E_ = it >= 1;
       const uint32_t e = (uint32_t)(it - 1), ebuf = e & 1u, epar = (e >> 1) & 1u;
-      const uint32_t t_acc = t_lane + T_ACC + ebuf * 128u, t_nrm = t_lane + T_NORM;
+      const uint32_t t_acc = t_lane + T_ACC + ebuf * 128u + (uint32_t)(part * CHP), t_nrm = t_lane + T_NORM + (uint32_t)(part * CHP);
       const int ps = it % NP;
       const float* pp = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(patch) + ps * P1_SLOT) + pp_off;
-      uint64_t xk[32];                          // x = acc + bias: xk[g*16 + i] = channels g*64 + half*32 + 2i, +1
+      uint64_t xk[2 * NW];                      // x = acc + bias: xk[g*NW + i] = channels g*64 + part*CHP + 2i, +1
 
-      // x^2 (hi | lo) of the 32 channels g*64 + half*32 .. this thread read, stored over the columns they came from
-      auto x2_work = [&](const int g, const uint32_t (&raw)[32]) {
-        const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + g * 64 + half * 32);
-        uint32_t w[32];
+      // x^2 (hi | lo) of the CHP channels g*64 + part*CHP .. this thread read, stored over the columns they came from
+      auto x2_work = [&](const int g, const uint32_t (&raw)[CHP]) {
+        const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + g * 64 + part * CHP);
+        uint32_t w[CHP];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < NW; ++i) {
           const uint64_t x2 = add2(pk2(raw[2 * i], raw[2 * i + 1]), bias2[i]);
-          xk[g * 16 + i] = x2;
+          xk[g * NW + i] = x2;
           float v0, v1;
           upk2(mul2(x2, x2), v0, v1);
           w[i] = cvt_bf16x2(v0, v1);
-          w[16 + i] = lo_of(v0, v1, w[i]);
+          w[NW + i] = lo_of(v0, v1, w[i]);
         }
-        tmem_st32(t_acc + (uint32_t)(g * 64 + half * 32), w);
+        tmem_stN(t_acc + (uint32_t)(g * 64), w);
       };
       auto build = [&](auto kbc) {
         constexpr int KB = decltype(kbc)::value;
-        uint32_t w[32];
-        if (half == 0) conv1_build_regs<KB, 0>(pp, w);
-        else conv1_build_regs<KB, 1>(pp, w);
-        tmem_st32(t_ring + (uint32_t)((KB & 1) * 64), w);
+        uint32_t w[CHP];
+        conv1_build_part<KB, NPART>(pp, part, w);
+        tmem_stN(t_ring + (uint32_t)((KB & 1) * 64), w);
       };
       // my TMEM stores are complete and ordered before the arrival that follows
       auto publish = [&]() {
@@ -383,8 +419,8 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
         mbar_wait(&accum_full[ebuf], epar);
         tcgen05_fence_after();
         T1_MARK(2, mark);                          // [2] conv accumulator ready
-        uint32_t raw[32];
-        tmem_ld32(t_acc + (uint32_t)(half * 32), raw);
+        uint32_t raw[CHP];
+        tmem_ldN(t_acc, raw);
         tmem_ld_wait();
         x2_work(0, raw);
         publish();
@@ -393,8 +429,8 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
       }
       // ---- phase C: k-block 2 of tile `it` (while the gamma MMAs of round 0 run), x^2 round 1
       {
-        uint32_t raw[32];
-        if (E_) tmem_ld32(t_acc + (uint32_t)(64 + half * 32), raw);
+        uint32_t raw[CHP];
+        if (E_) tmem_ldN(t_acc + 64u, raw);
         if (B_) {
           mbar_wait(&a_empty[0], 0u);              // use 2*it + 1
           tcgen05_fence_after();
@@ -422,44 +458,46 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
       }
       // ---- phase E: final pass of tile it-1: y = x * rsqrt(beta + norm) -> NHWC bf16 (hi, lo).
       // 16-column chunks, the TMEM load of chunk j+1 in flight while chunk j is computed (MUFU) and staged; after the
-      // two chunks of a 64-channel block the warp's lane 0 issues the block's two TMA stores.
+      // last chunk of a 64-channel block the warp's lane 0 issues the block's two TMA stores.
       if (E_) {
         mbar_wait(norm_full, e & 1u);
         tcgen05_fence_after();
         T1_MARK(2, mark);                          // [6] norm ready
+        constexpr int CPB = CHP / 16;              // chunks per 64-channel block
         uint32_t rawn[2][16];
-        tmem_ld16(t_nrm + (uint32_t)(half * 32), rawn[0]);
+        tmem_ld16(t_nrm, rawn[0]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {            // chunk j: channels (j >> 1) * 64 + half * 32 + (j & 1) * 16 .. +15
+        for (int j = 0; j < 2 * CPB; ++j) {      // chunk j: channels (j / CPB) * 64 + part * CHP + (j % CPB) * 16 .. +15
+          const int blk = j / CPB, sub = j % CPB;
           tmem_ld_wait();
-          if (j < 3) tmem_ld16(t_nrm + (uint32_t)(((j + 1) >> 1) * 64 + half * 32 + ((j + 1) & 1) * 16), rawn[(j + 1) & 1]);
-          const int c0 = (j >> 1) * 64 + half * 32 + (j & 1) * 16;
-          const uint64_t* beta2 = reinterpret_cast<const uint64_t*>(s_beta + c0);
+          if (j + 1 < 2 * CPB)
+            tmem_ld16(t_nrm + (uint32_t)(((j + 1) / CPB) * 64 + ((j + 1) % CPB) * 16), rawn[(j + 1) & 1]);
+          const uint64_t* beta2 = reinterpret_cast<const uint64_t*>(s_beta + blk * 64 + part * CHP + sub * 16);
           uint32_t hp[8], lp[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float n0, n1, y0, y1;
             upk2(add2(pk2(rawn[j & 1][2 * i], rawn[j & 1][2 * i + 1]), beta2[i]), n0, n1);
             const uint64_t sc = pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
-            upk2(mul2(xk[(j >> 1) * 16 + (j & 1) * 8 + i], sc), y0, y1);
+            upk2(mul2(xk[blk * NW + sub * 8 + i], sc), y0, y1);
             hp[i] = cvt_bf16x2(y0, y1);
             lp[i] = lo_of(y0, y1, hp[i]);
           }
-          uint8_t* sb = my_stg + (uint32_t)(j >> 1) * (2 * STG_PLANE);
-          if ((j & 1) == 0) {                    // the stores that last read this block's slice (previous tile) are done
+          uint8_t* sb = my_stg + (uint32_t)blk * (2 * STG_PLANE);
+          if (sub == 0) {                        // the stores that last read this block's slice (previous tile) are done
             if (lane == 0 && stores >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncwarp();
           }
-          const uint32_t k0 = (uint32_t)(j & 1) * 2u;           // 16-byte chunks k0, k0 + 1 of the 64-byte row
+          const uint32_t k0 = (uint32_t)sub * 2u;                // 16-byte chunks k0, k0 + 1 of the row
           *reinterpret_cast<uint4*>(sb + st_row + (((k0) ^ st_x) << 4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
           *reinterpret_cast<uint4*>(sb + st_row + (((k0 + 1) ^ st_x) << 4)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
           *reinterpret_cast<uint4*>(sb + STG_PLANE + st_row + (((k0) ^ st_x) << 4)) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
           *reinterpret_cast<uint4*>(sb + STG_PLANE + st_row + (((k0 + 1) ^ st_x) << 4)) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
-          if (j & 1) {
+          if (sub == CPB - 1) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              const int cc = (j >> 1) * 64 + half * 32;
+              const int cc = blk * 64 + part * CHP;
               tma_store_4d(&tmO_hi, sb, cc, e_ox0, e_oy0 + 2 * q, e_img);
               tma_store_4d(&tmO_lo, sb + STG_PLANE, cc, e_ox0, e_oy0 + 2 * q, e_img);
               tma_store_commit();
@@ -495,17 +533,17 @@ conv1_gdn_ts_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------ host side
-// NHWC bf16 output [B][Hg][Wg][128] for the per-warp stores: box = 32 channels x 16 x 2 pixels, SWIZZLE_64B
-static int make_warp_out_map(CUtensorMap* m, const void* base, int B, int Hg, int Wg) {
+// NHWC bf16 output [B][Hg][Wg][128] for the per-warp stores: box = chp channels x 16 x 2 pixels, SWIZZLE_64B / _32B
+static int make_warp_out_map(CUtensorMap* m, const void* base, int B, int Hg, int Wg, int chp) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wg * C * 2, (cuuint64_t)Hg * Wg * C * 2};
-  cuuint32_t box[4] = {32, (cuuint32_t)TW, 2, 1};
+  cuuint32_t box[4] = {(cuuint32_t)chp, (cuuint32_t)TW, 2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, chp == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(warp output) failed: %d", (int)r); return B2C_ECUDA; }
   return B2C_OK;
 }
@@ -513,17 +551,31 @@ static int make_warp_out_map(CUtensorMap* m, const void* base, int B, int Hg, in
 // Returns 1 when the layer is not the one this kernel covers (the caller then tries the shared-memory form),
 // otherwise the launch status.  B2C_TC_PERSIST_CONV1: 2 (default) = this kernel, 1 = shared-memory operands
 // (b2c_conv1_tcp.cu), 0 = per-tile kernel.
+template <int NPART>
+static int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);
+
 int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   static const int mode = [] {
     const char* e = getenv("B2C_TC_PERSIST_CONV1");
     return e ? atoi(e) : 2;
   }();
   if (mode != 2) return 1;
+  static const int nparts = [] {               // B2C_CONV1_PARTS=4: 16 worker warps per CTA instead of 8 (measured
+                                               // slower: 0.171 vs 0.158 ms - 96-register cap, twice the arrivals)
+    const char* e = getenv("B2C_CONV1_PARTS");
+    return e && atoi(e) == 4 ? 4 : 2;
+  }();
+  return nparts == 2 ? launch<2>(L, stream, trace) : launch<4>(L, stream, trace);
+}
+
+template <int NPART>
+static int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
+  constexpr int NTHREADS = Cfg<NPART>::NTHREADS;
   const int channels = L->channels ? L->channels : 128;
   if (L->kind != B2C_TC_CONV1 || channels != 128 || !L->split3 || L->gdn != 1 || L->out_f32_nchw || !L->out_lo ||
       L->saved_y || !L->w_lo || !L->gamma_lo)
     return 1;
-  auto kern = conv1_gdn_ts_kernel;
+  auto kern = conv1_gdn_ts_kernel<NPART>;
 
   Params p;
   memset(&p, 0, sizeof(p));
@@ -579,8 +631,8 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   if ((rc = make_mat_map(&mB_lo, L->w_lo, NKB * C, KBLK, C / 2))) return rc;
   if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C, C, C / 2))) return rc;
   if ((rc = make_mat_map(&mG_lo, L->gamma_lo, C, C, C / 2))) return rc;
-  if ((rc = make_warp_out_map(&mO_hi, L->out_hi, L->B, p.Hg, p.Wg))) return rc;
-  if ((rc = make_warp_out_map(&mO_lo, L->out_lo, L->B, p.Hg, p.Wg))) return rc;
+  if ((rc = make_warp_out_map(&mO_hi, L->out_hi, L->B, p.Hg, p.Wg, Cfg<NPART>::CHP))) return rc;
+  if ((rc = make_warp_out_map(&mO_lo, L->out_lo, L->B, p.Hg, p.Wg, Cfg<NPART>::CHP))) return rc;
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) adam_clamp_kernel(const AdamTable T, cons
                                                          float* __restrict__ m, float* __restrict__ v,
                                                          const int* __restrict__ step_dev,
                                                          const float* __restrict__ lr_dev, float beta1, float beta2,
-                                                         float eps, float clip) {
+                                                         float omb1, float omb2, float eps, float clip) {
   __shared__ float s_step_size, s_bc2_sqrt;
   __shared__ unsigned s_start[ADAM_MAX_TENSORS + 1];
   if (threadIdx.x <= T.n) s_start[threadIdx.x] = T.start[threadIdx.x];
@@ -40,8 +40,10 @@ __global__ void __launch_bounds__(256) adam_clamp_kernel(const AdamTable T, cons
     }
     float gi = g[i];
     if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);                 // p.grad.data.clamp_(-5, 5)
-    const float mi = fmaf(1.f - beta1, gi - m[i], m[i]);                 // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = fmaf(1.f - beta2, gi * gi, v[i] * beta2);           // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    // omb = (float)(1.0 - (double)beta): torch forms 1 - beta in double before the scalar becomes fp32
+    // (1.f - 0.999f differs from 0.001f by 4.7e-5 relative)
+    const float mi = fmaf(omb1, gi - m[i], m[i]);                        // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(omb2, gi * gi, v[i] * beta2);                  // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
@@ -56,7 +58,7 @@ using namespace b2c;
 
 extern "C" int b2c_adam_clamp_step(float* const* params, const size_t* numel, int n_tensors, const float* grads_flat,
                                    float* exp_avg, float* exp_avg_sq, const int* step_dev, const float* lr_dev,
-                                   float beta1, float beta2, float eps, float grad_clip, void* stream) {
+                                   double beta1, double beta2, double eps, float grad_clip, void* stream) {
   B2C_REQUIRE(params && numel && grads_flat && exp_avg && exp_avg_sq && step_dev && lr_dev, "adam_clamp_step: null pointer");
   B2C_REQUIRE(n_tensors > 0 && n_tensors <= ADAM_MAX_TENSORS, "adam_clamp_step: 1..%d tensors", ADAM_MAX_TENSORS);
   AdamTable T;
@@ -72,8 +74,9 @@ extern "C" int b2c_adam_clamp_step(float* const* params, const size_t* numel, in
   T.n = n_tensors;
   unsigned blocks = (unsigned)((off + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_clamp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(T, grads_flat, exp_avg, exp_avg_sq, step_dev, lr_dev, beta1,
-                                                             beta2, eps, grad_clip);
+  adam_clamp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(T, grads_flat, exp_avg, exp_avg_sq, step_dev, lr_dev,
+                                                             (float)beta1, (float)beta2, (float)(1.0 - beta1),
+                                                             (float)(1.0 - beta2), (float)eps, grad_clip);
   count_launch();
   return check_launch("adam_clamp_step");
 }

@@ -269,10 +269,11 @@ int b2c_tc_nhwc_to_nchw(const void* in_hi, const void* in_lo, float* out, int B,
  * (host arrays of device pointers / element counts); grads_flat, exp_avg, exp_avg_sq: flat fp32 device buffers holding
  * the gradients and both moments concatenated in the same order; step_dev: device int32 holding the 1-based step number
  * of THIS update; lr_dev: device float learning rate (both read on the device, so a CUDA graph can replay the launch
- * while the host advances them).  grad_clip <= 0 disables the clamp. */
+ * while the host advances them).  grad_clip <= 0 disables the clamp.  beta1 / beta2 / eps are doubles because torch
+ * forms 1 - beta in double before rounding the scalar to fp32. */
 int b2c_adam_clamp_step(float* const* params, const size_t* numel, int n_tensors, const float* grads_flat,
-                        float* exp_avg, float* exp_avg_sq, const int* step_dev, const float* lr_dev, float beta1,
-                        float beta2, float eps, float grad_clip, void* stream);
+                        float* exp_avg, float* exp_avg_sq, const int* step_dev, const float* lr_dev, double beta1,
+                        double beta2, double eps, float grad_clip, void* stream);
 
 /* ---- ImageCompressor_new encoder tail (next row N1): sigmoid + straight-through binarizer --------------------------
  * models/analysis_17_new.py:35-37 + models/binarizer.py:19-27.  y: conv3 output, fp32 NCHW [B,C,HW]; sig = sigmoid(y),
