@@ -404,7 +404,10 @@ def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
             "value": 8 * world / (ms / 1e3), "unit": "img/s", "ms_per_step": ms,
             "allreduce": ("none (1 GPU)" if world == 1 else
                           ("libb2c NVLink kernel over symmetric memory (" + ("NVLS multimem" if graphed._symm.multicast else "peer loads/stores")
-                           + "), bracketed by two cross-rank barriers, after the graphed step") if getattr(graphed, "_symm", None) is not None else
+                           + "), cross-rank barrier + reduction + barrier in ONE launch, "
+                           + (("captured as the last node of the step graph" if getattr(graphed, "_symm_buckets", 1) == 1 else
+                               "two buckets captured inside the step graph")
+                              if getattr(graphed, "_symm_in_graph", False) else "after the graphed step")) if getattr(graphed, "_symm", None) is not None else
                           ("two-bucket NCCL all-reduce captured inside the step graph" if getattr(graphed, "ar_in_graph", False)
                            else "one NCCL all-reduce (mean) of the flat 7 MB gradient buffer after the graphed step")
                           if graphed is not None else

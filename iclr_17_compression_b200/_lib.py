@@ -65,6 +65,11 @@ SIGNATURES.update({
     "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_tc_wgrad9_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
     "b2c_allreduce_symm": (_c_i, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_i, _c_i, _c_sz, ctypes.c_float, _c_f]),
+    "b2c_allreduce_symm_flag_words": (_c_i, []),
+    "b2c_allreduce_symm_fused": (_c_i, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_i, _c_i, _c_sz, _c_sz, _c_sz,
+                                        ctypes.c_float, _c_i, _c_f]),
+    "b2c_allreduce_symm_range": (_c_i, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_i, _c_i, _c_sz, _c_sz, ctypes.c_float,
+                                        _c_i, _c_f]),
     "b2c_rans_build_tables": (_c_i, [_PP, _c_i, _c_i, _c_i, _c_f, _c_f, _c_f]),
     "b2c_rans_num_blocks": (_c_i, [_c_i, _c_i, _c_i]),
     "b2c_rans_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),

@@ -180,11 +180,18 @@ class SymmAllReduce:
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
+        from . import _lib
         q = 4 * self.world
         self.count = (numel + q - 1) // q * q
-        self.buf = symm.empty(self.count, dtype=torch.float32, device=device)
-        self.buf.zero_()
-        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        # behind the data: flag blocks of the fused kernel (barrier -> reduce -> barrier in one launch), one per channel
+        self.flag_words = int(_lib.load().b2c_allreduce_symm_flag_words())
+        self.channels = 4
+        self._alloc = symm.empty(self.count + self.channels * self.flag_words, dtype=torch.float32, device=device)
+        self._alloc.zero_()
+        self.buf = self._alloc[:self.count]
+        self.hdl = symm.rendezvous(self._alloc, self.group.group_name)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)                 # every rank's flags are zero before anybody's first launch
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
         self.multicast = mc != 0
         self._mc = ctypes.c_void_p(mc)
@@ -201,4 +208,36 @@ class SymmAllReduce:
                                                       self.world, self.count, ct.c_float(1.0 / self.world if mean else 1.0),
                                                       ct.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)),
                        "allreduce_symm")
+        self.hdl.barrier(channel=1)
+
+    def all_reduce_fused(self, begin: int = 0, count: Optional[int] = None, channel: int = 0, mean: bool = True,
+                         max_blocks: int = 0):
+        """ONE launch on the current stream: cross-rank barrier, reduction of elements [begin, begin + count), cross-rank
+        barrier - the flags live behind the data in the symmetric buffer (``channel`` selects the flag block: use one
+        per bucket).  Capturable in a CUDA graph.  Every rank must issue the same sequence of calls per channel."""
+        from . import _lib
+        count = self.count - begin if count is None else count
+        if begin % 4 or count % 4 or count <= 0 or begin + count > self.count or not 0 <= channel < self.channels:
+            raise ValueError("all_reduce_fused: begin / count must be multiples of 4 inside the buffer, channel < 4")
+        ct = self._ctypes
+        with torch.cuda.device(self.buf.device):
+            _lib.check(_lib.load().b2c_allreduce_symm_fused(
+                ct.cast(self._ptrs, ct.POINTER(ct.c_void_p)), self._mc, self.rank, self.world, begin, count,
+                self.count + channel * self.flag_words, ct.c_float(1.0 / self.world if mean else 1.0), int(max_blocks),
+                ct.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)), "allreduce_symm_fused")
+
+    def all_reduce_range(self, begin: int, count: int, mean: bool = True, max_blocks: int = 0):
+        """the same for elements [begin, begin + count) only (multiples of 4), with at most ``max_blocks`` CTAs: a
+        bucket of the gradient buffer, reducible while other kernels of the step still run.  Enqueued on the current
+        stream: barrier -> reduce -> barrier; every rank must issue its range calls in the same order."""
+        from . import _lib
+        if begin % 4 or count % 4 or count <= 0 or begin + count > self.count:
+            raise ValueError("all_reduce_range: begin / count must be multiples of 4 inside the buffer")
+        ct = self._ctypes
+        self.hdl.barrier(channel=0)
+        with torch.cuda.device(self.buf.device):
+            _lib.check(_lib.load().b2c_allreduce_symm_range(
+                ct.cast(self._ptrs, ct.POINTER(ct.c_void_p)), self._mc, self.rank, self.world, begin, count,
+                ct.c_float(1.0 / self.world if mean else 1.0), int(max_blocks),
+                ct.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)), "allreduce_symm_range")
         self.hdl.barrier(channel=1)

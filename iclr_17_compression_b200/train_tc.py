@@ -403,12 +403,37 @@ class GraphedTrainStep:
         n_par = sum(p.numel() for p in self.params)
         n_par_pad = (n_par + 63) // 64 * 64
         scratch = (4 * 25 * 128 * 128 + 4 * (128 * 128 + 128) + B * N * (H // 16) * (W // 16) + 1024) if direct else 0
-        # allreduce="symm" (or B2C_AR=symm): the gradient buffer lives in symmetric memory and the mean over ranks runs as
-        # libb2c's own NVLink / NVLS kernel (ddp.SymmAllReduce) instead of an NCCL call
+        # allreduce (or B2C_AR=...): "nccl" = one NCCL all-reduce after the replay.  "symm" / "symm_graph" /
+        # "symm_graph2": the gradient buffer lives in symmetric memory and the mean over ranks is libb2c's own NVLink /
+        # NVLS kernel (ddp.SymmAllReduce.all_reduce_fused: cross-rank barrier, reduction and barrier in ONE launch)
+        #   symm         launched right after the replay (default when world > 1 and symmetric memory is available)
+        #   symm_graph   captured as the LAST node of the step graph (the fused optimizer can then follow inside the
+        #                graph: one replay = one whole data-parallel iteration)
+        #   symm_graph2  two buckets inside the graph, Decoder + bitEstimator gradients reduced by a few CTAs while the
+        #                encoder backward still runs
+        # Measured step, batch 8 per GPU (profiles/symm_graph_check.py): 2 GPUs nccl 0.405 / symm 0.387 / symm_graph
+        # 0.450 / symm_graph2 0.454 ms; 8 GPUs nccl 0.444 / symm 0.404 / symm_graph2 0.485 ms (1 GPU: 0.357 ms).  Both
+        # in-graph forms are SLOWER than the same kernel launched after the replay - a kernel that spins on its peers
+        # inside the graph delays the replay by ~60 us - so they stay opt-in.
         self._symm = None
-        if self.world > 1 and direct and (allreduce or os.environ.get("B2C_AR", "nccl")) == "symm":
+        ar_mode = allreduce or os.environ.get("B2C_AR", "auto")
+        if ar_mode == "auto":
+            ar_mode = "symm" if (self.world > 1 and direct) else "nccl"
+        self._symm_in_graph = False
+        self._symm_buckets = 1
+        if self.world > 1 and direct and ar_mode in ("symm", "symm_graph", "symm_graph2"):
             from .ddp import SymmAllReduce
-            self._symm = SymmAllReduce(n_par_pad, dev, group)
+            try:
+                self._symm = SymmAllReduce(n_par_pad, dev, group)
+            except Exception as e:        # no symmetric memory / peer access on this system: NCCL carries the gradients
+                if allreduce is not None or os.environ.get("B2C_AR"):
+                    raise
+                import warnings
+                warnings.warn(f"symmetric-memory all-reduce unavailable ({e!r}); using NCCL")
+                self._symm = None
+            if self._symm is not None:
+                self._symm_in_graph = ar_mode != "symm"
+                self._symm_buckets = 2 if ar_mode == "symm_graph2" else 1
             self._grads = self._symm.buf
             self.buf = torch.zeros(scratch + 64, device=dev, dtype=torch.float32)
             self._scratch_off = 0
@@ -437,7 +462,8 @@ class GraphedTrainStep:
         if allreduce_in_graph is None:
             allreduce_in_graph = os.environ.get("B2C_AR_IN_GRAPH", "0") == "1"
         self.ar_in_graph = bool(allreduce_in_graph and direct and self.world > 1 and self._symm is None)
-        self._opt_in_graph = self.optimizer is not None and direct and (self.world == 1 or self.ar_in_graph)
+        self._opt_in_graph = self.optimizer is not None and direct and (self.world == 1 or self.ar_in_graph
+                                                                        or self._symm_in_graph)
         if direct:
             from .models import Analysis_net_17
             if type(getattr(model, "_enc", None)) is not Analysis_net_17:
@@ -472,21 +498,30 @@ class GraphedTrainStep:
         comm = self._comm_stream
 
         def decoder_done(fork):
-            if not self.ar_in_graph:
+            if not (self.ar_in_graph or (self._symm_in_graph and self._symm_buckets == 2)):
                 return
             comm.wait_stream(main)
             for s in fork.used:
                 comm.wait_stream(s)
             with torch.cuda.stream(comm):
-                dist.all_reduce(self.flat[enc_elems:], op=dist.ReduceOp.AVG, group=self.group)
+                if self._symm_in_graph:          # few CTAs: runs beside the encoder backward kernels
+                    self._symm.all_reduce_fused(enc_elems, self._symm.count - enc_elems, channel=1,
+                                                max_blocks=int(os.environ.get("B2C_AR_BLOCKS", "32")))
+                else:
+                    dist.all_reduce(self.flat[enc_elems:], op=dist.ReduceOp.AVG, group=self.group)
 
         step_backward(st, self._g_sse, self._g_bits, out=gviews, pool=pool, on_decoder_done=decoder_done)
-        if self.ar_in_graph:
+        if self._symm_in_graph and self._symm_buckets == 1:
+            self._symm.all_reduce_fused()                 # last node of the backward pass, on the main stream
+        elif self.ar_in_graph or self._symm_in_graph:
             # both buckets go through the SAME stream: collectives of one communicator must be issued in the same
             # order on every rank, and two unordered graph branches would let each rank's replay pick its own order
             comm.wait_stream(main)
             with torch.cuda.stream(comm):
-                dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
+                if self._symm_in_graph:
+                    self._symm.all_reduce_fused(0, enc_elems, channel=0)
+                else:
+                    dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
             main.wait_stream(comm)
         main.wait_stream(stat)
         if with_optimizer and self._opt_in_graph:
@@ -560,8 +595,8 @@ class GraphedTrainStep:
         else:
             self.noise.copy_(noise, non_blocking=True)
         self.graph.replay()
-        if self._symm is not None:
-            self._symm.all_reduce()                                  # barrier, NVLink reduce kernel, barrier
+        if self._symm is not None and not self._symm_in_graph:
+            self._symm.all_reduce_fused()                            # barrier, NVLink reduce, barrier: one launch
         elif self.world > 1 and not self.ar_in_graph:
             import torch.distributed as dist
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)

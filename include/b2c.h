@@ -316,6 +316,20 @@ int b2c_u8_to_f32(const void* in_u8, float* out, size_t count, void* stream);
  * a cross-rank barrier on the same stream (all inputs written before, all results visible after). */
 int b2c_allreduce_symm(void* const* peer_ptrs, void* multicast_ptr, int rank, int world, size_t count, float scale,
                        void* stream);
+/* The same over elements [begin, begin + count) only (both multiples of 4; the float4s are split over the ranks as
+ * evenly as possible) and with at most max_blocks CTAs (<= 0: no cap): one gradient bucket reduced beside the compute
+ * kernels of the rest of the backward pass (train_tc.GraphedTrainStep captures two such launches in its step graph). */
+int b2c_allreduce_symm_range(void* const* peer_ptrs, void* multicast_ptr, int rank, int world, size_t begin,
+                             size_t count, float scale, int max_blocks, void* stream);
+/* Barrier -> reduce -> barrier in ONE launch.  The symmetric buffer carries b2c_allreduce_symm_flag_words() uint32
+ * words per channel behind its data, zero-filled once (flag_offset: first word of the channel used by this launch, in
+ * elements from the buffer base, >= begin + count; one channel per gradient bucket).  peer_ptrs is always required
+ * (flags travel through peer memory), multicast_ptr selects the NVLS data path.  The launch number lives in the flag
+ * block, not in an argument: the launch can be captured in a CUDA graph and replayed.  Every rank must launch the
+ * same sequence per channel.  max_blocks <= 0: up to 148 CTAs. */
+int b2c_allreduce_symm_flag_words(void);
+int b2c_allreduce_symm_fused(void* const* peer_ptrs, void* multicast_ptr, int rank, int world, size_t begin,
+                             size_t count, size_t flag_offset, float scale, int max_blocks, void* stream);
 
 /* ---- real bitstream for the integer latents (the reference only estimates the size, model.py:71-74, and
  * approximates files with gzip(np.packbits(latent == 0)), NewTests/testModelRecon.py:80) ----------------------------
