@@ -898,6 +898,9 @@ namespace b2c {
 namespace tcp {
 int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   // b2c_conv_tcp.cu; 1 = not covered
 }
+namespace tcp1rs {
+int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   // b2c_conv1_rs.cu; 1 = not covered
+}
 namespace tcp1ts {
 int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   // b2c_conv1_ts.cu; 1 = not covered
 }
@@ -997,6 +1000,8 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   {   // persistent kernels for the TMA-fed 128-channel inference layers
     int rc = b2c::tcp::try_launch(L, stream, g_tc_trace);
+    if (rc != 1) return rc;
+    rc = b2c::tcp1rs::try_launch(L, stream, g_tc_trace);      // CONV1 + GDN1, operands in TMEM, builder / epilogue warps
     if (rc != 1) return rc;
     rc = b2c::tcp1ts::try_launch(L, stream, g_tc_trace);      // CONV1 + GDN1 with both A operands in TMEM
     if (rc != 1) return rc;

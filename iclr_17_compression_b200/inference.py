@@ -14,13 +14,19 @@ from . import _lib
 class HostPipeline:
     """compress(x_host) for a fixed batch shape; buffers are allocated once."""
 
-    def __init__(self, model, batch, height, width, chunk=8, device=None, use_graphs=True, ramp=True):
+    def __init__(self, model, batch, height, width, chunk=8, device=None, use_graphs=True, ramp=True, sizes=None):
         """chunk: images per copy/compute slice.  ramp: the first and the last slice are half-size, so the first
-        kernels start (and the last ones finish) sooner next to the PCIe copy that bounds the call."""
-        if batch % chunk:
+        kernels start (and the last ones finish) sooner next to the PCIe copy that bounds the call.  sizes: an explicit
+        slice plan (list of slice sizes summing to batch, each <= chunk) instead."""
+        if sizes is not None:
+            sizes = [int(v) for v in sizes]
+            if sum(sizes) != batch or min(sizes) < 1 or max(sizes) > chunk:
+                raise ValueError("sizes must be positive, sum to batch and not exceed chunk")
+        elif batch % chunk:
             raise ValueError("batch must be a multiple of chunk")
-        sizes = [chunk] * (batch // chunk)
-        if ramp and chunk >= 2 and len(sizes) >= 2:
+        else:
+            sizes = [chunk] * (batch // chunk)
+        if sizes is None or (ramp and chunk >= 2 and len(sizes) >= 2 and len(set(sizes)) == 1 and sizes[0] == chunk):
             h = chunk // 2
             sizes = [h] + [chunk] * (batch // chunk - 1) + [chunk - h]
         self.sizes = sizes

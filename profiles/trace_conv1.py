@@ -25,14 +25,16 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
     print("conv1+gdn1 ms", e0.elapsed_time(e1) / 20)
-    buf = torch.zeros(3 * 64, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(4 * 64, dtype=torch.int64, device="cuda")
     lib.b2c_tc_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
     fn()
     torch.cuda.synchronize()
     lib.b2c_tc_debug_set_trace(ctypes.c_void_p(0))
-t = buf.cpu().view(3, 64)
+t = buf.cpu().view(4, 64)
 t0 = min(int(v) for v in t.flatten() if v > 0)
-for role, nm in enumerate(["producer", "mma", "worker"]):
+for role, nm in enumerate(["producer", "mma", "worker / epilogue", "builder"]):
     vals = [int(v) - t0 for v in t[role] if v > 0]
+    if not vals:
+        continue
     print(nm, vals)
     print("   deltas", [b - a for a, b in zip(vals, vals[1:])])
