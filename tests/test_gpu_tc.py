@@ -271,3 +271,46 @@ def test_conv5s2_bf16_split_k(tc, shape, ksplit):
     base = torch.full_like(y1, 0.25)                                  # accumulate on top of existing contents
     y2 = tc.layer_run(tc.TC_CONV5S2, xh, None, wp, b, out_f32_nchw=True, ksplit=ksplit, out=base)
     assert _rel(y2 - 0.25, y1) < 1e-5
+
+
+_CONV1_FORM_SCRIPT = r"""
+import sys, torch, torch.nn.functional as F
+sys.path.insert(0, %r)
+import iclr_17_compression_b200.tc as tc
+from oracle import balle17_oracle as O
+torch.backends.cudnn.allow_tf32 = False
+g = torch.Generator().manual_seed(3)
+worst = 0.0
+for (B, H, W) in [(1, 64, 96), (3, 48, 80), (1, 16, 16), (2, 272, 400)]:      # incl. odd tile counts / ragged borders
+    x = torch.rand(B, 3, H, W, generator=g).cuda()
+    w = (torch.randn(128, 3, 9, 9, generator=g) * 0.2).cuda()
+    b = torch.randn(128, generator=g).cuda()
+    beta = torch.sqrt(0.5 + torch.rand(128, generator=g))
+    gamma = torch.sqrt(0.1 * torch.eye(128) + 0.02 * torch.rand(128, 128, generator=g) + O.PEDESTAL)
+    conv = F.conv2d(x.double().cpu(), w.double().cpu(), b.double().cpu(), stride=4, padding=4)
+    ref = O.gdn(conv, beta.double(), gamma.double(), False)
+    wp = tc.pack_weights(tc.TC_CONV1, w, True)
+    gp = tc.pack_gdn(beta.cuda(), gamma.cuda(), True)
+    for rep in range(2):                                                       # second call: steady-state barriers / flags
+        yh, yl = tc.layer_run(tc.TC_CONV1, x, None, wp, b, gdn=gp, gdn_mode=1, split3=True)
+    y = tc.nhwc_to_nchw(yh, yl).double().cpu()
+    worst = max(worst, ((y - ref).norm() / ref.norm()).item())
+print("WORST", worst)
+"""
+
+
+@pytest.mark.parametrize("form", ["3", "2", "1", "0"])
+def test_conv1_every_kernel_form(form):
+    """B2C_TC_PERSIST_CONV1 selects the CONV1 + GDN1 kernel (3 = role-specialised with the MMA A operands in TMEM, the
+    default; 2 = single worker group, operands in TMEM; 1 = operands in shared memory; 0 = per-tile kernel).  The switch
+    is read once per process, so every form runs in its own interpreter, against the fp64 oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B2C_TC_PERSIST_CONV1=form)
+    out = subprocess.run([sys.executable, "-c", _CONV1_FORM_SCRIPT % root], capture_output=True, text=True, env=env,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float(out.stdout.strip().split("WORST")[-1])
+    assert worst < 5e-5, worst
