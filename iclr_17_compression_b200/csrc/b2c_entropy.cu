@@ -305,22 +305,28 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut_kernel(const floa
 // is XOR-swizzled at 16-byte granularity (chunk ^ ((row >> 2) & 7)) instead of padded, so both the 4-byte writes and
 // the 16-byte row reads of the copy-out are bank-conflict free and the copy-out is LDS.128 / STG.128.
 // lane = (pixel quad q 0..7, pair k 0..3); warp w: pixel group w & 3, 8-channel chunk half w >> 2; a pass = 16 channels.
-__global__ void __launch_bounds__(256) quant_entropy_infer_lut2_kernel(const float* __restrict__ y, BitPtrs bp,
+// NSUB = 2: 512 threads cover 256 pixels, so the two 512-byte halves of a 1 KB piece of every channel row are requested
+// together (a DRAM page sees one visit instead of two: the 128-pixel form is bound by its access pattern, not by
+// instructions).
+template <int NSUB>
+__global__ void __launch_bounds__(256 * NSUB) quant_entropy_infer_lut2_kernel(const float* __restrict__ y, BitPtrs bp,
                                                                        const float* __restrict__ lut, int L,
                                                                        float* __restrict__ z,
                                                                        __nv_bfloat16* __restrict__ z_nhwc,
                                                                        float* __restrict__ partial, int C, int HW,
-                                                                       int chunks, int* __restrict__ range_flag) {
+                                                                       int chunks, int* __restrict__ range_flag,
+                                                                       int stream_hint) {
   extern __shared__ float qi_smem[];
-  uint32_t* tile = reinterpret_cast<uint32_t*>(qi_smem);     // [LQ_PIX][C / 2] bf16x2 words, 16-byte chunks swizzled
+  const bool STREAM = stream_hint != 0;
+  uint32_t* tile = reinterpret_cast<uint32_t*>(qi_smem);     // [LQ_PIX * NSUB][C / 2] bf16x2 words, 16-byte chunks swizzled
   __shared__ float red[32];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned n = blockIdx.x / chunks, chunk = blockIdx.x - n * chunks;
-  const unsigned pix0 = chunk * LQ_PIX;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned pix0 = chunk * (LQ_PIX * NSUB);
+  const unsigned lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7, sub = threadIdx.x >> 8;
   const unsigned q = lane & 7, k = lane >> 3;
-  const unsigned lp = (warp & 3) * 32 + q * 4;               // first of this thread's 4 pixels inside the chunk
+  const unsigned lp = sub * LQ_PIX + (warp & 3) * 32 + q * 4;   // first of this thread's 4 pixels inside the chunk
   const unsigned half = warp >> 2;
   const unsigned wpr = C / 2, W = 2 * L + 1;                 // words per tile row; table row length
   const bool in_image = pix0 + lp < (unsigned)HW;            // whole quads: HW % 4 == 0
@@ -336,12 +342,17 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut2_kernel(const flo
   for (unsigned pass = 0; pass < (unsigned)C / 16; ++pass, c += 16, yp += cstep, zp += cstep, row += 16 * W) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (in_image) {
-      a = __ldg(reinterpret_cast<const float4*>(yp));
-      b = __ldg(reinterpret_cast<const float4*>(yp + HW));
+      a = STREAM ? __ldcs(reinterpret_cast<const float4*>(yp)) : __ldg(reinterpret_cast<const float4*>(yp));
+      b = STREAM ? __ldcs(reinterpret_cast<const float4*>(yp + HW)) : __ldg(reinterpret_cast<const float4*>(yp + HW));
       a.x = rintf(a.x); a.y = rintf(a.y); a.z = rintf(a.z); a.w = rintf(a.w);
       b.x = rintf(b.x); b.y = rintf(b.y); b.z = rintf(b.z); b.w = rintf(b.w);
-      *reinterpret_cast<float4*>(zp) = a;
-      *reinterpret_cast<float4*>(zp + HW) = b;
+      if (STREAM) {                                          // y is read once and z is not re-read by this kernel
+        __stcs(reinterpret_cast<float4*>(zp), a);
+        __stcs(reinterpret_cast<float4*>(zp + HW), b);
+      } else {
+        *reinterpret_cast<float4*>(zp) = a;
+        *reinterpret_cast<float4*>(zp + HW) = b;
+      }
       const float e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
       const float* row1 = row + W;
       float bits[8];
@@ -371,13 +382,13 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_lut2_kernel(const flo
   sum = block_sum(sum, red);                                 // also the __syncthreads() for `tile`
   if (threadIdx.x == 0) partial[blockIdx.x] = sum;
   if (z_nhwc) {
-    const unsigned npix = min((unsigned)LQ_PIX, (unsigned)HW - pix0);
+    const unsigned npix = min((unsigned)(LQ_PIX * NSUB), (unsigned)HW - pix0);
     const unsigned cpr = C / 8;                              // 16-byte chunks per row
     const uint4* src = reinterpret_cast<const uint4*>(tile);
     uint4* dst = reinterpret_cast<uint4*>(z_nhwc + ((size_t)n * HW + pix0) * C);
-    for (unsigned i = threadIdx.x; i < npix * cpr; i += 256) {
+    for (unsigned i = threadIdx.x; i < npix * cpr; i += 256 * NSUB) {
       const unsigned r = i / cpr, ch = i - r * cpr;
-      dst[i] = src[r * cpr + (ch ^ ((r >> 2) & 7))];
+      dst[i] = src[r * cpr + (ch ^ ((r >> 2) & 7))];         // (the decoder reads this next: default caching)
     }
   }
 }
@@ -697,10 +708,12 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
     B2C_REQUIRE(host_params[i], "quant_entropy_infer_lut: null parameter pointer %d", i);
     bp.p[i] = host_params[i];
   }
-  const int chunks = (HW + LQ_PIX - 1) / LQ_PIX;
   static const bool allow_v2 = [] { const char* e = getenv("B2C_ENTROPY_LUT_V1"); return !e || atoi(e) == 0; }();
+  static const int nsub_env = [] { const char* e = getenv("B2C_ENTROPY_LUT_SUB"); return e ? atoi(e) : 2; }();
   const bool v2 = allow_v2 && C % 64 == 0 && ((uintptr_t)z_nhwc_bf16 & 15) == 0;
-  const size_t smem = v2 ? (size_t)LQ_PIX * C * 2 : (size_t)LQ_PIX * (C + 2) * 2;
+  const int nsub = (v2 && nsub_env == 2 && HW >= 2 * LQ_PIX) ? 2 : 1;      // 256-pixel chunks when the image has them
+  const int chunks = (HW + LQ_PIX * nsub - 1) / (LQ_PIX * nsub);
+  const size_t smem = v2 ? (size_t)LQ_PIX * nsub * C * 2 : (size_t)LQ_PIX * (C + 2) * 2;
   {
     static std::mutex mu;
     static bool done[64] = {false};
@@ -711,8 +724,11 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
       cudaError_t e = cudaFuncSetAttribute(quant_entropy_infer_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            LQ_PIX * (256 + 2) * 2);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
-      e = cudaFuncSetAttribute(quant_entropy_infer_lut2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(quant_entropy_infer_lut2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                LQ_PIX * 256 * 2);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
+      e = cudaFuncSetAttribute(quant_entropy_infer_lut2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               2 * LQ_PIX * 256 * 2);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
       if (dev >= 0 && dev < 64) done[dev] = true;
     }
@@ -724,16 +740,25 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * chunks));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(256 * nsub);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, v2 ? quant_entropy_infer_lut2_kernel : quant_entropy_infer_lut_kernel, y, bp, lut,
-                                     half_range, z, (__nv_bfloat16*)z_nhwc_bf16, (float*)workspace, C, HW, chunks,
-                                     range_flag);
+  static const int stream_hint = [] { const char* e = getenv("B2C_ENTROPY_STREAM"); return e ? atoi(e) : 1; }();
+  cudaError_t e;
+  if (v2 && nsub == 2)
+    e = cudaLaunchKernelEx(&cfg, quant_entropy_infer_lut2_kernel<2>, y, bp, lut, half_range, z, (__nv_bfloat16*)z_nhwc_bf16,
+                           (float*)workspace, C, HW, chunks, range_flag, stream_hint);
+  else if (v2)
+    e = cudaLaunchKernelEx(&cfg, quant_entropy_infer_lut2_kernel<1>, y, bp, lut, half_range, z, (__nv_bfloat16*)z_nhwc_bf16,
+                           (float*)workspace, C, HW, chunks, range_flag, stream_hint);
+  else
+    e = cudaLaunchKernelEx(&cfg, quant_entropy_infer_lut_kernel, y, bp, lut, half_range, z, (__nv_bfloat16*)z_nhwc_bf16,
+                           (float*)workspace, C, HW, chunks, range_flag);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(quant_entropy_infer_lut): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
   cfg.gridDim = dim3((unsigned)B);
+  cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = 0;
   e = cudaLaunchKernelEx(&cfg, partial_reduce_kernel, (const float*)workspace, image_bits, chunks, 1);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(partial_reduce): %s", cudaGetErrorString(e)); return B2C_ECUDA; }

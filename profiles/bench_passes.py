@@ -32,8 +32,8 @@ dp, keep2 = _lib.ptr_array(dpar)
 gb = torch.ones(1, device="cuda")
 sig, code = torch.empty_like(y), torch.empty_like(y)
 cases = {
-    "quant_entropy_infer (read y, write z fp32 + z bf16)": (10, lambda: lib.b2c_quant_entropy_infer(p_(y), pp, p_(z), p_(zh), p_(ib), B, C, H * W, p_(ws), wsn, cs())),
-    "quant_entropy_infer_lut (read y, write z fp32 + z bf16, table)": (10, lambda: lib.b2c_quant_entropy_infer_lut(p_(y), pp, p_(lut), 32, p_(z), p_(zh), p_(ib), B, C, H * W, p_(ws), wsn, cs())),
+    "quant_entropy_infer (read y, write z fp32 + z bf16)": (10, lambda: lib.b2c_quant_entropy_infer(p_(y), pp, p_(z), p_(zh), p_(ib), vp(0), B, C, H * W, p_(ws), wsn, cs())),
+    "quant_entropy_infer_lut (read y, write z fp32 + z bf16, table)": (10, lambda: lib.b2c_quant_entropy_infer_lut(p_(y), pp, p_(lut), 32, p_(z), p_(zh), p_(ib), vp(0), B, C, H * W, p_(ws), wsn, cs())),
     "quant_entropy_fwd train (read y, noise, write z)": (12, lambda: lib.b2c_quant_entropy_fwd(p_(y), p_(noise), pp, p_(z), p_(pb), p_(ib), B, C, H * W, cs())),
     "entropy_bwd (read z, write dz)": (8, lambda: lib.b2c_entropy_bwd(p_(z), pp, p_(gb), p_(dz), dp, B, C, H * W, cs())),
     "sigmoid_binarize_fwd (read y, write sig, code, code bf16)": (14, lambda: lib.b2c_sigmoid_binarize_fwd(p_(y), p_(sig), p_(code), p_(zh), B, C, H * W, cs())),
