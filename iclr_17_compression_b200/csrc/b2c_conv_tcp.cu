@@ -22,6 +22,11 @@
 #include "b2c_tc_im2col.cuh"
 #include "b2c_tc_host.cuh"
 #include "b2c_tcp_util.cuh"
+#include "b2c_tc_ts.cuh"
+
+#ifndef B2C_TCP_TS_EPI
+#define B2C_TCP_TS_EPI 1    /* 0: x^2 through shared memory and block-wide staging, as in round 1 */
+#endif
 
 namespace b2c {
 namespace tcp {
@@ -93,8 +98,30 @@ __device__ __forceinline__ void p_tap(int gi, int t, int phase, int& wgroup, int
   }
 }
 
-template <int KIND, bool SPLIT3, bool PAIR, int GDN>
+// ---- DECONV5S2 with RESIDENT A boxes (pair form).  Tap t of sub-pixel row ry reads the input rows starting at
+// oy0 + 1 - t whatever ry is, so ONE box per (x shift, k-block) with origin row oy0 - 1 and TH + 2 rows serves all four
+// phases of a spatial tile: six boxes per tile instead of twenty (A fill 400 -> 120 KB per tile; once the epilogue is
+// off the critical path these layers are bound by the L2 -> shared-memory fill).  The six boxes own fixed slots;
+// phases run in the order (ry,rx) = (0,0) (1,0) (0,1) (1,1) so that the x shift -1 boxes (only used when rx = 0) are
+// released half way and the next tile's first boxes arrive under the rx = 1 phases.
+__device__ __forceinline__ int r_phase(int pi) { return ((pi & 1) << 1) | (pi >> 1); }        // pi -> phase = ry*2 + rx
+__device__ __forceinline__ int r_ngroups(int phase) { return (phase & 1) ? 2 * NCB : 3 * NCB; }
+// group gi of a phase: k-block cb, x shift index jx (x_off = 1 - jx); rx = 0 visits jx = 2, 0, 1, rx = 1 visits 0, 1
+__device__ __forceinline__ void r_group(int gi, int phase, int& cb, int& jx) {
+  cb = gi & 1;
+  const int j = gi >> 1;
+  jx = (phase & 1) ? j : (j == 0 ? 2 : j - 1);
+}
+__device__ __forceinline__ void r_tap(int jx, int t, int phase, int& wgroup, int& row_off) {
+  const int ry = phase >> 1, rx = phase & 1;
+  wgroup = (ry + 2 * t) * 5 + rx + 2 * jx;
+  row_off = 2 - t;
+}
+
+template <int KIND, bool SPLIT3, bool PAIR, int GDN, bool ARES>
 struct PCfg {
+  static constexpr bool A_RES = ARES;                                           // resident A boxes (6 fixed slots)
+  static_assert(!ARES || (KIND == B2C_TC_DECONV5S2 && PAIR && !SPLIT3), "resident A boxes: bf16 pair DECONV5S2 only");
   static constexpr bool B_RES = KIND == B2C_TC_DECONV3;                         // weights resident
   static constexpr int N_TILE = B_RES ? 48 : C;
   static constexpr int B_BYTES = N_TILE * 128 / (PAIR ? 2 : 1);                 // one weight / gamma k-block tile
@@ -106,9 +133,10 @@ struct PCfg {
   static constexpr int EXTRA = 1024 /*align*/ + 1024 /*bias, beta*/ + 512 /*barriers*/;
   static constexpr int MAX_SMEM = 227 * 1024;
   static constexpr int LEFT = MAX_SMEM - EXTRA - GAMMA_BYTES - XS - W_RES;
-  static constexpr int NA = SPLIT3 ? (GDN ? 2 : 3) : (B_RES ? 5 : (PAIR ? 4 : 3));
+  static constexpr int NA = A_RES ? 3 * NCB : (SPLIT3 ? (GDN ? 2 : 3) : (B_RES ? 5 : (PAIR ? 4 : 3)));
   static constexpr int NB_RAW = B_RES ? 0 : (LEFT - NA * A_SLOT) / B_SLOT;
-  static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
+  static constexpr int NB = NB_RAW > 12 ? 12 : NB_RAW;     // (weight tiles arrive ~2.6 k clk after their request:
+                                                           // a ring of 7-8 four-MMA tiles ran at 70 % of the tensor rate)
   static_assert(B_RES || NB >= 4, "weight ring too shallow");
   static constexpr int SMEM = NA * A_SLOT + NB * B_SLOT + W_RES + GAMMA_BYTES + XS + EXTRA;
   static_assert(SMEM <= MAX_SMEM, "shared memory budget");
@@ -116,16 +144,17 @@ struct PCfg {
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
 };
 
-template <int KIND, bool SPLIT3, int GDN, int OUT_MODE, bool PAIR>
+template <int KIND, bool SPLIT3, int GDN, int OUT_MODE, bool PAIR, bool ARES = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const __grid_constant__ CUtensorMap tmG_hi, const __grid_constant__ CUtensorMap tmG_lo,
                  const __grid_constant__ POutMaps tmO, const PParams p) {
-  using Cfg = PCfg<KIND, SPLIT3, PAIR, GDN>;
+  using Cfg = PCfg<KIND, SPLIT3, PAIR, GDN, ARES>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB;
   constexpr int NBX = NB > 0 ? NB : 1;
   constexpr bool B_RES = Cfg::B_RES;
+  constexpr bool A_RES = Cfg::A_RES;
   constexpr int N_TILE = Cfg::N_TILE;
   constexpr uint32_t A_SLOT = Cfg::A_SLOT, B_SLOT = Cfg::B_SLOT, B_BYTES = Cfg::B_BYTES;
   constexpr int IN_STRIDE = (KIND == B2C_TC_CONV5S2) ? 2 : 1;
@@ -134,6 +163,14 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   constexpr uint32_t NPAIR = PAIR ? 2u : 1u;
   constexpr uint32_t ACC_STRIDE = Cfg::ACC_STRIDE;
   constexpr bool PREFETCH = false;   // measured slower (TMA queue shared with the demand loads): conv2 0.250 -> 0.258 ms
+  // TS epilogue (bf16 pair layers with a fused GDN / IGDN and NHWC bf16 output = the two transposed 5x5 convs): the
+  // worker epilogue - not the main loop - bounded these layers (deconv2: x^2 1.9 k + norm wait 1.9 k + final 2.2 k clk
+  // per sub-tile against 3.7 k clk of MMAs, profiles/r2_notes.md).  As in b2c_conv1_ts.cu the x^2 operand of the gamma
+  // product is written over the accumulator columns it was read from (tcgen05.mma takes A from TMEM), the workers
+  // never meet on a block barrier (per-warp mbarrier arrivals) and every warp stores its own 32 pixels x 64 channels
+  // through its own 4 KB staging slice and TMA box.
+  constexpr bool TS_EPI = !SPLIT3 && GDN != 0 && OUT_MODE == OUT_BF16 && PAIR && B2C_TCP_TS_EPI;
+  constexpr uint32_t NWARPS_W = NWORKERS / 32;
   static_assert(OUT_MODE != OUT_BF16 || GDN != 0, "bf16 NHWC output stages through the x^2 buffer");
   static_assert(!SPLIT3 || PAIR, "the bf16x3 rings only fit as a CTA pair");
   static_assert(!B_RES || (!PAIR && !SPLIT3 && GDN == 0 && OUT_MODE == OUT_F32_NCHW_PS4), "DECONV3 form");
@@ -184,9 +221,9 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&accum_full[i], 1);
       mbar_init(&norm_full[i], 1);
-      mbar_init(&acc_empty[i], NPAIR);     // one elected worker per CTA arrives (after a named barrier)
-    }
-    mbar_init(xs_full, NPAIR);
+      mbar_init(&acc_empty[i], TS_EPI ? NPAIR * NWARPS_W : NPAIR);   // one elected worker per CTA (after a named
+    }                                                                // barrier), or every worker warp (TS epilogue)
+    mbar_init(xs_full, TS_EPI ? NPAIR * NWARPS_W : NPAIR);
     mbar_init(xs_empty, 1);
     mbar_init(res_full, 1);
     fence_barrier_init();
@@ -253,6 +290,35 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const int nty = nrem / p.tiles_x;
           pf_y = nty * TH * IN_STRIDE; pf_x = (nrem - nty * p.tiles_x) * TW * IN_STRIDE;
           if (pf_img >= p.B) pf_img = -1;
+        }
+        if (A_RES) {
+          const uint32_t ut = (uint32_t)((unit - unit0) / unit_stride);     // spatial tiles this CTA has started
+          for (int pi = 0; pi < NPH; ++pi) {
+            const int phase = r_phase(pi);
+            const int ng = r_ngroups(phase), ntaps = 3 - (phase >> 1);
+            for (int gi = 0; gi < ng; ++gi) {
+              int cb, jx;
+              r_group(gi, phase, cb, jx);
+              if (pi == 0) {                      // first visit of this tile's box (jx, cb): fixed slot
+                const uint32_t as = (uint32_t)(jx * NCB + cb);
+                mbar_wait(&a_empty[as], (ut & 1u) ^ 1u);
+                TCP_MARK(0, true);
+                uint8_t* a_hi = smem + as * A_SLOT;
+                if (leader) mbar_arrive_expect_tx(&a_full[as], 2u * A_SLOT);
+                tma_load_4d_pair(a_hi, &tmA_hi, &a_full[as], cb * KBLK, ox0 + 1 - jx, oy0 - 1, n_img);
+              }
+              for (int t = 0; t < ntaps; ++t, ++gb) {
+                int wgroup, row_off;
+                r_tap(jx, t, phase, wgroup, row_off);
+                const uint32_t bs = gb % NBX;
+                mbar_wait(&b_empty[bs], ((gb / NBX) & 1) ^ 1);
+                uint8_t* b_hi = b_ring + bs * B_SLOT;
+                if (leader) mbar_arrive_expect_tx(&b_full[bs], 2u * B_SLOT);
+                tma_load_2d_pair(b_hi, &tmB_hi, &b_full[bs], cb * KBLK, wgroup * C + (int)cta_rank * (C / 2));
+              }
+            }
+          }
+          continue;
         }
         for (int phase = 0; phase < NPH; ++phase) {
           const int ng = p_ngroups<KIND>(phase);
@@ -339,6 +405,14 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 umma_bf16(d, a_lo + 2 * k4, b_hi + 2 * k4, idesc_g, 1u);
               }
             }
+          } else if (TS_EPI) {
+            // x^2 of worker half h = kk >> 2 sits in the accumulator's own columns 64h .. 64h + 31 (two bf16 per column)
+            const uint32_t a0 = tb + (uint32_t)pend_buf * ACC_STRIDE;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t b = gam_d + ((uint32_t)(kk >> 2) * B_BYTES >> 4) + 2 * (kk & 3);
+              umma_bf16_pair_ts(d, a0 + (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8), b, idesc_g, kk > 0 ? 1u : 0u);
+            }
           } else {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
@@ -368,9 +442,10 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
       if (GDN || B_RES) mbar_wait(res_full, 0);
       for (int unit = unit0; unit < n_units; unit += unit_stride) {
-        for (int phase = 0; phase < NPH; ++phase, ++st) {
+        for (int pi = 0; pi < NPH; ++pi, ++st) {
+          const int phase = A_RES ? r_phase(pi) : pi;
           const uint32_t buf = st & 1u;
-          const int ng = p_ngroups<KIND>(phase);
+          const int ng = A_RES ? r_ngroups(phase) : p_ngroups<KIND>(phase);
           // the workers must have drained this accumulator set (sub-tile st-2)
           TCP_FINE_MMA();
           if (PAIR) mbar_wait_cluster(&acc_empty[buf], ((st >> 1) & 1u) ^ 1u);
@@ -379,11 +454,18 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           TCP_FINE_MMA();
           const uint32_t d = tb + buf * ACC_STRIDE;
           for (int gi = 0; gi < ng; ++gi, ++ga) {
-            int cb, x_off, y_off, ntaps;
-            p_group<KIND>(gi, phase, cb, x_off, y_off, ntaps);
+            int cb, x_off, y_off, ntaps, jx = 0;
+            if (A_RES) {
+              r_group(gi, phase, cb, jx);
+              ntaps = 3 - (phase >> 1);
+            } else {
+              p_group<KIND>(gi, phase, cb, x_off, y_off, ntaps);
+            }
             if (GDN && pend_buf >= 0 && xs_ready()) issue_gdn_round();
-            const uint32_t as = ga % NA;
-            mbar_wait(&a_full[as], (ga / NA) & 1);
+            const uint32_t ut = (uint32_t)((unit - unit0) / unit_stride);
+            const uint32_t as = A_RES ? (uint32_t)(jx * NCB + cb) : ga % NA;
+            if (!A_RES) mbar_wait(&a_full[as], (ga / NA) & 1);
+            else if (pi == 0) mbar_wait(&a_full[as], ut & 1u);       // later phases re-use the resident box
             if (!B_RES) {   // all weight tiles of the group (the producer fills them without waiting on anything else)
 #pragma unroll
               for (int t = 0; t < 3; ++t)
@@ -399,7 +481,8 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               for (int t = 0; t < 3; ++t) {
                 if (t < ntaps) {
                   int wgroup, row_off;
-                  p_tap<KIND>(gi, t, phase, wgroup, row_off);
+                  if (A_RES) r_tap(jx, t, phase, wgroup, row_off);
+                  else p_tap<KIND>(gi, t, phase, wgroup, row_off);
                   const uint32_t bs = (gb + t) % NBX;
                   const uint64_t a_hi = a_box + ((uint32_t)(row_off * ROW_BYTES) >> 4), a_lo = a_hi + (A_PLANE >> 4);
                   const uint64_t b_hi = B_RES ? wres_d + ((uint32_t)((wgroup * NCB + cb) * B_BYTES) >> 4)
@@ -428,8 +511,10 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                   }
                 }
               }
+              // resident boxes are handed back after their last phase: x shift -1 after the second rx = 0 phase
+              const bool a_done = !A_RES || (jx == 2 ? pi == 1 : pi == NPH - 1);
               if (PAIR) {
-                umma_commit_pair(&a_empty[as]);
+                if (a_done) umma_commit_pair(&a_empty[as]);
                 if (last_group) umma_commit_pair(&accum_full[buf]);
               } else {
                 umma_commit(&a_empty[as]);
@@ -500,7 +585,8 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
       }
 
-      for (int phase = 0; phase < NPH; ++phase, ++st) {
+      for (int pi = 0; pi < NPH; ++pi, ++st) {
+        const int phase = A_RES ? r_phase(pi) : pi;
         const uint32_t buf = st & 1u, par = (st >> 1) & 1u;
         const uint32_t t_acc = t_lane + buf * ACC_STRIDE, t_nrm = t_acc + 128u;
         TCP_MARK(2, threadIdx.x == 64);
@@ -512,6 +598,70 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // 64 B/clk per SM: re-reading the accumulator would cost as much as the gamma MMAs)
         //   SPLIT3: xk[g*16 + i] = channels g*64 + half*32 + 2i, +1     bf16: xk[hh*16 + i] = half*64 + hh*32 + 2i, +1
         uint64_t xk[GDN ? 32 : 1];
+        if constexpr (TS_EPI) {
+          // ---- x^2 of this thread's 64 channels over accumulator columns it has itself read: xk[hh*16 + i] = channels
+          // half*64 + hh*32 + 2i, +1; the 32 packed words land in columns half*64 .. half*64 + 31
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t raw[32], w[16];
+            tmem_ld32(t_acc + (uint32_t)(half * 64 + hh * 32), raw);
+            tmem_ld_wait();
+            const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + half * 64 + hh * 32);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t x2 = add2(pk2(raw[2 * i], raw[2 * i + 1]), bias2[i]);
+              xk[hh * 16 + i] = x2;
+              float v0, v1;
+              upk2(mul2(x2, x2), v0, v1);
+              w[i] = cvt_bf16x2(v0, v1);
+            }
+            tmem_st16(t_acc + (uint32_t)(half * 64 + hh * 16), w);
+          }
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta0(xs_full);
+          TCP_MARK(2, threadIdx.x == 64);
+          mbar_wait(&norm_full[buf], par);
+          tcgen05_fence_after();
+          TCP_MARK(2, threadIdx.x == 64);
+          // ---- final pass: y = x * sqrt(beta + n) (IGDN) or x * rsqrt(beta + n) (GDN) -> this warp's staging slice
+          // (32 pixels x 64 channels, 128-byte rows, SWIZZLE_128B) -> one TMA store of a {64 ch, 16, 2} box
+          uint8_t* my_stg = xs + (uint32_t)(warp - 2) * 4096u;
+          if (lane == 0 && store_pending) { tma_store_wait_read(); store_pending = false; }
+          __syncwarp();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t rawn[32];
+            tmem_ld32(t_nrm + (uint32_t)(half * 64 + hh * 32), rawn);
+            tmem_ld_wait();
+            if (hh == 1) tcgen05_fence_before();
+            const uint64_t* beta2 = reinterpret_cast<const uint64_t*>(s_beta + half * 64 + hh * 32);
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+              uint32_t hp[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float n0, n1, y0, y1;
+                upk2(add2(pk2(rawn[ci * 8 + 2 * j], rawn[ci * 8 + 2 * j + 1]), beta2[ci * 4 + j]), n0, n1);
+                const uint64_t sc = (GDN == 2) ? pkf2(sqrt_fast(n0), sqrt_fast(n1)) : pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
+                upk2(mul2(xk[hh * 16 + ci * 4 + j], sc), y0, y1);
+                hp[j] = cvt_bf16x2(y0, y1);
+              }
+              sts128(my_stg, lane, hh * 4 + ci, hp[0], hp[1], hp[2], hp[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cta0(&acc_empty[buf]);       // this warp's TMEM reads of the set are complete
+            const int mi = (KIND == B2C_TC_DECONV5S2) ? phase : 0;
+            tma_store_4d(&tmO.m[4 + mi], my_stg, half * KBLK, ox0, oy0 + 2 * q, n_img);
+            tma_store_commit();
+            store_pending = true;
+          }
+          continue;
+        }
         if (GDN) {
           // ---- x^2 as the K-major swizzled A tile of the gamma product
 #pragma unroll
@@ -726,7 +876,7 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
       }
     }
-    if (elected && store_pending) tma_store_wait_read();
+    if ((TS_EPI ? lane == 0 : elected) && store_pending) tma_store_wait_read();
     TCP_MARK(2, threadIdx.x == 64);
 #undef WORKER_SYNC
   }
@@ -757,12 +907,12 @@ static int make_act_box_map(CUtensorMap* m, const void* base, int B, int H, int 
   return B2C_OK;
 }
 
-template <int KIND, bool SPLIT3, int GDN, int OUT_MODE, bool PAIR>
+template <int KIND, bool SPLIT3, int GDN, int OUT_MODE, bool PAIR, bool ARES = false>
 static int launch_p(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
-  using Cfg = PCfg<KIND, SPLIT3, PAIR, GDN>;
+  using Cfg = PCfg<KIND, SPLIT3, PAIR, GDN, ARES>;
   constexpr size_t SMEM = Cfg::SMEM;
   constexpr int N_TILE = Cfg::N_TILE;
-  auto kern = igemm_tcp_kernel<KIND, SPLIT3, GDN, OUT_MODE, PAIR>;
+  auto kern = igemm_tcp_kernel<KIND, SPLIT3, GDN, OUT_MODE, PAIR, ARES>;
 
   PParams p;
   memset(&p, 0, sizeof(p));
@@ -845,6 +995,10 @@ static int launch_p(const b2c_tc_layer* L, cudaStream_t stream, long long* trace
       if ((rc = make_out_map(&mO.m[ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, p.ps, ry, rx, C))) return rc;
       if (SPLIT3 && (rc = make_out_map(&mO.m[4 + ph], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, p.ps, ry, rx, C)))
         return rc;
+      // TS epilogue: the same lattice with per-warp boxes (64 channels x 16 x 2 pixels) in the (otherwise unused) lo maps
+      if (!SPLIT3 && GDN != 0 && PAIR &&
+          (rc = make_out_map(&mO.m[4 + ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, p.ps, ry, rx, C, 2)))
+        return rc;
     }
   }
   cudaLaunchConfig_t cfg = {};
@@ -886,6 +1040,10 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   }
   if (L->kind == B2C_TC_DECONV5S2 && !L->split3 && L->gdn == 2 && !L->out_f32_nchw && !L->out_lo) {
     if (mode & 2) return launch_p<B2C_TC_DECONV5S2, false, 2, OUT_BF16, false>(L, stream, trace);
+    // B2C_TCP_A_RES=1: six resident A boxes per spatial tile + a 7-deep weight ring; 0: a streaming ring of 4 A boxes
+    // (one per phase, x shift and k-block) + a 12-deep weight ring
+    static const int a_res = [] { const char* e = getenv("B2C_TCP_A_RES"); return e ? atoi(e) : 1; }();
+    if (a_res) return launch_p<B2C_TC_DECONV5S2, false, 2, OUT_BF16, true, true>(L, stream, trace);
     return launch_p<B2C_TC_DECONV5S2, false, 2, OUT_BF16, true>(L, stream, trace);
   }
   if (L->kind == B2C_TC_DECONV3 && !L->split3 && L->gdn == 0 && L->out_f32_nchw && !(mode & 4))

@@ -711,7 +711,9 @@ int b2c_quant_entropy_infer_lut(const float* y, const float* const* host_params,
   static const bool allow_v2 = [] { const char* e = getenv("B2C_ENTROPY_LUT_V1"); return !e || atoi(e) == 0; }();
   static const int nsub_env = [] { const char* e = getenv("B2C_ENTROPY_LUT_SUB"); return e ? atoi(e) : 2; }();
   const bool v2 = allow_v2 && C % 64 == 0 && ((uintptr_t)z_nhwc_bf16 & 15) == 0;
-  const int nsub = (v2 && nsub_env == 2 && HW >= 2 * LQ_PIX) ? 2 : 1;      // 256-pixel chunks when the image has them
+  // 256-pixel chunks (512 threads) when that still leaves >= 2 CTAs per SM: on the 18.9 MB latents of a Kodak batch
+  // the larger CTAs (144 of them) measured slower than 288 of 128 pixels
+  const int nsub = (v2 && nsub_env == 2 && (long long)B * ((HW + 2 * LQ_PIX - 1) / (2 * LQ_PIX)) >= 2 * 148) ? 2 : 1;
   const int chunks = (HW + LQ_PIX * nsub - 1) / (LQ_PIX * nsub);
   const size_t smem = v2 ? (size_t)LQ_PIX * nsub * C * 2 : (size_t)LQ_PIX * (C + 2) * 2;
   {
