@@ -301,15 +301,16 @@ def main():
         peak = pk["hbm_gbs"]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}
     traffic = None
-    try:   # DRAM bytes of this kernel from the committed ncu --set full capture (8 images), scaled to this batch
-        nt = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    try:   # DRAM bytes of this kernel from the committed ncu --set full capture of the same batch (24 images)
+        nt = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
         for key, v in nt["kernels"].items():
             if top_name.startswith(key):
-                traffic = v["dram_mbytes_per_launch_8_images"] * 1e6 * IMAGES / nt["images"]
+                traffic = v["dram_mbytes_per_launch"] * 1e6 * IMAGES / nt["images"]
                 roof["tensor_pipe_active_pct_ncu"] = v["tensor_pipe_active_pct"]
     except Exception:
         pass
-    roof.update({"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, scaled from 8 images)",
+    roof.update({"traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                                     "profiles/r2_ncu_traffic.json, same batch)",
                  "kernel": top_name, "kernel_ms": top["ms_avg"],
                  "share_of_step": top["ms_total"] / total_ms, "peak_source": pk_kind,
                  "kernel_timing": "CUDA-event pair around every launch in a second pass of the same K steps "
