@@ -5,7 +5,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb2c.so")
+# B2C_LIB: another build of the same library (A/B measurements of kernel variants on one box)
+LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_PKG, "libb2c.so")
 
 _c_f = ctypes.c_void_p      # device pointers travel as void*
 _c_i = ctypes.c_int

@@ -129,7 +129,10 @@ struct PCfg {
   static constexpr int B_SLOT = (SPLIT3 ? 2 : 1) * B_BYTES;
   static constexpr int W_RES = B_RES ? 9 * NCB * B_BYTES : 0;
   static constexpr int GAMMA_BYTES = GDN ? (SPLIT3 ? 2 : 1) * NCB * B_BYTES : 0;
-  static constexpr int XS = GDN ? XS_BYTES : 0;
+  // x^2 tile / output staging; the TS epilogue (bf16 pair layers, see TS_EPI in the kernel) only stages 2 KB per
+  // worker warp at a time, which buys two more weight-ring slots
+  static constexpr bool TS_LAYOUT = !SPLIT3 && GDN != 0 && PAIR && B2C_TCP_TS_EPI;
+  static constexpr int XS = GDN ? (TS_LAYOUT ? XS_BYTES / 2 : XS_BYTES) : 0;
   static constexpr int EXTRA = 1024 /*align*/ + 1024 /*bias, beta*/ + 512 /*barriers*/;
   static constexpr int MAX_SMEM = 227 * 1024;
   static constexpr int LEFT = MAX_SMEM - EXTRA - GAMMA_BYTES - XS - W_RES;
@@ -625,11 +628,12 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           mbar_wait(&norm_full[buf], par);
           tcgen05_fence_after();
           TCP_MARK(2, threadIdx.x == 64);
-          // ---- final pass: y = x * sqrt(beta + n) (IGDN) or x * rsqrt(beta + n) (GDN) -> this warp's staging slice
-          // (32 pixels x 64 channels, 128-byte rows, SWIZZLE_128B) -> one TMA store of a {64 ch, 16, 2} box
-          uint8_t* my_stg = xs + (uint32_t)(warp - 2) * 4096u;
-          if (lane == 0 && store_pending) { tma_store_wait_read(); store_pending = false; }
-          __syncwarp();
+          // ---- final pass: y = x * sqrt(beta + n) (IGDN) or x * rsqrt(beta + n) (GDN) -> this warp's 2 KB staging
+          // slice (32 pixels x 32 channels, 64-byte rows, SWIZZLE_64B) -> one TMA store of a {32 ch, 16, 2} box per
+          // 32-channel block; the slice is re-used for the second block once the first store has read it
+          uint8_t* my_stg = xs + (uint32_t)(warp - 2) * 2048u;
+          const uint32_t st_row = (uint32_t)lane * 64u, st_x = ((uint32_t)lane >> 1) & 3u;
+          const int mi = (KIND == B2C_TC_DECONV5S2) ? phase : 0;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t rawn[32];
@@ -637,28 +641,29 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tmem_ld_wait();
             if (hh == 1) tcgen05_fence_before();
             const uint64_t* beta2 = reinterpret_cast<const uint64_t*>(s_beta + half * 64 + hh * 32);
+            uint32_t hp[16];
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
-              uint32_t hp[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float n0, n1, y0, y1;
-                upk2(add2(pk2(rawn[ci * 8 + 2 * j], rawn[ci * 8 + 2 * j + 1]), beta2[ci * 4 + j]), n0, n1);
-                const uint64_t sc = (GDN == 2) ? pkf2(sqrt_fast(n0), sqrt_fast(n1)) : pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
-                upk2(mul2(xk[hh * 16 + ci * 4 + j], sc), y0, y1);
-                hp[j] = cvt_bf16x2(y0, y1);
-              }
-              sts128(my_stg, lane, hh * 4 + ci, hp[0], hp[1], hp[2], hp[3]);
+            for (int i = 0; i < 16; ++i) {
+              float n0, n1, y0, y1;
+              upk2(add2(pk2(rawn[2 * i], rawn[2 * i + 1]), beta2[i]), n0, n1);
+              const uint64_t sc = (GDN == 2) ? pkf2(sqrt_fast(n0), sqrt_fast(n1)) : pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
+              upk2(mul2(xk[hh * 16 + i], sc), y0, y1);
+              hp[i] = cvt_bf16x2(y0, y1);
             }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive_cta0(&acc_empty[buf]);       // this warp's TMEM reads of the set are complete
-            const int mi = (KIND == B2C_TC_DECONV5S2) ? phase : 0;
-            tma_store_4d(&tmO.m[4 + mi], my_stg, half * KBLK, ox0, oy0 + 2 * q, n_img);
-            tma_store_commit();
-            store_pending = true;
+            if (lane == 0 && store_pending) { tma_store_wait_read(); store_pending = false; }
+            __syncwarp();
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+              *reinterpret_cast<uint4*>(my_stg + st_row + ((((uint32_t)ci) ^ st_x) << 4)) =
+                  make_uint4(hp[ci * 4 + 0], hp[ci * 4 + 1], hp[ci * 4 + 2], hp[ci * 4 + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (hh == 1) mbar_arrive_cta0(&acc_empty[buf]);       // this warp's TMEM reads of the set are complete
+              tma_store_4d(&tmO.m[4 + mi], my_stg, half * KBLK + hh * 32, ox0, oy0 + 2 * q, n_img);
+              tma_store_commit();
+              store_pending = true;
+            }
           }
           continue;
         }
@@ -995,9 +1000,10 @@ static int launch_p(const b2c_tc_layer* L, cudaStream_t stream, long long* trace
       if ((rc = make_out_map(&mO.m[ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, p.ps, ry, rx, C))) return rc;
       if (SPLIT3 && (rc = make_out_map(&mO.m[4 + ph], L->out_lo, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, p.ps, ry, rx, C)))
         return rc;
-      // TS epilogue: the same lattice with per-warp boxes (64 channels x 16 x 2 pixels) in the (otherwise unused) lo maps
+      // TS epilogue: the same lattice with per-warp boxes (32 channels x 16 x 2 pixels, SWIZZLE_64B) in the (otherwise
+      // unused) lo maps
       if (!SPLIT3 && GDN != 0 && PAIR &&
-          (rc = make_out_map(&mO.m[4 + ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, p.ps, ry, rx, C, 2)))
+          (rc = make_out_map(&mO.m[4 + ph], L->out_hi, L->B, p.Hg, p.Wg, p.Hfull, p.Wfull, p.ps, ry, rx, C, 2, 32)))
         return rc;
     }
   }

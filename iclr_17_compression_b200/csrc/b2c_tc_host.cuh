@@ -59,17 +59,18 @@ static inline int make_act_map(CUtensorMap* m, const void* base, int B, int H, i
 // NHWC bf16 output lattice: pixel (oy*ps + ry, ox*ps + rx) of [B][Hfull][Wfull][128] seen as a dense
 // [B][Hg][Wg][128] tensor with strides; box = 64 channels x TW x TH pixels (TMA clips at the image border)
 static inline int make_out_map(CUtensorMap* m, const void* base, int B, int Hg, int Wg, int Hfull, int Wfull, int ps, int ry,
-                        int rx, int C, int box_rows = TH) {
+                        int rx, int C, int box_rows = TH, int box_ch = KBLK) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
   const char* origin = reinterpret_cast<const char*>(base) + ((size_t)ry * Wfull + rx) * C * 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wg, (cuuint64_t)Hg, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ps * C * 2, (cuuint64_t)ps * Wfull * C * 2,
                            (cuuint64_t)Hfull * Wfull * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)KBLK, (cuuint32_t)TW, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_ch, (cuuint32_t)TW, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(origin), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_ch == KBLK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output) failed: %d", (int)r); return B2C_ECUDA; }
   return B2C_OK;
