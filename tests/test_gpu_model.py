@@ -674,3 +674,41 @@ def test_latent_range_guard_of_the_bf16_synthesis_path():
         assert _rel(r_big, m.Decoder(z)) < 1e-6
         z_small = torch.round(z / 400.0)
         assert _rel(m.decode_tc(z_small), m.Decoder(z_small)) < 2e-2
+
+
+def test_tc_random_shapes_and_repeated_launches():
+    """Protocol stress of the persistent tensor-core kernels (per-warp mbarrier hand-offs, TMEM operand rings, resident
+    boxes): random batch / image sizes - odd tile counts give one CTA of a pair a fully masked tile, small images leave
+    most CTAs without work - and many back-to-back launches of one shape; every run against the exact-fp32 kernels."""
+    import random
+    from oracle import balle17_oracle as O
+    c = Case("eval_W1_U_n128_64")
+    m = _model(c).eval()
+    sd64 = {k: v.cuda().double() for k, v in c.sd.items()}
+    rng = random.Random(7)
+    shapes = [(rng.randint(1, 5), 16 * rng.randint(1, 24), 16 * rng.randint(1, 30)) for _ in range(10)] + [(7, 80, 1040)]
+    with torch.no_grad():
+        for (B, H, W) in shapes:
+            x = O.synth_images("U", B, H, W, 1000 + H + W).cuda()
+            m.fast_inference = True
+            clipped, z, bpp = m(x)
+            assert m.last_path == "tcgen05"
+            sse = m.last["sse"].clone()
+            m.fast_inference = False
+            c2, z2, bpp2 = m(x)
+            y64 = O.analysis(x.double(), sd64)
+            check_latents(z, z2, y64)
+            assert abs(bpp.item() - bpp2.item()) <= REL_BPP_MSE * bpp2.item(), (B, H, W)
+            assert _rel(sse[:, 0], m.last["sse"][:, 0]) <= REL_BPP_MSE, (B, H, W)
+            assert (clipped - c2).abs().max().item() < 0.25, (B, H, W)
+        # the same shape 60 times: every launch must give the same bits
+        m.fast_inference = True
+        x = O.synth_images("S", 3, 208, 336, 99).cuda()
+        ref = None
+        for _ in range(60):
+            clipped, z, bpp = m(x)
+            cur = (z.clone(), clipped.clone(), bpp.clone())
+            if ref is None:
+                ref = cur
+            else:
+                assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]) and torch.equal(cur[2], ref[2])
