@@ -1,6 +1,6 @@
 """Measures the BASELINE.json configurations that bench.py's single headline line does not cover, plus the
 reference algorithm executed by PyTorch eager (cuDNN) on the same B200 as a second comparator
-(BASELINE.md section 4, item 3).  Writes profiles/r1_configs.json.
+(BASELINE.md section 4, item 3).  Writes profiles/r2_configs.json.
 
     python profiles/bench_configs.py            # on a B200 box
 """
@@ -143,7 +143,7 @@ for N in (192, 256):
     out[f"cfg5_2k_n{N}_reference_eager_cuda_tf32_batch1"] = {"ms": ms_ref, "mpix_s": 1536 * 2048 / 1e6 / ms_ref * 1e3}
     del mw
 
-path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "r1_configs.json")
+path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "r2_configs.json")
 os.makedirs(os.path.dirname(path), exist_ok=True)
 json.dump(out, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))
