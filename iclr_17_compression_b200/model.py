@@ -92,6 +92,10 @@ class ImageCompressor(nn.Module):
         # training + out_channel_N == 128: bf16 tensor-core forward/backward (train_tc.TrainStepTC); gradients
         # match the fp32 path within 1e-2 relative L2.  Set False for the exact-fp32 kernels.
         self.fast_training = os.environ.get("B2C_FAST_TRAINING", "1") == "1"
+        # ... and, from the second step with the same input shape on, as two CUDA-graph replays (forward, backward)
+        # under autograd: the reference's own loop (train.py:97-112) is host bound otherwise (train_tc._StepGraphs).
+        # One set of saved activations per shape: backward() must run before the next training forward.
+        self.graph_training = os.environ.get("B2C_TRAIN_AUTOGRAPH", "1") == "1"
         self.last_path = None
         self._packed = None
         self._packed_key = None
@@ -205,7 +209,7 @@ class ImageCompressor(nn.Module):
             from .train_tc import train_forward
             x = B2F._prep(x, "input image")
             clipped_recon_image, mse_loss, bpp_feature, z = train_forward(self, x, self._noise(x))
-            self.last_path = "tcgen05-bf16-train"
+            self.last_path = "tcgen05-bf16-train" + ("-graphed" if self.__dict__.get("_last_train_graphed") else "")
             self.last = {"mse_loss": mse_loss.detach()}      # detached: must not keep the autograd graph alive
             if self.return_mode == "mse":
                 return clipped_recon_image, mse_loss, bpp_feature

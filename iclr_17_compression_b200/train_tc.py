@@ -360,11 +360,133 @@ class TrainStepTC(torch.autograd.Function):
         return (None, None) + tuple(grads[k].reshape(prm[k].shape) for k in PARAM_ORDER)
 
 
+class _StepGraphs:
+    """Forward and backward of the tensor-core training step captured as TWO CUDA graphs for one input shape and one
+    set of parameter tensors, for callers that drive the step through autograd (the reference's unmodified loop:
+    ``net(input)`` ... ``rd_loss.backward()``, train.py:97-105).  Eager, that loop is host bound: ~60 libb2c launches
+    per step with their TMA descriptors and tensor allocations cost 3.4 ms against 0.36 ms of device time.  The graphs
+    read the LIVE parameter tensors (in-place optimizer updates are seen), take the input, the noise and the two loss
+    cotangents through static buffers, and keep the saved activations in their private pool."""
+
+    def __init__(self, x, noise, params):
+        dev = x.device
+        self.x, self.noise = torch.empty_like(x), torch.empty_like(noise)
+        self.g_sse = torch.zeros((1,), device=dev, dtype=torch.float32)
+        self.g_bits = torch.zeros((1,), device=dev, dtype=torch.float32)
+        self.key = _graph_key(x, params)
+        prm = dict(zip(PARAM_ORDER, [p.detach() for p in params]))
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                       # warm-up on a side stream, as graph capture requires
+            self.x.copy_(x)
+            self.noise.copy_(noise)
+            for _ in range(2):
+                st = step_forward(self.x, self.noise, prm)
+                step_backward(st, self.g_sse, self.g_bits)
+            del st
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd):
+            self.st = step_forward(self.x, self.noise, prm)
+            self.total_bits = self.st["image_bits"].sum()
+            self.sse_total = self.st["sse"][:, 0].sum()
+        self.bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.bwd, pool=self.fwd.pool()):
+            grads = step_backward(self.st, self.g_sse, self.g_bits)
+            self.flat = torch.cat([grads[k].reshape(-1) for k in PARAM_ORDER])     # one buffer to hand out per step
+        self.sizes = [prm[k].numel() for k in PARAM_ORDER]
+        self.generation = 0
+
+
+def _graph_key(x, params):
+    return (tuple(x.shape), x.device.index) + tuple(p.data_ptr() for p in params)
+
+
+class TrainStepTCGraphed(torch.autograd.Function):
+    """TrainStepTC as two graph replays: (graphs, x, noise, *30 params) -> (clipped, sse_total, total_bits, z)"""
+
+    @staticmethod
+    def forward(ctx, graphs, x, noise, *params):
+        graphs.x.copy_(x)
+        graphs.noise.copy_(noise)
+        graphs.fwd.replay()
+        graphs.generation += 1
+        ctx.graphs, ctx.generation = graphs, graphs.generation
+        ctx.shapes = [p.shape for p in params]
+        ctx.set_materialize_grads(False)
+        st = graphs.st
+        # the graph's buffers are overwritten by the next replay: the caller gets its own copies
+        return st["clipped"].clone(), graphs.sse_total.clone(), graphs.total_bits.clone(), st["z"].clone()
+
+    @staticmethod
+    def backward(ctx, g_clipped, g_sse, g_bits, g_z):
+        G = ctx.graphs
+        if G.generation != ctx.generation:
+            raise _lib.B2CError("the graphed training step keeps ONE set of saved activations per input shape: "
+                                "another training forward of this model ran before this backward.  Call backward "
+                                "first, or set model.graph_training = False")
+        dev = G.x.device
+        zero = torch.zeros((1,), device=dev, dtype=torch.float32)
+        g_sse = g_sse.reshape(1).float() if g_sse is not None else zero
+        g_bits = g_bits.reshape(1).float() if g_bits is not None else zero
+        if g_clipped is not None or g_z is not None:
+            # a loss built from the clamped reconstruction / the latent (model.py:80 tuple): eager backward over the
+            # activations the forward graph saved
+            grads = step_backward(G.st, g_sse.contiguous(), g_bits.contiguous(),
+                                  g_clipped=g_clipped.float().contiguous() if g_clipped is not None else None,
+                                  g_z=g_z.float().contiguous() if g_z is not None else None)
+            return (None, None, None) + tuple(grads[k].reshape(sh) for k, sh in zip(PARAM_ORDER, ctx.shapes))
+        G.g_sse.copy_(g_sse)
+        G.g_bits.copy_(g_bits)
+        G.bwd.replay()
+        flat = G.flat.clone()
+        outs = [t.view(sh) for t, sh in zip(torch.split(flat, G.sizes), ctx.shapes)]
+        return (None, None, None) + tuple(outs)
+
+
+def _auto_graphs(model, x, noise, params):
+    """the _StepGraphs of (shape, parameter tensors), captured the SECOND time that combination is seen (a replica that
+    nn.DataParallel rebuilds every step never repeats and stays eager); None = run the eager Function"""
+    if not getattr(model, "graph_training", False) or torch.cuda.is_current_stream_capturing():
+        return None
+    if not all(p.is_contiguous() and p.dtype == torch.float32 for p in params) or x.dtype != torch.float32:
+        return None
+    cache = model.__dict__.setdefault("_train_graphs", {})
+    key = _graph_key(x, params)
+    hit = cache.get(key)
+    if isinstance(hit, _StepGraphs):
+        return hit
+    if hit is None:
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache)))
+        cache[key] = 1
+        return None
+    if hit == "failed":
+        return None
+    try:
+        with torch.no_grad():
+            cache[key] = _StepGraphs(x.detach(), noise.detach(), params)
+    except Exception as e:                       # capture is an optimisation: the eager step stays correct
+        import warnings
+        warnings.warn(f"CUDA-graph capture of the training step failed ({e!r}); running it eagerly")
+        cache[key] = "failed"
+        return None
+    return cache[key]
+
+
 def train_forward(model, x, noise):
     """ImageCompressor training forward on tensor cores: returns (clipped, mse_loss, bpp, z) and fills model.last"""
     params = dict(model.canonical_named_parameters() if hasattr(model, "canonical_named_parameters")
                   else model.named_parameters())
-    clipped, sse_total, total_bits, z = TrainStepTC.apply(x, noise, *[params[k] for k in PARAM_ORDER])
+    plist = [params[k] for k in PARAM_ORDER]
+    graphs = _auto_graphs(model, x, noise, plist)
+    model.__dict__["_last_train_graphed"] = graphs is not None
+    if graphs is not None:
+        clipped, sse_total, total_bits, z = TrainStepTCGraphed.apply(graphs, x, noise, *plist)
+    else:
+        clipped, sse_total, total_bits, z = TrainStepTC.apply(x, noise, *plist)
     mse = sse_total / x.numel()
     bpp = total_bits / (x.size(0) * x.size(2) * x.size(3))
     return clipped, mse, bpp, z

@@ -712,3 +712,51 @@ def test_tc_random_shapes_and_repeated_launches():
                 ref = cur
             else:
                 assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]) and torch.equal(cur[2], ref[2])
+
+
+def test_autograd_training_loop_runs_as_graph_replays():
+    """The reference's own loop (train.py:97-112: net(input); rd_loss.backward(); clamp; optimizer.step()) on the drop-in
+    module: from the second step with the same shape on, forward and backward are CUDA-graph replays under autograd
+    (train_tc._StepGraphs).  Same losses / gradients / parameters as the eager tensor-core step, in-place optimizer
+    updates are seen by the graphs, a smaller last batch falls back, and a forward that overwrites the saved
+    activations before backward fails loudly."""
+    from iclr_17_compression_b200._lib import B2CError
+    c = Case("train_W1_S_n128_64")
+    x, noise = c.x.cuda(), c.noise.cuda()
+    models, opts, hist = {}, {}, {}
+    for graphed in (True, False):
+        m = _model(c, return_mode="mse").train()
+        m.graph_training = graphed
+        models[graphed], opts[graphed], hist[graphed] = m, torch.optim.Adam(m.parameters(), lr=1e-4), []
+    for step in range(5):
+        for graphed in (True, False):
+            m, opt = models[graphed], opts[graphed]
+            m.noise_override = noise
+            xs = x if step != 3 else x[:1]                       # step 3: a smaller batch (another shape)
+            m.noise_override = noise if step != 3 else noise[:1]
+            opt.zero_grad()
+            _, mse, bpp = m(xs)
+            loss = c.lam * mse + bpp
+            loss.backward()
+            for p in m.parameters():
+                p.grad.data.clamp_(-5, 5)                        # train.py:106-111
+            hist[graphed].append((loss.item(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+            opt.step()
+            want = "tcgen05-bf16-train" + ("-graphed" if graphed and step in (1, 2, 4) else "")
+            assert m.last_path == want, (step, graphed, m.last_path)
+    for step in range(5):
+        (la, ga), (lb, gb) = hist[True][step], hist[False][step]
+        assert abs(la - lb) <= 2e-3 * abs(lb), (step, la, lb)
+        if step == 0:                                            # later steps: Adam amplifies the atomics' rounding noise
+            for k in ga:
+                assert _rel(ga[k], gb[k]) < 2e-3, (step, k)
+    for (k, pa), pb in zip(models[True].named_parameters(), models[False].parameters()):
+        assert (pa - pb).abs().max().item() <= 1.2e-3, k        # 5 Adam steps of 1e-4 each way at most
+    # two forwards, then backward of the first: the saved activations are gone -> loud failure
+    m = models[True]
+    m.noise_override = noise
+    _, mse1, bpp1 = m(x)
+    _, mse2, bpp2 = m(x)
+    with pytest.raises(B2CError):
+        (c.lam * mse1 + bpp1).backward()
+    (c.lam * mse2 + bpp2).backward()                             # the latest one is fine
