@@ -52,7 +52,7 @@ class TcLayer(ctypes.Structure):
                 ("channels", _c_i), ("grad_out", _c_f), ("grad_scale", ctypes.c_float), ("ksplit", _c_i)]
 
 
-TC_CONV1, TC_CONV5S2, TC_DECONV5S2, TC_DECONV3 = 0, 1, 2, 3
+TC_CONV1, TC_CONV5S2, TC_DECONV5S2, TC_DECONV3, TC_DECONV3X = 0, 1, 2, 3, 4
 
 SIGNATURES.update({
     "b2c_tc_packed_weight_elems": (_c_sz, [_c_i, _c_i]),

@@ -907,6 +907,12 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   
 namespace tcp1 {
 int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   // b2c_conv1_tcp.cu; 1 = not covered
 }
+namespace tcp3x {                                                                // b2c_deconv3x.cu
+int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);
+int pack(const float* w, void* out, cudaStream_t stream);
+size_t packed_elems();
+int tiles_per_image(int Hin, int Win);
+}
 }  // namespace b2c
 
 using namespace b2c;
@@ -929,6 +935,7 @@ size_t b2c_tc_packed_weight_elems(int kind, int channels) {
     case B2C_TC_CONV5S2:
     case B2C_TC_DECONV5S2: return 25 * C * C;
     case B2C_TC_DECONV3: return 9 * 48 * C;
+    case B2C_TC_DECONV3X: return channels == 128 ? b2c::tcp3x::packed_elems() : 0;
     default: return 0;
   }
 }
@@ -936,6 +943,7 @@ size_t b2c_tc_packed_weight_elems(int kind, int channels) {
 int b2c_tc_pack_weights(int kind, int channels, const float* w, void* w_hi, void* w_lo, void* stream) {
   const size_t n = b2c_tc_packed_weight_elems(kind, channels);
   B2C_REQUIRE(n > 0 && w && w_hi, "tc_pack_weights: bad arguments (channels must be 128, 192 or 256)");
+  if (kind == B2C_TC_DECONV3X) return b2c::tcp3x::pack(w, w_hi, (cudaStream_t)stream);   // plain bf16 only (no lo plane)
   pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       kind, w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, (int)n, channels);
   count_launch();
@@ -980,6 +988,7 @@ int b2c_tc_nhwc_to_nchw(const void* in_hi, const void* in_lo, float* out, int B,
 
 int b2c_tc_tiles_per_image(int kind, int Hin, int Win) {
   int Hg, Wg;
+  if (kind == B2C_TC_DECONV3X) return b2c::tcp3x::tiles_per_image(Hin, Win);
   switch (kind) {
     case B2C_TC_CONV1: Hg = Hin / 4; Wg = Win / 4; break;
     case B2C_TC_CONV5S2: Hg = (Hin - 1) / 2 + 1; Wg = (Win - 1) / 2 + 1; break;
@@ -998,6 +1007,12 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   B2C_REQUIRE(!L->gdn || (L->gamma_hi && L->beta_eff && (!L->split3 || L->gamma_lo)), "tc_layer_run: gdn needs gamma/beta");
   B2C_REQUIRE(L->out_f32_nchw || !L->split3 || L->out_lo, "tc_layer_run: split3 bf16 output needs out_lo");
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (L->kind == B2C_TC_DECONV3X) {
+    B2C_REQUIRE((L->channels == 0 || L->channels == 128) && !L->split3 && !L->gdn && L->out_f32_nchw && !L->saved_y,
+                "tc_layer_run: DECONV3X is the plain-bf16 128-channel last synthesis layer with fp32 NCHW output");
+    B2C_REQUIRE(!L->ref_image || L->sse_partial, "tc_layer_run: ref_image and sse_partial go together");
+    return b2c::tcp3x::launch(L, stream, g_tc_trace);
+  }
   {   // persistent kernels for the TMA-fed 128-channel inference layers
     int rc = b2c::tcp::try_launch(L, stream, g_tc_trace);
     if (rc != 1) return rc;

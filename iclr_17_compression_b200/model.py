@@ -138,7 +138,7 @@ class ImageCompressor(nn.Module):
                 "gdn2": B2TC.pack_gdn(E.gdn2.beta, E.gdn2.gamma, True),
                 "deconv1": B2TC.pack_weights(B2TC.TC_DECONV5S2, D.deconv1.weight, False),
                 "deconv2": B2TC.pack_weights(B2TC.TC_DECONV5S2, D.deconv2.weight, False),
-                "deconv3": B2TC.pack_weights(B2TC.TC_DECONV3, D.deconv3.weight, False),
+                "deconv3": B2TC.pack_weights(B2TC.deconv3_kind(self.out_channel_N), D.deconv3.weight, False),
                 "igdn1": B2TC.pack_gdn(D.igdn1.beta, D.igdn1.gamma, False),
                 "igdn2": B2TC.pack_gdn(D.igdn2.beta, D.igdn2.gamma, False),
                 # bits[c][z] for integer z: the inference entropy pass becomes a table read (functional.entropy_lut)
@@ -183,8 +183,8 @@ class ImageCompressor(nn.Module):
         zh = z_nhwc if z_nhwc is not None else B2TC.nchw_to_nhwc(z, False)[0]   # integer |z| <= 256: exact in bf16
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, zh, None, P["deconv1"], D.deconv1.bias, gdn=P["igdn1"], gdn_mode=2)
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, h[0], None, P["deconv2"], D.deconv2.bias, gdn=P["igdn2"], gdn_mode=2)
-        return B2TC.layer_run(B2TC.TC_DECONV3, h[0], None, P["deconv3"], D.deconv3.bias, out_f32_nchw=True,
-                              ref_image=ref_image)
+        return B2TC.layer_run(B2TC.deconv3_kind(self.out_channel_N), h[0], None, P["deconv3"], D.deconv3.bias,
+                              out_f32_nchw=True, ref_image=ref_image)
 
     def _forward_tc(self, x):
         """the tensor-core eval pipeline: 7 fused launches + 1 reduction"""

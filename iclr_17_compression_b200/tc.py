@@ -2,11 +2,12 @@
 activations and fused layer launches through libb2c's C ABI (include/b2c.h, b2c_tc_*).
 Inference only (no autograd); out_channel_N must be 128."""
 import ctypes
+import os
 
 import torch
 
 from . import _lib
-from ._lib import TC_CONV1, TC_CONV5S2, TC_DECONV3, TC_DECONV5S2, TcLayer  # noqa: F401
+from ._lib import TC_CONV1, TC_CONV5S2, TC_DECONV3, TC_DECONV3X, TC_DECONV5S2, TcLayer  # noqa: F401
 from .functional import _timed
 
 _vp = ctypes.c_void_p
@@ -18,6 +19,15 @@ def _p(t):
 
 def _stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def deconv3_kind(channels):
+    """Layer kind of the last synthesis layer (synthesis_17.py:23): the x-folded persistent kernel (DECONV3X: N = 112,
+    24 MMAs per tile) for 128 channels, the 3x3-shift form (DECONV3) for the wider models.  B2C_DECONV3X=0 selects the
+    3x3-shift form everywhere (A/B measurements).  The two kinds have different packed-weight layouts."""
+    if channels == 128 and os.environ.get("B2C_DECONV3X", "1") != "0":
+        return TC_DECONV3X
+    return TC_DECONV3
 
 
 def pack_weights(kind, w, need_lo):
@@ -70,7 +80,7 @@ def nhwc_to_nchw(hi, lo=None):
 
 def _flops_per_out_pixel(kind, C):
     return {TC_CONV1: 2 * 243 * C, TC_CONV5S2: 2 * 25 * C * C, TC_DECONV5S2: 2 * 25 * C * C / 4,
-            TC_DECONV3: 2 * C * 243 / 16}[kind]
+            TC_DECONV3: 2 * C * 243 / 16, TC_DECONV3X: 2 * C * 243 / 16}[kind]
 
 
 def pack_gdn_t(beta, gamma):

@@ -158,7 +158,7 @@ def step_forward(x, noise, prm, pool=None, grad_scale=None):
             "w3": T.pack_weights(T.TC_CONV5S2, W3, False),
             "d1": T.pack_weights(T.TC_DECONV5S2, D1, False), "gi1": T.pack_gdn(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], False),
             "d2": T.pack_weights(T.TC_DECONV5S2, D2, False), "gi2": T.pack_gdn(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], False),
-            "d3": T.pack_weights(T.TC_DECONV3, D3, False),
+            "d3": T.pack_weights(T.deconv3_kind(128), D3, False),
         }
         ev_fwd = torch.cuda.Event()
         ev_fwd.record(side)
@@ -203,12 +203,12 @@ def step_forward(x, noise, prm, pool=None, grad_scale=None):
     if grad_scale is not None:
         # distortion forward AND backward fused into the last layer's epilogue: clamp, both squared-error sums and
         # d loss / d recon = grad_scale * (recon - x) leave the kernel together (grad_scale = 2 lambda / numel)
-        clipped, sse_partial, g_recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"],
+        clipped, sse_partial, g_recon = T.layer_run(T.deconv3_kind(128), i2, None, pk["d3"], prm["Decoder.deconv3.bias"],
                                                     out_f32_nchw=True, ref_image=x, grad_scale=grad_scale,
                                                     reduce_sse=False)
         recon, sse = None, None
     else:
-        recon = T.layer_run(T.TC_DECONV3, i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
+        recon = T.layer_run(T.deconv3_kind(128), i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
         # ---- distortion
         clipped = torch.empty_like(recon)
         sse = torch.empty((B, 2), device=dev, dtype=torch.float32)

@@ -175,6 +175,10 @@ int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped
 #define B2C_TC_DECONV3 3   /* 9x9 s4 p4 op3 transposed, 128->3, as a 3x3 conv to 16 phases x 3 channels
                               (models/synthesis_17.py:23) */
 
+#define B2C_TC_DECONV3X 4  /* the same layer (128 channels only) with the horizontal input shifts folded into the GEMM's
+                              N dimension (N = 112, 24 MMAs per tile instead of 72 of N = 48) and summed by warp shuffles
+                              in the epilogue; tiles advance by 14 columns.  Own packed-weight layout: pack with this kind. */
+
 /* `channels` = out_channel_N in {128, 192, 256} (model.py:39; 192 / 256 are the wider-latent variants of
  * BASELINE config 5; the training kinds - gdn 3/4, the norm plane, b2c_tc_wgrad* - exist for 128 only). */
 /* bf16 elements in ONE packed weight plane (hi or lo) of a layer kind. */
@@ -207,7 +211,7 @@ typedef struct b2c_tc_layer {
   const float* beta_eff;
   void* out_hi;
   void* out_lo;
-  /* DECONV3 only, optional fused distortion (model.py:59,61; train.py:172): with ref_image = x (fp32 NCHW)
+  /* DECONV3 / DECONV3X only, optional fused distortion (model.py:59,61; train.py:172): with ref_image = x (fp32 NCHW)
    * out_hi receives clamp(recon, 0, 1) and sse_partial[B][tiles][2] the per-tile sums of (recon - x)^2 and
    * (clamp(recon) - x)^2; reduce them with b2c_partial_reduce(sse_partial, sse, B, tiles, 2). */
   const float* ref_image;
@@ -226,7 +230,9 @@ typedef struct b2c_tc_layer {
                        For small batches where one CTA per tile leaves most SMs idle (training, batch 8).   */
 } b2c_tc_layer;
 
-/* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid */
+/* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid = the `tiles`
+ * dimension of sse_partial (DECONV3X: tiles advance by 14 columns and every one of a tile's 16 epilogue warps owns a
+ * partial-sum slot, so this is 16 x the tile count) */
 int b2c_tc_tiles_per_image(int kind, int Hin, int Win);
 
 int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);

@@ -132,6 +132,37 @@ def test_deconv3_bf16(tc, shape):
     assert _rel(y, ref) < 2e-5, _rel(y, ref)
 
 
+@pytest.mark.parametrize("shape", [(1, 16, 32), (2, 32, 48), (1, 20, 24), (1, 8, 14), (3, 9, 29), (1, 40, 70)])
+def test_deconv3x_bf16(tc, shape):
+    """DECONV3X (horizontal shifts folded into N, summed by warp shuffles; tiles advance by 14 columns): same values
+    as the transposed convolution of the bf16-rounded operands, plain and with the fused clamp + squared errors +
+    distortion gradient; widths that are / are not multiples of 14 and 16, ragged heights."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn(B, 128, H, W, generator=g).cuda()
+    w = (torch.randn(128, 3, 9, 9, generator=g) * 0.05).cuda()
+    b = torch.randn(3, generator=g).cuda()
+    img = torch.rand(B, 3, 4 * H, 4 * W, generator=g).cuda()
+    xh, _ = tc.nchw_to_nhwc(x, False)
+    xq = xh.float().permute(0, 3, 1, 2).double().cpu()
+    wq = w.to(torch.bfloat16).double().cpu()
+    ref = F.conv_transpose2d(xq, wq, b.double().cpu(), stride=4, padding=4, output_padding=3)
+    wp = tc.pack_weights(tc.TC_DECONV3X, w, False)
+    y = tc.layer_run(tc.TC_DECONV3X, xh, None, wp, b, split3=False, out_f32_nchw=True)
+    assert y.shape == ref.shape
+    assert _rel(y, ref) < 2e-5, _rel(y, ref)
+    clipped, sse, g_recon = tc.layer_run(tc.TC_DECONV3X, xh, None, wp, b, out_f32_nchw=True, ref_image=img,
+                                         grad_scale=0.25)
+    xi = img.double().cpu()
+    assert torch.allclose(clipped.double().cpu(), ref.clamp(0, 1), atol=2e-5)
+    sse_ref = torch.stack([((ref - xi) ** 2).flatten(1).sum(1), ((ref.clamp(0, 1) - xi) ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(sse.double().cpu(), sse_ref, rtol=1e-4), (sse, sse_ref)
+    assert _rel(g_recon, 0.25 * (ref - xi)) < 2e-5
+    # the 3x3-shift form computes the same layer
+    y3 = tc.layer_run(tc.TC_DECONV3, xh, None, tc.pack_weights(tc.TC_DECONV3, w, False), b, out_f32_nchw=True)
+    assert _rel(y, y3.double().cpu()) < 1e-5
+
+
 @pytest.mark.parametrize("shape", [(1, 16, 32), (2, 32, 32), (3, 24, 40)])
 def test_wgrad_5x5s2(tc, shape):
     """tensor-core weight gradient (MN-major MMAs) vs autograd, conv and transposed-conv forms."""
