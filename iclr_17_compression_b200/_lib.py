@@ -49,10 +49,18 @@ class TcLayer(ctypes.Structure):
                 ("in_hi", _c_f), ("in_lo", _c_f), ("w_hi", _c_f), ("w_lo", _c_f), ("bias", _c_f),
                 ("gamma_hi", _c_f), ("gamma_lo", _c_f), ("beta_eff", _c_f), ("out_hi", _c_f), ("out_lo", _c_f),
                 ("ref_image", _c_f), ("sse_partial", _c_f), ("saved_y", _c_f), ("saved_n", _c_f),
-                ("channels", _c_i), ("grad_out", _c_f), ("grad_scale", ctypes.c_float), ("ksplit", _c_i)]
+                ("channels", _c_i), ("grad_out", _c_f), ("grad_scale", ctypes.c_float), ("ksplit", _c_i),
+                ("dbias_out", _c_f)]
 
 
 TC_CONV1, TC_CONV5S2, TC_DECONV5S2, TC_DECONV3, TC_DECONV3X = 0, 1, 2, 3, 4
+TC_PACK_GDN, TC_PACK_GDN_T = 16, 17          # b2c_tc_pack_job.kind beyond the layer kinds
+
+
+class TcPackJob(ctypes.Structure):
+    """struct b2c_tc_pack_job (include/b2c.h)"""
+    _fields_ = [("kind", _c_i), ("channels", _c_i), ("src", _c_f), ("src2", _c_f), ("dst_hi", _c_f), ("dst_lo", _c_f),
+                ("beta_eff", _c_f)]
 
 SIGNATURES.update({
     "b2c_tc_packed_weight_elems": (_c_sz, [_c_i, _c_i]),
@@ -63,6 +71,8 @@ SIGNATURES.update({
     "b2c_tc_tiles_per_image": (_c_i, [_c_i, _c_i, _c_i]),
     "b2c_tc_wgrad": (_c_i, [_c_f, _c_f, _c_f] + [_c_i] * 8 + [_c_f, _c_sz, _c_f]),
     "b2c_tc_wgrad_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
+    "b2c_tc_wgrad_untap": (_c_i, [_c_f, _c_f, _c_i, _c_i, _c_f]),
+    "b2c_tc_pack_many": (_c_i, [_c_f, _c_i, _c_f]),
     "b2c_tc_wgrad9": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f, _c_sz, _c_f]),
     "b2c_tc_wgrad9_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
     "b2c_allreduce_symm": (_c_i, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_i, _c_i, _c_sz, ctypes.c_float, _c_f]),

@@ -20,6 +20,7 @@
 #include "b2c_tc.cuh"
 #include "b2c_tc_im2col.cuh"
 #include "b2c_tc_host.cuh"
+#include "b2c_deconv3x_pack.cuh"
 
 namespace b2c {
 namespace tc {
@@ -706,12 +707,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
 // ------------------------------------------------------------------------------------ packing kernels
 // weights -> bf16 (hi, lo) panels, row = (group, out channel), 128-byte K-major rows
-__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo, int total, int C) {
-  pdl_trigger();
-  pdl_wait();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+__device__ __forceinline__ void pack_weight_elem(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                                 __nv_bfloat16* __restrict__ lo, int idx, int C) {
   float v = 0.f;
   if (kind == B2C_TC_CONV1) {            // [kb 4][o C][j 64], k = kb*64 + j, w OIHW [C][3][9][9]
     const int j = idx & 63, o = (idx >> 6) % C, kb = idx / (64 * C);
@@ -736,12 +733,18 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_
   if (lo) lo[idx] = l;
 }
 
-__global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
-                                __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
-                                float* __restrict__ beta_eff, int transpose, int C) {
+__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int total, int C) {
   pdl_trigger();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  pack_weight_elem(kind, w, hi, lo, idx, C);
+}
+
+__device__ __forceinline__ void pack_gdn_elem(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
+                                              __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
+                                              float* __restrict__ beta_eff, int transpose, int C, int idx) {
   if (idx < C * C) {
     const int src = transpose ? ((idx % C) * C + (idx / C)) : idx;
     const float b = fmaxf(gamma_p[src], 3.814697265625e-06f);
@@ -754,6 +757,36 @@ __global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* _
   if (idx < C) {
     const float b = fmaxf(beta_p[idx], (float)0.0010000072759311445);
     beta_eff[idx] = b * b - 1.4551915228366852e-11f;
+  }
+}
+
+__global__ void pack_gdn_kernel(const float* __restrict__ beta_p, const float* __restrict__ gamma_p,
+                                __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
+                                float* __restrict__ beta_eff, int transpose, int C) {
+  pdl_trigger();
+  pdl_wait();
+  pack_gdn_elem(beta_p, gamma_p, ghi, glo, beta_eff, transpose, C, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// several packing jobs in one launch: blockIdx.y = job, blockIdx.x strides over the job's elements
+constexpr int PACK_MAX_JOBS = 16;
+struct PackJobs {
+  b2c_tc_pack_job j[PACK_MAX_JOBS];
+  int total[PACK_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) pack_many_kernel(const __grid_constant__ PackJobs J) {
+  pdl_trigger();
+  pdl_wait();
+  const b2c_tc_pack_job& job = J.j[blockIdx.y];
+  const int total = J.total[blockIdx.y];
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    if (job.kind == B2C_TC_PACK_GDN || job.kind == B2C_TC_PACK_GDN_T)
+      pack_gdn_elem(job.src, job.src2, (__nv_bfloat16*)job.dst_hi, (__nv_bfloat16*)job.dst_lo, job.beta_eff,
+                    job.kind == B2C_TC_PACK_GDN_T, job.channels, idx);
+    else if (job.kind == B2C_TC_DECONV3X)
+      ((__nv_bfloat16*)job.dst_hi)[idx] = __float2bfloat16_rn(tcp3x::deconv3x_weight(job.src, idx));
+    else
+      pack_weight_elem(job.kind, job.src, (__nv_bfloat16*)job.dst_hi, (__nv_bfloat16*)job.dst_lo, idx, job.channels);
   }
 }
 
@@ -948,6 +981,33 @@ int b2c_tc_pack_weights(int kind, int channels, const float* w, void* w_hi, void
       kind, w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, (int)n, channels);
   count_launch();
   return check_launch("tc_pack_weights");
+}
+
+int b2c_tc_pack_many(const b2c_tc_pack_job* jobs, int n_jobs, void* stream) {
+  B2C_REQUIRE(jobs && n_jobs > 0 && n_jobs <= PACK_MAX_JOBS, "tc_pack_many: 1..%d jobs", PACK_MAX_JOBS);
+  PackJobs J;
+  memset(&J, 0, sizeof(J));
+  int max_total = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const b2c_tc_pack_job& j = jobs[i];
+    B2C_REQUIRE(j.channels == 128 && j.src && j.dst_hi, "tc_pack_many: job %d: 128 channels, src and dst_hi required", i);
+    int total;
+    if (j.kind == B2C_TC_PACK_GDN || j.kind == B2C_TC_PACK_GDN_T) {
+      B2C_REQUIRE(j.src2 && j.beta_eff, "tc_pack_many: job %d: GDN jobs need gamma_p (src2) and beta_eff", i);
+      total = j.channels * j.channels;
+    } else {
+      total = (int)b2c_tc_packed_weight_elems(j.kind, j.channels);
+      B2C_REQUIRE(total > 0, "tc_pack_many: job %d: unknown kind %d", i, j.kind);
+    }
+    J.j[i] = j;
+    J.total[i] = total;
+    if (total > max_total) max_total = total;
+  }
+  int bx = (max_total + 255) / 256;
+  if (bx > 400) bx = 400;
+  pack_many_kernel<<<dim3(bx, n_jobs), 256, 0, (cudaStream_t)stream>>>(J);
+  count_launch();
+  return check_launch("tc_pack_many");
 }
 
 int b2c_tc_pack_gdn(int channels, const float* beta_p, const float* gamma_p, void* gamma_hi, void* gamma_lo,

@@ -28,6 +28,7 @@
 #include "b2c_tc.cuh"
 #include "b2c_tc_host.cuh"
 #include "b2c_tcp_util.cuh"
+#include "b2c_deconv3x_pack.cuh"
 
 namespace b2c {
 namespace tcp3x {
@@ -42,8 +43,8 @@ constexpr int NTHREADS = 64 + NWORKERS;
 constexpr int BOX_ROWS = TH + 2;
 constexpr int ROW_BYTES = TW * 128;                 // one tile row of a k-block: 2 KB
 constexpr int A_SLOT = BOX_ROWS * ROW_BYTES;        // 20 KB
-constexpr int NX = 112;                             // GEMM N: 4 sub-pixel rows x (12 dx=0, 12 dx=+1, 3 dx=-1, 1 zero)
-constexpr int PART_COLS = NX / 4;                   // 28 accumulator columns per sub-pixel row ry
+constexpr int NX = X_NX;                            // GEMM N: 4 sub-pixel rows x (12 dx=0, 12 dx=+1, 3 dx=-1, 1 zero)
+constexpr int PART_COLS = X_PART_COLS;              // 28 accumulator columns per sub-pixel row ry
 constexpr int B_BYTES = NX * 128;                   // one (tap, k-block) weight tile: 14 KB
 constexpr int W_RES = 3 * NCB * B_BYTES;            // 84 KB
 constexpr int TWX = TW - 2;                         // output block columns per tile
@@ -67,6 +68,7 @@ struct XParams {
   float* sse_partial;       // [B][tiles_per_image][16 worker warps][2]
   float* grad_out;          // training: grad_scale * (recon - x) or nullptr
   float grad_scale;
+  float* dbias;             // training: dbias[o] += sum of grad_out over (n, y, x) - the bias gradient - or nullptr
   long long* trace;         // debug: clock64 timeline of CTA 0: [3 roles][64 marks]
 };
 
@@ -194,6 +196,7 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 3) s_bias[threadIdx.x - 64] = p.bias ? __ldg(p.bias + threadIdx.x - 64) : 0.f;
     asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory");
     uint32_t st = 0;
+    float sb[3] = {0.f, 0.f, 0.f};     // running sums of (recon - x) per channel over this thread's tiles (bias gradient)
     for (int tile = unit0; tile < p.n_tiles; tile += unit_stride, ++st) {
       const int n_img = tile / p.tiles_per_image;
       const int trem = tile - n_img * p.tiles_per_image;
@@ -255,10 +258,12 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               dd = v4.z - x4.z; s0 = fmaf(dd, dd, s0); dd = v4.w - x4.w; s0 = fmaf(dd, dd, s0);
               dd = c4.x - x4.x; s1 = fmaf(dd, dd, s1); dd = c4.y - x4.y; s1 = fmaf(dd, dd, s1);
               dd = c4.z - x4.z; s1 = fmaf(dd, dd, s1); dd = c4.w - x4.w; s1 = fmaf(dd, dd, s1);
-              if (p.grad_out)   // d/d recon of (grad_scale / 2) * sum (recon - x)^2: the distortion backward, fused
+              if (p.grad_out) {   // d/d recon of (grad_scale / 2) * sum (recon - x)^2: the distortion backward, fused
                 *reinterpret_cast<float4*>(p.grad_out + off) =
                     make_float4(p.grad_scale * (v4.x - x4.x), p.grad_scale * (v4.y - x4.y),
                                 p.grad_scale * (v4.z - x4.z), p.grad_scale * (v4.w - x4.w));
+                sb[o] += ((v4.x - x4.x) + (v4.y - x4.y)) + ((v4.z - x4.z) + (v4.w - x4.w));
+              }
               v4 = c4;
             }
             *reinterpret_cast<float4*>(p.out_f32 + off) = v4;
@@ -278,6 +283,22 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       X_MARK(2, threadIdx.x == 64);
     }
+    if (p.dbias && p.grad_out) {     // bias gradient = sum of grad_out: per-CTA sum, three atomic adds per CTA
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) sb[o] += __shfl_xor_sync(0xffffffffu, sb[o], sh);
+      }
+      float* red = s_bias + 16;      // [16 warps][3]
+      if (lane == 0) { red[(warp - 2) * 3] = sb[0]; red[(warp - 2) * 3 + 1] = sb[1]; red[(warp - 2) * 3 + 2] = sb[2]; }
+      asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory");
+      if (warp == 2 && lane < 3) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARPS_W; ++w) a += red[w * 3 + lane];
+        atomicAdd(p.dbias + lane, p.grad_scale * a);
+      }
+    }
   }
 
   tcgen05_fence_before();
@@ -289,28 +310,12 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #undef X_MARK
 }
 
-// weights IOHW [128][3][9][9] -> [tap t = dy + 1][n2 112][c 128] bf16; column n2 = ry*28 + j of the GEMM:
-//   j in [0,12):  dx = 0,  j = rx*3 + o        j in [12,24): dx = +1, same decomposition of j - 12
-//   j in [24,27): dx = -1, rx = 0, o = j - 24  j = 27: zero
-// with ky = ry + 4 - 4 dy, kx = rx + 4 - 4 dx (zero where ky > 8)
 __global__ void pack_deconv3x_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int total) {
   pdl_trigger();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = idx % C, n2 = (idx / C) % NX, t = idx / (C * NX);
-  const int ry = n2 / PART_COLS, j = n2 - ry * PART_COLS;
-  float v = 0.f;
-  if (j < 27) {
-    int dx, rx, o;
-    if (j < 12) { dx = 0; rx = j / 3; o = j % 3; }
-    else if (j < 24) { dx = 1; rx = (j - 12) / 3; o = j % 3; }
-    else { dx = -1; rx = 0; o = j - 24; }
-    const int dy = t - 1;
-    const int ky = ry + 4 - 4 * dy, kx = rx + 4 - 4 * dx;
-    if (ky >= 0 && ky < 9 && kx >= 0 && kx < 9) v = w[((c * 3 + o) * 9 + ky) * 9 + kx];
-  }
-  out[idx] = __float2bfloat16_rn(v);
+  out[idx] = __float2bfloat16_rn(deconv3x_weight(w, idx));
 }
 
 size_t packed_elems() { return (size_t)3 * NX * C; }
@@ -366,6 +371,7 @@ int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   p.out_f32 = (float*)L->out_hi;
   p.ref_image = L->ref_image; p.sse_partial = L->sse_partial;
   p.grad_out = L->ref_image ? L->grad_out : nullptr; p.grad_scale = L->grad_scale;
+  p.dbias = p.grad_out ? L->dbias_out : nullptr;
   p.trace = trace;
 
   static std::mutex mu;

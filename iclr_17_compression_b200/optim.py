@@ -112,6 +112,31 @@ class FusedAdamClamp(torch.optim.Optimizer):
         self._lr_host = None                      # force the next sync_lr() to push param_groups[0]['lr']
         self.sync_lr()
 
+    # ---- a step in tensor ranges (GraphedTrainStep: each range is launched as soon as its gradients are final)
+    @torch.no_grad()
+    def begin_step(self):
+        """advance the shared step counter once, before the first ``step_range`` of an iteration"""
+        self.step_t.add_(1)
+
+    @torch.no_grad()
+    def step_range(self, first, last):
+        """clamp + Adam for parameter tensors [first, last) of the flat gradient buffer, on the current stream; no
+        learning-rate sync and no cache invalidation (the graph-replaying caller does both once per replay)"""
+        if self._flat is None:
+            raise _lib.B2CError("step_range needs flat_grads")
+        g = self.param_groups[0]
+        lib = _lib.load()
+        vp, sz = ctypes.c_void_p, ctypes.sizeof(ctypes.c_void_p)
+        off = sum(p.numel() for p in self._ps[:first]) * 4
+        with torch.cuda.device(self._flat.device):
+            _lib.check(lib.b2c_adam_clamp_step(
+                ctypes.cast(ctypes.byref(self._ptrs, first * sz), ctypes.POINTER(vp)),
+                ctypes.cast(ctypes.byref(self._sizes, first * ctypes.sizeof(ctypes.c_size_t)),
+                            ctypes.POINTER(ctypes.c_size_t)), last - first,
+                vp(self._flat.data_ptr() + off), vp(self.exp_avg.data_ptr() + off), vp(self.exp_avg_sq.data_ptr() + off),
+                _p(self.step_t), _p(self.lr_t), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                float(g["grad_clip"]), _stream()), "adam_clamp_step")
+
     @torch.no_grad()
     def step(self, closure=None, capturing=False):
         if closure is not None:

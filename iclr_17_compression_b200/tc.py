@@ -45,6 +45,38 @@ def pack_weights(kind, w, need_lo):
     return hi, lo
 
 
+def pack_many(jobs):
+    """Several packing jobs in ONE launch (b2c_tc_pack_many).  jobs: list of ("w", kind, weight) |
+    ("gdn", beta, gamma) | ("gdn_t", beta, gamma); 128 channels, plain bf16 (no lo planes).  Returns the packs in the
+    formats of pack_weights / pack_gdn / pack_gdn_t: (hi, None), (gamma, None, beta_eff)."""
+    lib = _lib.load()
+    outs, arr, keep = [], (_lib.TcPackJob * len(jobs))(), []
+    dev = jobs[0][2].device
+    for i, job in enumerate(jobs):
+        J = arr[i]
+        J.channels = 128
+        if job[0] == "w":
+            _, kind, w = job
+            n = lib.b2c_tc_packed_weight_elems(kind, 128)
+            w = w.detach().contiguous().float()
+            hi = torch.empty((n,), device=dev, dtype=torch.bfloat16)
+            J.kind, J.src, J.dst_hi = kind, w.data_ptr(), hi.data_ptr()
+            keep.append(w)
+            outs.append((hi, None))
+        else:
+            _, beta, gamma = job
+            beta, gamma = beta.detach().contiguous().float(), gamma.detach().contiguous().float()
+            g = torch.empty((128, 128), device=dev, dtype=torch.bfloat16)
+            be = torch.empty((128,), device=dev, dtype=torch.float32)
+            J.kind = _lib.TC_PACK_GDN if job[0] == "gdn" else _lib.TC_PACK_GDN_T
+            J.src, J.src2, J.dst_hi, J.beta_eff = beta.data_ptr(), gamma.data_ptr(), g.data_ptr(), be.data_ptr()
+            keep += [beta, gamma]
+            outs.append((g, None, be))
+    with torch.cuda.device(dev):
+        _lib.check(lib.b2c_tc_pack_many(ctypes.cast(arr, ctypes.c_void_p), len(jobs), _stream()), "tc_pack_many")
+    return outs
+
+
 def pack_gdn(beta, gamma, need_lo):
     lib = _lib.load()
     beta, gamma = beta.detach().contiguous().float(), gamma.detach().contiguous().float()
@@ -105,7 +137,7 @@ def reduce_partial_sse(partial):
 
 
 def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False, ref_image=None,
-              second_plane=False, saved=None, ksplit=1, out=None, grad_scale=None, reduce_sse=True):
+              second_plane=False, saved=None, ksplit=1, out=None, grad_scale=None, reduce_sse=True, dbias=None):
     """One fused layer.  x_hi/x_lo: NHWC bf16 (CONV1: x_hi = fp32 NCHW image).  w = (w_hi, w_lo);
     gdn = (gamma_hi, gamma_lo, beta_eff) with gdn_mode 1 (GDN) / 2 (IGDN).
     Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
@@ -157,6 +189,8 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         if grad_scale is not None:                 # training: distortion backward fused into the same epilogue
             grad_out = torch.empty_like(out_hi)
             L.grad_out, L.grad_scale = grad_out.data_ptr(), float(grad_scale)
+            if dbias is not None:                  # DECONV3X: the bias gradient (sum of grad_out) from the same epilogue
+                L.dbias_out = dbias.data_ptr()
     flops = int(_flops_per_out_pixel(kind, C) * B * Ho * Wo) + (2 * C * C * B * Ho * Wo if gdn_mode else 0)
     name = f"tc_layer[kind{kind},{B}x{Hin}x{Win},split{int(split3)},gdn{gdn_mode}]"
     with torch.cuda.device(dev), _timed(name, flops, 0):
@@ -198,10 +232,10 @@ def wgrad(small, big, k, stride, pad, tmp=None, out=None, deterministic=False):
                    "tc_wgrad")
     if k == 1:
         return dW.view(128, 128, 1, 1)
-    if out is not None:
-        out.view(128, 128, k, k).copy_(dW.permute(2, 3, 0, 1))
-        return out
-    return dW.permute(2, 3, 0, 1).contiguous()
+    res = out if out is not None else torch.empty((128, 128, k, k), device=small.device, dtype=torch.float32)
+    with torch.cuda.device(small.device):          # tap-major accumulator -> the parameter's layout
+        _lib.check(lib.b2c_tc_wgrad_untap(_p(dW), _p(res), k * k, 0, _stream()), "tc_wgrad_untap")
+    return res
 
 
 def wgrad9(small, image, out=None):

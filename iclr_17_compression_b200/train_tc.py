@@ -9,6 +9,7 @@ layers are NHWC bf16; parameters and their gradients are fp32 in the reference's
 Tolerance target (north star): every gradient tensor within 1e-2 relative L2 of the fp32 reference.
 """
 import ctypes
+import os
 
 import torch
 
@@ -70,13 +71,31 @@ def _colsum(t, out=None):
     return out
 
 
-def _gdn_param_grads(beta_p, gamma_p, y, n, dn, inverse, pool=None, out=None):
+def _gdn_param_grads(beta_p, gamma_p, y, n, dn, inverse, pool=None, out=None, xsq=None, fork=None):
     """d beta_p, d gamma_p from dL/dnorm: d gamma_eff = sum_pix dn_i x_j^2 (tcgen05 wgrad, 1 tap), d beta_eff = sum dn,
-    then the LowerBound / square reparametrisation (models/GDN.py:18-24,73-79)."""
+    then the LowerBound / square reparametrisation (models/GDN.py:18-24,73-79).  ``xsq``: (x^2 tensor, event) computed
+    ahead of time - it depends on the saved forward tensors only.  ``fork``: the column sum of dn runs as a branch of
+    its own beside the 1-tap weight gradient (both only read dn)."""
     dev = y.device
-    xsq = _xsq(y, n, inverse)
+    cur = torch.cuda.current_stream(dev)
+    if xsq is None:
+        xsq = _xsq(y, n, inverse)
+    else:
+        xsq, ev = xsq
+        cur.wait_event(ev)
+        xsq.record_stream(cur)
+    dbeta_acc = _zeros(pool, dev, 128)
+    if fork is not None:
+        side = fork.next_stream(avoid=cur)
+        side.wait_stream(cur)
+        dn.record_stream(side)
+        with torch.cuda.stream(side):
+            dbeta_eff = _colsum(dn, dbeta_acc)
     dgamma_eff = T.wgrad(dn, xsq, 1, 1, 0, tmp=_zeros(pool, dev, 1, 1, 128, 128)).view(128, 128)
-    dbeta_eff = _colsum(dn, _zeros(pool, dev, 128))
+    if fork is not None:
+        cur.wait_stream(side)
+    else:
+        dbeta_eff = _colsum(dn, dbeta_acc)
     dbeta_p, dgamma_p = out if out is not None else (torch.empty_like(beta_p), torch.empty_like(gamma_p))
     with torch.cuda.device(dev):
         _lib.check(_lib.load().b2c_gdn_reparam_bwd(_p(beta_p), _p(gamma_p), _p(dbeta_eff), _p(dgamma_eff), _p(dbeta_p),
@@ -90,13 +109,23 @@ class _Fork:
     independent branches are overlapped (also inside a captured CUDA graph, where they become parallel branches)."""
     _streams = {}
 
-    def __init__(self, dev, n=3):
+    def __init__(self, dev, n=None):
+        # One stream per branch (a step has 24 + nested ones): with 3 streams shared round-robin, unrelated branches
+        # queued behind each other and the dgrad chain - which joins the entropy backward's stream before the
+        # deconv1 dgrad - ended up waiting for a 37 us weight-gradient kernel that happened to share that stream
+        # (timeline: profiles/trace_train.py).  The last `n_hi` streams are high priority, for the branches that form
+        # the tail of the step (conv1 / gdn1 gradients: nothing else is left to hide them behind).
+        if n is None:
+            n = int(os.environ.get("B2C_TRAIN_FORKS", "32"))
         self.main = torch.cuda.current_stream(dev)
         key = (dev.index, n)
         if key not in _Fork._streams:
             _Fork._streams[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+            _Fork._streams[(dev.index, n, "hi")] = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(4)]
         self.sides = _Fork._streams[key]
+        self.hi = _Fork._streams[(dev.index, n, "hi")]
         self.i = 0
+        self.ih = 0
         self.used = []
         self.outs = []
 
@@ -108,19 +137,45 @@ class _Fork:
             _Fork._streams[key] = [torch.cuda.Stream(device=dev)]
         return _Fork._streams[key][0]
 
-    def run(self, fn, *inputs):
-        s = self.sides[self.i % len(self.sides)]
-        self.i += 1
+    def run(self, fn, *inputs, critical=False):
+        if critical and os.environ.get("B2C_TRAIN_TAIL_PRIORITY", "1") == "1":
+            s = self.hi[self.ih % len(self.hi)]
+            self.ih += 1
+        else:
+            s = self.sides[self.i % len(self.sides)]
+            self.i += 1
         s.wait_stream(self.main)                  # inputs were produced on the main stream
         for t in inputs:
             t.record_stream(s)
         with torch.cuda.stream(s):
             out = fn()
+        self.last_stream = s
+        self.last_event = torch.cuda.Event()      # completion of THIS branch (a stream may carry later branches too)
+        self.last_event.record(s)
         if s not in self.used:
             self.used.append(s)
         for o in (out if isinstance(out, (tuple, list)) else (out,)):
             self.outs.append(o)
         return out
+
+    def next_stream(self, avoid=None):
+        """a side stream for a nested branch (not ``avoid``, the stream the caller is running on); a branch nested in
+        a high-priority one is high priority too"""
+        if avoid is not None and avoid in self.hi:
+            s = self.hi[self.ih % len(self.hi)]
+            self.ih += 1
+            if s is avoid:
+                s = self.hi[self.ih % len(self.hi)]
+                self.ih += 1
+        else:
+            s = self.sides[self.i % len(self.sides)]
+            self.i += 1
+            if s is avoid:
+                s = self.sides[self.i % len(self.sides)]
+                self.i += 1
+        if s not in self.used:
+            self.used.append(s)
+        return s
 
     def join(self):
         for s in self.used:
@@ -136,7 +191,7 @@ def _ksplit():
     return max(1, min(25, int(os.environ.get("B2C_TRAIN_KSPLIT", "5"))))
 
 
-def step_forward(x, noise, prm, pool=None, grad_scale=None):
+def step_forward(x, noise, prm, pool=None, grad_scale=None, dbias3=None):
     """Forward of the training step on tensor cores (model.py:47-78 with the noise quantizer).  prm: name -> fp32
     CUDA tensor for the 30 parameters.  Returns the state dict the backward needs plus the per-image statistics."""
     lib = _lib.load()
@@ -148,27 +203,29 @@ def step_forward(x, noise, prm, pool=None, grad_scale=None):
     # ---- operand packing: only conv1 / gdn1 are needed immediately; every other pack of the step (forward and
     # dgrad forms, gamma and gamma^T) only depends on the parameters and runs on a side stream
     main = torch.cuda.current_stream(dev)
-    w1p = T.pack_weights(T.TC_CONV1, W1, False)
-    gp1 = T.pack_gdn(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], False)
+    # operand packing: THREE launches (b2c_tc_pack_many) instead of 21 - conv1's operands on the main stream, the other
+    # forward operands and the backward forms on a side stream (as separate launches the forward packs finished 19 us
+    # after conv1 did: the second layer waited for them)
     side = _Fork._side(dev)
     side.wait_stream(main)
+    (w1p, gp1) = T.pack_many([("w", T.TC_CONV1, W1), ("gdn", prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"])])
     with torch.cuda.stream(side):
-        pk = {
-            "w2": T.pack_weights(T.TC_CONV5S2, W2, False), "gp2": T.pack_gdn(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], False),
-            "w3": T.pack_weights(T.TC_CONV5S2, W3, False),
-            "d1": T.pack_weights(T.TC_DECONV5S2, D1, False), "gi1": T.pack_gdn(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], False),
-            "d2": T.pack_weights(T.TC_DECONV5S2, D2, False), "gi2": T.pack_gdn(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], False),
-            "d3": T.pack_weights(T.deconv3_kind(128), D3, False),
-        }
+        f = T.pack_many([
+            ("w", T.TC_CONV5S2, W2), ("gdn", prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"]),
+            ("w", T.TC_CONV5S2, W3),
+            ("w", T.TC_DECONV5S2, D1), ("gdn", prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"]),
+            ("w", T.TC_DECONV5S2, D2), ("gdn", prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"]),
+            ("w", T.deconv3_kind(128), D3)])
+        pk = dict(zip(("w2", "gp2", "w3", "d1", "gi1", "d2", "gi2", "d3"), f))
         ev_fwd = torch.cuda.Event()
         ev_fwd.record(side)
-        pk.update({     # backward forms
-            "d3_dg": T.pack_weights(T.TC_CONV1, D3, False), "gi2_t": T.pack_gdn_t(prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"]),
-            "d2_dg": T.pack_weights(T.TC_CONV5S2, D2, False), "gi1_t": T.pack_gdn_t(prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"]),
-            "d1_dg": T.pack_weights(T.TC_CONV5S2, D1, False),
-            "w3_dg": T.pack_weights(T.TC_DECONV5S2, W3, False), "gp2_t": T.pack_gdn_t(prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"]),
-            "w2_dg": T.pack_weights(T.TC_DECONV5S2, W2, False), "gp1_t": T.pack_gdn_t(prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"]),
-        })
+        b = T.pack_many([     # backward forms
+            ("w", T.TC_CONV1, D3), ("gdn_t", prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"]),
+            ("w", T.TC_CONV5S2, D2), ("gdn_t", prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"]),
+            ("w", T.TC_CONV5S2, D1),
+            ("w", T.TC_DECONV5S2, W3), ("gdn_t", prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"]),
+            ("w", T.TC_DECONV5S2, W2), ("gdn_t", prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"])])
+        pk.update(dict(zip(("d3_dg", "gi2_t", "d2_dg", "gi1_t", "d1_dg", "w3_dg", "gp2_t", "w2_dg", "gp1_t"), b)))
         ev_bwd = torch.cuda.Event()
         ev_bwd.record(side)
     for v in pk.values():
@@ -205,7 +262,7 @@ def step_forward(x, noise, prm, pool=None, grad_scale=None):
         # d loss / d recon = grad_scale * (recon - x) leave the kernel together (grad_scale = 2 lambda / numel)
         clipped, sse_partial, g_recon = T.layer_run(T.deconv3_kind(128), i2, None, pk["d3"], prm["Decoder.deconv3.bias"],
                                                     out_f32_nchw=True, ref_image=x, grad_scale=grad_scale,
-                                                    reduce_sse=False)
+                                                    reduce_sse=False, dbias=dbias3)
         recon, sse = None, None
     else:
         recon = T.layer_run(T.deconv3_kind(128), i2, None, pk["d3"], prm["Decoder.deconv3.bias"], out_f32_nchw=True)
@@ -221,10 +278,12 @@ def step_forward(x, noise, prm, pool=None, grad_scale=None):
     main.wait_event(ev_bwd)          # the backward packs are done long before; keeps stream bookkeeping simple
     return {"prm": prm, "pk": pk, "saved": (x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon),
             "image_bits": image_bits, "plane_bits": plane_bits, "sse": sse, "clipped": clipped, "z": z,
-            "sse_partial": sse_partial, "g_recon": g_recon}
+            "sse_partial": sse_partial, "g_recon": g_recon,
+            "dbias3_done": dbias3 is not None and grad_scale is not None and T.deconv3_kind(128) == T.TC_DECONV3X}
 
 
-def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, g_clipped=None, g_z=None):
+def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, g_clipped=None, g_z=None,
+                  on_backward_start=None, on_encoder_tail_done=None):
     """Backward of the training step: gradients of ``g_sse * sum (recon - x)^2 + g_bits * total_bits`` for the 30
     parameters (name -> tensor).  ``g_clipped`` / ``g_z``: optional cotangents of the clamped reconstruction and of
     the noisy latent - the route a caller takes who builds the loss from the HEAD return tuple (model.py:80:
@@ -232,7 +291,9 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, 
     the synthesis transform and the entropy model, so ``g_z`` simply adds to d loss / d z.  ``out`` (name -> zero-filled fp32 tensor of the parameter's shape, e.g. views of one
     flat buffer) receives the gradients in place; ``pool`` supplies zero-filled scratch.  ``on_decoder_done`` is
     called (on the main stream, with the fork object) once every Decoder.* and bitEstimator.* gradient kernel has
-    been enqueued - the hook a data-parallel caller uses to start reducing that bucket while the encoder backward runs."""
+    been enqueued - the hook a data-parallel caller uses to start reducing that bucket while the encoder backward runs.
+    ``on_encoder_tail_done(fork)``: the same once the gradients of Encoder.conv2 / gdn2 / conv3 are enqueued (only
+    conv1 / gdn1 are still to come); ``on_backward_start()`` runs before the first backward kernel."""
     lib = _lib.load()
     prm, pk = st["prm"], st["pk"]
     x, h1, n1, h2, n2, z, zh, i1, m1, i2, m2, recon = st["saved"]
@@ -248,6 +309,15 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, 
 
     fork = _Fork(dev)
     from .functional import _channel_sum_raw
+    if on_backward_start is not None:
+        on_backward_start()
+    # x^2 of the four GDN inputs (operands of the d gamma products) depend on saved forward tensors only: computed now,
+    # on side streams, instead of at the head of each parameter-gradient chain (the GDN1 chain is the tail of the step)
+    xsqs = {}
+    if os.environ.get("B2C_TRAIN_XSQ_EARLY", "1") == "1":
+        for key, yy, nn, inv in (("g1", h1, n1, False), ("g2", h2, n2, False), ("i1", i1, m1, True), ("i2", i2, m2, True)):
+            t = fork.run(lambda yy=yy, nn=nn, inv=inv: _xsq(yy, nn, inv), yy, nn)
+            xsqs[key] = (t, fork.last_event)
     # ---- entropy model: d bits / dz and the 11 parameter vectors (independent of the synthesis chain)
     bitp = [prm[k].reshape(-1) for k in PARAM_ORDER[19:]]
     C, HW = 128, z.shape[2] * z.shape[3]
@@ -262,7 +332,7 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, 
         return [dz_] + dbit
     ent = fork.run(entropy_bwd, g_bits)
     dz, dbit = ent[0], ent[1:]
-    ent_stream = fork.sides[0]
+    ent_done = fork.last_event
     for k, g in zip(PARAM_ORDER[19:], dbit):
         grads[k] = g.view(1, -1, 1, 1)
     # ---- distortion
@@ -277,11 +347,15 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, 
                             "reconstruction; run step_forward without grad_scale")
     # ---- deconv3 (9x9/4, 128 -> 3): weight grad (im2col MN-major tcgen05), dgrad (= conv 9x9/4) + IGDN2 backward fused
     grads["Decoder.deconv3.weight"] = fork.run(lambda: T.wgrad9(i2, g_recon, out=dst("Decoder.deconv3.weight")), g_recon)
-    grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon, dst("Decoder.deconv3.bias")), g_recon)
+    if st.get("dbias3_done"):          # accumulated by the forward launch of the last layer (fused distortion backward)
+        grads["Decoder.deconv3.bias"] = dst("Decoder.deconv3.bias")
+    else:
+        grads["Decoder.deconv3.bias"] = fork.run(lambda: _channel_sum_raw(g_recon, dst("Decoder.deconv3.bias")), g_recon)
     gp_d2, dn2 = T.layer_run(T.TC_CONV1, g_recon, None, pk["d3_dg"], None, gdn=pk["gi2_t"],
                              gdn_mode=4, second_plane=True, saved=(i2, m2))
     grads["Decoder.igdn2.beta"], grads["Decoder.igdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
-        prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn2, True, pool, gdn_dst("Decoder.igdn2")), dn2)
+        prm["Decoder.igdn2.beta"], prm["Decoder.igdn2.gamma"], i2, m2, dn2, True, pool, gdn_dst("Decoder.igdn2"),
+        xsqs.get("i2"), fork), dn2)
     # ---- deconv2
     grads["Decoder.deconv2.weight"] = fork.run(lambda: T.wgrad(
         i1, gp_d2, 5, 2, 2, tmp=_zeros(pool, dev, 5, 5, 128, 128), out=dst("Decoder.deconv2.weight")), gp_d2)
@@ -289,14 +363,15 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, 
     gp_d1, dn1 = T.layer_run(T.TC_CONV5S2, gp_d2, None, pk["d2_dg"], None, gdn=pk["gi1_t"],
                              gdn_mode=4, second_plane=True, saved=(i1, m1))
     grads["Decoder.igdn1.beta"], grads["Decoder.igdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
-        prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn1, True, pool, gdn_dst("Decoder.igdn1")), dn1)
+        prm["Decoder.igdn1.beta"], prm["Decoder.igdn1.gamma"], i1, m1, dn1, True, pool, gdn_dst("Decoder.igdn1"),
+        xsqs.get("i1"), fork), dn1)
     # ---- deconv1
     grads["Decoder.deconv1.weight"] = fork.run(lambda: T.wgrad(
         zh, gp_d1, 5, 2, 2, tmp=_zeros(pool, dev, 5, 5, 128, 128), out=dst("Decoder.deconv1.weight")), gp_d1)
     grads["Decoder.deconv1.bias"] = fork.run(lambda: _colsum(gp_d1, dst("Decoder.deconv1.bias")), gp_d1)
     if on_decoder_done is not None:
         on_decoder_done(fork)
-    fork.main.wait_stream(ent_stream)                  # dz comes from the entropy backward (first forked task)
+    fork.main.wait_event(ent_done)                     # dz comes from the entropy backward (first forked task)
     if g_z is not None:
         dz.add_(g_z)                                   # external cotangent of the noisy latent
     ks = _ksplit() if gp_d1.shape[0] * gp_d1.shape[1] * gp_d1.shape[2] <= 148 * 128 * 4 else 1
@@ -311,18 +386,23 @@ def step_backward(st, g_sse, g_bits, out=None, pool=None, on_decoder_done=None, 
     gp_c2, dng2 = T.layer_run(T.TC_DECONV5S2, gyh, None, pk["w3_dg"], None, gdn=pk["gp2_t"],
                               gdn_mode=3, second_plane=True, saved=(h2, n2))
     grads["Encoder.gdn2.beta"], grads["Encoder.gdn2.gamma"] = fork.run(lambda: _gdn_param_grads(
-        prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dng2, False, pool, gdn_dst("Encoder.gdn2")), dng2)
+        prm["Encoder.gdn2.beta"], prm["Encoder.gdn2.gamma"], h2, n2, dng2, False, pool, gdn_dst("Encoder.gdn2"),
+        xsqs.get("g2"), fork), dng2)
     # ---- conv2
     grads["Encoder.conv2.weight"] = fork.run(lambda: T.wgrad(
         gp_c2, h1, 5, 2, 2, tmp=_zeros(pool, dev, 5, 5, 128, 128), out=dst("Encoder.conv2.weight")), gp_c2)
     grads["Encoder.conv2.bias"] = fork.run(lambda: _colsum(gp_c2, dst("Encoder.conv2.bias")), gp_c2)
+    if on_encoder_tail_done is not None:
+        on_encoder_tail_done(fork)
     gp_c1, dng1 = T.layer_run(T.TC_DECONV5S2, gp_c2, None, pk["w2_dg"], None, gdn=pk["gp1_t"],
                               gdn_mode=3, second_plane=True, saved=(h1, n1))
     grads["Encoder.gdn1.beta"], grads["Encoder.gdn1.gamma"] = fork.run(lambda: _gdn_param_grads(
-        prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dng1, False, pool, gdn_dst("Encoder.gdn1")), dng1)
+        prm["Encoder.gdn1.beta"], prm["Encoder.gdn1.gamma"], h1, n1, dng1, False, pool, gdn_dst("Encoder.gdn1"),
+        xsqs.get("g1"), fork), dng1, critical=True)
     # ---- conv1 (9x9/4, 3 -> 128): weight grad (im2col MN-major tcgen05); the image needs no gradient
-    grads["Encoder.conv1.weight"] = fork.run(lambda: T.wgrad9(gp_c1, x, out=dst("Encoder.conv1.weight")), gp_c1)
-    grads["Encoder.conv1.bias"] = fork.run(lambda: _colsum(gp_c1, dst("Encoder.conv1.bias")), gp_c1)
+    grads["Encoder.conv1.weight"] = fork.run(lambda: T.wgrad9(gp_c1, x, out=dst("Encoder.conv1.weight")), gp_c1,
+                                             critical=True)
+    grads["Encoder.conv1.bias"] = fork.run(lambda: _colsum(gp_c1, dst("Encoder.conv1.bias")), gp_c1, critical=True)
     fork.join()
     return grads
 
@@ -609,7 +689,8 @@ class GraphedTrainStep:
         pool = _Pool(self.buf, self._scratch_off)
         import os
         fused = os.environ.get("B2C_TRAIN_FUSED_DISTORTION", "1") == "1"
-        st = step_forward(self.x, self.noise, prm, pool, grad_scale=(2.0 * self.lam / self.x.numel()) if fused else None)
+        st = step_forward(self.x, self.noise, prm, pool, grad_scale=(2.0 * self.lam / self.x.numel()) if fused else None,
+                          dbias3=gviews["Decoder.deconv3.bias"] if fused else None)
         stat = self._stat_stream
         stat.wait_stream(main)
         with torch.cuda.stream(stat):                                 # reporting only: off the critical path
@@ -632,7 +713,42 @@ class GraphedTrainStep:
                 else:
                     dist.all_reduce(self.flat[enc_elems:], op=dist.ReduceOp.AVG, group=self.group)
 
-        step_backward(st, self._g_sse, self._g_bits, out=gviews, pool=pool, on_decoder_done=decoder_done)
+        # The fused clamp + Adam launch of a one-GPU step is split into three tensor ranges, each launched on its own
+        # branch as soon as its gradients are final (Decoder + bitEstimator: after the deconv1 gradients; conv2 / gdn2 /
+        # conv3: before the last dgrad kernel), so only the conv1 / gdn1 range (48 k of 1.77 M elements) is left for
+        # the end of the step (B2C_TRAIN_ADAM_SPLIT=0: one launch at the end)
+        split_opt = (with_optimizer and self._opt_in_graph and not self.ar_in_graph and not self._symm_in_graph
+                     and self._opt_ranges is not None and os.environ.get("B2C_TRAIN_ADAM_SPLIT", "1") == "1")
+        n_head, n_enc, n_all = self._opt_ranges if self._opt_ranges is not None else (0, 0, 0)
+        opt_stream = self._opt_stream
+
+        def backward_start():
+            if split_opt:                       # step counter += 1, off the critical path (first use: opt_range below)
+                opt_stream.wait_stream(main)
+                with torch.cuda.stream(opt_stream):
+                    self.optimizer.begin_step()
+
+        def opt_range(fork, first, last):
+            opt_stream.wait_stream(main)
+            for s in fork.used:
+                opt_stream.wait_stream(s)
+            with torch.cuda.stream(opt_stream):
+                self.optimizer.step_range(first, last)
+
+        def decoder_done_all(fork):
+            decoder_done(fork)
+            if split_opt:
+                opt_range(fork, n_enc, n_all)
+
+        def encoder_tail_done(fork):
+            if split_opt:
+                opt_range(fork, n_head, n_enc)
+
+        step_backward(st, self._g_sse, self._g_bits, out=gviews, pool=pool, on_decoder_done=decoder_done_all,
+                      on_backward_start=backward_start, on_encoder_tail_done=encoder_tail_done)
+        if split_opt:
+            main.wait_stream(opt_stream)
+            self.optimizer.step_range(0, n_head)
         if self._symm_in_graph and self._symm_buckets == 1:
             self._symm.all_reduce_fused()                 # last node of the backward pass, on the main stream
         elif self.ar_in_graph or self._symm_in_graph:
@@ -646,7 +762,7 @@ class GraphedTrainStep:
                     dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
             main.wait_stream(comm)
         main.wait_stream(stat)
-        if with_optimizer and self._opt_in_graph:
+        if with_optimizer and self._opt_in_graph and not split_opt:
             self.optimizer.step(capturing=True)                      # inside the graph: gradients are final here
 
     @torch.no_grad()
@@ -661,10 +777,17 @@ class GraphedTrainStep:
         enc_elems = sum(p.numel() for k, p in named if k.startswith("Encoder."))
         if [k.split(".")[0] for k, _ in named] != sorted([k.split(".")[0] for k, _ in named], key=["Encoder", "Decoder", "bitEstimator"].index):
             raise _lib.B2CError("unexpected parameter order (Encoder, Decoder, bitEstimator expected)")
+        # tensor ranges of the split optimizer step: [conv1, gdn1 | rest of the encoder | decoder + entropy model]
+        names = [k for k, _ in named]
+        head = [k.startswith(("Encoder.conv1.", "Encoder.gdn1.")) for k in names]
+        n_head = sum(head)
+        self._opt_ranges = (n_head, sum(k.startswith("Encoder.") for k in names), len(names)) \
+            if all(head[:n_head]) and 0 < n_head < len(names) else None
         self._g_sse = torch.full((1,), self.lam / self.x.numel(), device=dev, dtype=torch.float32)
         self._g_bits = torch.full((1,), 1.0 / (B * H * W), device=dev, dtype=torch.float32)
         self._stat_stream = torch.cuda.Stream(device=dev)
         self._comm_stream = torch.cuda.Stream(device=dev)
+        self._opt_stream = torch.cuda.Stream(device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):

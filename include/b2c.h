@@ -193,6 +193,22 @@ int b2c_tc_pack_gdn(int channels, const float* beta_p, const float* gamma_p, voi
 int b2c_tc_pack_gdn_t(int channels, const float* beta_p, const float* gamma_p, void* gamma_t, float* beta_eff,
                       void* stream);
 
+/* Several packing jobs in ONE launch (a training step re-packs 19 operands after every optimizer step; as separate
+ * launches they sat on the critical path in front of the second layer).  kind = a layer kind (src = weights, dst_hi /
+ * dst_lo as b2c_tc_pack_weights) or B2C_TC_PACK_GDN / _GDN_T (src = beta_p, src2 = gamma_p, dst_hi / dst_lo = gamma,
+ * beta_eff as b2c_tc_pack_gdn / b2c_tc_pack_gdn_t).  Up to 16 jobs per call; 128 channels only. */
+#define B2C_TC_PACK_GDN 16
+#define B2C_TC_PACK_GDN_T 17
+typedef struct b2c_tc_pack_job {
+  int kind, channels;
+  const float* src;
+  const float* src2;
+  void* dst_hi;
+  void* dst_lo;
+  float* beta_eff;
+} b2c_tc_pack_job;
+int b2c_tc_pack_many(const b2c_tc_pack_job* jobs, int n_jobs, void* stream);
+
 typedef struct b2c_tc_layer {
   int kind;         /* B2C_TC_*                                                                   */
   int split3;       /* 1: (hi,lo) operands, 3 MMAs per product; 0: plain bf16                      */
@@ -228,6 +244,9 @@ typedef struct b2c_tc_layer {
   int ksplit;       /* 0 / 1: off.  2..25 (CONV5S2, out_f32_nchw, gdn == 0 only): the 25 taps are split over
                        ksplit CTAs per tile which ADD their partial sums into out_hi - the caller zero-fills it.
                        For small batches where one CTA per tile leaves most SMs idle (training, batch 8).   */
+  float* dbias_out; /* DECONV3X with grad_out (training), optional: dbias_out[o] += sum over (n, y, x) of grad_out -
+                       the gradient of Decoder.deconv3.bias (3 floats, accumulated with atomic adds: zero-fill or
+                       accumulate on purpose), instead of a separate pass over grad_out                          */
 } b2c_tc_layer;
 
 /* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid = the `tiles`
@@ -249,6 +268,9 @@ int b2c_tc_layer_run(const b2c_tc_layer* layer, void* stream);
 size_t b2c_tc_wgrad_workspace_bytes(int B, int hs, int ws, int k);
 int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int hs, int ws, int hb, int wb, int k,
                  int stride, int pad, void* workspace, size_t workspace_bytes, void* stream);
+/* The red.global form of b2c_tc_wgrad accumulates tap-major, tmp[tap][m][n]; this writes (accumulate = 0) or adds
+ * (1) it into the parameter's own layout out[m][n][tap] (OIHW / IOHW with ky*k + kx = tap). */
+int b2c_tc_wgrad_untap(const float* tmp, float* out, int ntaps, int accumulate, void* stream);
 
 /* 9x9 / stride-4 / pad-4 weight gradient on tensor cores: dW[m][c][ky][kx] += sum small[img,ys,xs,m] *
  * image[img,c,4ys-4+ky,4xs-4+kx]; small NHWC bf16 [B,h,w,128], image fp32 NCHW [B,3,4h,4w], dW fp32 [128][3][9][9]
