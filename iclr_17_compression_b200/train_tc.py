@@ -138,7 +138,7 @@ class _Fork:
         return _Fork._streams[key][0]
 
     def run(self, fn, *inputs, critical=False):
-        if critical and os.environ.get("B2C_TRAIN_TAIL_PRIORITY", "1") == "1":
+        if critical and os.environ.get("B2C_TRAIN_TAIL_PRIORITY", "0") == "1":   # measured slower: 308 vs 303 us
             s = self.hi[self.ih % len(self.hi)]
             self.ih += 1
         else:
@@ -713,12 +713,13 @@ class GraphedTrainStep:
                 else:
                     dist.all_reduce(self.flat[enc_elems:], op=dist.ReduceOp.AVG, group=self.group)
 
-        # The fused clamp + Adam launch of a one-GPU step is split into three tensor ranges, each launched on its own
-        # branch as soon as its gradients are final (Decoder + bitEstimator: after the deconv1 gradients; conv2 / gdn2 /
-        # conv3: before the last dgrad kernel), so only the conv1 / gdn1 range (48 k of 1.77 M elements) is left for
-        # the end of the step (B2C_TRAIN_ADAM_SPLIT=0: one launch at the end)
+        # B2C_TRAIN_ADAM_SPLIT=1 (opt-in): the fused clamp + Adam launch of a one-GPU step split into three tensor
+        # ranges, each launched on its own branch as soon as its gradients are final (Decoder + bitEstimator: after the
+        # deconv1 gradients; conv2 / gdn2 / conv3: before the last dgrad kernel; conv1 / gdn1 at the end).  Measured
+        # SLOWER (312 vs 303 us per step): the end of the step is bound by the SM time of the weight-gradient kernels,
+        # not by a dependency chain, and two more launches only add to it.
         split_opt = (with_optimizer and self._opt_in_graph and not self.ar_in_graph and not self._symm_in_graph
-                     and self._opt_ranges is not None and os.environ.get("B2C_TRAIN_ADAM_SPLIT", "1") == "1")
+                     and self._opt_ranges is not None and os.environ.get("B2C_TRAIN_ADAM_SPLIT", "0") == "1")
         n_head, n_enc, n_all = self._opt_ranges if self._opt_ranges is not None else (0, 0, 0)
         opt_stream = self._opt_stream
 

@@ -345,3 +345,21 @@ def test_conv1_every_kernel_form(form):
     assert out.returncode == 0, out.stderr[-2000:]
     worst = float(out.stdout.strip().split("WORST")[-1])
     assert worst < 5e-5, worst
+
+
+def test_pack_many_matches_single_packs(tc):
+    """b2c_tc_pack_many (one launch, 5x5 panels through shared memory) == the per-operand packing calls, bit for bit"""
+    g = torch.Generator().manual_seed(21)
+    w5 = (torch.randn(128, 128, 5, 5, generator=g) * 0.03).cuda()
+    w9 = (torch.randn(128, 3, 9, 9, generator=g) * 0.05).cuda()
+    beta, gamma = _gdn_params(g)
+    beta, gamma = beta.cuda(), gamma.cuda()
+    many = tc.pack_many([("w", tc.TC_CONV5S2, w5), ("w", tc.TC_DECONV5S2, w5), ("w", tc.TC_CONV1, w9),
+                         ("w", tc.TC_DECONV3, w9), ("w", tc.TC_DECONV3X, w9), ("gdn", beta, gamma),
+                         ("gdn_t", beta, gamma)])
+    for got, kind, w in zip(many[:5], (tc.TC_CONV5S2, tc.TC_DECONV5S2, tc.TC_CONV1, tc.TC_DECONV3, tc.TC_DECONV3X),
+                            (w5, w5, w9, w9, w9)):
+        assert torch.equal(got[0], tc.pack_weights(kind, w, False)[0]), kind
+    g1, g2 = tc.pack_gdn(beta, gamma, False), tc.pack_gdn_t(beta, gamma)
+    assert torch.equal(many[5][0], g1[0]) and torch.equal(many[5][2], g1[2])
+    assert torch.equal(many[6][0], g2[0]) and torch.equal(many[6][2], g2[2])
