@@ -526,6 +526,24 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
   const int n = blockIdx.x;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // no-ops unless launched as a programmatic dependent
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (width == 2) {        // the squared-error pairs of the last synthesis layer: both columns per 8-byte load, eight
+    const float2* src = reinterpret_cast<const float2*>(partial) + (size_t)n * per_image;   // loads in flight per thread
+    float s0 = 0.f, s1 = 0.f;
+    for (int i0 = threadIdx.x; i0 < per_image; i0 += 8 * blockDim.x) {
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * blockDim.x;
+        v[k] = i < per_image ? __ldg(src + i) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s0 += v[k].x; s1 += v[k].y; }
+    }
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red);
+    if (threadIdx.x == 0) { out[n * 2] = s0; out[n * 2 + 1] = s1; }
+    return;
+  }
   for (int j = 0; j < width; ++j) {
     float s = 0.f;
     for (int i = threadIdx.x; i < per_image; i += blockDim.x) s += partial[((size_t)n * per_image + i) * width + j];

@@ -27,6 +27,7 @@ constexpr int W_PAIR_BYTES = 2 * 128 * 64 * 2;  // two 64-channel boxes of 128 p
 constexpr int W_STAGES = 6;
 constexpr int W_TAPS = 4;                       // taps per CTA (4 x 128 fp32 columns = all of TMEM)
 constexpr int W_THREADS = 192;                  // producer warp, MMA warp, 4 epilogue warps
+constexpr int W_ROW_PAD = 528;                  // bytes between staged output rows (512 + 16: conflict-free 16-byte stores)
 
 struct WgParams {
   int B, hs, ws;          // small (tile) grid
@@ -34,6 +35,7 @@ struct WgParams {
   int ksz, stride, pad, ntaps;
   float* dW;              // [ntaps][128][128] (tap-major), accumulated with red.global.add when partial == nullptr
   float* partial;         // two-stage reduction: [nsplit][ntaps][128 n][128 m] per-CTA sums (no atomics), or nullptr
+  int bulk_reduce;        // 1: 512-byte bulk reductions from staged rows, 0: red.global.add.v4.f32 from registers
 };
 
 // MN-major SWIZZLE_128B operand: 64 channels (128 B) x 8 pixels per swizzle atom; atoms along the channel
@@ -159,22 +161,46 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
         }
       }
     } else if (my_tiles > 0) {
+      // tap-major partial layout dW[tap][m][n].  Each thread stages its row (128 floats) in the now idle pipeline
+      // buffers and adds it to global memory with ONE 512-byte bulk reduction (cp.reduce.async.bulk ... .add.f32:
+      // four full lines per operation).  The first form issued 32 red.global.add.v4.f32 per thread and tap, a warp
+      // instruction touching 32 different lines 16 bytes each - the split-K reduction, not the MMAs, was most of the
+      // kernel.  Rows are 528 bytes apart in shared memory (16-byte stores of a warp then spread over all banks);
+      // two tap buffers alternate.
+      static_assert(2 * 128 * W_ROW_PAD <= W_STAGES * W_PAIR_BYTES, "staging fits the pipeline buffers");
+      const bool bulk = p.bulk_reduce != 0;
       for (int j = 0; j < ntap; ++j) {
+        uint8_t* row = smem + (j & 1) * (128 * W_ROW_PAD) + m * W_ROW_PAD;
+        if (bulk && j >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this buffer's previous row
 #pragma unroll 1
         for (int h = 0; h < 4; ++h) {
           uint32_t raw[32];
           tmem_ld32(t_row + (uint32_t)(j * 128 + h * 32), raw);
           tmem_ld_wait();
-          // tap-major partial layout dW[tap][m][n]: each thread adds 32 contiguous floats with 16-byte reductions
           float* dst = p.dW + ((size_t)(tap0 + j) * 128 + m) * 128 + h * 32;
+          if (bulk) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(__uint_as_float(raw[c])),
-                         "f"(__uint_as_float(raw[c + 1])), "f"(__uint_as_float(raw[c + 2])),
-                         "f"(__uint_as_float(raw[c + 3]))
-                         : "memory");
+            for (int c = 0; c < 32; c += 4)
+              *reinterpret_cast<uint4*>(row + (h * 32 + c) * 4) = make_uint4(raw[c], raw[c + 1], raw[c + 2], raw[c + 3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(__uint_as_float(raw[c])),
+                           "f"(__uint_as_float(raw[c + 1])), "f"(__uint_as_float(raw[c + 2])),
+                           "f"(__uint_as_float(raw[c + 3]))
+                           : "memory");
+          }
+        }
+        if (bulk) {
+          fence_proxy_async_smem();      // this thread's generic-proxy writes of its own row -> visible to the bulk copy
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 512;" ::"l"(
+                           p.dW + ((size_t)(tap0 + j) * 128 + m) * 128),
+                       "r"(smem_u32(row))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
+      if (bulk) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
 
@@ -611,6 +637,8 @@ int b2c_tc_nhwc_colsum(const void* t, float* out, size_t P, void* stream) {
 
 static int wgrad_splits(int total_tiles, int ntaps) {
   const int groups = (ntaps + W_TAPS - 1) / W_TAPS;
+  static const int forced = [] { const char* e = getenv("B2C_WG_SPLITS"); return e ? atoi(e) : 0; }();
+  if (forced > 0) return forced < total_tiles ? forced : total_tiles;
   int splits = 148 / groups;
   if (splits > (total_tiles + 3) / 4) splits = (total_tiles + 3) / 4;   // >= 4 pixel tiles per CTA: fewer reductions
   if (splits < 1) splits = 1;
@@ -650,6 +678,8 @@ int b2c_tc_wgrad(const void* small_t, const void* big_t, float* dW, int B, int h
   p.ksz = k; p.stride = stride; p.pad = pad; p.ntaps = k * k;
   p.dW = dW;
   p.partial = nullptr;
+  static const int bulk = [] { const char* e = getenv("B2C_WG_BULK"); return e ? atoi(e) : 1; }();
+  p.bulk_reduce = bulk;
   CUtensorMap mS, mG;
   int rc;
   if ((rc = make_nhwc_map(&mS, small_t, B, hs, ws, 1))) return rc;
