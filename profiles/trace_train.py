@@ -15,19 +15,20 @@ torch.manual_seed(234)
 m = P.ImageCompressor(128, return_mode="mse").cuda().train()
 x = torch.rand(8, 3, 256, 256, device="cuda")
 step = GraphedTrainStep(m, x, 8192.0, optimizer="adam")
+step.x.copy_(x)
 for _ in range(10):
-    step(x)
+    step(step.x)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(6):
-        step(x)
+        step(step.x)
     torch.cuda.synchronize()
 path = "/tmp/train_trace.json"
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
-# the 5th step: from the 5th occurrence of the noise generator kernel to the next one
-starts = [i for i, e in enumerate(ev) if "distribution" in e["name"]]
+# the 5th step: from the 5th occurrence of the first-layer packing kernel to the next one
+starts = [i for i, e in enumerate(ev) if "pack_many" in e["name"] and e["args"].get("grid") == [128, 2, 1]]
 a, b = starts[4], starts[5]
 t0 = ev[a]["ts"]
 rows = []
