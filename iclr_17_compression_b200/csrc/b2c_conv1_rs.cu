@@ -16,6 +16,12 @@
 // Shared-memory loads of the builders thus overlap the TMEM loads / MUFU / staging of the epilogue warps, and the
 // per-tile time is the longest of the three roles instead of their sum.
 // TMEM (512 columns): conv accumulator x 2 | norm accumulator x 1 | A ring 2 x 64 (hi words 0-31, lo words 32-63).
+//
+// TRAIN = true is the forward launch of the bf16 training step (train_tc.step_forward): plain bf16 operands (one MMA
+// per product instead of three, no lo words anywhere) and the second output plane carries the norm n = beta + gamma x^2
+// the GDN backward needs instead of the lo half of y.  The per-tile kernel that ran this layer before built its
+// im2col tile in shared memory and ran prologue, main loop and epilogue of a tile one after the other: 18.6 us for the
+// 256 tiles of a batch-8 step (two waves), 9 % tensor pipe.
 #include <mutex>
 #include <type_traits>
 
@@ -57,6 +63,7 @@ struct Params {
   long long* trace;      // debug: clock64 timeline of CTA 0: [4 roles: producer, mma, epilogue, builder][64 marks]
 };
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_constant__ CUtensorMap tmB_hi,
                     const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmG_hi,
@@ -128,16 +135,17 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
-      if (leader) mbar_arrive_expect_tx(res_full, 2u * (W_RES + GAMMA_BYTES));
+      if (TRAIN) griddep_wait();  // training: the operands were packed by the launch in front of this one
+      if (leader) mbar_arrive_expect_tx(res_full, (TRAIN ? 1u : 2u) * (W_RES + GAMMA_BYTES));
 #pragma unroll
       for (int kb = 0; kb < NKB; ++kb) {
         tma_load_2d_pair(wres + kb * B_BYTES, &tmB_hi, res_full, 0, kb * C + (int)cta_rank * (C / 2));
-        tma_load_2d_pair(wres + (NKB + kb) * B_BYTES, &tmB_lo, res_full, 0, kb * C + (int)cta_rank * (C / 2));
+        if (!TRAIN) tma_load_2d_pair(wres + (NKB + kb) * B_BYTES, &tmB_lo, res_full, 0, kb * C + (int)cta_rank * (C / 2));
       }
 #pragma unroll
       for (int g = 0; g < NCB; ++g) {
         tma_load_2d_pair(gam + g * B_BYTES, &tmG_hi, res_full, g * KBLK, (int)cta_rank * (C / 2));
-        tma_load_2d_pair(gam + (NCB + g) * B_BYTES, &tmG_lo, res_full, g * KBLK, (int)cta_rank * (C / 2));
+        if (!TRAIN) tma_load_2d_pair(gam + (NCB + g) * B_BYTES, &tmG_lo, res_full, g * KBLK, (int)cta_rank * (C / 2));
       }
       griddep_wait();             // the image (and the buffers this kernel overwrites) are free from here on
       for (int it = 0; it < n_it; ++it) {
@@ -177,8 +185,10 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
             const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
             const uint32_t a_hi = a0 + (uint32_t)(k4 * 8), a_lo = a_hi + 32u;
             umma_bf16_pair_ts(d, a_hi, b_hi + 2 * k4, idesc, acc);
-            umma_bf16_pair_ts(d, a_hi, b_lo + 2 * k4, idesc, 1u);
-            umma_bf16_pair_ts(d, a_lo, b_hi + 2 * k4, idesc, 1u);
+            if (!TRAIN) {
+              umma_bf16_pair_ts(d, a_hi, b_lo + 2 * k4, idesc, 1u);
+              umma_bf16_pair_ts(d, a_lo, b_hi + 2 * k4, idesc, 1u);
+            }
           }
           umma_commit_pair(&a_empty[slot]);
           if (kb == NKB - 1) umma_commit_pair(&accum_full[buf]);
@@ -200,8 +210,10 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
             const uint32_t acc = (round > 0 || k4 > 0) ? 1u : 0u;
             const uint32_t a_hi = a0 + (uint32_t)((k4 >> 1) * 32 + (k4 & 1) * 8), a_lo = a_hi + 16u;
             umma_bf16_pair_ts(d, a_hi, b_hi + 2 * k4, idesc, acc);
-            umma_bf16_pair_ts(d, a_hi, b_lo + 2 * k4, idesc, 1u);
-            umma_bf16_pair_ts(d, a_lo, b_hi + 2 * k4, idesc, 1u);
+            if (!TRAIN) {
+              umma_bf16_pair_ts(d, a_hi, b_lo + 2 * k4, idesc, 1u);
+              umma_bf16_pair_ts(d, a_lo, b_hi + 2 * k4, idesc, 1u);
+            }
           }
           if (round == NCB - 1) umma_commit_pair(norm_full);
         }
@@ -271,10 +283,10 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
         uint32_t w[32];
         conv1_build_regs<KB, 0, 32>(pp, w);                    // k 0..31 of the block: w[0..15] hi, w[16..31] lo
         tmem_st16(t_ring + slot * 64u, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
-        tmem_st16(t_ring + slot * 64u + 32u, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
+        if (!TRAIN) tmem_st16(t_ring + slot * 64u + 32u, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
         conv1_build_regs<KB, 1, 32>(pp, w);                    // k 32..63
         tmem_st16(t_ring + slot * 64u + 16u, *reinterpret_cast<uint32_t(*)[16]>(&w[0]));
-        tmem_st16(t_ring + slot * 64u + 48u, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
+        if (!TRAIN) tmem_st16(t_ring + slot * 64u + 48u, *reinterpret_cast<uint32_t(*)[16]>(&w[16]));
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -332,10 +344,10 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
             float v0, v1;
             upk2(mul2(x2, x2), v0, v1);
             wh[i] = cvt_bf16x2(v0, v1);
-            wl[i] = lo_of(v0, v1, wh[i]);
+            if (!TRAIN) wl[i] = lo_of(v0, v1, wh[i]);
           }
           tmem_st8(t_acc + (uint32_t)(g * 64 + hh * 8), wh);
-          tmem_st8(t_acc + (uint32_t)(g * 64 + 16 + hh * 8), wl);
+          if (!TRAIN) tmem_st8(t_acc + (uint32_t)(g * 64 + 16 + hh * 8), wl);
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -364,7 +376,7 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
           const uint64_t sc = pkf2(rsqrt_fast(n0), rsqrt_fast(n1));
           upk2(mul2(xk[blk * 16 + sub * 8 + i], sc), y0, y1);
           hp[i] = cvt_bf16x2(y0, y1);
-          lp[i] = lo_of(y0, y1, hp[i]);
+          lp[i] = TRAIN ? cvt_bf16x2(n0, n1) : lo_of(y0, y1, hp[i]);      // training: the second plane is the norm
         }
         uint8_t* sb = my_stg + (uint32_t)blk * (2 * STG_PLANE);
         if (sub == 0) {                          // the stores that last read this block's slice (previous tile) are done
@@ -410,6 +422,9 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
 // Returns 1 when the layer is not the one this kernel covers or another form is selected (the caller then tries the
 // others), otherwise the launch status.  B2C_TC_PERSIST_CONV1: 3 (default) = this kernel, 2 = b2c_conv1_ts.cu,
 // 1 = shared-memory operands (b2c_conv1_tcp.cu), 0 = per-tile kernel.
+template <bool TRAIN>
+static int launch_rs(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);
+
 int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   static const int mode = [] {
     const char* e = getenv("B2C_TC_PERSIST_CONV1");
@@ -417,10 +432,17 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   }();
   if (mode != 3) return 1;
   const int channels = L->channels ? L->channels : 128;
-  if (L->kind != B2C_TC_CONV1 || channels != 128 || !L->split3 || L->gdn != 1 || L->out_f32_nchw || !L->out_lo ||
-      L->saved_y || !L->w_lo || !L->gamma_lo)
-    return 1;
-  auto kern = conv1_gdn_rs_kernel;
+  if (L->kind != B2C_TC_CONV1 || channels != 128 || L->gdn != 1 || L->out_f32_nchw || !L->out_lo || L->saved_y) return 1;
+  if (L->split3 && (!L->w_lo || !L->gamma_lo)) return 1;
+  // plain bf16 + a second output plane = the forward launch of the training step (B2C_TRAIN_CONV1_RS=0: per-tile kernel)
+  static const int train_rs = [] { const char* e = getenv("B2C_TRAIN_CONV1_RS"); return e ? atoi(e) : 1; }();
+  if (!L->split3 && !train_rs) return 1;
+  return L->split3 ? launch_rs<false>(L, stream, trace) : launch_rs<true>(L, stream, trace);
+}
+
+template <bool TRAIN>
+static int launch_rs(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
+  auto kern = conv1_gdn_rs_kernel<TRAIN>;
 
   Params p;
   memset(&p, 0, sizeof(p));
@@ -473,9 +495,9 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   int rc;
   if ((rc = make_image_map(&mImg, L->in_hi, L->B, L->Hin, L->Win))) return rc;
   if ((rc = make_mat_map(&mB_hi, L->w_hi, NKB * C, KBLK, C / 2))) return rc;
-  if ((rc = make_mat_map(&mB_lo, L->w_lo, NKB * C, KBLK, C / 2))) return rc;
+  if ((rc = make_mat_map(&mB_lo, TRAIN ? L->w_hi : L->w_lo, NKB * C, KBLK, C / 2))) return rc;
   if ((rc = make_mat_map(&mG_hi, L->gamma_hi, C, C, C / 2))) return rc;
-  if ((rc = make_mat_map(&mG_lo, L->gamma_lo, C, C, C / 2))) return rc;
+  if ((rc = make_mat_map(&mG_lo, TRAIN ? L->gamma_hi : L->gamma_lo, C, C, C / 2))) return rc;
   if ((rc = make_warp_out_map(&mO_hi, L->out_hi, L->B, p.Hg, p.Wg, 32))) return rc;
   if ((rc = make_warp_out_map(&mO_lo, L->out_lo, L->B, p.Hg, p.Wg, 32))) return rc;
 

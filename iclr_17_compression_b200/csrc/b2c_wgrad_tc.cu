@@ -640,7 +640,10 @@ static int wgrad_splits(int total_tiles, int ntaps) {
   static const int forced = [] { const char* e = getenv("B2C_WG_SPLITS"); return e ? atoi(e) : 0; }();
   if (forced > 0) return forced < total_tiles ? forced : total_tiles;
   int splits = 148 / groups;
-  if (splits > (total_tiles + 3) / 4) splits = (total_tiles + 3) / 4;   // >= 4 pixel tiles per CTA: fewer reductions
+  // >= 4 pixel tiles per CTA: fewer reductions (B2C_WG_MIN_TILES: for the 25-tap layers)
+  static const int min_tiles5 = [] { const char* e = getenv("B2C_WG_MIN_TILES"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
+  const int mt = ntaps > 1 ? min_tiles5 : 4;
+  if (splits > (total_tiles + mt - 1) / mt) splits = (total_tiles + mt - 1) / mt;
   if (splits < 1) splits = 1;
   return splits;
 }
