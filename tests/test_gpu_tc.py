@@ -163,6 +163,30 @@ def test_deconv3x_bf16(tc, shape):
     assert _rel(y, y3.double().cpu()) < 1e-5
 
 
+def test_deconv3x_full_size_properties(tc):
+    """BASELINE configs[1] size (24 x 128 x 192 x 128 -> 24 x 3 x 512 x 768): the x-folded kernel against the independent
+    3x3-shift kernel, linearity in the input, and the fused squared errors against a sum over the stored output."""
+    g = torch.Generator().manual_seed(16)
+    B, H, W = 24, 128, 192
+    x = torch.randn(B, H, W, 128, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(128, 3, 9, 9, generator=g) * 0.05).cuda()
+    b = torch.randn(3, generator=g).cuda()
+    wx, w3 = tc.pack_weights(tc.TC_DECONV3X, w, False), tc.pack_weights(tc.TC_DECONV3, w, False)
+    y = tc.layer_run(tc.TC_DECONV3X, x, None, wx, b, out_f32_nchw=True)
+    y3 = tc.layer_run(tc.TC_DECONV3, x, None, w3, b, out_f32_nchw=True)
+    assert _rel(y, y3) < 1e-5, _rel(y, y3)
+    # linearity: f(2x) - bias = 2 (f(x) - bias)   (2x is exact in bf16)
+    y2 = tc.layer_run(tc.TC_DECONV3X, x * 2, None, wx, b, out_f32_nchw=True)
+    bb = b.view(1, 3, 1, 1)
+    assert _rel(y2 - bb, 2 * (y - bb)) < 1e-6
+    img = torch.rand(B, 3, 4 * H, 4 * W, generator=g).cuda()
+    clipped, sse = tc.layer_run(tc.TC_DECONV3X, x, None, wx, b, out_f32_nchw=True, ref_image=img)
+    assert torch.equal(clipped, y.clamp(0, 1))
+    ref = torch.stack([((y.double() - img.double()) ** 2).flatten(1).sum(1),
+                       ((clipped.double() - img.double()) ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(sse.double(), ref, rtol=2e-5), (sse[:2], ref[:2])
+
+
 @pytest.mark.parametrize("shape", [(1, 16, 32), (2, 32, 32), (3, 24, 40)])
 def test_wgrad_5x5s2(tc, shape):
     """tensor-core weight gradient (MN-major MMAs) vs autograd, conv and transposed-conv forms."""
