@@ -120,6 +120,7 @@ conv1_gdn_rs_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_cons
     tma_prefetch_desc(&tmO_hi); tma_prefetch_desc(&tmO_lo);
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, T_COLS);
+  if (TRAIN) griddep_wait();     // training: beta_eff (and the packed operands) come from the launch right in front of this one
   if (threadIdx.x >= 64 && threadIdx.x < 64 + C) {
     const int c = threadIdx.x - 64;
     s_bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;

@@ -138,7 +138,8 @@ class FusedAdamClamp(torch.optim.Optimizer):
                 float(g["grad_clip"]), _stream()), "adam_clamp_step")
 
     @torch.no_grad()
-    def step(self, closure=None, capturing=False):
+    def step(self, closure=None, capturing=False, counted=False):
+        """``counted``: the caller has already advanced the step counter (``begin_step``) for this iteration."""
         if closure is not None:
             raise ValueError("closure is not supported")
         if not capturing:
@@ -147,7 +148,8 @@ class FusedAdamClamp(torch.optim.Optimizer):
         flat, runs = self._grads()
         if not runs:
             return None                                                # no parameter has a gradient: Adam does nothing
-        self.step_t.add_(1)
+        if not counted:
+            self.step_t.add_(1)
         lib = _lib.load()
         vp, sz = ctypes.c_void_p, ctypes.sizeof(ctypes.c_void_p)
         with torch.cuda.device(flat.device):

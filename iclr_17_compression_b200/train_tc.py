@@ -721,7 +721,7 @@ class GraphedTrainStep:
         opt_stream = self._opt_stream
 
         def backward_start():
-            if split_opt:                       # step counter += 1, off the critical path (first use: opt_range below)
+            if with_optimizer and self._opt_in_graph:   # step counter += 1, off the critical path
                 opt_stream.wait_stream(main)
                 with torch.cuda.stream(opt_stream):
                     self.optimizer.begin_step()
@@ -759,9 +759,13 @@ class GraphedTrainStep:
                 else:
                     dist.all_reduce(self.flat[:enc_elems], op=dist.ReduceOp.AVG, group=self.group)
             main.wait_stream(comm)
-        main.wait_stream(stat)
         if with_optimizer and self._opt_in_graph and not split_opt:
-            self.optimizer.step(capturing=True)                      # inside the graph: gradients are final here
+            # inside the graph: gradients are final here.  The step counter was advanced at the start of backward on a
+            # side stream, and the (low-priority) chain of small kernels that forms the reported loss is joined AFTER
+            # the optimizer - it used to end 4 us after the last gradient kernel and the optimizer waited for it
+            main.wait_stream(self._opt_stream)
+            self.optimizer.step(capturing=True, counted=True)
+        main.wait_stream(stat)
 
     @torch.no_grad()
     def _capture_direct(self, named, n_par_pad, warmup):
