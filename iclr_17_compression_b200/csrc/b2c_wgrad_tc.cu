@@ -642,7 +642,8 @@ static int wgrad_splits(int total_tiles, int ntaps) {
   int splits = 148 / groups;
   // >= 4 pixel tiles per CTA: fewer reductions (B2C_WG_MIN_TILES: for the 25-tap layers)
   static const int min_tiles5 = [] { const char* e = getenv("B2C_WG_MIN_TILES"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
-  const int mt = ntaps > 1 ? min_tiles5 : 4;
+  static const int min_tiles1 = [] { const char* e = getenv("B2C_WG_MIN_TILES1"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
+  const int mt = ntaps > 1 ? min_tiles5 : min_tiles1;
   if (splits > (total_tiles + mt - 1) / mt) splits = (total_tiles + mt - 1) / mt;
   if (splits < 1) splits = 1;
   return splits;
