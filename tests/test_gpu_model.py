@@ -388,6 +388,30 @@ def test_fused_adam_clamp_matches_torch_adam():
         assert (pb - pa).abs().max().item() <= 1e-6 * max(1.0, pa.abs().max().item()), k
 
 
+def test_fused_adam_step_in_ranges_matches_one_launch():
+    """begin_step() + step_range() over tensor ranges (GraphedTrainStep's opt-in split optimizer; odd element counts and
+    a 3-element tensor shift later tensors off 16-byte alignment: the kernel's scalar path) == one step() launch."""
+    from iclr_17_compression_b200.optim import FusedAdamClamp
+    torch.manual_seed(11)
+    shapes = [(31, 9), (128,), (3,), (128, 128), (1, 128, 1, 1), (7,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    n = sum(p.numel() for p in pa)
+    fa, fb = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    oa, ob = FusedAdamClamp(pa, lr=1e-2, flat_grads=fa), FusedAdamClamp(pb, lr=1e-2, flat_grads=fb)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for it in range(3):
+        gr = torch.randn(n, device="cuda", generator=g) * 4.0
+        fa.copy_(gr), fb.copy_(gr)
+        oa.step()
+        ob.begin_step()
+        ob.step_range(4, 6), ob.step_range(0, 2), ob.step_range(2, 4)
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)
+    assert torch.equal(oa.exp_avg, ob.exp_avg) and torch.equal(oa.exp_avg_sq, ob.exp_avg_sq)
+    assert int(oa.step_t) == int(ob.step_t) == 3
+
+
 def test_graphed_train_step_with_fused_optimizer():
     """whole iteration (forward, backward, clamp, Adam) as one CUDA graph replay == graphed step + torch Adam"""
     from iclr_17_compression_b200.train_tc import GraphedTrainStep
