@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(256) pack_many_kernel(const __grid_constant__ 
       pack_gdn_elem(job.src, job.src2, (__nv_bfloat16*)job.dst_hi, (__nv_bfloat16*)job.dst_lo, job.beta_eff,
                     job.kind == B2C_TC_PACK_GDN_T, job.channels, idx);
     else if (job.kind == B2C_TC_DECONV3X)
-      ((__nv_bfloat16*)job.dst_hi)[idx] = __float2bfloat16_rn(tcp3x::deconv3x_weight(job.src, idx));
+      ((__nv_bfloat16*)job.dst_hi)[idx] = __float2bfloat16_rn(tcp3x::deconv3x_weight(job.src, idx, job.channels));
     else
       pack_weight_elem(job.kind, job.src, (__nv_bfloat16*)job.dst_hi, (__nv_bfloat16*)job.dst_lo, idx, job.channels);
   }
@@ -970,8 +970,8 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);   
 }
 namespace tcp3x {                                                                // b2c_deconv3x.cu
 int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace);
-int pack(const float* w, void* out, cudaStream_t stream);
-size_t packed_elems();
+int pack(const float* w, void* out, int channels, cudaStream_t stream);
+size_t packed_elems(int channels);
 int tiles_per_image(int Hin, int Win);
 }
 }  // namespace b2c
@@ -996,7 +996,7 @@ size_t b2c_tc_packed_weight_elems(int kind, int channels) {
     case B2C_TC_CONV5S2:
     case B2C_TC_DECONV5S2: return 25 * C * C;
     case B2C_TC_DECONV3: return 9 * 48 * C;
-    case B2C_TC_DECONV3X: return channels == 128 ? b2c::tcp3x::packed_elems() : 0;
+    case B2C_TC_DECONV3X: return b2c::tcp3x::packed_elems(channels);
     default: return 0;
   }
 }
@@ -1004,7 +1004,7 @@ size_t b2c_tc_packed_weight_elems(int kind, int channels) {
 int b2c_tc_pack_weights(int kind, int channels, const float* w, void* w_hi, void* w_lo, void* stream) {
   const size_t n = b2c_tc_packed_weight_elems(kind, channels);
   B2C_REQUIRE(n > 0 && w && w_hi, "tc_pack_weights: bad arguments (channels must be 128, 192 or 256)");
-  if (kind == B2C_TC_DECONV3X) return b2c::tcp3x::pack(w, w_hi, (cudaStream_t)stream);   // plain bf16 only (no lo plane)
+  if (kind == B2C_TC_DECONV3X) return b2c::tcp3x::pack(w, w_hi, channels, (cudaStream_t)stream);   // plain bf16 only
   pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       kind, w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, (int)n, channels);
   count_launch();
@@ -1096,8 +1096,8 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
   B2C_REQUIRE(L->out_f32_nchw || !L->split3 || L->out_lo, "tc_layer_run: split3 bf16 output needs out_lo");
   cudaStream_t stream = (cudaStream_t)stream_;
   if (L->kind == B2C_TC_DECONV3X) {
-    B2C_REQUIRE((L->channels == 0 || L->channels == 128) && !L->split3 && !L->gdn && L->out_f32_nchw && !L->saved_y,
-                "tc_layer_run: DECONV3X is the plain-bf16 128-channel last synthesis layer with fp32 NCHW output");
+    B2C_REQUIRE((L->channels == 0 || tc_channels_ok(L->channels)) && !L->split3 && !L->gdn && L->out_f32_nchw && !L->saved_y,
+                "tc_layer_run: DECONV3X is the plain-bf16 last synthesis layer (128 / 192 / 256 channels), fp32 NCHW output");
     B2C_REQUIRE(!L->ref_image || L->sse_partial, "tc_layer_run: ref_image and sse_partial go together");
     return b2c::tcp3x::launch(L, stream, g_tc_trace);
   }

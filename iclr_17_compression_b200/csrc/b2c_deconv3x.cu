@@ -35,8 +35,6 @@ namespace tcp3x {
 
 using namespace b2c::tc;
 
-constexpr int C = 128;
-constexpr int NCB = 2;
 constexpr int NWORKERS = 512;                       // 16 epilogue warps: (TMEM lane quarter q, sub-pixel row ry)
 constexpr int NWARPS_W = NWORKERS / 32;
 constexpr int NTHREADS = 64 + NWORKERS;
@@ -46,15 +44,22 @@ constexpr int A_SLOT = BOX_ROWS * ROW_BYTES;        // 20 KB
 constexpr int NX = X_NX;                            // GEMM N: 4 sub-pixel rows x (12 dx=0, 12 dx=+1, 3 dx=-1, 1 zero)
 constexpr int PART_COLS = X_PART_COLS;              // 28 accumulator columns per sub-pixel row ry
 constexpr int B_BYTES = NX * 128;                   // one (tap, k-block) weight tile: 14 KB
-constexpr int W_RES = 3 * NCB * B_BYTES;            // 84 KB
 constexpr int TWX = TW - 2;                         // output block columns per tile
-constexpr int NA = 4;
-constexpr int NR = 2;                               // reference-image ring
 constexpr int R_W = 4 * TW, R_H = 4 * TH;           // 64 x 32 pixels x 3 channels of fp32
 constexpr int R_SLOT = 3 * R_H * R_W * 4;           // 24 KB
 constexpr int EXTRA = 1024 /*align*/ + 512 /*bias, reduction scratch*/ + 512 /*barriers*/;
-constexpr int SMEM = NA * A_SLOT + W_RES + NR * R_SLOT + EXTRA;
-static_assert(SMEM <= 227 * 1024, "shared memory budget");
+// channels C in {128, 192, 256} (model.py:39; the wider-latent models of BASELINE config 5): C / 64 k-blocks, resident
+// weights 84 / 126 / 168 KB.  What is left of the shared memory goes to the A ring and - except at 256 channels,
+// where it does not fit - the reference-image ring (there the epilogue fetches its reference pixels itself).
+template <int C>
+struct XCfg {
+  static constexpr int NCB = C / 64;
+  static constexpr int W_RES = 3 * NCB * B_BYTES;
+  static constexpr int NR = C <= 192 ? 2 : 0;                 // reference-image ring slots
+  static constexpr int NA = C == 128 ? 4 : 2;                 // A-box ring slots
+  static constexpr int SMEM = NA * A_SLOT + W_RES + NR * R_SLOT + EXTRA;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
 constexpr uint32_t ACC_STRIDE = 128;
 constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
 
@@ -72,9 +77,14 @@ struct XParams {
   long long* trace;         // debug: clock64 timeline of CTA 0: [3 roles][64 marks]
 };
 
+template <int C>
 __global__ void __launch_bounds__(NTHREADS, 1)
 deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmR, const XParams p) {
+  using Cfg = XCfg<C>;
+  constexpr int NCB = Cfg::NCB, NA = Cfg::NA, NR = Cfg::NR, W_RES = Cfg::W_RES;
+  constexpr int NRX = NR > 0 ? NR : 1;
+  constexpr bool REF_RING = NR > 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wres = smem + NA * A_SLOT;                 // [tap 3][kb 2] tiles of 112 rows x 128 B
@@ -87,8 +97,8 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* acc_empty = accum_full + 2;    // [2]  one arrival per worker warp
   uint64_t* res_full = acc_empty + 2;
   uint64_t* r_full = res_full + 1;         // [NR]
-  uint64_t* r_empty = r_full + NR;         // [NR] one arrival per worker warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + NR);
+  uint64_t* r_empty = r_full + NRX;        // [NR] one arrival per worker warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + NRX);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit0 = (int)blockIdx.x, unit_stride = (int)gridDim.x;
@@ -107,7 +117,7 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.ref_image) tma_prefetch_desc(&tmR);
+    if (REF_RING && p.ref_image) tma_prefetch_desc(&tmR);
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tcgen05_fence_before();
@@ -138,9 +148,9 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_arrive_expect_tx(&a_full[as], (uint32_t)A_SLOT);
           tma_load_4d(smem + as * A_SLOT, &tmA, &a_full[as], cb * KBLK, tile_x * TWX - 1, tile_y * TH - 1, n_img);
         }
-        if (p.ref_image) {        // the window of the reference image under this tile (out-of-image parts zero-filled)
-          const uint32_t rs = gr % NR;
-          mbar_wait(&r_empty[rs], ((gr / NR) & 1) ^ 1);
+        if (REF_RING && p.ref_image) {   // the window of the reference image under this tile (out-of-image parts zero-filled)
+          const uint32_t rs = gr % NRX;
+          mbar_wait(&r_empty[rs], ((gr / NRX) & 1) ^ 1);
           mbar_arrive_expect_tx(&r_full[rs], (uint32_t)R_SLOT);
           tma_load_4d(rring + rs * R_SLOT, &tmR, &r_full[rs], (tile_x * TWX - 1) * 4, tile_y * R_H, 0, n_img);
         }
@@ -205,6 +215,16 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool valid = tx >= 1 && tx <= TWX && oy < p.Hg && ox < p.Wg;
       const uint32_t buf = st & 1u, par = (st >> 1) & 1u;
 
+      // without the reference ring (256 channels): requested before waiting for the accumulator
+      float4 xpre[3];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) xpre[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!REF_RING && p.ref_image && valid) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o)
+          xpre[o] = __ldg(reinterpret_cast<const float4*>(
+              p.ref_image + (((size_t)n_img * 3 + o) * p.Hfull + (oy * 4 + ry)) * p.Wfull + ox * 4));
+      }
       X_MARK(2, threadIdx.x == 64);
       mbar_wait(&accum_full[buf], par);
       tcgen05_fence_after();
@@ -228,9 +248,12 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
       // fused distortion: this thread's 3 channels x 4 pixels of the reference window (TMA ring)
       float4 xref[3];
-      if (p.ref_image) {
-        const uint32_t rs = st % NR;
-        mbar_wait(&r_full[rs], (st / NR) & 1u);
+      if (!REF_RING) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) xref[o] = xpre[o];
+      } else if (p.ref_image) {
+        const uint32_t rs = st % NRX;
+        mbar_wait(&r_full[rs], (st / NRX) & 1u);
         const float* rw = reinterpret_cast<const float*>(rring + rs * R_SLOT) + (ty * 4 + ry) * R_W + tx * 4;
 #pragma unroll
         for (int o = 0; o < 3; ++o) xref[o] = *reinterpret_cast<const float4*>(rw + o * R_H * R_W);
@@ -310,19 +333,19 @@ deconv3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #undef X_MARK
 }
 
-__global__ void pack_deconv3x_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int total) {
+__global__ void pack_deconv3x_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int total, int C) {
   pdl_trigger();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  out[idx] = __float2bfloat16_rn(deconv3x_weight(w, idx));
+  out[idx] = __float2bfloat16_rn(deconv3x_weight(w, idx, C));
 }
 
-size_t packed_elems() { return (size_t)3 * NX * C; }
+size_t packed_elems(int channels) { return (size_t)3 * NX * channels; }
 
-int pack(const float* w, void* out, cudaStream_t stream) {
-  const int n = (int)packed_elems();
-  pack_deconv3x_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, (__nv_bfloat16*)out, n);
+int pack(const float* w, void* out, int channels, cudaStream_t stream) {
+  const int n = (int)packed_elems(channels);
+  pack_deconv3x_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, (__nv_bfloat16*)out, n, channels);
   count_launch();
   return check_launch("tc_pack_weights(deconv3x)");
 }
@@ -330,7 +353,7 @@ int pack(const float* w, void* out, cudaStream_t stream) {
 // partial-sum slots per image: one per (tile, worker warp)
 int tiles_per_image(int Hin, int Win) { return ((Win + TWX - 1) / TWX) * ((Hin + TH - 1) / TH) * NWARPS_W; }
 
-static int make_box_map(CUtensorMap* m, const void* base, int B, int H, int W) {
+static int make_box_map(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return B2C_ECUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -359,7 +382,9 @@ static int make_ref_map(CUtensorMap* m, const void* base, int B, int H, int W) {
   return B2C_OK;
 }
 
-int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
+template <int C>
+static int launch_c(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
+  constexpr int SMEM = XCfg<C>::SMEM;
   XParams p;
   memset(&p, 0, sizeof(p));
   p.B = L->B; p.Hg = L->Hin; p.Wg = L->Win;
@@ -382,7 +407,7 @@ int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   {
     std::lock_guard<std::mutex> lk(mu);
     if (dev < 0 || dev >= 64 || !n_sms[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(deconv3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      cudaError_t e = cudaFuncSetAttribute(deconv3x_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2C_ECUDA; }
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (const char* env = getenv("B2C_TCP_MAX_CTAS")) { const int v = atoi(env); if (v > 0 && v < sms) sms = v; }
@@ -397,9 +422,9 @@ int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   CUtensorMap mA, mB, mR;
   memset(&mR, 0, sizeof(mR));
   int rc;
-  if ((rc = make_box_map(&mA, L->in_hi, L->B, L->Hin, L->Win))) return rc;
+  if ((rc = make_box_map(&mA, L->in_hi, L->B, L->Hin, L->Win, C))) return rc;
   if ((rc = make_mat_map(&mB, L->w_hi, 3 * NX, C, NX))) return rc;
-  if (L->ref_image && (rc = make_ref_map(&mR, L->ref_image, L->B, p.Hfull, p.Wfull))) return rc;
+  if (XCfg<C>::NR > 0 && L->ref_image && (rc = make_ref_map(&mR, L->ref_image, L->B, p.Hfull, p.Wfull))) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTHREADS);
@@ -410,10 +435,19 @@ int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, deconv3x_kernel, mA, mB, mR, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, deconv3x_kernel<C>, mA, mB, mR, p);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(deconv3x): %s", cudaGetErrorString(e)); return B2C_ECUDA; }
   count_launch();
   return check_launch("tc_layer_run(deconv3x)");
+}
+
+int launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
+  switch (L->channels ? L->channels : 128) {
+    case 128: return launch_c<128>(L, stream, trace);
+    case 192: return launch_c<192>(L, stream, trace);
+    case 256: return launch_c<256>(L, stream, trace);
+    default: set_error("deconv3x: channels must be 128, 192 or 256"); return B2C_EINVAL;
+  }
 }
 
 }  // namespace tcp3x

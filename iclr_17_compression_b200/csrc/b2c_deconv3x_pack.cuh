@@ -5,16 +5,15 @@
 namespace b2c {
 namespace tcp3x {
 
-constexpr int X_C = 128;
 constexpr int X_NX = 112;                // GEMM N: 4 sub-pixel rows x (12 dx=0, 12 dx=+1, 3 dx=-1, 1 zero)
 constexpr int X_PART_COLS = X_NX / 4;    // 28 accumulator columns per sub-pixel row ry
 
-// weights IOHW [128][3][9][9] -> element idx of [tap t = dy + 1][n2 112][c 128]; column n2 = ry*28 + j of the GEMM:
+// weights IOHW [C][3][9][9] -> element idx of [tap t = dy + 1][n2 112][c C]; column n2 = ry*28 + j of the GEMM:
 //   j in [0,12):  dx = 0,  j = rx*3 + o        j in [12,24): dx = +1, same decomposition of j - 12
 //   j in [24,27): dx = -1, rx = 0, o = j - 24  j = 27: zero
 // with ky = ry + 4 - 4 dy, kx = rx + 4 - 4 dx (zero where ky > 8)
-__device__ __forceinline__ float deconv3x_weight(const float* __restrict__ w, int idx) {
-  const int c = idx % X_C, n2 = (idx / X_C) % X_NX, t = idx / (X_C * X_NX);
+__device__ __forceinline__ float deconv3x_weight(const float* __restrict__ w, int idx, int C = 128) {
+  const int c = idx % C, n2 = (idx / C) % X_NX, t = idx / (C * X_NX);
   const int ry = n2 / X_PART_COLS, j = n2 - ry * X_PART_COLS;
   float v = 0.f;
   if (j < 27) {

@@ -23,9 +23,9 @@ def _stream():
 
 def deconv3_kind(channels):
     """Layer kind of the last synthesis layer (synthesis_17.py:23): the x-folded persistent kernel (DECONV3X: N = 112,
-    24 MMAs per tile) for 128 channels, the 3x3-shift form (DECONV3) for the wider models.  B2C_DECONV3X=0 selects the
-    3x3-shift form everywhere (A/B measurements).  The two kinds have different packed-weight layouts."""
-    if channels == 128 and os.environ.get("B2C_DECONV3X", "1") != "0":
+    3 MMAs per vertical tap and 16-channel slice) - B2C_DECONV3X=0 selects the 3x3-shift form (DECONV3) for A/B
+    measurements.  The two kinds have different packed-weight layouts."""
+    if channels in (128, 192, 256) and os.environ.get("B2C_DECONV3X", "1") != "0":
         return TC_DECONV3X
     return TC_DECONV3
 

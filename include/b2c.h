@@ -175,7 +175,7 @@ int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped
 #define B2C_TC_DECONV3 3   /* 9x9 s4 p4 op3 transposed, 128->3, as a 3x3 conv to 16 phases x 3 channels
                               (models/synthesis_17.py:23) */
 
-#define B2C_TC_DECONV3X 4  /* the same layer (128 channels only) with the horizontal input shifts folded into the GEMM's
+#define B2C_TC_DECONV3X 4  /* the same layer (128 / 192 / 256 channels) with the horizontal input shifts folded into the GEMM's
                               N dimension (N = 112, 24 MMAs per tile instead of 72 of N = 48) and summed by warp shuffles
                               in the epilogue; tiles advance by 14 columns.  Own packed-weight layout: pack with this kind. */
 

@@ -163,6 +163,31 @@ def test_deconv3x_bf16(tc, shape):
     assert _rel(y, y3.double().cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("C", [192, 256])
+@pytest.mark.parametrize("shape", [(1, 16, 32), (2, 24, 30), (1, 9, 29)])
+def test_deconv3x_wide(tc, C, shape):
+    """DECONV3X at the wider latent widths of BASELINE config 5 (model.py:39): 3 / 4 k-blocks, reference image through
+    the TMA ring (192) or per-thread loads (256: the ring does not fit beside 168 KB of resident weights)."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, C, H, W, generator=g).cuda()
+    w = (torch.randn(C, 3, 9, 9, generator=g) * 0.05).cuda()
+    b = torch.randn(3, generator=g).cuda()
+    img = torch.rand(B, 3, 4 * H, 4 * W, generator=g).cuda()
+    xh, _ = tc.nchw_to_nhwc(x, False)
+    xq = xh.float().permute(0, 3, 1, 2).double().cpu()
+    wq = w.to(torch.bfloat16).double().cpu()
+    ref = F.conv_transpose2d(xq, wq, b.double().cpu(), stride=4, padding=4, output_padding=3)
+    wp = tc.pack_weights(tc.TC_DECONV3X, w, False)
+    y = tc.layer_run(tc.TC_DECONV3X, xh, None, wp, b, out_f32_nchw=True)
+    assert _rel(y, ref) < 2e-5, _rel(y, ref)
+    clipped, sse = tc.layer_run(tc.TC_DECONV3X, xh, None, wp, b, out_f32_nchw=True, ref_image=img)
+    xi = img.double().cpu()
+    assert torch.allclose(clipped.double().cpu(), ref.clamp(0, 1), atol=2e-5)
+    sse_ref = torch.stack([((ref - xi) ** 2).flatten(1).sum(1), ((ref.clamp(0, 1) - xi) ** 2).flatten(1).sum(1)], 1)
+    assert torch.allclose(sse.double().cpu(), sse_ref, rtol=1e-4), (sse, sse_ref)
+
+
 def test_deconv3x_full_size_properties(tc):
     """BASELINE configs[1] size (24 x 128 x 192 x 128 -> 24 x 3 x 512 x 768): the x-folded kernel against the independent
     3x3-shift kernel, linearity in the input, and the fused squared errors against a sum over the stored output."""
