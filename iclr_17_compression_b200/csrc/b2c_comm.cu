@@ -124,6 +124,13 @@ __global__ void __launch_bounds__(256) allreduce_fused_kernel(const FusedArgs a)
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = a.begin4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a.mc) {
+    for (; i + 7 * stride < a.end4; i += 8 * stride) {       // eight in-switch reductions in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = mm_ld_reduce(a.mc + (i + k * stride) * 4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mm_st(a.mc + (i + k * stride) * 4, v[k], a.scale);
+    }
     for (; i + 3 * stride < a.end4; i += 4 * stride) {
       float* a0 = a.mc + i * 4;
       float* a1 = a0 + stride * 4;
@@ -134,6 +141,30 @@ __global__ void __launch_bounds__(256) allreduce_fused_kernel(const FusedArgs a)
     }
     for (; i < a.end4; i += stride) mm_st(a.mc + i * 4, mm_ld_reduce(a.mc + i * 4), a.scale);
   } else {
+    auto ldv = [](const float* p) {
+      float4 v;
+      asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+      return v;
+    };
+    if (a.world == 2) {      // two ranks: four positions x two ranks = eight loads in flight per thread
+      for (; i + 3 * stride < a.end4; i += 4 * stride) {
+        float4 v[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[k][0] = ldv(a.peers[0] + (i + k * stride) * 4);
+          v[k][1] = ldv(a.peers[1] + (i + k * stride) * 4);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float4 s4;
+          s4.x = (v[k][0].x + v[k][1].x) * a.scale; s4.y = (v[k][0].y + v[k][1].y) * a.scale;
+          s4.z = (v[k][0].z + v[k][1].z) * a.scale; s4.w = (v[k][0].w + v[k][1].w) * a.scale;
+          *reinterpret_cast<float4*>(a.peers[0] + (i + k * stride) * 4) = s4;
+          *reinterpret_cast<float4*>(a.peers[1] + (i + k * stride) * 4) = s4;
+        }
+      }
+    }
     for (; i < a.end4; i += stride) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < a.world; ++r) {                       // fixed rank order: identical sums on every rank
@@ -146,10 +177,14 @@ __global__ void __launch_bounds__(256) allreduce_fused_kernel(const FusedArgs a)
       for (int r = 0; r < a.world; ++r) *reinterpret_cast<float4*>(a.peers[r] + i * 4) = s;
     }
   }
-  // ---- barrier 2: every rank's slice has landed everywhere
-  __threadfence_system();
+  // ---- barrier 2: every rank's slice has landed everywhere.  One system-scope fence per CTA, by the thread that takes
+  // the ticket, after the CTA barrier (fences are cumulative: it covers the stores of the whole CTA); 256 fence.sys per
+  // CTA, each waiting for the multimem stores to be acknowledged across NVLink, were a visible part of the kernel.
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
   __syncthreads();
   if (s_last) {
     if (threadIdx.x < a.world) {
@@ -191,8 +226,9 @@ extern "C" int b2c_allreduce_symm_fused(void* const* peer_ptrs, void* multicast_
   a.begin4 = begin / 4 + base4 * rank + ((size_t)rank < rem ? (size_t)rank : rem);
   a.end4 = a.begin4 + my4;
   a.scale = scale; a.rank = rank; a.world = world;
-  size_t blocks = (my4 + 1023) / 1024;            // 4 float4 per thread in flight
-  const size_t cap = max_blocks > 0 ? (size_t)max_blocks : 148;
+  size_t blocks = (my4 + 1023) / 1024;            // >= 4 float4 per thread in flight
+  static const int cap_default = [] { const char* e = getenv("B2C_AR_CAP"); const int v = e ? atoi(e) : 148; return v > 0 ? v : 148; }();
+  const size_t cap = max_blocks > 0 ? (size_t)max_blocks : (size_t)cap_default;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   allreduce_fused_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);

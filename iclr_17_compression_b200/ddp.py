@@ -12,6 +12,7 @@ collective, only a host-side gather of per-image statistics (``gather_stats``).
 
 Works with any backend (the CPU tests use gloo, world_size 2).
 """
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -172,7 +173,9 @@ class SymmAllReduce:
     peer loads / stores otherwise) -> barrier.  For the 7 MB gradient buffer of the training step this replaces a
     ~58 us NCCL all-reduce (protocol latency bound at this size).  CUDA only; there is no fallback."""
 
-    def __init__(self, numel: int, device, group=None, use_multicast: bool = True):
+    def __init__(self, numel: int, device, group=None, use_multicast: Optional[bool] = None, extra: int = 0):
+        """``extra``: fp32 elements of caller scratch allocated right behind the reduced buffer (``self.region`` =
+        buffer + scratch as one contiguous tensor, so that a training step clears both with a single memset)."""
         import ctypes
         import torch.distributed._symmetric_memory as symm
         if not dist.is_initialized():
@@ -186,12 +189,20 @@ class SymmAllReduce:
         # behind the data: flag blocks of the fused kernel (barrier -> reduce -> barrier in one launch), one per channel
         self.flag_words = int(_lib.load().b2c_allreduce_symm_flag_words())
         self.channels = 4
-        self._alloc = symm.empty(self.count + self.channels * self.flag_words, dtype=torch.float32, device=device)
+        self.extra = (int(extra) + 63) // 64 * 64
+        self.flag_base = self.count + self.extra
+        self._alloc = symm.empty(self.flag_base + self.channels * self.flag_words, dtype=torch.float32, device=device)
         self._alloc.zero_()
         self.buf = self._alloc[:self.count]
+        self.region = self._alloc[:self.flag_base]
         self.hdl = symm.rendezvous(self._alloc, self.group.group_name)
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)                 # every rank's flags are zero before anybody's first launch
+        if use_multicast is None:
+            # in-switch reduction (NVLS multimem) from three ranks on; between TWO GPUs plain peer loads / stores are
+            # faster (7 MB: 27.9 vs 37.7 us per call, profiles/symm_micro.py).  B2C_AR_MC=0 / 1 overrides.
+            env = os.environ.get("B2C_AR_MC")
+            use_multicast = (env == "1") if env in ("0", "1") else self.world > 2
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
         self.multicast = mc != 0
         self._mc = ctypes.c_void_p(mc)
@@ -223,7 +234,7 @@ class SymmAllReduce:
         with torch.cuda.device(self.buf.device):
             _lib.check(_lib.load().b2c_allreduce_symm_fused(
                 ct.cast(self._ptrs, ct.POINTER(ct.c_void_p)), self._mc, self.rank, self.world, begin, count,
-                self.count + channel * self.flag_words, ct.c_float(1.0 / self.world if mean else 1.0), int(max_blocks),
+                self.flag_base + channel * self.flag_words, ct.c_float(1.0 / self.world if mean else 1.0), int(max_blocks),
                 ct.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream)), "allreduce_symm_fused")
 
     def all_reduce_range(self, begin: int, count: int, mean: bool = True, max_blocks: int = 0):

@@ -624,7 +624,7 @@ class GraphedTrainStep:
         if self.world > 1 and direct and ar_mode in ("symm", "symm_graph", "symm_graph2"):
             from .ddp import SymmAllReduce
             try:
-                self._symm = SymmAllReduce(n_par_pad, dev, group)
+                self._symm = SymmAllReduce(n_par_pad, dev, group, extra=scratch + 64)
             except Exception as e:        # no symmetric memory / peer access on this system: NCCL carries the gradients
                 if allreduce is not None or os.environ.get("B2C_AR"):
                     raise
@@ -634,13 +634,15 @@ class GraphedTrainStep:
             if self._symm is not None:
                 self._symm_in_graph = ar_mode != "symm"
                 self._symm_buckets = 2 if ar_mode == "symm_graph2" else 1
-            self._grads = self._symm.buf
-            self.buf = torch.zeros(scratch + 64, device=dev, dtype=torch.float32)
-            self._scratch_off = 0
+        if self._symm is not None:
+            # gradients and the step's scratch are ONE contiguous piece of the symmetric allocation: one memset per step
+            # (as two tensors the second fill started 9 us after the first had finished, profiles/trace_train_ddp.py)
+            self.buf = self._symm.region
+            self._scratch_off = self._symm.count
         else:
             self.buf = torch.zeros(n_par_pad + scratch, device=dev, dtype=torch.float32)
-            self._grads = self.buf
             self._scratch_off = n_par_pad
+        self._grads = self.buf
         self.flat = self._grads[:n_par]
         views, o = [], 0
         for p in self.params:
@@ -682,8 +684,6 @@ class GraphedTrainStep:
         dev = self.x.device
         main = torch.cuda.current_stream(dev)
         self.buf.zero_()                                              # ONE memset: gradients + all accumulators
-        if self._grads is not self.buf:
-            self._grads.zero_()                                       # (symmetric gradient buffer: its own memset)
         pool = _Pool(self.buf, self._scratch_off)
         fused = os.environ.get("B2C_TRAIN_FUSED_DISTORTION", "1") == "1"
         st = step_forward(self.x, self.noise, prm, pool, grad_scale=(2.0 * self.lam / self.x.numel()) if fused else None,
