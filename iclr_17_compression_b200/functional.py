@@ -423,6 +423,32 @@ def quant_entropy_infer(y, params, lut=None, range_flag=None):
     return z, zh, image_bits
 
 
+_stats_tickets = {}
+
+
+def infer_stats(sse_partial, image_bits, numel, pixels):
+    """End of an eval forward in one launch (b2c_infer_stats; model.py:61,73,78): per-tile squared-error partial sums
+    [B, tiles, 2] + per-image bits [B] -> (sse [B, 2], totals [4] = total bits, total squared error, mse, bpp).
+    The kernel finds its last block through a self-resetting ticket word; calls take the 64 words of a per-device pool in
+    turn, so forwards in flight on different streams (or captured in different graphs) do not share one."""
+    B, tiles, _ = sse_partial.shape
+    dev = sse_partial.device
+    pool = _stats_tickets.get(dev.index)
+    if pool is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.B2CError("infer_stats: first call on this device inside a CUDA-graph capture; run one eager "
+                                "forward first")
+        pool = _stats_tickets[dev.index] = [torch.zeros((64,), device=dev, dtype=torch.int32), 0]
+    ticket = pool[0][pool[1] % 64:pool[1] % 64 + 1]
+    pool[1] += 1
+    sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
+    totals = torch.empty((4,), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev), _timed("infer_stats", 0, sse_partial.numel() * 4):
+        _lib.check(_lib.load().b2c_infer_stats(_p(sse_partial), B, tiles, _p(image_bits), float(numel), float(pixels),
+                                               _p(sse), _p(totals), _p(ticket), _stream()), "infer_stats")
+    return sse, totals
+
+
 class _SigmoidBinarize(torch.autograd.Function):
     """models/analysis_17_new.py:35-37 + models/binarizer.py:7-27: (code, sigmoid) with the straight-through gradient"""
 

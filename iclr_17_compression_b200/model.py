@@ -168,7 +168,7 @@ class ImageCompressor(nn.Module):
                                 "synthesis path cannot represent exactly: its reconstruction is invalid.  "
                                 "fast_inference is now off (exact-fp32 kernels); run the batch again.")
 
-    def decode_tc(self, z, ref_image=None, z_nhwc=None):
+    def decode_tc(self, z, ref_image=None, z_nhwc=None, reduce_sse=True):
         """synthesis transform on tensor cores (bf16) -> unclamped reconstruction, fp32 NCHW; with ref_image
         the distortion is fused into the last layer: returns (clamped reconstruction, sse[B,2]).
         A caller-supplied ``z`` without its bf16 copy is range-checked (one host sync): beyond +-256 the exact-fp32
@@ -184,7 +184,7 @@ class ImageCompressor(nn.Module):
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, zh, None, P["deconv1"], D.deconv1.bias, gdn=P["igdn1"], gdn_mode=2)
         h = B2TC.layer_run(B2TC.TC_DECONV5S2, h[0], None, P["deconv2"], D.deconv2.bias, gdn=P["igdn2"], gdn_mode=2)
         return B2TC.layer_run(B2TC.deconv3_kind(self.out_channel_N), h[0], None, P["deconv3"], D.deconv3.bias,
-                              out_f32_nchw=True, ref_image=ref_image)
+                              out_f32_nchw=True, ref_image=ref_image, reduce_sse=reduce_sse)
 
     def _forward_tc(self, x):
         """the tensor-core eval pipeline: 7 fused launches + 1 reduction"""
@@ -192,8 +192,11 @@ class ImageCompressor(nn.Module):
         z, zh, image_bits = B2F.quant_entropy_infer(feature, [p.detach().reshape(-1) for p in
                                                               self.bitEstimator.param_list()],
                                                     lut=self._packed_weights()["bits_lut"], range_flag=self._zflag)
-        clipped, sse = self.decode_tc(z, ref_image=x, z_nhwc=zh)
-        return clipped, z, image_bits, sse, image_bits.sum(), sse[:, 0].sum()
+        # (reduce_sse=False: the per-tile partial sums come back and ONE launch forms the per-image squared errors, the
+        # batch totals, mse and bpp - model.py:61,73,78)
+        clipped, partial = self.decode_tc(z, ref_image=x, z_nhwc=zh, reduce_sse=False)
+        sse, totals = B2F.infer_stats(partial, image_bits, x.numel(), x.size(0) * x.size(2) * x.size(3))
+        return clipped, z, image_bits, sse, totals[0], totals[1], totals[2], totals[3]
 
     # Small eval batches (the reference's testKodak feeds ONE image per call, train.py:162-171) are host bound: the 8
     # launches with their TMA descriptors and output allocations cost ~0.4 ms against ~0.06 ms of device time per
@@ -278,8 +281,12 @@ class ImageCompressor(nn.Module):
             if self._zflag is None:
                 self._zflag = B2F.RangeFlag()
             x = B2F._prep(x.float(), "input image")
-            clipped_recon_image, z, image_bits, sse, total_bits, sse_total = self._forward_tc_maybe_graphed(x)
-            plane_bits = None                                    # per-plane bits only on the fp32 path
+            clipped_recon_image, z, image_bits, sse, total_bits, sse_total, mse_loss, bpp_feature = \
+                self._forward_tc_maybe_graphed(x)
+            self.last = {"image_bits": image_bits, "plane_bits": None, "sse": sse, "mse_loss": mse_loss.detach()}
+            if self.return_mode == "mse":
+                return clipped_recon_image, mse_loss, bpp_feature
+            return clipped_recon_image, z, bpp_feature
         else:
             feature = self._enc(x)
             noise = self._noise(x) if self.training else None

@@ -156,6 +156,13 @@ int b2c_clamp_sse_fwd(const float* recon, const float* x, float* clipped, float*
 size_t b2c_clamp_sse_workspace_bytes(int B, int CHW);
 /* out[n*width + j] = sum_i partial[(n*per_image + i)*width + j], fixed order (deterministic); width <= 4. */
 int b2c_partial_reduce(const float* partial, float* out, int B, int per_image, int width, void* stream);
+
+/* End of an inference forward in ONE launch (model.py:61,73,78): sse[B][2] = fixed-order sums of the last layer's
+ * per-tile partial sums sse_partial[B][tiles][2]; totals[4] = {sum of image_bits, sum of sse[:,0], that / numel (mse on
+ * the unclamped reconstruction), bits / pixels (bpp)}.  `ticket`: one zero-initialised device word the library uses to
+ * find the last block; the kernel leaves it at zero. */
+int b2c_infer_stats(const float* sse_partial, int B, int tiles, const float* image_bits, double numel, double pixels,
+                    float* sse, float* totals, unsigned* ticket, void* stream);
 /* grad_recon = g_clipped * 1[0<=recon<=1] + g_sse[0] * 2 (recon - x);
  * g_clipped may be NULL; g_sse is a DEVICE scalar (dL/d total unclamped SSE). */
 int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped,
