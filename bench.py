@@ -417,6 +417,8 @@ def train_bench(model, dev, world, rank, barrier, steps=10, warmup=3):
                            else "one NCCL all-reduce (mean) of the flat 7 MB gradient buffer after the graphed step")
                           if graphed is not None else
                           "nccl bucketed, overlapped with backward"),
+            "input": ("batch resident in the step's static input buffer, where a loader's host-to-device copy would put it "
+                      "(no per-step device-to-device copy)") if graphed is not None else "device tensor",
             "path": getattr(model, "last_path", None), "cuda_graph": graphed is not None,
             "direct": bool(getattr(graphed, "direct", False)),
             "ops": {k: round(v["ms_total"] / steps, 4) for k, v in sorted(ops.items(), key=lambda kv: -kv[1]["ms_total"])},
