@@ -50,7 +50,8 @@ class TcLayer(ctypes.Structure):
                 ("gamma_hi", _c_f), ("gamma_lo", _c_f), ("beta_eff", _c_f), ("out_hi", _c_f), ("out_lo", _c_f),
                 ("ref_image", _c_f), ("sse_partial", _c_f), ("saved_y", _c_f), ("saved_n", _c_f),
                 ("channels", _c_i), ("grad_out", _c_f), ("grad_scale", ctypes.c_float), ("ksplit", _c_i),
-                ("dbias_out", _c_f)]
+                ("dbias_out", _c_f), ("lut", _c_f), ("lut_half_range", _c_i), ("bit_params", _c_f), ("z_nhwc_out", _c_f),
+                ("bits_partial", _c_f), ("range_flag", _c_f)]
 
 
 TC_CONV1, TC_CONV5S2, TC_DECONV5S2, TC_DECONV3, TC_DECONV3X = 0, 1, 2, 3, 4

@@ -1111,6 +1111,8 @@ int b2c_tc_layer_run(const b2c_tc_layer* L, void* stream_) {
     rc = b2c::tcp1::try_launch(L, stream, g_tc_trace);
     if (rc != 1) return rc;
   }
+  B2C_REQUIRE(!L->lut, "tc_layer_run: the fused quantizer / entropy epilogue (lut) is implemented by the persistent 128-channel "
+                       "CONV5S2 kernel only (split3, gdn 0, out_f32_nchw, B2C_TC_PERSIST on)");
   B2C_REQUIRE(!L->grad_out, "tc_layer_run: grad_out needs the persistent DECONV3 kernel (ref_image set, 128 channels, "
                             "B2C_TC_PERSIST on)");
   TcParams p;

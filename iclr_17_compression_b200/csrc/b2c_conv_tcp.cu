@@ -23,6 +23,7 @@
 #include "b2c_tc_host.cuh"
 #include "b2c_tcp_util.cuh"
 #include "b2c_tc_ts.cuh"
+#include "b2c_entropy_formula.cuh"
 
 #ifndef B2C_TCP_TS_EPI
 #define B2C_TCP_TS_EPI 1    /* 0: x^2 through shared memory and block-wide staging, as in round 1 */
@@ -56,6 +57,15 @@ struct PParams {
   float* sse_partial;
   float* grad_out;          // DECONV3 + ref_image (training): grad_scale * (recon - x), fp32 NCHW, or nullptr
   float grad_scale;
+  // last analysis layer at inference (CONV5S2, fp32 NCHW output, no GDN): with `lut` the epilogue is the quantizer and
+  // the entropy model too (model.py:55-56,71-73) - out_f32 receives z = rint(y), z_nhwc its bf16 NHWC copy (what the
+  // synthesis transform reads), bits_partial[B][tiles][8 warps] the bits of every (tile, epilogue warp)
+  const float* lut;         // bits[c][z + L], |z| <= L (b2c_entropy_lut_build) or nullptr
+  int lut_L;
+  BitPtrs bp;               // the 11 Bitparm vectors, for |z| > L
+  __nv_bfloat16* z_nhwc;
+  float* bits_partial;
+  int* range_flag;          // raised when some |z| > 256 (the bf16 copy is inexact beyond), may be nullptr
   long long* trace;         // debug: clock64 timeline of CTA 0: [3 roles][64 marks]
 };
 
@@ -787,6 +797,8 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
           }
         } else if (OUT_MODE == OUT_F32_NCHW) {
+          const bool latent = !GDN && KIND == B2C_TC_CONV5S2 && p.lut != nullptr;
+          float bits_sum = 0.f;
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             const int c0 = half * 64 + h * 32;
@@ -802,6 +814,42 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 else mbar_arrive(&acc_empty[buf]);
               }
             }
+            if (!GDN && KIND == B2C_TC_CONV5S2 && latent) {
+              // quantizer + entropy model in the epilogue: z = rint(y) (half to even, model.py:56), its bits from the
+              // per-channel table (one cached read per element; the formula itself only beyond the table), z as fp32
+              // NCHW (the API tensor) and as bf16 NHWC (this thread's 32 channels = 64 contiguous bytes)
+              if (valid) {
+                const float fL = (float)p.lut_L;
+                const int Wt = 2 * p.lut_L + 1;
+                const float* row = p.lut + (size_t)c0 * Wt + p.lut_L;
+                float zv[32], amax = 0.f, bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  zv[j] = rintf(__uint_as_float(raw[j]) + s_bias[c0 + j]);
+                  amax = fmaxf(amax, fabsf(zv[j]));
+                  const int idx = (int)fminf(fmaxf(zv[j], -fL), fL);
+                  bs[j & 3] += __ldg(row + (size_t)j * Wt + idx);
+                  p.out_f32[(((size_t)n_img * C + c0 + j) * p.Hfull + oyf) * p.Wfull + oxf] = zv[j];
+                }
+                float bsum = (bs[0] + bs[1]) + (bs[2] + bs[3]);
+                if (!(amax <= fL)) {             // rare: outside the table (or NaN) - the same formula directly
+                  if (p.range_flag && !(amax <= BF16_EXACT_INT)) *p.range_flag = 1;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (!(fabsf(zv[j]) <= fL)) {
+                      const int idx = (int)fminf(fmaxf(zv[j], -fL), fL);     // (NaN -> -L, as above)
+                      bsum += bits_outside_table(p.bp, c0 + j, zv[j]) - __ldg(row + (size_t)j * Wt + idx);
+                    }
+                }
+                bits_sum += bsum;
+                uint4* dst = reinterpret_cast<uint4*>(p.z_nhwc + (((size_t)n_img * p.Hfull + oyf) * p.Wfull + oxf) * C + c0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  dst[k] = make_uint4(cvt_bf16x2(zv[8 * k], zv[8 * k + 1]), cvt_bf16x2(zv[8 * k + 2], zv[8 * k + 3]),
+                                      cvt_bf16x2(zv[8 * k + 4], zv[8 * k + 5]), cvt_bf16x2(zv[8 * k + 6], zv[8 * k + 7]));
+              }
+              continue;
+            }
             if (valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -814,6 +862,12 @@ igemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 p.out_f32[(((size_t)n_img * C + c0 + j) * p.Hfull + oyf) * p.Wfull + oxf] = xv;
               }
             }
+          }
+          if (!GDN && KIND == B2C_TC_CONV5S2 && latent) {     // bits of this (tile, warp): fixed-order butterfly
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bits_sum += __shfl_xor_sync(0xffffffffu, bits_sum, o);
+            if (lane == 0 && n_img < p.B)
+              p.bits_partial[((size_t)n_img * p.tiles_per_image + trem) * (NWORKERS / 32) + (warp - 2)] = bits_sum;
           }
         } else {
           // NHWC bf16 through the (now idle) x^2 buffer + TMA stores: hi plane first, lo plane second
@@ -932,6 +986,11 @@ static int launch_p(const b2c_tc_layer* L, cudaStream_t stream, long long* trace
   p.out_f32 = (float*)L->out_hi;
   p.ref_image = L->ref_image; p.sse_partial = L->sse_partial;
   p.grad_out = L->ref_image ? L->grad_out : nullptr; p.grad_scale = L->grad_scale;
+  if (L->lut) {
+    p.lut = L->lut; p.lut_L = L->lut_half_range;
+    for (int i = 0; i < B2C_NUM_BITPARAMS; ++i) p.bp.p[i] = L->bit_params[i];
+    p.z_nhwc = (__nv_bfloat16*)L->z_nhwc_out; p.bits_partial = L->bits_partial; p.range_flag = L->range_flag;
+  }
   p.trace = trace;
 
   // grid: one CTA (pair) per SM, never more than can be co-resident (a persistent CTA that waits for a slot
@@ -1040,8 +1099,16 @@ int try_launch(const b2c_tc_layer* L, cudaStream_t stream, long long* trace) {
   if (L->kind == B2C_TC_CONV5S2 && L->split3) {
     if (L->gdn == 1 && !L->out_f32_nchw && L->out_lo)
       return launch_p<B2C_TC_CONV5S2, true, 1, OUT_BF16, true>(L, stream, trace);
-    if (L->gdn == 0 && L->out_f32_nchw)
+    if (L->gdn == 0 && L->out_f32_nchw) {
+      if (L->lut) {
+        B2C_REQUIRE(L->lut_half_range >= 1 && L->bit_params && L->z_nhwc_out && L->bits_partial,
+                    "tc_layer_run: the fused quantizer / entropy epilogue needs lut_half_range, bit_params, z_nhwc_out, "
+                    "bits_partial");
+        for (int i = 0; i < B2C_NUM_BITPARAMS; ++i)
+          B2C_REQUIRE(L->bit_params[i], "tc_layer_run: null Bitparm pointer %d", i);
+      }
       return launch_p<B2C_TC_CONV5S2, true, 0, OUT_F32_NCHW, true>(L, stream, trace);
+    }
     return 1;
   }
   if (L->kind == B2C_TC_DECONV5S2 && !L->split3 && L->gdn == 2 && !L->out_f32_nchw && !L->out_lo) {

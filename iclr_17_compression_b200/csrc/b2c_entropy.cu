@@ -11,39 +11,15 @@
 #include <mutex>
 
 #include "b2c_common.cuh"
+#include "b2c_entropy_formula.cuh"
 
 namespace b2c {
 
-struct BitPtrs {
-  const float* p[B2C_NUM_BITPARAMS];
-};
 struct BitGradPtrs {
   float* p[B2C_NUM_BITPARAMS];
 };
 
-struct ChanConst {
-  float sp[4];  // softplus(h_k)
-  float b[4];
-  float ta[3];  // tanh(a_k)
-};
-
-__device__ __forceinline__ float softplus_t(float h) {  // torch F.softplus, beta=1, threshold=20
-  return h > 20.f ? h : log1pf(expf(h));
-}
 __device__ __forceinline__ float sigmoid_t(float t) { return 1.f / (1.f + expf(-t)); }
-
-__device__ __forceinline__ ChanConst load_chan(const BitPtrs& bp, int c) {
-  ChanConst k;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    k.sp[i] = softplus_t(__ldg(bp.p[3 * i] + c));
-    k.b[i] = __ldg(bp.p[3 * i + 1] + c);
-    k.ta[i] = tanhf(__ldg(bp.p[3 * i + 2] + c));
-  }
-  k.sp[3] = softplus_t(__ldg(bp.p[9] + c));
-  k.b[3] = __ldg(bp.p[10] + c);
-  return k;
-}
 
 __device__ __forceinline__ float cdf(const ChanConst& k, float v) {
 #pragma unroll
@@ -123,25 +99,9 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, float* 
 // per-element chain (relative error ~2^-11 per tanh changes the total bit count by ~1e-6 relative, far inside the
 // 1e-3 bpp bar; the per-channel softplus / tanh constants stay exact).  One CTA = 32 pixels x all channels of one
 // image, so the rounded latent is also emitted as the NHWC bf16 tensor the tensor-core synthesis transform reads.
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float cdf_fast(const float* k, float v) {   // k: sp1 b1 ta1 sp2 b2 ta2 sp3 b3 ta3 sp4 b4
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const float t = fmaf(v, k[3 * i], k[3 * i + 1]);
-    v = fmaf(tanh_fast(t), k[3 * i + 2], t);
-  }
-  const float t4 = fmaf(v, k[9], k[10]);
-  return __fdividef(1.f, 1.f + __expf(-t4));
-}
-
 constexpr int QI_PIX = 32;
 // integers up to 256 are exact in bf16 (8 significand bits); the NHWC bf16 latent the tensor-core synthesis transform
 // reads is only valid below that.  The inference kernels raise *range_flag (sticky, never cleared here) otherwise.
-constexpr float BF16_EXACT_INT = 256.f;
 
 __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* __restrict__ y, BitPtrs bp,
                                                                   float* __restrict__ z,
@@ -203,11 +163,6 @@ __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* _
 // bits[c][z + L], |z| <= L, built once per weight version with the SAME per-element formula as the kernel above, turns
 // the pass into pure data movement (read y, write z fp32 + z bf16, one cached table read) - the SFU chain (11 MUFU ops
 // per element, which held the direct kernel at 36 % of HBM peak) only runs for the rare |z| > L.
-__device__ __forceinline__ float elem_bits_fast(const float* k, float zv) {
-  const float p = cdf_fast(k, zv + 0.5f) - cdf_fast(k, zv - 0.5f);
-  return fminf(fmaxf(-__log2f(p + 1e-10f), 0.f), 50.f);
-}
-
 __global__ void entropy_lut_build_kernel(BitPtrs bp, float* __restrict__ lut, int C, int L) {
   const int c = blockIdx.x;
   __shared__ float k[12];
@@ -220,14 +175,6 @@ __global__ void entropy_lut_build_kernel(BitPtrs bp, float* __restrict__ lut, in
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * L + 1; i += blockDim.x) lut[(size_t)c * (2 * L + 1) + i] = elem_bits_fast(k, (float)(i - L));
-}
-
-// |z| beyond the table: the direct formula, kept out of line so the hot loop stays small (registers -> occupancy)
-__device__ __noinline__ float bits_outside_table(const BitPtrs& bp, int c, float zv) {
-  const ChanConst kc = load_chan(bp, c);
-  const float k[12] = {kc.sp[0], kc.b[0], kc.ta[0], kc.sp[1], kc.b[1], kc.ta[1], kc.sp[2], kc.b[2], kc.ta[2],
-                       kc.sp[3], kc.b[3], 0.f};
-  return elem_bits_fast(k, zv);
 }
 
 // CTA = LQ_PIX (128) pixels x all channels of one image: 512 contiguous bytes per channel row on the NCHW side (32-pixel

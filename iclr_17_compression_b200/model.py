@@ -147,13 +147,15 @@ class ImageCompressor(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def encode_tc(self, x):
-        """analysis transform on tensor cores (error-compensated bf16x3) -> y, fp32 NCHW"""
+    def encode_tc(self, x, latent=None):
+        """analysis transform on tensor cores (error-compensated bf16x3) -> y, fp32 NCHW.  ``latent`` (see
+        tc.layer_run): quantizer + entropy model in the last layer's epilogue -> (z, z bf16 NHWC, image_bits)."""
         P, E = self._packed_weights(), self._enc
         h = B2TC.layer_run(B2TC.TC_CONV1, x, None, P["conv1"], E.conv1.bias, gdn=P["gdn1"], gdn_mode=1, split3=True)
         h = B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv2"], E.conv2.bias, gdn=P["gdn2"], gdn_mode=1,
                            split3=True)
-        return B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv3"], None, split3=True, out_f32_nchw=True)
+        return B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv3"], None, split3=True, out_f32_nchw=True,
+                              latent=latent)
 
     def check_latent_range(self):
         """The tensor-core synthesis transform reads the rounded latent as bf16, exact only for |z| <= 256.  The
@@ -188,10 +190,16 @@ class ImageCompressor(nn.Module):
 
     def _forward_tc(self, x):
         """the tensor-core eval pipeline: 7 fused launches + 1 reduction"""
-        feature = self.encode_tc(x)
-        z, zh, image_bits = B2F.quant_entropy_infer(feature, [p.detach().reshape(-1) for p in
-                                                              self.bitEstimator.param_list()],
-                                                    lut=self._packed_weights()["bits_lut"], range_flag=self._zflag)
+        bitp = [p.detach().reshape(-1) for p in self.bitEstimator.param_list()]
+        lut = self._packed_weights()["bits_lut"]
+        if self.out_channel_N == 128 and os.environ.get("B2C_FUSED_LATENT", "1") == "1" \
+                and os.environ.get("B2C_TC_PERSIST", "1") != "0":
+            # the quantizer and the entropy model run in the epilogue of the last analysis layer: no separate pass over y
+            z, zh, image_bits = self.encode_tc(x, latent=(lut, B2F.LUT_HALF_RANGE, [B2F._prep(p, "bit-estimator parameter")
+                                                                                   for p in bitp], self._zflag))
+        else:
+            feature = self.encode_tc(x)
+            z, zh, image_bits = B2F.quant_entropy_infer(feature, bitp, lut=lut, range_flag=self._zflag)
         # (reduce_sse=False: the per-tile partial sums come back and ONE launch forms the per-image squared errors, the
         # batch totals, mse and bpp - model.py:61,73,78)
         clipped, partial = self.decode_tc(z, ref_image=x, z_nhwc=zh, reduce_sse=False)

@@ -137,10 +137,14 @@ def reduce_partial_sse(partial):
 
 
 def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out_f32_nchw=False, ref_image=None,
-              second_plane=False, saved=None, ksplit=1, out=None, grad_scale=None, reduce_sse=True, dbias=None):
+              second_plane=False, saved=None, ksplit=1, out=None, grad_scale=None, reduce_sse=True, dbias=None,
+              latent=None):
     """One fused layer.  x_hi/x_lo: NHWC bf16 (CONV1: x_hi = fp32 NCHW image).  w = (w_hi, w_lo);
     gdn = (gamma_hi, gamma_lo, beta_eff) with gdn_mode 1 (GDN) / 2 (IGDN).
-    Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw."""
+    Returns (out_hi, out_lo) NHWC bf16, or the fp32 NCHW tensor when out_f32_nchw.
+    ``latent`` = (bits table, half range, list of the 11 Bitparm vectors, RangeFlag or None): the last analysis layer
+    at inference with the quantizer and the entropy model in its epilogue - returns (z fp32 NCHW, z bf16 NHWC,
+    image_bits [B])."""
     if kind == TC_CONV1:
         B, _, Hin, Win = x_hi.shape
         C = w[0].numel() // (4 * 64)
@@ -179,6 +183,19 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
     L.out_hi, L.out_lo = out_hi.data_ptr(), (out_lo.data_ptr() if out_lo is not None else 0)
     if saved is not None:
         L.saved_y, L.saved_n = saved[0].data_ptr(), saved[1].data_ptr()
+    lat = None
+    if latent is not None:                         # CONV5S2 -> z = rint(y), its bf16 NHWC copy and the bits per image
+        lib = _lib.load()
+        lut, half_range, params, flag = latent
+        slots = lib.b2c_tc_tiles_per_image(kind, Hin, Win) * 8
+        zh = torch.empty((B, Ho, Wo, Cout), device=dev, dtype=torch.bfloat16)
+        bits_partial = torch.empty((B, slots), device=dev, dtype=torch.float32)
+        image_bits = torch.empty((B,), device=dev, dtype=torch.float32)
+        pp, keep = _lib.ptr_array(params)
+        L.lut, L.lut_half_range, L.bit_params = lut.data_ptr(), int(half_range), ctypes.cast(pp, ctypes.c_void_p).value
+        L.z_nhwc_out, L.bits_partial = zh.data_ptr(), bits_partial.data_ptr()
+        L.range_flag = flag.ptr().value if flag is not None else 0
+        lat = (zh, bits_partial, image_bits, slots, keep)
     sse = None
     if ref_image is not None:                      # DECONV3: fused clamp + squared errors
         lib = _lib.load()
@@ -197,6 +214,10 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         _lib.check(_lib.load().b2c_tc_layer_run(ctypes.byref(L), _stream()), "tc_layer_run")
         if sse is not None and reduce_sse:
             _lib.check(_lib.load().b2c_partial_reduce(_p(partial), _p(sse), B, tiles, 2, _stream()), "partial_reduce")
+        if lat is not None:
+            _lib.check(_lib.load().b2c_partial_reduce(_p(lat[1]), _p(lat[2]), B, lat[3], 1, _stream()), "partial_reduce")
+    if lat is not None:
+        return out_hi, lat[0], lat[2]
     if sse is not None:
         if grad_scale is not None:
             return out_hi, (sse if reduce_sse else partial), grad_out

@@ -254,6 +254,18 @@ typedef struct b2c_tc_layer {
   float* dbias_out; /* DECONV3X with grad_out (training), optional: dbias_out[o] += sum over (n, y, x) of grad_out -
                        the gradient of Decoder.deconv3.bias (3 floats, accumulated with atomic adds: zero-fill or
                        accumulate on purpose), instead of a separate pass over grad_out                          */
+  /* Last analysis layer at inference (CONV5S2, split3, gdn 0, out_f32_nchw, 128 channels: the persistent kernel), optional:
+   * with `lut` (b2c_entropy_lut_build, half range lut_half_range) the epilogue is the quantizer and the entropy model too
+   * (model.py:55-56,71-73): out_hi receives z = rint(conv3 output) instead of the pre-quantization value, z_nhwc_out its
+   * bf16 NHWC copy (what the synthesis transform reads), bits_partial[B][8 * tiles] the bits of every (tile, epilogue warp)
+   * - reduce with b2c_partial_reduce(bits_partial, image_bits, B, 8 * tiles, 1); bit_params = HOST array of the 11 Bitparm
+   * device vectors (for |z| beyond the table); range_flag as in b2c_quant_entropy_infer (may be NULL). */
+  const float* lut;
+  int lut_half_range;
+  const float* const* bit_params;
+  void* z_nhwc_out;
+  float* bits_partial;
+  int* range_flag;
 } b2c_tc_layer;
 
 /* number of 8x16-pixel tiles (CTAs per image and phase) a layer kind launches for an input grid = the `tiles`
