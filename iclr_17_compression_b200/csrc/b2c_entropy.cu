@@ -99,9 +99,8 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, float* 
 // per-element chain (relative error ~2^-11 per tanh changes the total bit count by ~1e-6 relative, far inside the
 // 1e-3 bpp bar; the per-channel softplus / tanh constants stay exact).  One CTA = 32 pixels x all channels of one
 // image, so the rounded latent is also emitted as the NHWC bf16 tensor the tensor-core synthesis transform reads.
+// (tanh_fast / cdf_fast / elem_bits_fast, BF16_EXACT_INT: b2c_entropy_formula.cuh)
 constexpr int QI_PIX = 32;
-// integers up to 256 are exact in bf16 (8 significand bits); the NHWC bf16 latent the tensor-core synthesis transform
-// reads is only valid below that.  The inference kernels raise *range_flag (sticky, never cleared here) otherwise.
 
 __global__ void __launch_bounds__(256) quant_entropy_infer_kernel(const float* __restrict__ y, BitPtrs bp,
                                                                   float* __restrict__ z,
