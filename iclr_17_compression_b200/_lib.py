@@ -101,7 +101,8 @@ SIGNATURES.update({
     "b2c_tc_nhwc_colsum": (_c_i, [_c_f, _c_f, _c_sz, _c_f]),
     "b2c_gdn_reparam_bwd": (_c_i, [_c_f] * 6 + [_c_i, _c_f]),
     "b2c_partial_reduce": (_c_i, [_c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
-    "b2c_infer_stats": (_c_i, [_c_f, _c_i, _c_i, _c_f, ctypes.c_double, ctypes.c_double, _c_f, _c_f, _c_f, _c_f]),
+    "b2c_infer_stats": (_c_i, [_c_f, _c_i, _c_i, _c_f, _c_f, _c_i, ctypes.c_double, ctypes.c_double, _c_f, _c_f, _c_f,
+                               _c_f]),
     "b2c_tc_nchw_to_nhwc": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
     "b2c_tc_nhwc_to_nchw": (_c_i, [_c_f, _c_f, _c_f, _c_i, _c_i, _c_i, _c_f]),
 })

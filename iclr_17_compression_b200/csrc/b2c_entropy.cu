@@ -505,12 +505,19 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
 // launch - adds the per-image bits and squared errors in index order and forms mse and bpp.  The eval forward used to
 // end with five small launches for this (partial reduction, two sums, two divisions): ~15 us of a 0.68 ms step.
 __global__ void __launch_bounds__(256) infer_stats_kernel(const float* __restrict__ partial, int per_image,
-                                                          const float* __restrict__ image_bits, float numel,
-                                                          float pixels, float* __restrict__ sse,
+                                                          float* __restrict__ image_bits,
+                                                          const float* __restrict__ bits_partial, int bits_slots,
+                                                          float numel, float pixels, float* __restrict__ sse,
                                                           float* __restrict__ totals, unsigned* __restrict__ ticket) {
   __shared__ float red[32];
   __shared__ unsigned s_last;
   const int n = blockIdx.x, B = gridDim.x;
+  if (bits_partial) {        // image n's bits from the per-(tile, warp) sums of the last analysis layer, fixed order
+    float b = 0.f;
+    for (int i = threadIdx.x; i < bits_slots; i += blockDim.x) b += __ldg(bits_partial + (size_t)n * bits_slots + i);
+    b = block_sum(b, red);
+    if (threadIdx.x == 0) image_bits[n] = b;
+  }
   const float2* src = reinterpret_cast<const float2*>(partial) + (size_t)n * per_image;
   float s0 = 0.f, s1 = 0.f;
   for (int i0 = threadIdx.x; i0 < per_image; i0 += 8 * blockDim.x) {
@@ -825,12 +832,14 @@ int b2c_partial_reduce(const float* partial, float* out, int B, int per_image, i
   return check_launch("partial_reduce");
 }
 
-int b2c_infer_stats(const float* sse_partial, int B, int tiles, const float* image_bits, double numel, double pixels,
-                    float* sse, float* totals, unsigned* ticket, void* stream) {
+int b2c_infer_stats(const float* sse_partial, int B, int tiles, float* image_bits, const float* bits_partial,
+                    int bits_slots, double numel, double pixels, float* sse, float* totals, unsigned* ticket,
+                    void* stream) {
   B2C_REQUIRE(sse_partial && image_bits && sse && totals && ticket && B > 0 && B <= 65535 && tiles > 0 && numel > 0 &&
-                  pixels > 0, "infer_stats: bad arguments");
-  infer_stats_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(sse_partial, tiles, image_bits, (float)numel,
-                                                                    (float)pixels, sse, totals, ticket);
+                  pixels > 0 && (!bits_partial || bits_slots > 0), "infer_stats: bad arguments");
+  infer_stats_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(sse_partial, tiles, image_bits, bits_partial,
+                                                                    bits_slots, (float)numel, (float)pixels, sse, totals,
+                                                                    ticket);
   count_launch();
   return check_launch("infer_stats");
 }

@@ -426,9 +426,11 @@ def quant_entropy_infer(y, params, lut=None, range_flag=None):
 _stats_tickets = {}
 
 
-def infer_stats(sse_partial, image_bits, numel, pixels):
+def infer_stats(sse_partial, image_bits, numel, pixels, bits_partial=None):
     """End of an eval forward in one launch (b2c_infer_stats; model.py:61,73,78): per-tile squared-error partial sums
     [B, tiles, 2] + per-image bits [B] -> (sse [B, 2], totals [4] = total bits, total squared error, mse, bpp).
+    ``bits_partial`` [B, slots]: per-(tile, warp) bit sums of the fused quantizer epilogue - ``image_bits`` is then
+    filled by this launch as well.
     The kernel finds its last block through a self-resetting ticket word; calls take the 64 words of a per-device pool in
     turn, so forwards in flight on different streams (or captured in different graphs) do not share one."""
     B, tiles, _ = sse_partial.shape
@@ -444,8 +446,9 @@ def infer_stats(sse_partial, image_bits, numel, pixels):
     sse = torch.empty((B, 2), device=dev, dtype=torch.float32)
     totals = torch.empty((4,), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev), _timed("infer_stats", 0, sse_partial.numel() * 4):
-        _lib.check(_lib.load().b2c_infer_stats(_p(sse_partial), B, tiles, _p(image_bits), float(numel), float(pixels),
-                                               _p(sse), _p(totals), _p(ticket), _stream()), "infer_stats")
+        _lib.check(_lib.load().b2c_infer_stats(_p(sse_partial), B, tiles, _p(image_bits), _p(bits_partial),
+                                               bits_partial.shape[1] if bits_partial is not None else 0, float(numel),
+                                               float(pixels), _p(sse), _p(totals), _p(ticket), _stream()), "infer_stats")
     return sse, totals
 
 

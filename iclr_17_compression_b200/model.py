@@ -147,7 +147,7 @@ class ImageCompressor(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def encode_tc(self, x, latent=None):
+    def encode_tc(self, x, latent=None, reduce_bits=True):
         """analysis transform on tensor cores (error-compensated bf16x3) -> y, fp32 NCHW.  ``latent`` (see
         tc.layer_run): quantizer + entropy model in the last layer's epilogue -> (z, z bf16 NHWC, image_bits)."""
         P, E = self._packed_weights(), self._enc
@@ -155,7 +155,7 @@ class ImageCompressor(nn.Module):
         h = B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv2"], E.conv2.bias, gdn=P["gdn2"], gdn_mode=1,
                            split3=True)
         return B2TC.layer_run(B2TC.TC_CONV5S2, h[0], h[1], P["conv3"], None, split3=True, out_f32_nchw=True,
-                              latent=latent)
+                              latent=latent, reduce_sse=reduce_bits)
 
     def check_latent_range(self):
         """The tensor-core synthesis transform reads the rounded latent as bf16, exact only for |z| <= 256.  The
@@ -195,15 +195,17 @@ class ImageCompressor(nn.Module):
         if self.out_channel_N == 128 and os.environ.get("B2C_FUSED_LATENT", "1") == "1" \
                 and os.environ.get("B2C_TC_PERSIST", "1") != "0":
             # the quantizer and the entropy model run in the epilogue of the last analysis layer: no separate pass over y
-            z, zh, image_bits = self.encode_tc(x, latent=(lut, B2F.LUT_HALF_RANGE, [B2F._prep(p, "bit-estimator parameter")
-                                                                                   for p in bitp], self._zflag))
+            z, zh, image_bits, bits_partial = self.encode_tc(
+                x, latent=(lut, B2F.LUT_HALF_RANGE, [B2F._prep(p, "bit-estimator parameter") for p in bitp], self._zflag),
+                reduce_bits=False)                 # (the statistics launch at the end reduces the per-warp bit sums)
         else:
+            bits_partial = None
             feature = self.encode_tc(x)
             z, zh, image_bits = B2F.quant_entropy_infer(feature, bitp, lut=lut, range_flag=self._zflag)
         # (reduce_sse=False: the per-tile partial sums come back and ONE launch forms the per-image squared errors, the
         # batch totals, mse and bpp - model.py:61,73,78)
         clipped, partial = self.decode_tc(z, ref_image=x, z_nhwc=zh, reduce_sse=False)
-        sse, totals = B2F.infer_stats(partial, image_bits, x.numel(), x.size(0) * x.size(2) * x.size(3))
+        sse, totals = B2F.infer_stats(partial, image_bits, x.numel(), x.size(0) * x.size(2) * x.size(3), bits_partial)
         return clipped, z, image_bits, sse, totals[0], totals[1], totals[2], totals[3]
 
     # Small eval batches (the reference's testKodak feeds ONE image per call, train.py:162-171) are host bound: the 8

@@ -214,10 +214,10 @@ def layer_run(kind, x_hi, x_lo, w, bias, gdn=None, gdn_mode=0, split3=False, out
         _lib.check(_lib.load().b2c_tc_layer_run(ctypes.byref(L), _stream()), "tc_layer_run")
         if sse is not None and reduce_sse:
             _lib.check(_lib.load().b2c_partial_reduce(_p(partial), _p(sse), B, tiles, 2, _stream()), "partial_reduce")
-        if lat is not None:
+        if lat is not None and reduce_sse:
             _lib.check(_lib.load().b2c_partial_reduce(_p(lat[1]), _p(lat[2]), B, lat[3], 1, _stream()), "partial_reduce")
-    if lat is not None:
-        return out_hi, lat[0], lat[2]
+    if lat is not None:         # (reduce_sse=False: the caller reduces the bit sums, e.g. functional.infer_stats)
+        return (out_hi, lat[0], lat[2]) if reduce_sse else (out_hi, lat[0], lat[2], lat[1])
     if sse is not None:
         if grad_scale is not None:
             return out_hi, (sse if reduce_sse else partial), grad_out

@@ -159,10 +159,12 @@ int b2c_partial_reduce(const float* partial, float* out, int B, int per_image, i
 
 /* End of an inference forward in ONE launch (model.py:61,73,78): sse[B][2] = fixed-order sums of the last layer's
  * per-tile partial sums sse_partial[B][tiles][2]; totals[4] = {sum of image_bits, sum of sse[:,0], that / numel (mse on
- * the unclamped reconstruction), bits / pixels (bpp)}.  `ticket`: one zero-initialised device word the library uses to
- * find the last block; the kernel leaves it at zero. */
-int b2c_infer_stats(const float* sse_partial, int B, int tiles, const float* image_bits, double numel, double pixels,
-                    float* sse, float* totals, unsigned* ticket, void* stream);
+ * the unclamped reconstruction), bits / pixels (bpp)}.  With bits_partial[B][bits_slots] (the fused quantizer / entropy
+ * epilogue of b2c_tc_layer.lut) image_bits is an OUTPUT, reduced here first; otherwise it is read.  `ticket`: one
+ * zero-initialised device word the library uses to find the last block; the kernel leaves it at zero. */
+int b2c_infer_stats(const float* sse_partial, int B, int tiles, float* image_bits, const float* bits_partial,
+                    int bits_slots, double numel, double pixels, float* sse, float* totals, unsigned* ticket,
+                    void* stream);
 /* grad_recon = g_clipped * 1[0<=recon<=1] + g_sse[0] * 2 (recon - x);
  * g_clipped may be NULL; g_sse is a DEVICE scalar (dL/d total unclamped SSE). */
 int b2c_clamp_sse_bwd(const float* recon, const float* x, const float* g_clipped,
